@@ -1,0 +1,123 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (utils/loss.py imported from
+/root/reference) on seeded synthetic inputs.  TEST INFRASTRUCTURE ONLY.
+
+Run in the build container (the reference tree does not exist on the GPU box):
+
+    python oracle/gen_golden.py            # rewrites tests/golden/
+
+The fixtures pin the oracle (tests/test_oracle.py) and, through it and directly, the CUDA path
+(tests/test_gpu_parity.py).  Inputs are regenerated from seeds by ``oracle.ucd_oracle.synthetic_case``;
+each fixture stores input checksums so generator drift is detected instead of silently accepted.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = os.environ.get("UCD_REFERENCE", "/root/reference")
+sys.path.insert(0, ROOT)
+sys.path.insert(0, REF)
+warnings.filterwarnings("ignore")
+
+from oracle.ucd_oracle import synthetic_case  # noqa: E402
+from utils.loss import (PixelConLossV2, UnbiasedCrossEntropy,  # noqa: E402  (the reference)
+                        UnbiasedKnowledgeDistillationLoss, pre_contrastive_pixel)
+
+OUT = os.path.join(ROOT, "tests", "golden")
+STRIDE = 997  # gradient sampling stride (prime)
+
+CASES = {
+    # name: (B, h, w, H, W, C, C_old, correlated)
+    "voc15-5_b2_513": (2, 33, 33, 513, 513, 21, 16, False),     # BASELINE config 1 / Appendix B row 1
+    "voc15-5s_b3_512": (3, 32, 32, 512, 512, 17, 16, False),    # per-GPU slice of config 2
+    "city13-6_b3": (3, 32, 64, 512, 1024, 20, 14, False),       # per-GPU slice of config 4
+    "voc15-5s_b2_corr": (2, 32, 32, 512, 512, 17, 16, True),    # class-correlated features
+    "tiny_b2": (2, 8, 8, 128, 128, 6, 4, False),                # full tensors stored
+}
+
+
+def run_reference(case, dtype):
+    d = {k: (v.to(dtype) if v.is_floating_point() else v.clone()) for k, v in case.items()}
+    f_n = d["f_n"].requires_grad_(True)
+    lr = d["logits_lr"].requires_grad_(True)
+    labels = d["labels"]
+    H, W = labels.shape[-2:]
+    c_old = d["l_po"].shape[1]
+    outputs = F.interpolate(lr, size=(H, W), mode="bilinear", align_corners=False)
+    outputs_old = F.interpolate(d["l_po"], size=(H, W), mode="bilinear", align_corners=False)
+    tup = pre_contrastive_pixel(f_n, labels, l_po=d["l_po"], f_o=d["f_o"])
+    A, Cst, la, lc, P = tup
+    con = PixelConLossV2(temperature=0.07)(A, Cst, la, lc, P)
+    lab_ce = labels.clone()
+    ce_px = UnbiasedCrossEntropy(old_cl=c_old, reduction="none", ignore_index=255)(outputs, lab_ce)
+    ce = ce_px.mean()
+    kd = UnbiasedKnowledgeDistillationLoss(alpha=1.0)(outputs, outputs_old)
+    (g_fn,) = torch.autograd.grad(con, f_n, retain_graph=True)
+    (g_lr,) = torch.autograd.grad(ce + 10 * kd, lr)
+    # the v2 branch leaves the mixed labels in label_n; the plain branch returns the clamped map
+    _, lab_flat = pre_contrastive_pixel(d["f_n"], labels)
+    return dict(A=A.detach(), Cst=Cst, la=la, lc=lc, P=P, con=con.detach(), ce=ce.detach(), kd=kd.detach(),
+                ce_px=ce_px.detach(), g_fn=g_fn, g_lr=g_lr, lab_ce=lab_ce, label_n=lab_flat,
+                outputs=outputs.detach())
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    for name, (B, h, w, H, W, C, C_old, corr) in CASES.items():
+        case = synthetic_case(B, h, w, H, W, C, C_old, correlated=corr)
+        r32 = run_reference(case, torch.float32)
+        r64 = run_reference(case, torch.float64)
+        fx = dict(
+            shape=np.array([B, h, w, H, W, C, C_old, int(corr)]),
+            in_sums=np.array([case[k].double().sum().item() for k in ("f_n", "f_o", "l_po", "logits_lr", "labels")]),
+            la=r32["la"].numpy().astype(np.int8), lc=r32["lc"].numpy().astype(np.int8),
+            label_n=r32["label_n"].numpy().astype(np.int8).reshape(B, h, w),
+            lab_ce_changed=np.array([(r32["lab_ce"] != case["labels"]).sum().item()]),
+            p_ones=np.array([(r32["P"] == 1).sum().item()]),
+            p_sum=np.array([r64["P"].sum().item()]),
+            con=np.array([r32["con"].item(), r64["con"].item()]),
+            ce=np.array([r32["ce"].item(), r64["ce"].item()]),
+            kd=np.array([r32["kd"].item(), r64["kd"].item()]),
+            g_fn_norm=np.array([r32["g_fn"].norm().item(), r64["g_fn"].norm().item()]),
+            g_lr_norm=np.array([r32["g_lr"].norm().item(), r64["g_lr"].norm().item()]),
+            g_fn_sample=r64["g_fn"].reshape(-1)[::STRIDE].numpy(),
+            g_lr_sample=r64["g_lr"].reshape(-1)[::STRIDE].numpy(),
+            ce_px_sample=r64["ce_px"].reshape(-1)[::STRIDE].numpy(),
+            out_sample=r32["outputs"].reshape(-1)[::STRIDE].numpy(),
+            stride=np.array([STRIDE]),
+        )
+        if name.startswith("tiny"):
+            fx.update(full_A=r64["A"].numpy(), full_Cst=r64["Cst"].numpy(), full_P=r64["P"].numpy(),
+                      full_g_fn=r64["g_fn"].numpy(), full_g_lr=r64["g_lr"].numpy(),
+                      full_ce_px=r64["ce_px"].numpy())
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **fx)
+        print(f"{name}: N_a={len(fx['la'])} N_c={len(fx['lc'])} sum_la={fx['la'].astype(int).sum()} "
+              f"sum_lc={fx['lc'].astype(int).sum()} P1={fx['p_ones'][0]} con={fx['con']} ce={fx['ce']} kd={fx['kd']} "
+              f"|g_fn|={fx['g_fn_norm'][0]:.6g} |g_lr|={fx['g_lr_norm'][0]:.6g}")
+
+    # label-downsample vectors: the reference's own resize+cast+clamp on assorted label maps
+    rng = torch.Generator().manual_seed(77)
+    lab_fx = {}
+    for i, (H, W, h, w) in enumerate([(513, 513, 33, 33), (512, 512, 32, 32), (321, 321, 21, 21),
+                                      (500, 375, 32, 24), (512, 1024, 32, 64), (129, 257, 9, 17)]):
+        lab = torch.randint(0, 21, (2, H, W), generator=rng)
+        # coarse blocks so that constant regions (the rounding hazard) exist, plus an ignore band
+        blk = torch.randint(0, 21, (2, H // 37 + 1, W // 29 + 1), generator=rng)
+        lab_b = blk.repeat_interleave(37, 1).repeat_interleave(29, 2)[:, :H, :W].clone()
+        lab_b[:, : H // 20] = 255
+        for tag, L in (("rand", lab), ("block", lab_b)):
+            f_dummy = torch.zeros(2, 4, h, w)
+            _, flat = pre_contrastive_pixel(f_dummy, L)
+            lab_fx[f"{tag}{i}_in"] = L.numpy().astype(np.uint8)
+            lab_fx[f"{tag}{i}_out"] = flat.numpy().astype(np.int8).reshape(2, h, w)
+    np.savez_compressed(os.path.join(OUT, "label_downsample.npz"), **lab_fx)
+    print("label_downsample: ", len(lab_fx) // 2, "maps")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,402 @@
+"""CPU oracle for the UCD distillation-loss hot path.  TEST INFRASTRUCTURE ONLY.
+
+This module is the checker, never the product: only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline / ``--impl reference``
+legs may import it.  Nothing under ``ucd_b200/`` imports it, and the product path
+raises if the CUDA library is missing instead of falling back to this code.
+
+It restates, in closed form (numpy for the integer/label work, torch-CPU for the
+floating point so that autograd yields reference gradients), what the reference
+computes on this path:
+
+* ``downsample_labels`` / ``prep_labels``  <- utils/loss.py:259-270, 354-361
+* ``pre_contrastive_pixel``               <- utils/loss.py:273-276, 363-395
+* ``pixel_con_loss`` (+ closed-form grad) <- utils/loss.py:412-466
+* ``unbiased_ce``                         <- utils/loss.py:96-109
+* ``unbiased_kd``                         <- utils/loss.py:148-184
+* ``upsample_bilinear``                   <- segmentation_module.py:133
+
+The arithmetic of ``F.interpolate(mode='bilinear', align_corners=False)`` lives in
+a third-party dependency (PyTorch ATen; requirements.txt pins torch==1.2.0, this
+image runs 2.11.0).  Its CPU kernel is restated in ``bilinear_taps`` /
+``_bilinear_eval_f32`` with the exact fp32 operation order that the x86 build
+uses (found by exhaustive search over association orders and verified bit-exact
+in tests/test_oracle.py against ``F.interpolate``): this matters because the
+reference truncates the interpolated *label map* to int8, so the last ulp decides
+labels (SURVEY.md §7 hard part 1).
+
+Pinning: the reference ships no tests or golden vectors for this path.  The oracle
+is pinned against outputs of the reference itself, run in the build container by
+``oracle/gen_golden.py`` and committed under ``tests/golden/`` (see
+tests/test_oracle.py).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+F32 = np.float32
+
+
+# ----------------------------------------------------------------------------
+# bilinear taps (ATen area_pixel_compute_source_index, align_corners=False)
+# ----------------------------------------------------------------------------
+def bilinear_taps(in_size: int, out_size: int, ft=F32):
+    """Source indices and weights of ATen's bilinear kernel along one axis, computed in the
+    tensor's own float type ``ft`` (fp32 for the label map and fp32 logits).
+
+    scale = ft(in)/out ; src = max(0, scale*(dst+0.5)-0.5) ; i0 = floor(src)
+    i1 = i0 + (i0 < in-1) ; w1 = src - i0 ; w0 = 1 - w1
+    """
+    if in_size == out_size:
+        idx = np.arange(out_size, dtype=np.int64)
+        return idx, idx.copy(), np.ones(out_size, ft), np.zeros(out_size, ft)
+    scale = ft(in_size) / ft(out_size)
+    dst = np.arange(out_size, dtype=ft)
+    src = (scale * (dst + ft(0.5))).astype(ft) - ft(0.5)
+    src = np.maximum(src, ft(0)).astype(ft)
+    i0 = np.minimum(np.floor(src).astype(np.int64), in_size - 1)
+    i1 = i0 + (i0 < in_size - 1)
+    w1 = np.clip((src - i0.astype(ft)).astype(ft), ft(0), ft(1)).astype(ft)
+    w0 = (ft(1) - w1).astype(ft)
+    return i0, i1, w0, w1
+
+
+def _fma32(a, b, c):
+    """fp32 fused multiply-add emulated through fp64 (product of two fp32 is exact)."""
+    return (np.asarray(a, F32).astype(np.float64) * np.asarray(b, F32).astype(np.float64)
+            + np.asarray(c, F32).astype(np.float64)).astype(F32)
+
+
+def _bilinear_eval_f32(x: np.ndarray, out_h: int, out_w: int) -> np.ndarray:
+    """Bit-exact restatement of ATen's CPU bilinear kernel on fp32 [..., H, W].
+
+    out = fma(h1*w1, x11, fma(h1*w0, x10, fma(h0*w0, x00, (h0*w1)*x01)))
+    with the four weight products rounded to fp32 first.
+    """
+    x = np.asarray(x, F32)
+    H, W = x.shape[-2:]
+    y0, y1, hy0, hy1 = bilinear_taps(H, out_h)
+    x0, x1, wx0, wx1 = bilinear_taps(W, out_w)
+    v00 = x[..., y0[:, None], x0[None, :]]
+    v01 = x[..., y0[:, None], x1[None, :]]
+    v10 = x[..., y1[:, None], x0[None, :]]
+    v11 = x[..., y1[:, None], x1[None, :]]
+    k00 = (hy0[:, None] * wx0[None, :]).astype(F32)
+    k01 = (hy0[:, None] * wx1[None, :]).astype(F32)
+    k10 = (hy1[:, None] * wx0[None, :]).astype(F32)
+    k11 = (hy1[:, None] * wx1[None, :]).astype(F32)
+    acc = (k01 * v01).astype(F32)
+    acc = _fma32(np.broadcast_to(k00, v00.shape), v00, acc)
+    acc = _fma32(np.broadcast_to(k10, v10.shape), v10, acc)
+    acc = _fma32(np.broadcast_to(k11, v11.shape), v11, acc)
+    return acc
+
+
+# ----------------------------------------------------------------------------
+# label part of pre_contrastive_pixel (integer results, must be bit exact)
+# ----------------------------------------------------------------------------
+def downsample_labels(labels, out_h: int, out_w: int, max_label: int = 20) -> np.ndarray:
+    """utils/loss.py:261-270: bilinear-resize the label map in fp32, truncate toward
+    zero, and zero everything outside [0, max_label].  int64 [B, h, w]."""
+    lab = np.asarray(labels).astype(F32)
+    g = np.trunc(_bilinear_eval_f32(lab, out_h, out_w)).astype(np.int64)
+    # .type(int8) wraps values >= 128 to negatives on CPU; together with the two
+    # masked fills (<0 -> 0, >max -> 0) this is "keep iff 0 <= g <= max_label".
+    g[(g < 0) | (g > max_label)] = 0
+    return g
+
+
+@dataclass
+class LabelPrep:
+    label_n: np.ndarray     # int64 [B,h,w]  clamped low-res GT labels
+    pseudo: np.ndarray      # int64 [B,h,w]  argmax_c l_po (first max)
+    mix: np.ndarray         # int64 [B,h,w]  GT-new label if >0 else pseudo label
+    anchor: np.ndarray      # bool  [B*h*w]  mix > 0
+    pseudo_mask: np.ndarray  # bool [B*h*w]  anchor & ~is_new
+    is_new: np.ndarray      # bool  [B*h*w]
+    min_new: int            # min over GT-new labels
+
+
+def prep_labels(labels, l_po, max_label: int = 20) -> LabelPrep:
+    """utils/loss.py:354-361 (v2 branch)."""
+    l_po = np.asarray(l_po, F32)
+    B, _, h, w = l_po.shape
+    g = downsample_labels(labels, h, w, max_label)
+    is_new = g.reshape(-1) > 0
+    if not is_new.any():
+        raise ValueError("no new-class pixel in the batch (reference raises at utils/loss.py:355)")
+    min_new = int(g.reshape(-1)[is_new].min())
+    pseudo = np.argmax(l_po, axis=1).astype(np.int64)   # first maximal index, like torch.max
+    mix = np.where(g > 0, g, pseudo)
+    anchor = mix.reshape(-1) > 0
+    return LabelPrep(g, pseudo, mix, anchor, anchor & ~is_new, is_new, min_new)
+
+
+# ----------------------------------------------------------------------------
+# feature part + joint probability matrix
+# ----------------------------------------------------------------------------
+def _rows(x: torch.Tensor) -> torch.Tensor:
+    """[B,C,h,w] -> [B*h*w, C] in (b,y,x) order."""
+    B, C, h, w = x.shape
+    return x.permute(0, 2, 3, 1).reshape(B * h * w, C)
+
+
+def _unit(x: torch.Tensor, eps: float = 1e-12) -> torch.Tensor:
+    return x / x.norm(dim=1, keepdim=True).clamp_min(eps)
+
+
+def pre_contrastive_pixel(f_n: torch.Tensor, labels: torch.Tensor, l_po: torch.Tensor,
+                          f_o: torch.Tensor, max_label: int = 20):
+    """Restatement of the v2 branch, utils/loss.py:354-395.
+
+    Returns (A, Cst, la, lc, P, prep): A keeps the autograd link to ``f_n``; Cst and P
+    are detached, la/lc are int64 tensors, prep is the LabelPrep of the batch.
+    """
+    prep = prep_labels(labels.detach().cpu().numpy(), l_po.detach().cpu().numpy(), max_label)
+    anchor = torch.from_numpy(prep.anchor)
+    pseudo = torch.from_numpy(prep.pseudo_mask)
+    mix = torch.from_numpy(prep.mix.reshape(-1))
+    A = _unit(_rows(f_n)[anchor])
+    Cst = torch.cat([A, _unit(_rows(f_o.detach())[pseudo])], dim=0).detach()
+    la = mix[anchor]
+    lc = torch.cat([la, mix[pseudo]])
+    p = torch.softmax(_rows(l_po.detach()), dim=1)
+    P = p[anchor] @ torch.cat([p[anchor], p[pseudo]]).T
+    gt_a = la >= prep.min_new
+    gt_c = lc >= prep.min_new
+    P = torch.where(gt_a[:, None] & gt_c[None, :], torch.ones((), dtype=P.dtype), P)
+    return A, Cst, la, lc, P.detach(), prep
+
+
+# ----------------------------------------------------------------------------
+# PixelConLossV2 (closed form of SURVEY.md Appendix A.2)
+# ----------------------------------------------------------------------------
+def pixel_con_loss(A: torch.Tensor, Cst: torch.Tensor, la: torch.Tensor, lc: torch.Tensor,
+                   P: Optional[torch.Tensor] = None, temperature: float = 0.07,
+                   self_col: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """utils/loss.py:435-466.  ``self_col[i]`` is the contrast column holding anchor i
+    itself (default i, the reference's ``eye`` on the first N_a columns)."""
+    n_a = A.shape[0]
+    same = (la.view(-1, 1) == lc.view(1, -1)).to(A.dtype)
+    pos = same.clone()
+    if self_col is None:
+        self_col = torch.arange(n_a)
+    ok = self_col >= 0
+    pos[torch.arange(n_a)[ok], self_col[ok]] -= 1.0
+    s = (A @ Cst.T) / temperature
+    neg = (torch.exp(s) * (1.0 - same)).sum(dim=1, keepdim=True)        # unshifted
+    sh = s - s.max(dim=1, keepdim=True).values.detach()
+    w = pos if P is None else pos * P
+    per_row = (w * (torch.log(torch.exp(sh)) - torch.log(torch.exp(sh) + neg))).sum(dim=1)
+    num = pos.sum(dim=1)
+    keep = num != 0
+    return (-(per_row[keep] / num[keep])).mean()
+
+
+def pixel_con_loss_closed_form(A, Cst, la, lc, P=None, temperature=0.07, self_col=None):
+    """Loss and dL/dA without autograd (Appendix A.2) - used to cross-check autograd and
+    as the specification of what the fused CUDA sweeps accumulate (V, U, T)."""
+    A = A.detach()
+    n_a = A.shape[0]
+    same = (la.view(-1, 1) == lc.view(1, -1)).to(A.dtype)
+    pos = same.clone()
+    if self_col is None:
+        self_col = torch.arange(n_a)
+    ok = self_col >= 0
+    pos[torch.arange(n_a)[ok], self_col[ok]] -= 1.0
+    s = (A @ Cst.T) / temperature
+    e = torch.exp(s)
+    neg = (e * (1 - same)).sum(1, keepdim=True)
+    m = s.max(1, keepdim=True).values
+    sh = s - m
+    den = torch.exp(sh) + neg
+    w = pos if P is None else pos * P
+    num = pos.sum(1)
+    keep = num != 0
+    M = int(keep.sum())
+    row = (w * (sh - torch.log(den))).sum(1)
+    loss = (-(row[keep] / num[keep])).sum() / M
+    kappa = torch.where(keep, 1.0 / (M * torch.where(keep, num, torch.ones_like(num))),
+                        torch.zeros_like(num))
+    T = (w / den).sum(1)
+    V = (e * (1 - same)) @ Cst                      # sum_k exp(s_ik) c_k over negatives
+    U = (w * neg / den) @ Cst                       # sum_j w_ij neg_i/den_ij c_j
+    dA = (kappa / temperature)[:, None] * (T[:, None] * V - U)
+    return loss, dA
+
+
+# ----------------------------------------------------------------------------
+# MiB unbiased cross-entropy / knowledge distillation
+# ----------------------------------------------------------------------------
+def unbiased_ce(x: torch.Tensor, y: torch.Tensor, old_cl: int, ignore_index: int = 255,
+                reduction: str = "mean", mutate_labels: bool = True) -> torch.Tensor:
+    """utils/loss.py:96-109.  ``y`` is remapped in place (y < old_cl -> 0) like the reference."""
+    lse_all = torch.logsumexp(x, dim=1)
+    lse_old = torch.logsumexp(x[:, :old_cl], dim=1)
+    yy = y if mutate_labels else y.clone()
+    yy[yy < old_cl] = 0
+    ign = yy == ignore_index
+    gather_idx = torch.where(ign, torch.zeros_like(yy), yy).unsqueeze(1)
+    picked = x.gather(1, gather_idx).squeeze(1)
+    per_px = torch.where(yy == 0, lse_all - lse_old, lse_all - picked)
+    per_px = torch.where(ign, torch.zeros_like(per_px), per_px)
+    if reduction == "none":
+        return per_px
+    if reduction == "sum":
+        return per_px.sum()
+    return per_px.sum() / (~ign).sum()          # nll_loss 'mean' divides by #non-ignored
+
+
+def unbiased_kd(x: torch.Tensor, t: torch.Tensor, alpha: float = 1.0, reduction: str = "mean",
+                mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """utils/loss.py:148-184 (the dead gamma/enc_out code at :155-156 has no effect)."""
+    c_old = t.shape[1]
+    lse_all = torch.logsumexp(x, dim=1)
+    bkg_idx = [0] + list(range(c_old, x.shape[1]))
+    lse_bkg = torch.logsumexp(x[:, bkg_idx], dim=1)
+    q = torch.softmax(t * alpha, dim=1)
+    per_px = (q[:, 0] * (lse_bkg - lse_all)
+              + (q[:, 1:] * (x[:, 1:c_old] - lse_all.unsqueeze(1))).sum(dim=1)) / c_old
+    if mask is not None:
+        per_px = per_px * mask.to(per_px.dtype)
+    if reduction == "mean":
+        return -per_px.mean()
+    if reduction == "sum":
+        return -per_px.sum()
+    return -per_px
+
+
+# ----------------------------------------------------------------------------
+# bilinear logit upsample (differentiable restatement)
+# ----------------------------------------------------------------------------
+def upsample_bilinear(x: torch.Tensor, out_h: int, out_w: int) -> torch.Tensor:
+    """segmentation_module.py:133 - F.interpolate(bilinear, align_corners=False), written as
+    explicit 4-tap gathers so autograd gives the adjoint the CUDA backward must match."""
+    H, W = x.shape[-2:]
+    ft = np.float64 if x.dtype == torch.float64 else F32
+    y0, y1, hy0, hy1 = bilinear_taps(H, out_h, ft)
+    x0, x1, wx0, wx1 = bilinear_taps(W, out_w, ft)
+    ty0, ty1, tx0, tx1 = (torch.from_numpy(a) for a in (y0, y1, x0, x1))
+    h0 = torch.from_numpy(hy0).to(x.dtype)[:, None]
+    h1 = torch.from_numpy(hy1).to(x.dtype)[:, None]
+    w0 = torch.from_numpy(wx0).to(x.dtype)[None, :]
+    w1 = torch.from_numpy(wx1).to(x.dtype)[None, :]
+    top, bot = x[..., ty0, :], x[..., ty1, :]
+    return ((h0 * w1) * top[..., tx1] + (h0 * w0) * top[..., tx0]
+            + (h1 * w0) * bot[..., tx0] + (h1 * w1) * bot[..., tx1])
+
+
+# ----------------------------------------------------------------------------
+# whole hot path, as train.py:115-116,133 combines it (5-tuple convention)
+# ----------------------------------------------------------------------------
+@dataclass
+class HotPathResult:
+    con: torch.Tensor
+    ce: torch.Tensor
+    kd: torch.Tensor
+    total: torch.Tensor
+    n_anchor: int
+    n_contrast: int
+
+
+def hot_path(f_n, f_o, l_po, logits_lr, labels, old_cl: int, temperature: float = 0.07,
+             alpha: float = 1.0, kd_weight: float = 10.0, max_label: int = 20) -> HotPathResult:
+    """loss = UNCE(outputs, labels).mean() + con/100 + kd_weight*UNKD(outputs, outputs_old)."""
+    H, W = labels.shape[-2:]
+    outputs = upsample_bilinear(logits_lr, H, W)
+    outputs_old = upsample_bilinear(l_po.detach(), H, W).detach()
+    A, Cst, la, lc, P, _ = pre_contrastive_pixel(f_n, labels, l_po, f_o, max_label)
+    con = pixel_con_loss(A, Cst, la, lc, P, temperature)
+    ce = unbiased_ce(outputs, labels.clone(), old_cl, 255, "none").mean()
+    kd = unbiased_kd(outputs, outputs_old, alpha)
+    return HotPathResult(con, ce, kd, ce + con / 100 + kd_weight * kd, A.shape[0], Cst.shape[0])
+
+
+# ----------------------------------------------------------------------------
+# multi-rank oracle: global-batch negatives
+# ----------------------------------------------------------------------------
+def pre_contrastive_pixel_global(f_n_list: Sequence[torch.Tensor], labels_list, l_po_list, f_o_list,
+                                 max_label: int = 20):
+    """Rank-sharded extension: rows stay per rank, columns are the concatenation over ranks of
+    every rank's [anchors ; pseudo] block, min_new is the global minimum.  Returns per-rank
+    (A_r, la_r, P_r, self_col_r) plus the shared (Cst, lc)."""
+    preps = [prep_labels(l.cpu().numpy(), lp.detach().cpu().numpy(), max_label)
+             for l, lp in zip(labels_list, l_po_list)]
+    min_new = min(p.min_new for p in preps)
+    A_l, C_l, la_l, lc_l, pa_l, pc_l, off = [], [], [], [], [], [], []
+    col = 0
+    for prep, f_n, f_o, l_po in zip(preps, f_n_list, f_o_list, l_po_list):
+        anchor = torch.from_numpy(prep.anchor)
+        pseudo = torch.from_numpy(prep.pseudo_mask)
+        mix = torch.from_numpy(prep.mix.reshape(-1))
+        A = _unit(_rows(f_n)[anchor])
+        A_l.append(A)
+        C_l.append(torch.cat([A.detach(), _unit(_rows(f_o.detach())[pseudo])]))
+        la_l.append(mix[anchor])
+        lc_l.append(torch.cat([mix[anchor], mix[pseudo]]))
+        p = torch.softmax(_rows(l_po.detach()), dim=1)
+        pa_l.append(p[anchor])
+        pc_l.append(torch.cat([p[anchor], p[pseudo]]))
+        off.append(col)
+        col += C_l[-1].shape[0]
+    Cst, lc, pc = torch.cat(C_l), torch.cat(lc_l), torch.cat(pc_l)
+    out = []
+    for A, la, pa, o in zip(A_l, la_l, pa_l, off):
+        P = pa @ pc.T
+        P = torch.where((la >= min_new)[:, None] & (lc >= min_new)[None, :], torch.ones((), dtype=P.dtype), P)
+        out.append((A, la, P, o + torch.arange(A.shape[0])))
+    return out, Cst, lc, min_new
+
+
+def pixel_con_loss_global(per_rank, Cst, lc, temperature: float = 0.07) -> torch.Tensor:
+    """Mean over all ranks' valid rows == the reference loss on the rank-concatenated batch
+    (up to the column order, which the loss does not depend on)."""
+    tot, cnt = 0.0, 0
+    for A, la, P, self_col in per_rank:
+        same = (la.view(-1, 1) == lc.view(1, -1)).to(A.dtype)
+        pos = same.clone()
+        pos[torch.arange(A.shape[0]), self_col] -= 1.0
+        s = (A @ Cst.T) / temperature
+        neg = (torch.exp(s) * (1 - same)).sum(1, keepdim=True)
+        sh = s - s.max(1, keepdim=True).values.detach()
+        row = (pos * P * (sh - torch.log(torch.exp(sh) + neg))).sum(1)
+        num = pos.sum(1)
+        keep = num != 0
+        tot = tot + (-(row[keep] / num[keep])).sum()
+        cnt += int(keep.sum())
+    return tot / cnt
+
+
+# ----------------------------------------------------------------------------
+# synthetic inputs (SURVEY.md §8d / Appendix B generators)
+# ----------------------------------------------------------------------------
+def gen(seed: int, *shape, scale: float = 1.0) -> torch.Tensor:
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed)) * scale
+
+
+def blob_labels(B: int, H: int, W: int, c_old: int, c_tot: int) -> torch.Tensor:
+    lab = torch.zeros(B, H, W, dtype=torch.int64)
+    lab[:, H // 5:3 * H // 5, W // 5:3 * W // 5] = c_old
+    lab[:, 3 * H // 5:4 * H // 5, W // 10:2 * W // 5] = c_tot - 1
+    lab[:, :H // 25, :] = 255
+    return lab
+
+
+def synthetic_case(B: int, h: int, w: int, H: int, W: int, c_tot: int, c_old: int, rank: int = 0,
+                   correlated: bool = False):
+    """Seeds 1..4 (+1000*rank) for f_n, f_o, l_po, low-res new logits; blob labels."""
+    o = 1000 * rank
+    f_n, f_o = gen(1 + o, B, 256, h, w), gen(2 + o, B, 256, h, w)
+    l_po = gen(3 + o, B, c_old, h, w, scale=3.0)
+    lr = gen(4 + o, B, c_tot, h, w, scale=3.0)
+    if correlated:
+        proto = gen(9, c_tot, 256)
+        cls = l_po.argmax(1)
+        add = proto[cls].permute(0, 3, 1, 2)
+        f_n, f_o = 0.3 * f_n + 0.7 * add, 0.3 * f_o + 0.7 * add
+    return dict(f_n=f_n, f_o=f_o, l_po=l_po, logits_lr=lr, labels=blob_labels(B, H, W, c_old, c_tot))
