@@ -1,0 +1,157 @@
+/*
+ * ucd_b200 C ABI - the drop-in boundary of the B200-native UCD distillation-loss hot path.
+ *
+ * One shared library (ucd_b200/libucd_b200.so), extern "C", plain pointers and sizes, no torch
+ * types.  Every pointer is a DEVICE pointer unless its name ends in _host.  Every entry point is
+ * asynchronous on `stream` (a cudaStream_t passed as void*), allocates nothing, keeps no global
+ * mutable state and returns 0 on success or a negative UCD_E* code; the message of the last
+ * failure on the calling thread is available from ucd_last_error().
+ *
+ * Each function names the reference interface (file:line under the UCD tree) it replaces.  The
+ * reference is pure PyTorch, so "FFI binding" means the ctypes stubs in ucd_b200/_lib.py; see
+ * INTEGRATION.md for the loss-module classes a maintainer swaps in.
+ */
+#ifndef UCD_B200_H
+#define UCD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UCD_OK 0
+#define UCD_EINVAL (-1)   /* bad argument (shape, alignment, unsupported size) */
+#define UCD_ECUDA (-2)    /* a CUDA runtime call or launch failed */
+#define UCD_ENOSUP (-3)   /* valid request this build does not support yet */
+
+#define UCD_REDUCTION_NONE 0
+#define UCD_REDUCTION_MEAN 1
+#define UCD_REDUCTION_SUM 2
+
+/* feature width of the pixel embeddings (DeepLab head_channels, segmentation_module.py:23,45) */
+#define UCD_FEAT_DIM 256
+/* rows/columns of one similarity tile; all packed buffers are padded to multiples of it */
+#define UCD_TILE 128
+
+int ucd_version(void);
+const char* ucd_last_error(void);
+/* 1 if a CUDA device of compute capability 10.x is present, else 0 (no other side effects). */
+int ucd_device_ok(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Unbiased cross-entropy   (utils/loss.py:96-109, alt utils/loss_new.py:89-115)
+ *   x      [B,C,HW] fp32 logits (NCHW contiguous)       y [B,HW] int64 labels, REMAPPED IN PLACE
+ *   loss_px[B,HW]   per-pixel loss (reduction 'none')   (y < old_cl -> 0, like loss.py:104-105)
+ *   lse_all/lse_old [B,HW] saved log-sum-exp over all / over the first old_cl channels
+ *   stats  float[2] : {sum of per-pixel losses, number of non-ignored pixels} (for mean/sum)
+ * ---------------------------------------------------------------------------------------- */
+int ucd_unce_fwd(const float* x, int64_t* y, float* loss_px, float* lse_all, float* lse_old,
+                 float* stats /*or NULL*/, float* scratch /*float[ucd_reduce_scratch_floats()], with stats*/,
+                 int B, int C, int old_cl, int64_t HW, int ignore_index, void* stream);
+/* dx = g * dloss/dx.  g_px [B,HW] per-pixel upstream gradient or NULL; then the upstream gradient is
+ * the scalar *g_scalar (device) times g_mul (host), and with mean_over_valid != 0 it is additionally
+ * divided by stats[1] (nll_loss 'mean' semantics). */
+int ucd_unce_bwd(const float* x, const int64_t* y, const float* lse_all, const float* lse_old,
+                 const float* g_px, const float* g_scalar, float g_mul, const float* stats,
+                 int mean_over_valid, float* dx, int B, int C, int old_cl, int64_t HW,
+                 int ignore_index, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Unbiased knowledge distillation   (utils/loss.py:148-184, alt utils/loss_new.py:216-263)
+ *   x [B,C,HW] new logits, t [B,C_old,HW] old logits, mask [B,HW] fp32 or NULL
+ *   out_px [B,HW] = -loss_px (written when non-NULL; what reduction 'none' returns)
+ *   stats float[1] = sum over pixels of loss_px (caller negates / divides)
+ *   lse3 [3,B,HW] saved {lse_all(x), lse_bkg(x over {0} U new), lse(alpha t)}
+ *   scratch: float[ucd_reduce_scratch_floats()]
+ * ---------------------------------------------------------------------------------------- */
+int ucd_unkd_fwd(const float* x, const float* t, const float* mask, float alpha, float* out_px,
+                 float* stats, float* lse3, float* scratch, int B, int C, int C_old, int64_t HW,
+                 void* stream);
+/* dx = upstream * d(-loss_px)/dx; upstream is g_px[B,HW] if non-NULL else *g_scalar * g_mul. */
+int ucd_unkd_bwd(const float* x, const float* t, const float* mask, float alpha, const float* lse3,
+                 const float* g_px, const float* g_scalar, float g_mul, float* dx, int B, int C,
+                 int C_old, int64_t HW, void* stream);
+size_t ucd_reduce_scratch_floats(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Bilinear logit upsample, align_corners=False   (segmentation_module.py:133)
+ *   in [N,h,w] -> out [N,H,W]   (N = B*C planes), and its adjoint.
+ * ---------------------------------------------------------------------------------------- */
+int ucd_upsample_bilinear_fwd(const float* in, float* out, int64_t planes, int h, int w, int H, int W,
+                              void* stream);
+int ucd_upsample_bilinear_bwd(const float* gout, float* gin, int64_t planes, int h, int w, int H, int W,
+                              void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Contrastive prep   (utils/loss.py:258-395 v2 branch == utils/utils.py:256-397)
+ *
+ * Step 1 (labels):  per low-res pixel p=(b,y,x): label_n = clamp(trunc(bilinear(labels))),
+ *   pseudo = argmax_c l_po, mix, flags (bit0 anchor, bit1 pseudo, bit2 GT-new), the rank of the pixel
+ *   among anchors / pseudos, and counts = {N_a, N_o, min_new, n_px}.
+ * Step 2 (pack): writes, for anchors (from f_n) and pseudo pixels (from f_o):
+ *   - unit-norm fp32 rows  anchor_f32 [N_a,256], contrast_f32 [N_a+N_o,256] (reference order b,y,x)
+ *   - bf16 tiles for the tensor-core sweeps: feat_tiles [T][32][128][8], prob_tiles [T][Kp/8][128][8]
+ *     (softmax of l_po), lab_tiles [T][128] (-1 = padding), T = ucd_con_max_tiles(n_px)
+ *   - row metadata: row_pix [n_px] pixel index of each anchor, inv_norm [n_px]
+ * Layout of a tile: element (row r, feature k) at ((k/8)*128 + r)*8 + k%8  (UMMA no-swizzle
+ * canonical layout, K-major for S=A*C^T and MN-major for V=E*C from the same bytes).
+ * ---------------------------------------------------------------------------------------- */
+int64_t ucd_con_max_tiles(int64_t n_px);          /* ceil(2*n_px/128)+1 */
+int ucd_con_prob_kpad(int C_old);                 /* C_old rounded up to a multiple of 16 */
+int ucd_con_prep_labels(const int64_t* labels, const float* l_po, int B, int C_old, int h, int w,
+                        int H, int W, int max_label, int32_t* label_n, int32_t* mix, int32_t* flags,
+                        int32_t* rank_a, int32_t* rank_o, int32_t* block_cnt, int32_t* counts,
+                        void* stream);
+int ucd_con_prep_pack(const float* f_n, const float* f_o, const float* l_po, const int32_t* mix,
+                      const int32_t* flags, const int32_t* rank_a, const int32_t* rank_o,
+                      const int32_t* block_cnt, const int32_t* counts, int B, int C_old, int h, int w,
+                      float* anchor_f32, float* contrast_f32, int32_t* la, int32_t* lc,
+                      void* feat_tiles, void* prob_tiles, int32_t* lab_tiles, int32_t* row_pix,
+                      float* inv_norm, int64_t max_tiles, void* stream);
+/* adjoint of the anchor gather + F.normalize: df_n[b,:,y,x] = (g - (g.a)a) * inv_norm for anchors, 0 else */
+int ucd_con_prep_bwd(const float* g_anchor, const float* anchor_f32, const float* inv_norm,
+                     const int32_t* flags, const int32_t* rank_a, const int32_t* block_cnt,
+                     float* df_n, int B, int h, int w, void* stream);
+/* compat path of PixelConLossV2.forward with caller-supplied dense tensors: fp32 rows -> bf16 tiles */
+int ucd_con_pack_rows(const float* rows, const int32_t* labels, int64_t n, void* feat_tiles,
+                      int32_t* lab_tiles, int64_t max_tiles, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * PixelConLossV2   (utils/loss.py:412-466), fused: the N_a x N_c matrices are never materialised.
+ *
+ * Columns (the contrast set) come as `n_chunks` chunks (one per rank after the all-gather) of
+ * `chunk_tiles` tiles each; chunk_counts [n_chunks][2] = {N_a, N_o} of that rank (device), the chunk
+ * holds N_a+N_o valid columns.  Rows (anchors) come as their own tile pointers (row block rb = tile rb;
+ * in the fused path they alias the first tiles of the local chunk), *n_rows of them are valid.
+ * self_tile0: column tile that holds row block 0 itself (row i of block rb is column i of tile
+ * self_tile0+rb - the reference's `eye` on the first N_a columns, loss.py:437), or -1.
+ * p_mode: 0 = P is None, 1 = joint probability pA.pC^T from the prob tiles with the GT-new override
+ * (both labels >= *min_new -> 1, loss.py:380-393), 2 = dense fp32 P [N_a, ldp] (single chunk).
+ *
+ * ucd_con_fwd runs sweep 1 (row max, negative sum, positive count, V = sum_neg exp(s) c), the
+ * combine, sweep 2 (loss terms, T, U) and the finalize; it writes
+ *   out float[2]  = {sum_i loss_i over rows with num_i != 0, number of such rows}
+ *   grad_unit [max_row_tiles*128, 256] = d(sum_i loss_i)/d a_i   (scaled by g/M in ucd_con_bwd)
+ * ---------------------------------------------------------------------------------------- */
+size_t ucd_con_workspace_bytes(int64_t max_row_tiles, int64_t max_col_tiles);
+int ucd_con_fwd(const void* feat_tiles, const void* prob_tiles, const int32_t* lab_tiles,
+                const int32_t* chunk_counts, int n_chunks, int64_t chunk_tiles, const void* row_feat_tiles,
+                const void* row_prob_tiles, const int32_t* row_lab_tiles, const int32_t* n_rows,
+                int64_t self_tile0, const int32_t* min_new, int p_mode, int kpad, const float* dense_p,
+                int64_t ldp, float inv_temperature, int need_grad, float* out, float* grad_unit,
+                void* workspace, size_t workspace_bytes, int64_t max_row_tiles, void* stream);
+/* d_anchor[i,:] = (*g_scalar) * g_mul / out[1] * grad_unit[i,:] for i < min(*n_rows, max_rows) */
+int ucd_con_bwd(const float* grad_unit, const float* out, const float* g_scalar, float g_mul,
+                const int32_t* n_rows, float* d_anchor, int64_t max_rows, void* stream);
+
+/* Self-test of the tcgen05/TMEM/bulk-copy building blocks: C[M=128,N] = A[128,K] * B[N,K]^T in bf16
+ * with the production tile layout, and D[128,256] = E[128,128] * Bt (MN-major B). Returns max abs
+ * error through *max_err_host (synchronises). */
+int ucd_selftest_umma(int variant, float* max_err_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UCD_B200_H */

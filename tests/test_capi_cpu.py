@@ -1,0 +1,96 @@
+"""CPU tests of the boundary: the C-ABI library builds, loads and exports every symbol that
+include/ucd_b200.h declares; host-side argument validation works without a GPU; the product refuses
+CPU tensors instead of falling back."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def L():
+    from ucd_b200 import _lib, build
+    build.build()
+    return _lib
+
+
+def declared_functions():
+    src = open(os.path.join(ROOT, "include", "ucd_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ucd_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported_and_bound(L):
+    names = declared_functions()
+    assert len(names) >= 20
+    h = ctypes.CDLL(L.LIB_PATH)
+    for n in names:
+        assert hasattr(h, n), "libucd_b200.so does not export %s" % n
+        assert n in L.EXPORTED, "ucd_b200/_lib.py has no ctypes prototype for %s" % n
+    assert sorted(L.EXPORTED) == names, "ctypes prototypes and header disagree"
+
+
+def test_version_and_sizes(L):
+    lib = L.lib()
+    assert lib.ucd_version() >= 100
+    assert lib.ucd_reduce_scratch_floats() > 0
+    assert lib.ucd_con_max_tiles(3072) == 49
+    assert lib.ucd_con_prob_kpad(16) == 16 and lib.ucd_con_prob_kpad(14) == 16 and lib.ucd_con_prob_kpad(17) == 32
+    assert lib.ucd_con_workspace_bytes(24, 49) > 24 * 128 * 256 * 4 * 2
+    assert lib.ucd_con_workspace_bytes(0, 49) == 0
+
+
+def test_argument_validation_reports_errors(L):
+    lib = L.lib()
+    rc = lib.ucd_unce_fwd(None, None, None, None, None, None, None, 1, 1, 1, 1, 255, None)
+    assert rc == -1 and b"null pointer" in lib.ucd_last_error()
+    with pytest.raises(RuntimeError, match="null pointer"):
+        L.check(rc, "unce_fwd")
+    err = ctypes.c_float()
+    assert lib.ucd_selftest_umma(7, ctypes.byref(err)) == -1
+
+
+def test_product_refuses_cpu_tensors(L):
+    import ucd_b200
+    x = torch.randn(1, 4, 8, 8)
+    y = torch.zeros(1, 8, 8, dtype=torch.int64)
+    with pytest.raises(RuntimeError, match="no CPU"):
+        ucd_b200.UnbiasedCrossEntropy(old_cl=2)(x, y)
+    with pytest.raises(RuntimeError, match="no CPU"):
+        ucd_b200.UnbiasedKnowledgeDistillationLoss()(x, x[:, :2])
+    with pytest.raises(RuntimeError, match="no CPU"):
+        ucd_b200.interpolate_bilinear(x, (16, 16))
+    f = torch.randn(1, 256, 4, 4)
+    with pytest.raises(RuntimeError, match="no CPU"):
+        ucd_b200.pre_contrastive_pixel(f, torch.zeros(1, 64, 64, dtype=torch.int64), l_po=torch.randn(1, 4, 4, 4), f_o=f)
+
+
+def test_reference_signatures_preserved():
+    """Constructor / forward signatures the trainer relies on (train.py:32,38,50,115-116,133)."""
+    import inspect
+    import ucd_b200 as U
+    assert list(inspect.signature(U.UnbiasedCrossEntropy.__init__).parameters)[1:] == ["old_cl", "reduction", "ignore_index"]
+    assert list(inspect.signature(U.UnbiasedKnowledgeDistillationLoss.__init__).parameters)[1:] == ["reduction", "alpha"]
+    assert list(inspect.signature(U.PixelConLossV2.__init__).parameters)[1:3] == ["sample_method", "temperature"]
+    assert list(inspect.signature(U.PixelConLossV2.forward).parameters)[1:] == [
+        "anchor_features", "contrast_feature", "anchor_labels", "contrast_labels", "P"]
+    assert list(inspect.signature(U.UnbiasedCrossEntropy.forward).parameters)[1:] == ["inputs", "targets"]
+    assert list(inspect.signature(U.UnbiasedKnowledgeDistillationLoss.forward).parameters)[1:] == ["inputs", "targets", "mask"]
+    assert list(inspect.signature(U.pre_contrastive_pixel).parameters)[:4] == ["f_n", "l_n", "l_po", "f_o"]
+    assert U.pre_contractive_pixel is U.pre_contrastive_pixel
+    m = U.PixelConLossV2(temperature=0.07)
+    assert len(list(m.parameters())) == 0 and len(list(m.buffers())) == 0
+
+
+def test_no_product_import_of_oracle():
+    """The product path must never import, include, load or execute anything under oracle/."""
+    bad = re.compile(r"^\s*(from|import)\s+oracle|#include\s*[\"<][^\n]*oracle|(CDLL|open|exec|system|run)\([^\n]*oracle", re.M)
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "ucd_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not bad.search(src), os.path.join(dirpath, f)

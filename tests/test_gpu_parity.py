@@ -1,0 +1,279 @@
+"""GPU parity tests (run on the B200 box: ``pytest -m gpu``): the CUDA path, called through the
+reference-shaped modules / the C ABI, against the CPU oracle and the golden fixtures.
+
+Bars (BASELINE.json): bit-exact for label maps, pseudo labels, masks, counts, ignore handling and the
+in-place label remap; loss within 1e-3 relative; gradient cosine >= 0.999.
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import ucd_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-3      # loss tolerance stated by north_star
+COS = 0.999     # gradient cosine stated by north_star
+
+
+@pytest.fixture(scope="module")
+def U():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import ucd_b200
+    from ucd_b200 import _lib
+    assert _lib.lib().ucd_device_ok() == 1, "ucd_b200 needs a compute-capability 10.x device"
+    return ucd_b200
+
+
+def cos(a, b):
+    a, b = a.double().reshape(-1).cpu(), b.double().reshape(-1).cpu()
+    return float(a @ b / (a.norm() * b.norm()).clamp_min(1e-300))
+
+
+def load_case(golden_dir, name):
+    fx = np.load(os.path.join(golden_dir, name + ".npz"))
+    B, h, w, H, W, C, C_old, corr = (int(v) for v in fx["shape"])
+    return fx, O.synthetic_case(B, h, w, H, W, C, C_old, correlated=bool(corr)), (B, h, w, H, W, C, C_old)
+
+
+# ------------------------------------------------------------------------------------------------
+def test_umma_selftest(U):
+    from ucd_b200 import _lib
+    for variant in (0, 1):
+        err = ctypes.c_float(-1.0)
+        _lib.check(_lib.lib().ucd_selftest_umma(variant, ctypes.byref(err)), "selftest")
+        assert 0 <= err.value < 2e-3, (variant, err.value)
+
+
+@pytest.mark.parametrize("shape,size", [((2, 5, 9, 13), (144, 208)), ((2, 21, 33, 33), (513, 513)),
+                                        ((1, 17, 32, 32), (512, 512)), ((1, 3, 32, 64), (512, 1024)),
+                                        ((1, 2, 7, 5), (7, 5)), ((1, 1, 16, 16), (40, 24))])
+def test_upsample_fwd_bwd(U, shape, size):
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(*shape, generator=g)
+    go = torch.randn(*shape[:2], *size, generator=g)
+    xr = x.clone().requires_grad_(True)
+    ref = F.interpolate(xr, size=size, mode="bilinear", align_corners=False)
+    ref.backward(go)
+    xc = x.cuda().requires_grad_(True)
+    out = U.interpolate_bilinear(xc, size)
+    out.backward(go.cuda())
+    torch.testing.assert_close(out.cpu(), ref.detach(), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(xc.grad.cpu(), xr.grad, rtol=1e-4, atol=1e-5)
+    # restated oracle agrees as well
+    torch.testing.assert_close(out.cpu(), O.upsample_bilinear(x, *size), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("shape", [(2, 7, 9, 11), (2, 21, 64, 64), (1, 17, 33, 33), (3, 151, 16, 20)])
+@pytest.mark.parametrize("reduction", ["none", "mean", "sum"])
+def test_unce(U, shape, reduction):
+    B, C, H, W = shape
+    old_cl = max(1, (C * 3) // 4)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, C, H, W, generator=g) * 3
+    y = torch.randint(0, C, (B, H, W), generator=g)
+    y[0, :2] = 255
+    y[-1, -1, -3:] = 255
+    xr = x.double().requires_grad_(True)
+    y_ref = y.clone()
+    ref = O.unbiased_ce(xr, y_ref, old_cl, 255, reduction)
+    w8 = torch.randn(B, H, W, generator=g).double()
+    (ref * w8).sum().backward() if reduction == "none" else ref.backward()
+    xc, yc = x.cuda().requires_grad_(True), y.cuda()
+    out = U.UnbiasedCrossEntropy(old_cl=old_cl, reduction=reduction, ignore_index=255)(xc, yc)
+    (out * w8.cuda().float()).sum().backward() if reduction == "none" else out.backward()
+    assert torch.equal(yc.cpu(), y_ref), "in-place label remap must be bit exact"
+    torch.testing.assert_close(out.cpu().double(), ref.detach(), rtol=2e-5, atol=2e-5)
+    if reduction == "none":
+        assert (out.cpu()[y_ref == 255] == 0).all()
+    assert cos(xc.grad, xr.grad) > 1 - 1e-6
+    torch.testing.assert_close(xc.grad.cpu().double(), xr.grad, rtol=1e-3, atol=1e-6 * float(xr.grad.abs().max()) + 1e-9)
+
+
+def test_unce_broadcast_grad_and_noncontiguous_targets(U):
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 6, 8, 12, generator=g)
+    y = torch.randint(0, 6, (2, 8, 24), generator=g)[:, :, ::2]          # non-contiguous view
+    y_ref = y.clone()
+    xr = x.double().requires_grad_(True)
+    O.unbiased_ce(xr, y_ref, 4, 255, "none").mean().backward()
+    xc = x.cuda().requires_grad_(True)
+    yc = torch.zeros(2, 8, 24, dtype=torch.int64, device="cuda")[:, :, ::2]
+    yc.copy_(y.cuda())
+    assert not yc.is_contiguous()
+    U.UnbiasedCrossEntropy(old_cl=4, reduction="none")(xc, yc).mean().backward()   # train.py:116 usage
+    assert torch.equal(yc.cpu(), y_ref)
+    assert cos(xc.grad, xr.grad) > 1 - 1e-6
+
+
+@pytest.mark.parametrize("shape,c_old", [((2, 7, 9, 11), 4), ((2, 21, 64, 64), 16), ((1, 17, 33, 33), 16),
+                                         ((2, 151, 16, 20), 101), ((1, 5, 8, 8), 5)])
+@pytest.mark.parametrize("reduction,alpha,use_mask", [("mean", 1.0, False), ("sum", 0.5, True), ("none", 2.0, True)])
+def test_unkd(U, shape, c_old, reduction, alpha, use_mask):
+    B, C, H, W = shape
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(B, C, H, W, generator=g) * 3
+    t = torch.randn(B, c_old, H, W, generator=g) * 3
+    mask = (torch.rand(B, H, W, generator=g) > 0.3) if use_mask else None
+    xr = x.double().requires_grad_(True)
+    ref = O.unbiased_kd(xr, t.double(), alpha, reduction, mask)
+    w8 = torch.randn(B, H, W, generator=g).double()
+    (ref * w8).sum().backward() if reduction == "none" else ref.backward()
+    xc = x.cuda().requires_grad_(True)
+    mod = U.UnbiasedKnowledgeDistillationLoss(reduction=reduction, alpha=alpha)
+    out = mod(xc, t.cuda(), None if mask is None else mask.cuda())
+    (out * w8.cuda().float()).sum().backward() if reduction == "none" else out.backward()
+    torch.testing.assert_close(out.cpu().double(), ref.detach(), rtol=5e-5, atol=5e-5)
+    assert cos(xc.grad, xr.grad) > 1 - 1e-6
+    torch.testing.assert_close(xc.grad.cpu().double(), xr.grad, rtol=1e-3, atol=1e-6 * float(xr.grad.abs().max()) + 1e-9)
+
+
+# ------------------------------------------------------------------------------------------------
+def test_label_downsample_bit_exact(U, golden_dir):
+    """label_n of the prep kernel == the reference's resize+int8+clamp on every golden label map."""
+    from ucd_b200.losses import _build_pack
+    fx = np.load(os.path.join(golden_dir, "label_downsample.npz"))
+    for n in sorted(k[:-3] for k in fx.files if k.endswith("_in")):
+        lab = torch.from_numpy(fx[n + "_in"].astype(np.int64)).cuda()
+        want = fx[n + "_out"].astype(np.int64)
+        B, h, w = want.shape
+        l_po = torch.zeros(B, 2, h, w, device="cuda")
+        l_po[:, 1] = 1.0                                           # pseudo label 1 everywhere -> every pixel anchors
+        f = torch.randn(B, 256, h, w, device="cuda")
+        pk = _build_pack(f, f, l_po, lab, 20)
+        assert np.array_equal(pk.label_n.view(B, h, w).cpu().numpy().astype(np.int64), want), n
+        assert np.array_equal(pk.label_n.cpu().numpy(), O.downsample_labels(fx[n + "_in"].astype(np.int64), h, w).reshape(-1)), n
+
+
+@pytest.mark.parametrize("name", ["tiny_b2", "voc15-5_b2_513", "voc15-5s_b3_512", "city13-6_b3", "voc15-5s_b2_corr"])
+def test_contrastive_prep_integer_artefacts_and_rows(U, golden_dir, name):
+    fx, case, (B, h, w, H, W, C, C_old) = load_case(golden_dir, name)
+    tup = U.pre_contrastive_pixel(case["f_n"].cuda(), case["labels"].cuda(), l_po=case["l_po"].cuda(),
+                                  f_o=case["f_o"].cuda())
+    A, Cst, la, lc, JP = tup
+    pk = JP.pack
+    prep = O.prep_labels(case["labels"].numpy(), case["l_po"].numpy())
+    # bit-exact integer artefacts: vs the reference's fixture and vs the oracle
+    assert np.array_equal(la.cpu().numpy(), fx["la"]) and np.array_equal(lc.cpu().numpy(), fx["lc"])
+    assert np.array_equal(pk.label_n.cpu().numpy().reshape(B, h, w), fx["label_n"].astype(np.int32))
+    assert pk.min_new == prep.min_new and pk.n_a == int(prep.anchor.sum()) and pk.n_o == int(prep.pseudo_mask.sum())
+    flags = pk.flags.cpu().numpy()
+    assert np.array_equal((flags & 1) > 0, prep.anchor) and np.array_equal((flags & 2) > 0, prep.pseudo_mask)
+    assert np.array_equal(pk.mix.cpu().numpy(), prep.mix.reshape(-1))
+    # normalised rows and the dense joint-probability matrix
+    Ao, Co, lao, lco, Po, _ = O.pre_contrastive_pixel(case["f_n"], case["labels"], case["l_po"], case["f_o"])
+    torch.testing.assert_close(A.cpu(), Ao, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(Cst.cpu(), Co, rtol=1e-5, atol=1e-6)
+    Pd = JP.dense().cpu()
+    assert int((Pd == 1).sum()) == int(fx["p_ones"][0])
+    torch.testing.assert_close(Pd, Po, rtol=1e-4, atol=1e-6)
+    # packed bf16 tiles hold the same rows (bf16 rounding only) and padding labels are -1
+    ft = pk.feat_tiles.float().cpu()                     # [T, 32, 128, 8]
+    rows = ft.permute(0, 2, 1, 3).reshape(-1, 256)[:pk.n_c]
+    assert float((rows - Co).abs().max()) < 2 ** -8
+    lt = pk.lab_tiles.cpu().reshape(-1)
+    assert np.array_equal(lt[:pk.n_c].numpy(), fx["lc"].astype(np.int32)) and bool((lt[pk.n_c:] == -1).all())
+
+
+@pytest.mark.parametrize("name", ["tiny_b2", "voc15-5_b2_513", "voc15-5s_b3_512", "city13-6_b3", "voc15-5s_b2_corr"])
+def test_contrastive_loss_and_grad_vs_reference_fixture(U, golden_dir, name):
+    fx, case, (B, h, w, H, W, C, C_old) = load_case(golden_dir, name)
+    f_n = case["f_n"].cuda().requires_grad_(True)
+    tup = U.pre_contrastive_pixel(f_n, case["labels"].cuda(), l_po=case["l_po"].cuda(), f_o=case["f_o"].cuda())
+    loss = U.PixelConLossV2(temperature=0.07)(*tup)
+    loss.backward()
+    assert loss.item() == pytest.approx(fx["con"][1], rel=REL)
+    s = int(fx["stride"][0])
+    got = f_n.grad.reshape(-1)[::s].cpu()
+    assert cos(got, torch.from_numpy(fx["g_fn_sample"])) >= COS
+    assert float(f_n.grad.norm()) == pytest.approx(fx["g_fn_norm"][1], rel=2e-2)
+    if "full_g_fn" in fx.files:
+        assert cos(f_n.grad, torch.from_numpy(fx["full_g_fn"])) >= COS
+
+
+@pytest.mark.parametrize("n_a,n_c,with_p", [(200, 333, "none"), (200, 333, "dense"), (129, 128, "dense"),
+                                            (64, 700, "none"), (300, 300, "dense")])
+def test_pixelconloss_compat_dense_inputs(U, n_a, n_c, with_p):
+    """PixelConLossV2.forward with plain dense tensors, arbitrary labels, P None / dense (loss.py:412-466)."""
+    g = torch.Generator().manual_seed(n_a * 1000 + n_c)
+    A = F.normalize(torch.randn(n_a, 256, generator=g), dim=1)
+    Cst = F.normalize(torch.randn(n_c, 256, generator=g), dim=1)
+    k = min(n_a, n_c)
+    Cst[:k] = A[:k]
+    la = torch.randint(1, 6, (n_a,), generator=g)
+    lc = torch.randint(1, 6, (n_c,), generator=g)
+    lc[:k] = la[:k]
+    P = torch.rand(n_a, n_c, generator=g) if with_p == "dense" else None
+    Ar = A.double().requires_grad_(True)
+    ref = O.pixel_con_loss(Ar, Cst.double(), la, lc, None if P is None else P.double(), 0.07,
+                           self_col=torch.where(torch.arange(n_a) < n_c, torch.arange(n_a), -torch.ones(n_a, dtype=torch.long)))
+    ref.backward()
+    Ac = A.cuda().requires_grad_(True)
+    out = U.PixelConLossV2(temperature=0.07)(Ac, Cst.cuda(), la.to(torch.int8).cuda(), lc.to(torch.int8).cuda(),
+                                             None if P is None else P.cuda())
+    out.backward()
+    assert out.item() == pytest.approx(ref.item(), rel=REL)
+    assert cos(Ac.grad, Ar.grad) >= COS
+
+
+@pytest.mark.parametrize("name", ["voc15-5_b2_513", "voc15-5s_b3_512"])
+def test_whole_hot_path_matches_reference(U, golden_dir, name):
+    """train.py:115-116,133: UNCE(outputs,labels).mean() + con/100 + 10*UNKD(outputs, outputs_old)."""
+    fx, case, (B, h, w, H, W, C, C_old) = load_case(golden_dir, name)
+    f_n = case["f_n"].cuda().requires_grad_(True)
+    lr = case["logits_lr"].cuda().requires_grad_(True)
+    labels = case["labels"].cuda()
+    l_po, f_o = case["l_po"].cuda(), case["f_o"].cuda()
+    outputs = U.interpolate_bilinear(lr, (H, W))
+    with torch.no_grad():
+        outputs_old = U.interpolate_bilinear(l_po, (H, W))
+    con = U.PixelConLossV2(temperature=0.07)(*U.pre_contrastive_pixel(f_n, labels, l_po=l_po, f_o=f_o))
+    ce = U.UnbiasedCrossEntropy(old_cl=C_old, ignore_index=255, reduction="none")(outputs, labels).mean()
+    kd = U.UnbiasedKnowledgeDistillationLoss(alpha=1.0)(outputs, outputs_old)
+    (ce + con / 100 + 10 * kd).backward()
+    assert con.item() == pytest.approx(fx["con"][1], rel=REL)
+    assert ce.item() == pytest.approx(fx["ce"][1], rel=REL)
+    assert kd.item() == pytest.approx(fx["kd"][1], rel=REL)
+    s = int(fx["stride"][0])
+    assert cos(lr.grad.reshape(-1)[::s], torch.from_numpy(fx["g_lr_sample"])) >= COS
+    assert float(lr.grad.norm()) == pytest.approx(fx["g_lr_norm"][1], rel=1e-3)
+    assert int((labels.cpu() != case["labels"]).sum()) == int(fx["lab_ce_changed"][0])
+
+
+# ------------------------------------------------------------------------------------------------
+# size-independent properties at BASELINE config-2 size (batch 24 @ 512x512)
+# ------------------------------------------------------------------------------------------------
+def _run_con(U, case, order=None):
+    f_n = case["f_n"].cuda()
+    labels, l_po, f_o = case["labels"].cuda(), case["l_po"].cuda(), case["f_o"].cuda()
+    if order is not None:
+        f_n, labels, l_po, f_o = f_n[order], labels[order], l_po[order], f_o[order]
+    f_n = f_n.clone().requires_grad_(True)
+    loss = U.PixelConLossV2(temperature=0.07)(*U.pre_contrastive_pixel(f_n, labels, l_po=l_po, f_o=f_o))
+    loss.backward()
+    return loss.detach(), f_n.grad
+
+
+def test_full_size_properties(U):
+    case = O.synthetic_case(24, 32, 32, 512, 512, 17, 16, correlated=True)
+    l1, g1 = _run_con(U, case)
+    l2, g2 = _run_con(U, case)
+    assert torch.isfinite(l1) and torch.isfinite(g1).all()
+    assert torch.equal(l1, l2) and torch.equal(g1, g2), "fixed-order reductions: runs must be bit-identical"
+    # the loss is invariant to the order of images (rows and columns are both permuted)
+    perm = torch.randperm(24, generator=torch.Generator().manual_seed(1)).cuda()
+    l3, g3 = _run_con(U, case, perm)
+    assert l3.item() == pytest.approx(l1.item(), rel=1e-4)
+    assert cos(g3, g1[perm]) > 0.9999
+    # normalisation adjoint: the gradient of every pixel is orthogonal to its feature vector
+    dots = (g1 * case["f_n"].cuda()).sum(1)
+    assert float(dots.abs().max()) < 1e-3 * float(g1.abs().max()) * float(case["f_n"].norm(dim=1).max())
+    # non-anchor pixels get exactly zero gradient
+    prep = O.prep_labels(case["labels"].numpy(), case["l_po"].numpy())
+    gz = g1.permute(0, 2, 3, 1).reshape(-1, 256)[torch.from_numpy(~prep.anchor).cuda()]
+    assert gz.numel() == 0 or float(gz.abs().max()) == 0.0

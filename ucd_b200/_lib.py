@@ -1,0 +1,74 @@
+"""ctypes binding of libucd_b200.so - the C ABI declared in include/ucd_b200.h.
+
+This is the "reference-side FFI stub": the reference is pure PyTorch, so the maintainer-facing
+binding is these ctypes prototypes plus the nn.Module classes in ucd_b200/losses.py.
+There is no fallback: if the shared library is missing or fails to load, every entry point raises.
+"""
+import ctypes
+import os
+from ctypes import c_float, c_int, c_int64, c_size_t, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libucd_b200.so")
+
+_lib = None
+
+P = c_void_p
+_PROTOS = {
+    "ucd_version": (c_int, []),
+    "ucd_last_error": (ctypes.c_char_p, []),
+    "ucd_device_ok": (c_int, []),
+    "ucd_reduce_scratch_floats": (c_size_t, []),
+    "ucd_unce_fwd": (c_int, [P, P, P, P, P, P, P, c_int, c_int, c_int, c_int64, c_int, P]),
+    "ucd_unce_bwd": (c_int, [P, P, P, P, P, P, c_float, P, c_int, P, c_int, c_int, c_int, c_int64, c_int, P]),
+    "ucd_unkd_fwd": (c_int, [P, P, P, c_float, P, P, P, P, c_int, c_int, c_int, c_int64, P]),
+    "ucd_unkd_bwd": (c_int, [P, P, P, c_float, P, P, P, c_float, P, c_int, c_int, c_int, c_int64, P]),
+    "ucd_upsample_bilinear_fwd": (c_int, [P, P, c_int64, c_int, c_int, c_int, c_int, P]),
+    "ucd_upsample_bilinear_bwd": (c_int, [P, P, c_int64, c_int, c_int, c_int, c_int, P]),
+    "ucd_con_max_tiles": (c_int64, [c_int64]),
+    "ucd_con_prob_kpad": (c_int, [c_int]),
+    "ucd_con_prep_labels": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P]),
+    "ucd_con_prep_pack": (c_int, [P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, P,
+                                  c_int64, P]),
+    "ucd_con_prep_bwd": (c_int, [P, P, P, P, P, P, P, c_int, c_int, c_int, P]),
+    "ucd_con_pack_rows": (c_int, [P, P, c_int64, P, P, c_int64, P]),
+    "ucd_con_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "ucd_con_fwd": (c_int, [P, P, P, P, c_int, c_int64, P, P, P, P, c_int64, P, c_int, c_int, P, c_int64, c_float,
+                            c_int, P, P, P, c_size_t, c_int64, P]),
+    "ucd_con_bwd": (c_int, [P, P, P, c_float, P, P, c_int64, P]),
+    "ucd_selftest_umma": (c_int, [c_int, ctypes.POINTER(c_float)]),
+}
+EXPORTED = tuple(_PROTOS)
+
+
+def lib():
+    """The loaded library; raises (never falls back) when it is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "ucd_b200: %s is missing - build it with `python -m ucd_b200.build` "
+                "(there is no CPU or PyTorch fallback for this path)" % LIB_PATH)
+        h = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _PROTOS.items():
+            fn = getattr(h, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = h
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().ucd_last_error().decode("utf-8", "replace")
+        raise RuntimeError("ucd_b200 %s failed (code %d): %s" % (what, rc, msg))
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def cur_stream():
+    import torch
+    return c_void_p(torch.cuda.current_stream().cuda_stream)

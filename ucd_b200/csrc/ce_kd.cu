@@ -1,0 +1,473 @@
+// MiB unbiased cross-entropy and unbiased knowledge distillation, forward and backward.
+// Reference semantics: utils/loss.py:96-109 (UnbiasedCrossEntropy.forward) and
+// utils/loss.py:148-184 (UnbiasedKnowledgeDistillationLoss.forward); closed forms and gradients
+// in SURVEY.md Appendix A.3.
+//
+// All four kernels are HBM-bound streaming kernels over NCHW fp32 logits: a thread owns VEC
+// consecutive pixels (VEC=4 -> 128-bit coalesced accesses, a warp touches 512 contiguous bytes per
+// channel), walks the C channels with stride H*W and keeps every log-sum-exp it needs as an online
+// (max, sum) pair in registers, so x (and t) are read exactly once per pass.  One MUFU.EX2 per
+// element (see lse_push).  Partial sums go to a per-block slot and are reduced by a second
+// fixed-order kernel, so results are run-to-run deterministic.
+#include "common.cuh"
+
+namespace ucd {
+
+constexpr int kStreamThreads = 256;
+constexpr int kStreamMaxBlocks = kNumSMs * 8;
+constexpr int kScratchFloats = 4 * kStreamMaxBlocks + 64;
+
+template <int VEC>
+struct Vec;
+template <>
+struct Vec<4> {
+  static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
+    float4 t = ldg_stream4(p);
+    v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
+  }
+  static __device__ __forceinline__ void load_cached(const float* p, float (&v)[4]) {
+    float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+  static __device__ __forceinline__ void store_stream(float* p, const float (&v)[4]) {
+    stg_stream4(p, make_float4(v[0], v[1], v[2], v[3]));
+  }
+};
+template <>
+struct Vec<1> {
+  static __device__ __forceinline__ void load(const float* p, float (&v)[1]) { v[0] = ldg_stream1(p); }
+  static __device__ __forceinline__ void load_cached(const float* p, float (&v)[1]) { v[0] = *p; }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[1]) { *p = v[0]; }
+  static __device__ __forceinline__ void store_stream(float* p, const float (&v)[1]) { stg_stream1(p, v[0]); }
+};
+
+// fixed-order final reduction of per-block partial sums: out[k] = sum_b part[k*nblk + b]
+__global__ void reduce_partials_kernel(const float* __restrict__ part, int nblk, int nk, float* __restrict__ out) {
+  __shared__ float red[32];
+  for (int k = 0; k < nk; ++k) {
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < nblk; i += blockDim.x) acc += part[(size_t)k * nblk + i];
+    float r = block_sum(acc, red);
+    if (threadIdx.x == 0) out[k] = r;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// UNCE forward
+// ------------------------------------------------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(kStreamThreads)
+unce_fwd_kernel(const float* __restrict__ x, long long* __restrict__ y, float* __restrict__ loss_px,
+                float* __restrict__ lse_all_out, float* __restrict__ lse_old_out, float* __restrict__ part,
+                int B, int C, int old_cl, long long HW, int ignore_index) {
+  const long long gpi = HW / VEC;  // groups per image
+  const long long n_groups = gpi * B;
+  float loss_acc = 0.f, valid_acc = 0.f;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n_groups;
+       g += (long long)gridDim.x * blockDim.x) {
+    const long long b = g / gpi, p = (g - b * gpi) * VEC;
+    const float* xp = x + (b * C) * HW + p;
+    long long* yp = y + b * HW + p;
+    long long lab[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      long long t = yp[i];
+      if (t < old_cl) {  // loss.py:104-105: labels[targets < old_cl] = 0 (in place)
+        if (t != 0) yp[i] = 0;
+        t = 0;
+      }
+      lab[i] = t;
+    }
+    float m[VEC], s[VEC], picked[VEC], lse_old2[VEC];
+    {
+      float v[VEC];
+      Vec<VEC>::load(xp, v);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        m[i] = v[i] * kLog2e;
+        s[i] = 1.f;
+        picked[i] = (lab[i] == 0) ? v[i] : 0.f;
+        lse_old2[i] = m[i];
+      }
+    }
+#pragma unroll 4
+    for (int c = 1; c < C; ++c) {
+      float v[VEC];
+      Vec<VEC>::load(xp + (long long)c * HW, v);
+      if (c == old_cl) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) lse_old2[i] = m[i] + lg2f(s[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        lse_push(m[i], s[i], v[i] * kLog2e);
+        picked[i] = (lab[i] == c) ? v[i] : picked[i];
+      }
+    }
+    float out[VEC], la[VEC], lo[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const float lse2 = m[i] + lg2f(s[i]);
+      if (old_cl >= C) lse_old2[i] = lse2;
+      la[i] = lse2 * kLn2;
+      lo[i] = lse_old2[i] * kLn2;
+      const bool ign = lab[i] == ignore_index;
+      float l = (lab[i] == 0 && old_cl > 0) ? (la[i] - lo[i]) : (la[i] - picked[i]);
+      // labels outside [0,C) that are not ignore_index are a caller error (nll_loss asserts); give 0
+      if (ign || lab[i] < 0 || lab[i] >= C) l = 0.f;
+      out[i] = l;
+      loss_acc += l;
+      valid_acc += ign ? 0.f : 1.f;
+    }
+    Vec<VEC>::store(loss_px + b * HW + p, out);
+    Vec<VEC>::store(lse_all_out + b * HW + p, la);
+    Vec<VEC>::store(lse_old_out + b * HW + p, lo);
+  }
+  if (part != nullptr) {
+    __shared__ float red[32];
+    float r0 = block_sum(loss_acc, red);
+    float r1 = block_sum(valid_acc, red);
+    if (threadIdx.x == 0) {
+      part[blockIdx.x] = r0;
+      part[gridDim.x + blockIdx.x] = r1;
+    }
+  }
+}
+
+// UNCE backward:  dx_c = g * [y != ignore] * ( softmax(x)_c - (y==0 ? [c<old] exp(x_c - lse_old) : [c==y]) )
+template <int VEC>
+__global__ void __launch_bounds__(kStreamThreads)
+unce_bwd_kernel(const float* __restrict__ x, const long long* __restrict__ y, const float* __restrict__ lse_all,
+                const float* __restrict__ lse_old, const float* __restrict__ g_px,
+                const float* __restrict__ g_scalar, float g_mul, const float* __restrict__ stats,
+                int mean_over_valid, float* __restrict__ dx, int B, int C, int old_cl, long long HW,
+                int ignore_index) {
+  const long long gpi = HW / VEC;
+  const long long n_groups = gpi * B;
+  float gs = 0.f;
+  if (g_px == nullptr) {
+    gs = g_scalar[0] * g_mul;
+    if (mean_over_valid) gs = gs / stats[1];
+  }
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n_groups;
+       g += (long long)gridDim.x * blockDim.x) {
+    const long long b = g / gpi, p = (g - b * gpi) * VEC;
+    const float* xp = x + (b * C) * HW + p;
+    float* dp = dx + (b * C) * HW + p;
+    const long long* yp = y + b * HW + p;
+    float la2[VEC], up[VEC], fold[VEC];
+    int lab[VEC];
+    {
+      float la[VEC], lo[VEC], gp[VEC];
+      Vec<VEC>::load_cached(lse_all + b * HW + p, la);
+      Vec<VEC>::load_cached(lse_old + b * HW + p, lo);
+      if (g_px != nullptr) Vec<VEC>::load_cached(g_px + b * HW + p, gp);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        long long t = yp[i];
+        if (t < old_cl) t = 0;
+        const bool dead = (t == ignore_index) || t < 0 || t >= C;
+        lab[i] = dead ? -1 : (int)t;
+        up[i] = dead ? 0.f : (g_px != nullptr ? gp[i] : gs);
+        la2[i] = la[i] * kLog2e;
+        // exp(x - lse_old) = exp(x - lse_all) * exp(lse_all - lse_old)
+        fold[i] = ex2f((la[i] - lo[i]) * kLog2e);
+      }
+    }
+#pragma unroll 4
+    for (int c = 0; c < C; ++c) {
+      float v[VEC], o[VEC];
+      Vec<VEC>::load(xp + (long long)c * HW, v);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const float pr = ex2f(fmaf(v[i], kLog2e, -la2[i]));
+        float sub;
+        if (lab[i] == 0 && old_cl > 0)
+          sub = (c < old_cl) ? pr * fold[i] : 0.f;
+        else
+          sub = (c == lab[i]) ? 1.f : 0.f;
+        o[i] = up[i] * (pr - sub);
+      }
+      Vec<VEC>::store_stream(dp + (long long)c * HW, o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// UNKD forward:  q = softmax(alpha t);  S_b = {0} U {C_old..C-1}
+//   loss_px = [ q0 (lse_b - lse) + sum_{1<=c<C_old} q_c (x_c - lse) ] / C_old
+// ------------------------------------------------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(kStreamThreads)
+unkd_fwd_kernel(const float* __restrict__ x, const float* __restrict__ t, const float* __restrict__ mask,
+                float alpha, float* __restrict__ out_px, float* __restrict__ lse3, float* __restrict__ part,
+                int B, int C, int C_old, long long HW) {
+  const long long gpi = HW / VEC;
+  const long long n_groups = gpi * B;
+  const long long plane = (long long)B * HW;
+  const float a2 = alpha * kLog2e;
+  const float inv_cold = 1.f / (float)C_old;
+  float acc = 0.f;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n_groups;
+       g += (long long)gridDim.x * blockDim.x) {
+    const long long b = g / gpi, p = (g - b * gpi) * VEC;
+    const float* xp = x + (b * C) * HW + p;
+    const float* tp = t + (b * C_old) * HW + p;
+    // x: lse over all channels (m,s) and over S_b (mb,sb); t: lse (mt,st) and weighted sum wx = sum_{c>=1} 2^(t_c-mt) x_c
+    float m[VEC], s[VEC], mb[VEC], sb[VEC], mt[VEC], st[VEC], wx[VEC], t0[VEC];
+    {
+      float v[VEC], u[VEC];
+      Vec<VEC>::load(xp, v);
+      Vec<VEC>::load(tp, u);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        m[i] = mb[i] = v[i] * kLog2e;
+        s[i] = sb[i] = 1.f;
+        mt[i] = t0[i] = u[i] * a2;
+        st[i] = 1.f;
+        wx[i] = 0.f;
+      }
+    }
+#pragma unroll 4
+    for (int c = 1; c < C_old; ++c) {
+      float v[VEC], u[VEC];
+      Vec<VEC>::load(xp + (long long)c * HW, v);
+      Vec<VEC>::load(tp + (long long)c * HW, u);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        lse_push(m[i], s[i], v[i] * kLog2e);
+        const float tv = u[i] * a2;
+        const float d = tv - mt[i];
+        const float e = ex2f(-fabsf(d));
+        if (d > 0.f) {
+          st[i] = fmaf(st[i], e, 1.f);
+          wx[i] = fmaf(wx[i], e, v[i]);
+          mt[i] = tv;
+        } else {
+          st[i] += e;
+          wx[i] = fmaf(e, v[i], wx[i]);
+        }
+      }
+    }
+#pragma unroll 4
+    for (int c = C_old; c < C; ++c) {
+      float v[VEC];
+      Vec<VEC>::load(xp + (long long)c * HW, v);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const float v2 = v[i] * kLog2e;
+        lse_push(m[i], s[i], v2);
+        lse_push(mb[i], sb[i], v2);
+      }
+    }
+    float o[VEC], l_all[VEC], l_bkg[VEC], l_t[VEC];
+    float mk[VEC];
+    if (mask != nullptr) Vec<VEC>::load_cached(mask + b * HW + p, mk);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const float lse2 = m[i] + lg2f(s[i]);
+      const float lseb2 = mb[i] + lg2f(sb[i]);
+      const float lset2 = mt[i] + lg2f(st[i]);
+      l_all[i] = lse2 * kLn2;
+      l_bkg[i] = lseb2 * kLn2;
+      l_t[i] = lset2 * kLn2;
+      const float q0 = ex2f(t0[i] - lset2);
+      const float dot = wx[i] / st[i];  // sum_{c>=1} q_c x_c
+      float l = (q0 * (l_bkg[i] - l_all[i]) + dot - (1.f - q0) * l_all[i]) * inv_cold;
+      if (mask != nullptr) l *= mk[i];
+      o[i] = -l;
+      acc += l;
+    }
+    if (out_px != nullptr) Vec<VEC>::store(out_px + b * HW + p, o);
+    Vec<VEC>::store(lse3 + b * HW + p, l_all);
+    Vec<VEC>::store(lse3 + plane + b * HW + p, l_bkg);
+    Vec<VEC>::store(lse3 + 2 * plane + b * HW + p, l_t);
+  }
+  __shared__ float red[32];
+  float r = block_sum(acc, red);
+  if (threadIdx.x == 0) part[blockIdx.x] = r;
+}
+
+// UNKD backward: d(-loss_px)/dx_c = ( p_c - [c in S_b] q0 exp(x_c - lse_b) - [1<=c<C_old] q_c ) / C_old
+template <int VEC>
+__global__ void __launch_bounds__(kStreamThreads)
+unkd_bwd_kernel(const float* __restrict__ x, const float* __restrict__ t, const float* __restrict__ mask,
+                float alpha, const float* __restrict__ lse3, const float* __restrict__ g_px,
+                const float* __restrict__ g_scalar, float g_mul, float* __restrict__ dx, int B, int C,
+                int C_old, long long HW) {
+  const long long gpi = HW / VEC;
+  const long long n_groups = gpi * B;
+  const long long plane = (long long)B * HW;
+  const float a2 = alpha * kLog2e;
+  const float inv_cold = 1.f / (float)C_old;
+  const float gs = (g_px == nullptr) ? g_scalar[0] * g_mul : 0.f;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n_groups;
+       g += (long long)gridDim.x * blockDim.x) {
+    const long long b = g / gpi, p = (g - b * gpi) * VEC;
+    const float* xp = x + (b * C) * HW + p;
+    const float* tp = t + (b * C_old) * HW + p;
+    float* dp = dx + (b * C) * HW + p;
+    float la2[VEC], lt2[VEC], up[VEC], fb[VEC];  // fb = q0 * exp(lse_all - lse_bkg)
+    {
+      float la[VEC], lb[VEC], lt[VEC], gp[VEC], mk[VEC], u0[VEC];
+      Vec<VEC>::load_cached(lse3 + b * HW + p, la);
+      Vec<VEC>::load_cached(lse3 + plane + b * HW + p, lb);
+      Vec<VEC>::load_cached(lse3 + 2 * plane + b * HW + p, lt);
+      Vec<VEC>::load_cached(tp, u0);
+      if (g_px != nullptr) Vec<VEC>::load_cached(g_px + b * HW + p, gp);
+      if (mask != nullptr) Vec<VEC>::load_cached(mask + b * HW + p, mk);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        la2[i] = la[i] * kLog2e;
+        lt2[i] = lt[i] * kLog2e;
+        float u = (g_px != nullptr ? gp[i] : gs) * inv_cold;
+        if (mask != nullptr) u *= mk[i];
+        up[i] = u;
+        const float q0 = ex2f(fmaf(u0[i], a2, -lt2[i]));
+        fb[i] = q0 * ex2f((la[i] - lb[i]) * kLog2e);
+      }
+    }
+    {  // channel 0: in S_b, not an old foreground class
+      float v[VEC], o[VEC];
+      Vec<VEC>::load(xp, v);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const float pr = ex2f(fmaf(v[i], kLog2e, -la2[i]));
+        o[i] = up[i] * (pr - pr * fb[i]);
+      }
+      Vec<VEC>::store_stream(dp, o);
+    }
+#pragma unroll 4
+    for (int c = 1; c < C_old; ++c) {
+      float v[VEC], u[VEC], o[VEC];
+      Vec<VEC>::load(xp + (long long)c * HW, v);
+      Vec<VEC>::load(tp + (long long)c * HW, u);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const float pr = ex2f(fmaf(v[i], kLog2e, -la2[i]));
+        const float q = ex2f(fmaf(u[i], a2, -lt2[i]));
+        o[i] = up[i] * (pr - q);
+      }
+      Vec<VEC>::store_stream(dp + (long long)c * HW, o);
+    }
+#pragma unroll 4
+    for (int c = C_old; c < C; ++c) {
+      float v[VEC], o[VEC];
+      Vec<VEC>::load(xp + (long long)c * HW, v);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const float pr = ex2f(fmaf(v[i], kLog2e, -la2[i]));
+        o[i] = up[i] * (pr - pr * fb[i]);
+      }
+      Vec<VEC>::store_stream(dp + (long long)c * HW, o);
+    }
+  }
+}
+
+static int stream_grid(long long n_groups) {
+  long long blocks = (n_groups + kStreamThreads - 1) / kStreamThreads;
+  if (blocks > kStreamMaxBlocks) blocks = kStreamMaxBlocks;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+static bool can_vec4(long long HW, std::initializer_list<const void*> ptrs) {
+  if (HW % 4 != 0) return false;
+  for (const void* p : ptrs)
+    if (p != nullptr && !aligned16(p)) return false;
+  return true;
+}
+
+}  // namespace ucd
+
+using namespace ucd;
+
+extern "C" size_t ucd_reduce_scratch_floats(void) { return (size_t)kScratchFloats; }
+
+extern "C" int ucd_unce_fwd(const float* x, int64_t* y, float* loss_px, float* lse_all, float* lse_old,
+                            float* stats, float* scratch, int B, int C, int old_cl, int64_t HW,
+                            int ignore_index, void* stream) {
+  UCD_CHECK_ARG(x && y && loss_px && lse_all && lse_old, "ucd_unce_fwd: null pointer");
+  UCD_CHECK_ARG(B > 0 && C > 0 && HW > 0, "ucd_unce_fwd: bad shape B=%d C=%d HW=%lld", B, C, (long long)HW);
+  UCD_CHECK_ARG(old_cl >= 0 && old_cl <= C, "ucd_unce_fwd: old_cl=%d outside [0,%d]", old_cl, C);
+  UCD_CHECK_ARG(stats == nullptr || scratch != nullptr, "ucd_unce_fwd: stats requested without scratch");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* part = stats ? scratch : nullptr;
+  const bool v4 = can_vec4(HW, {x, loss_px, lse_all, lse_old}) && aligned16(y);
+  const int grid = stream_grid((long long)B * HW / (v4 ? 4 : 1));
+  if (v4)
+    unce_fwd_kernel<4><<<grid, kStreamThreads, 0, st>>>(x, (long long*)y, loss_px, lse_all, lse_old, part, B, C,
+                                                        old_cl, HW, ignore_index);
+  else
+    unce_fwd_kernel<1><<<grid, kStreamThreads, 0, st>>>(x, (long long*)y, loss_px, lse_all, lse_old, part, B, C,
+                                                        old_cl, HW, ignore_index);
+  UCD_CHECK_LAUNCH("unce_fwd_kernel");
+  if (stats) {
+    reduce_partials_kernel<<<1, 256, 0, st>>>(part, grid, 2, stats);
+    UCD_CHECK_LAUNCH("reduce_partials_kernel");
+  }
+  return UCD_OK;
+}
+
+extern "C" int ucd_unce_bwd(const float* x, const int64_t* y, const float* lse_all, const float* lse_old,
+                            const float* g_px, const float* g_scalar, float g_mul, const float* stats,
+                            int mean_over_valid, float* dx, int B, int C, int old_cl, int64_t HW,
+                            int ignore_index, void* stream) {
+  UCD_CHECK_ARG(x && y && lse_all && lse_old && dx, "ucd_unce_bwd: null pointer");
+  UCD_CHECK_ARG(g_px || g_scalar, "ucd_unce_bwd: need g_px or g_scalar");
+  UCD_CHECK_ARG(!mean_over_valid || stats, "ucd_unce_bwd: mean_over_valid needs stats");
+  UCD_CHECK_ARG(B > 0 && C > 0 && HW > 0, "ucd_unce_bwd: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool v4 = can_vec4(HW, {x, lse_all, lse_old, g_px, dx}) && aligned16(y);
+  const int grid = stream_grid((long long)B * HW / (v4 ? 4 : 1));
+  if (v4)
+    unce_bwd_kernel<4><<<grid, kStreamThreads, 0, st>>>(x, (const long long*)y, lse_all, lse_old, g_px, g_scalar,
+                                                        g_mul, stats, mean_over_valid, dx, B, C, old_cl, HW,
+                                                        ignore_index);
+  else
+    unce_bwd_kernel<1><<<grid, kStreamThreads, 0, st>>>(x, (const long long*)y, lse_all, lse_old, g_px, g_scalar,
+                                                        g_mul, stats, mean_over_valid, dx, B, C, old_cl, HW,
+                                                        ignore_index);
+  UCD_CHECK_LAUNCH("unce_bwd_kernel");
+  return UCD_OK;
+}
+
+extern "C" int ucd_unkd_fwd(const float* x, const float* t, const float* mask, float alpha, float* out_px,
+                            float* stats, float* lse3, float* scratch, int B, int C, int C_old, int64_t HW,
+                            void* stream) {
+  UCD_CHECK_ARG(x && t && stats && lse3 && scratch, "ucd_unkd_fwd: null pointer");
+  UCD_CHECK_ARG(B > 0 && HW > 0 && C_old >= 1 && C >= C_old, "ucd_unkd_fwd: bad shape C=%d C_old=%d", C, C_old);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool v4 = can_vec4(HW, {x, t, mask, out_px, lse3}) && ((long long)B * HW) % 4 == 0;
+  const int grid = stream_grid((long long)B * HW / (v4 ? 4 : 1));
+  if (v4)
+    unkd_fwd_kernel<4><<<grid, kStreamThreads, 0, st>>>(x, t, mask, alpha, out_px, lse3, scratch, B, C, C_old, HW);
+  else
+    unkd_fwd_kernel<1><<<grid, kStreamThreads, 0, st>>>(x, t, mask, alpha, out_px, lse3, scratch, B, C, C_old, HW);
+  UCD_CHECK_LAUNCH("unkd_fwd_kernel");
+  reduce_partials_kernel<<<1, 256, 0, st>>>(scratch, grid, 1, stats);
+  UCD_CHECK_LAUNCH("reduce_partials_kernel");
+  return UCD_OK;
+}
+
+extern "C" int ucd_unkd_bwd(const float* x, const float* t, const float* mask, float alpha, const float* lse3,
+                            const float* g_px, const float* g_scalar, float g_mul, float* dx, int B, int C,
+                            int C_old, int64_t HW, void* stream) {
+  UCD_CHECK_ARG(x && t && lse3 && dx, "ucd_unkd_bwd: null pointer");
+  UCD_CHECK_ARG(g_px || g_scalar, "ucd_unkd_bwd: need g_px or g_scalar");
+  UCD_CHECK_ARG(B > 0 && HW > 0 && C_old >= 1 && C >= C_old, "ucd_unkd_bwd: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool v4 = can_vec4(HW, {x, t, mask, g_px, lse3, dx}) && ((long long)B * HW) % 4 == 0;
+  const int grid = stream_grid((long long)B * HW / (v4 ? 4 : 1));
+  if (v4)
+    unkd_bwd_kernel<4><<<grid, kStreamThreads, 0, st>>>(x, t, mask, alpha, lse3, g_px, g_scalar, g_mul, dx, B, C,
+                                                        C_old, HW);
+  else
+    unkd_bwd_kernel<1><<<grid, kStreamThreads, 0, st>>>(x, t, mask, alpha, lse3, g_px, g_scalar, g_mul, dx, B, C,
+                                                        C_old, HW);
+  UCD_CHECK_LAUNCH("unkd_bwd_kernel");
+  return UCD_OK;
+}

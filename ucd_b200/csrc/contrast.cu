@@ -1,0 +1,651 @@
+// Fused PixelConLossV2 (utils/loss.py:412-466) with the joint-probability weights of
+// pre_contrastive_pixel (utils/loss.py:369-393) computed in-kernel.  The N_a x N_c similarity,
+// mask and P matrices are never materialised.
+//
+// Math.  For anchor row i and contrast column j:
+//   s_ij = a_i.c_j / tau ; same_ij = [la_i == lc_j] ; mp_ij = same_ij - [j is i itself]
+//   neg_i = sum_j (1-same_ij) exp(s_ij)   (unshifted) ;  m_i = max_j s_ij ;  num_i = sum_j mp_ij
+//   den_ij = exp(s_ij - m_i) + neg_i ;  w_ij = mp_ij * P_ij
+//   L_i = sum_j w_ij (s_ij - m_i - log den_ij) ;  loss = mean_{num_i != 0} ( -L_i / num_i )
+//   d(-L_i/num_i)/d a_i = (T_i V_i - U_i) / (tau num_i)
+//      V_i = sum_j (1-same_ij) exp(s_ij) c_j ;  T_i = sum_j w_ij / den_ij ;  U_i = sum_j w_ij neg_i/den_ij c_j
+//
+// Two tensor-core sweeps over the column tiles, same kernel template:
+//   sweep 1: S = A C^T (tcgen05, K=256) -> epilogue: exp, masks, row max/neg/num; E = masked exp(S)
+//            in bf16 -> smem -> V += E C (tcgen05 with the SAME C tile read MN-major).
+//   sweep 2: S again and P = pA pC^T (K = padded C_old) -> epilogue: den, log, weights, L_i, T_i;
+//            Ucoef in bf16 -> smem -> U += Ucoef C.
+// The gradient needs no third sweep: backward is a scaled copy of (T V - U)/(tau num).
+//
+// CTA = one 128-row block x one contiguous range of column tiles ("split").  Warp roles: warp 0 issues
+// bulk async copies (TMA engine) of pre-tiled bf16 operands, warp 1 owns TMEM and issues tcgen05.mma,
+// warps 2-5 are the epilogue (one thread per row, accumulators read with tcgen05.ld).
+#include "umma.cuh"
+
+namespace ucd {
+
+constexpr int kConThreads = 192;
+constexpr uint32_t kTileBytes = 65536;  // 128 rows x 256 bf16
+constexpr uint32_t kChunkB = 2048;      // one 8-element k-chunk for 128 rows
+constexpr uint32_t kESub = 16384;       // 128 rows x 64 columns bf16
+
+// shared memory map (bytes)
+constexpr uint32_t OFF_A = 0;
+constexpr uint32_t OFF_C = 65536;     // 2 stages
+constexpr uint32_t OFF_E = 196608;    // sweep 1: 2 x 16 KB ; sweep 2: 1 x 16 KB
+constexpr uint32_t OFF_PA = 212992;   // sweep 2: row probabilities, <= 8 KB
+constexpr uint32_t OFF_PC = 221184;   // sweep 2: column probabilities, <= 8 KB, single stage
+constexpr uint32_t OFF_LAB = 229376;  // 2 x 128 int32
+constexpr uint32_t OFF_BAR = 230400;
+constexpr uint32_t kConSmem = OFF_BAR + 256;
+constexpr int kMaxChunks = 64;
+
+enum { BAR_A = 0, BAR_CF = 1, BAR_CE = 3, BAR_SF = 5, BAR_SE = 7, BAR_EF = 9, BAR_EE = 11, BAR_PF = 13, BAR_PE = 14, BAR_V = 15 };
+
+struct ConArgs {
+  const __nv_bfloat16* feat_tiles;
+  const __nv_bfloat16* prob_tiles;
+  const int* lab_tiles;
+  const int* chunk_counts;  // [n_chunks][2] = {N_a, N_o}
+  int n_chunks;
+  long long chunk_tiles;
+  const __nv_bfloat16* row_feat;  // row (anchor) tiles: [row_block][32][128][8]
+  const __nv_bfloat16* row_prob;  // [row_block][kpad/8][128][8]
+  const int* row_lab;             // [row_block][128]
+  const int* n_rows;              // device scalar: number of valid rows
+  long long self_tile0;           // column tile holding row block 0 itself (block rb <-> self_tile0 + rb), -1: none
+  const int* min_new;
+  const float* dense_p;
+  long long ldp;
+  float inv_tau;
+  int splits;
+  int need_grad;
+  int kpad;
+  long long rows_pad;
+  float* stats_part;   // [splits][3][rows_pad]   sweep 1 out: raw row max, neg, num
+  float* acc_part;     // [splits][rows_pad][256] sweep 1: V ; sweep 2: U
+  const float* stats;  // [3][rows_pad]           sweep 2 in (combined)
+  float* loss_part;    // [splits][2][rows_pad]   sweep 2 out: L_i, T_i
+};
+
+struct TileLoc {
+  long long gtile;  // tile index in the gathered buffers
+  int nvalid;       // valid columns in this tile (1..128)
+  long long dcol0;  // first column in "dense" numbering (single-chunk compat path)
+};
+
+__device__ __forceinline__ TileLoc locate_tile(int k, const int* pre, const int* ncols, int n_chunks,
+                                               long long chunk_tiles) {
+  int c = 0;
+  while (c + 1 < n_chunks && k >= pre[c + 1]) ++c;
+  const int lt = k - pre[c];
+  TileLoc t;
+  t.gtile = (long long)c * chunk_tiles + lt;
+  t.nvalid = min(128, ncols[c] - lt * 128);
+  t.dcol0 = (long long)lt * 128;
+  return t;
+}
+
+__device__ __forceinline__ uint32_t bf16x2_bits(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// ---- sweep 1 epilogue on 32 columns ---------------------------------------------------------
+template <bool FULL, bool SELF>
+__device__ __forceinline__ void sweep1_cols(const uint32_t (&r)[32], const int* __restrict__ lab, int cbase, int nv,
+                                            int la, int rself, float sc, float& mx, float& neg, float& num,
+                                            uint32_t (&pk)[16]) {
+#pragma unroll
+  for (int j4 = 0; j4 < 32; j4 += 4) {
+    const int4 l4 = *reinterpret_cast<const int4*>(lab + cbase + j4);
+    const int ls[4] = {l4.x, l4.y, l4.z, l4.w};
+    float e[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int col = cbase + j4 + u;
+      const float acc = __uint_as_float(r[j4 + u]);
+      const bool same = ls[u] == la;
+      float ev = same ? 0.f : ex2f(acc * sc);
+      float cnt = same ? 1.f : 0.f;
+      float mv = acc;
+      if (!FULL) {
+        const bool ok = col < nv;
+        ev = ok ? ev : 0.f;
+        cnt = ok ? cnt : 0.f;
+        mv = ok ? acc : -3.0e38f;
+      }
+      if (SELF) cnt -= (col == rself) ? 1.f : 0.f;
+      mx = fmaxf(mx, mv);
+      neg += ev;
+      num += cnt;
+      e[u] = ev;
+    }
+    pk[j4 / 2] = bf16x2_bits(e[0], e[1]);
+    pk[j4 / 2 + 1] = bf16x2_bits(e[2], e[3]);
+  }
+}
+
+// ---- sweep 2 epilogue on 32 columns ---------------------------------------------------------
+// PMODE 0: P == 1 ; 1: P from the prob GEMM with GT-new override ; 2: dense P in global memory
+template <bool FULL, bool SELF, int PMODE>
+__device__ __forceinline__ void sweep2_cols(const uint32_t (&r)[32], const uint32_t (&pr)[32],
+                                            const int* __restrict__ lab, int cbase, int nv, int la, int rself,
+                                            float sc, float mraw, float negi, bool gt_row, int min_new,
+                                            const float* __restrict__ dp, float& lacc, float& tacc,
+                                            uint32_t (&pk)[16]) {
+#pragma unroll
+  for (int j4 = 0; j4 < 32; j4 += 4) {
+    const int4 l4 = *reinterpret_cast<const int4*>(lab + cbase + j4);
+    const int ls[4] = {l4.x, l4.y, l4.z, l4.w};
+    float uo[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int col = cbase + j4 + u;
+      const float acc = __uint_as_float(r[j4 + u]);
+      const float sh2 = (acc - mraw) * sc;  // (s - m) * log2(e)
+      const float den = ex2f(sh2) + negi;
+      const float l2 = lg2f(den);
+      const float rd = rcpf(den);
+      float mp = (ls[u] == la) ? 1.f : 0.f;
+      if (SELF) mp -= (col == rself) ? 1.f : 0.f;
+      if (!FULL) mp = (col < nv) ? mp : 0.f;
+      float pv = 1.f;
+      if (PMODE == 1) pv = (gt_row && ls[u] >= min_new) ? 1.f : __uint_as_float(pr[j4 + u]);
+      if (PMODE == 2) pv = (FULL || col < nv) ? __ldg(dp + col) : 0.f;
+      const float w = mp * pv;
+      lacc = fmaf(w, sh2 - l2, lacc);
+      const float wr = w * rd;
+      tacc += wr;
+      uo[u] = wr * negi;
+    }
+    pk[j4 / 2] = bf16x2_bits(uo[0], uo[1]);
+    pk[j4 / 2 + 1] = bf16x2_bits(uo[2], uo[3]);
+  }
+}
+
+template <int PHASE, int PMODE>
+__global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ int s_pre[kMaxChunks + 1];
+  __shared__ int s_ncols[kMaxChunks];
+  __shared__ uint32_t s_tmem;
+
+  constexpr int NE = (PHASE == 1) ? 2 : 1;  // E sub-tile buffers
+  constexpr int NS = (PHASE == 1) ? 2 : 1;  // S accumulator buffers in TMEM
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rb = blockIdx.x / a.splits, split = blockIdx.x - rb * a.splits;
+  const int n_rows = *a.n_rows;
+  if ((long long)rb * 128 >= n_rows) return;  // uniform: nothing to do for this row block
+
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar0 = sbase + OFF_BAR;
+  auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int c = 0; c < a.n_chunks; ++c) {
+      const int nc = a.chunk_counts[2 * c] + a.chunk_counts[2 * c + 1];
+      s_ncols[c] = nc;
+      s_pre[c] = acc;
+      acc += (nc + 127) >> 7;
+    }
+    s_pre[a.n_chunks] = acc;
+    mbar_init(BAR(BAR_A), 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(BAR(BAR_CF + i), 1);
+      mbar_init(BAR(BAR_CE + i), 5);  // tcgen05.commit + the 4 epilogue warps (they read the stage's labels)
+      mbar_init(BAR(BAR_SF + i), 1);
+      mbar_init(BAR(BAR_SE + i), 4);
+      mbar_init(BAR(BAR_EF + i), 4);
+      mbar_init(BAR(BAR_EE + i), 1);
+    }
+    mbar_init(BAR(BAR_PF), 1);
+    mbar_init(BAR(BAR_PE), 1);
+    mbar_init(BAR(BAR_V), 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&s_tmem), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+
+  const int n_total = s_pre[a.n_chunks];
+  const int per = (n_total + a.splits - 1) / a.splits;
+  const int k0 = split * per;
+  const int k1 = min(n_total, k0 + per);
+  const int n = max(0, k1 - k0);
+  const long long self_tile = a.self_tile0 >= 0 ? a.self_tile0 + rb : -1;  // the anchors' own column tile
+  const int pchunks = a.kpad >> 3;
+
+  if (warp == 0) {
+    // ===================== producer: bulk async copies =====================
+    if (lane == 0 && n > 0) {
+      const uint8_t* ft = reinterpret_cast<const uint8_t*>(a.feat_tiles);
+      const uint8_t* pt = reinterpret_cast<const uint8_t*>(a.prob_tiles);
+      const uint8_t* rft = reinterpret_cast<const uint8_t*>(a.row_feat);
+      const uint8_t* rpt = reinterpret_cast<const uint8_t*>(a.row_prob);
+      const uint32_t pbytes = (uint32_t)a.kpad * 256u;
+      mbar_arrive_expect_tx(BAR(BAR_A), kTileBytes + ((PHASE == 2 && PMODE == 1) ? pbytes : 0u));
+      for (int q = 0; q < 4; ++q)
+        bulk_g2s(sbase + OFF_A + q * 16384u, rft + (size_t)rb * kTileBytes + q * 16384u, 16384u, BAR(BAR_A));
+      if (PHASE == 2 && PMODE == 1) bulk_g2s(sbase + OFF_PA, rpt + (size_t)rb * pbytes, pbytes, BAR(BAR_A));
+      for (int t = 0; t < n; ++t) {
+        const int stage = t & 1;
+        const TileLoc loc = locate_tile(k0 + t, s_pre, s_ncols, a.n_chunks, a.chunk_tiles);
+        mbar_wait(BAR(BAR_CE + stage), ((t >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(BAR(BAR_CF + stage), kTileBytes + 512u);
+        const uint32_t dst = sbase + OFF_C + stage * kTileBytes;
+        for (int q = 0; q < 4; ++q)
+          bulk_g2s(dst + q * 16384u, ft + (size_t)loc.gtile * kTileBytes + q * 16384u, 16384u, BAR(BAR_CF + stage));
+        bulk_g2s(sbase + OFF_LAB + stage * 512u, a.lab_tiles + loc.gtile * 128, 512u, BAR(BAR_CF + stage));
+        if (PHASE == 2 && PMODE == 1) {
+          mbar_wait(BAR(BAR_PE), (t & 1) ^ 1);
+          mbar_arrive_expect_tx(BAR(BAR_PF), pbytes);
+          bulk_g2s(sbase + OFF_PC, pt + (size_t)loc.gtile * pbytes, pbytes, BAR(BAR_PF));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0 && n > 0) {
+      constexpr uint32_t idesc_s = umma_idesc(128, 128, 0, 0);   // S / P : A K-major, B K-major
+      constexpr uint32_t idesc_v = umma_idesc(128, 256, 0, 1);   // V / U : A K-major, B MN-major
+      const uint32_t tS = tmem;             // S buffers at columns [0,128) and [128,256)
+      const uint32_t tP = tmem + 128;       // sweep 2: P at [128,256)
+      const uint32_t tV = tmem + 256;       // V / U accumulator at [256,512)
+      mbar_wait(BAR(BAR_A), 0);
+      auto issue_s = [&](int t) {
+        const int stage = t & 1, sb = t % NS;
+        mbar_wait(BAR(BAR_CF + stage), (t >> 1) & 1);
+        mbar_wait(BAR(BAR_SE + sb), ((t / NS) & 1) ^ 1);
+        if (PHASE == 2 && PMODE == 1) mbar_wait(BAR(BAR_PF), t & 1);
+        tc_fence_after();
+        const uint32_t sc = sbase + OFF_C + stage * kTileBytes;
+#pragma unroll
+        for (int ks = 0; ks < 16; ++ks)
+          umma_bf16(tS + sb * 128, umma_desc(sbase + OFF_A + ks * 2 * kChunkB, kChunkB, 128),
+                    umma_desc(sc + ks * 2 * kChunkB, kChunkB, 128), idesc_s, ks > 0);
+        if (PHASE == 2 && PMODE == 1) {
+          for (int ks = 0; ks < (pchunks >> 1); ++ks)
+            umma_bf16(tP, umma_desc(sbase + OFF_PA + ks * 2 * kChunkB, kChunkB, 128),
+                      umma_desc(sbase + OFF_PC + ks * 2 * kChunkB, kChunkB, 128), idesc_s, ks > 0);
+          umma_commit(BAR(BAR_PE));
+        }
+        umma_commit(BAR(BAR_SF + sb));
+      };
+      auto issue_v = [&](int t) {
+        const int stage = t & 1;
+        const uint32_t sc = sbase + OFF_C + stage * kTileBytes;
+        for (int h = 0; h < 2; ++h) {
+          const int q = 2 * t + h, buf = q % NE;
+          mbar_wait(BAR(BAR_EF + buf), (q / NE) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_bf16(tV, umma_desc(sbase + OFF_E + buf * kESub + kk * 2 * kChunkB, kChunkB, 128),
+                      umma_desc(sc + (uint32_t)(h * 64 + kk * 16) * 16u, 128, kChunkB), idesc_v,
+                      (t > 0 || h > 0 || kk > 0) ? 1u : 0u);
+          umma_commit(BAR(BAR_EE + buf));
+        }
+      };
+      if (PHASE == 1) {
+        for (int it = 0; it <= n; ++it) {
+          if (it < n) issue_s(it);
+          if (it >= 1) {
+            if (a.need_grad) issue_v(it - 1);
+            umma_commit(BAR(BAR_CE + ((it - 1) & 1)));
+          }
+        }
+      } else {
+        for (int t = 0; t < n; ++t) {
+          issue_s(t);
+          if (a.need_grad) issue_v(t);
+          umma_commit(BAR(BAR_CE + (t & 1)));
+        }
+      }
+      umma_commit(BAR(BAR_V));
+    }
+  } else {
+    // ===================== epilogue: one thread per row =====================
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;  // row within the block == TMEM lane
+    const long long grow = (long long)rb * 128 + r;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const int la = (grow < n_rows) ? __ldg(a.row_lab + (size_t)rb * 128 + r) : -2;
+    const float sc = a.inv_tau * kLog2e;
+    float mx = -3.0e38f, neg = 0.f, num = 0.f;   // sweep 1
+    float lacc = 0.f, tacc = 0.f;                // sweep 2
+    float mraw = 0.f, negi = 0.f;
+    int min_new = 0;
+    bool gt_row = false;
+    if (PHASE == 2) {
+      mraw = a.stats[grow];
+      negi = a.stats[a.rows_pad + grow];
+      if (PMODE == 1) {
+        min_new = *a.min_new;
+        gt_row = la >= min_new;
+      }
+    }
+    for (int t = 0; t < n; ++t) {
+      const int stage = t & 1, sb = t % NS;
+      const TileLoc loc = locate_tile(k0 + t, s_pre, s_ncols, a.n_chunks, a.chunk_tiles);
+      const bool full = loc.nvalid == 128;
+      const bool self = loc.gtile == self_tile;
+      const int* lab = reinterpret_cast<const int*>(smem + OFF_LAB + stage * 512);
+      const float* dp = (PMODE == 2) ? a.dense_p + (size_t)min(grow, (long long)n_rows - 1) * a.ldp + loc.dcol0 : nullptr;
+      mbar_wait(BAR(BAR_SF + sb), (t / NS) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t rv[32], pk[16];
+        tmem_ld32(tmem + lane_addr + sb * 128 + cc * 32, rv);
+        if (PHASE == 1) {
+          tmem_ld_wait();
+          if (full && !self)
+            sweep1_cols<true, false>(rv, lab, cc * 32, 128, la, r, sc, mx, neg, num, pk);
+          else
+            sweep1_cols<false, true>(rv, lab, cc * 32, loc.nvalid, la, self ? r : -1, sc, mx, neg, num, pk);
+        } else {
+          uint32_t pv[32];
+          if (PMODE == 1) tmem_ld32(tmem + lane_addr + 128 + cc * 32, pv);
+          tmem_ld_wait();
+          if (full && !self)
+            sweep2_cols<true, false, PMODE>(rv, pv, lab, cc * 32, 128, la, r, sc, mraw, negi, gt_row, min_new, dp,
+                                            lacc, tacc, pk);
+          else
+            sweep2_cols<false, true, PMODE>(rv, pv, lab, cc * 32, loc.nvalid, la, self ? r : -1, sc, mraw, negi,
+                                            gt_row, min_new, dp, lacc, tacc, pk);
+        }
+        if (a.need_grad) {
+          const int q = 2 * t + (cc >> 1), buf = q % NE;
+          if ((cc & 1) == 0) mbar_wait(BAR(BAR_EE + buf), ((q / NE) & 1) ^ 1);
+          uint8_t* eb = smem + OFF_E + buf * kESub + (uint32_t)((cc & 1) * 4) * kChunkB + (uint32_t)r * 16u;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            *reinterpret_cast<uint4*>(eb + k * kChunkB) = make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
+          if (cc & 1) {
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(BAR_EF + buf));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(BAR(BAR_SE + sb));
+        mbar_arrive(BAR(BAR_CE + stage));
+      }
+    }
+    // ---- per-row outputs ----
+    const size_t prow = (size_t)split * a.rows_pad + grow;
+    if (PHASE == 1) {
+      a.stats_part[(size_t)split * 3 * a.rows_pad + grow] = mx;
+      a.stats_part[(size_t)split * 3 * a.rows_pad + a.rows_pad + grow] = neg;
+      a.stats_part[(size_t)split * 3 * a.rows_pad + 2 * a.rows_pad + grow] = num;
+    } else {
+      a.loss_part[(size_t)split * 2 * a.rows_pad + grow] = lacc * kLn2;
+      a.loss_part[(size_t)split * 2 * a.rows_pad + a.rows_pad + grow] = tacc;
+    }
+    if (a.need_grad) {
+      float4* dst = reinterpret_cast<float4*>(a.acc_part + prow * 256);
+      if (n > 0) {
+        mbar_wait(BAR(BAR_V), 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int cc = 0; cc < 8; ++cc) {
+          uint32_t rv[32];
+          tmem_ld32(tmem + lane_addr + 256 + cc * 32, rv);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            dst[cc * 8 + k] = make_float4(__uint_as_float(rv[4 * k]), __uint_as_float(rv[4 * k + 1]),
+                                          __uint_as_float(rv[4 * k + 2]), __uint_as_float(rv[4 * k + 3]));
+        }
+      } else {
+        for (int k = 0; k < 64; ++k) dst[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// combine sweep-1 partials over splits: stats[0]=row max (raw dot), [1]=neg, [2]=num
+__global__ void con_combine_kernel(const float* __restrict__ part, int splits, long long rows_pad,
+                                   float* __restrict__ stats) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows_pad) return;
+  float m = -3.0e38f, neg = 0.f, num = 0.f;
+  for (int s = 0; s < splits; ++s) {
+    const float* p = part + (size_t)s * 3 * rows_pad;
+    m = fmaxf(m, p[i]);
+    neg += p[rows_pad + i];
+    num += p[2 * rows_pad + i];
+  }
+  stats[i] = m;
+  stats[rows_pad + i] = neg;
+  stats[2 * rows_pad + i] = num;
+}
+
+// finalize: per-row loss terms, unit gradient, per-block partial sums.  block = 256 threads (one per feature)
+__global__ void __launch_bounds__(256)
+con_finalize_kernel(const float* __restrict__ stats, const float* __restrict__ loss_part,
+                    const float* __restrict__ v_part, const float* __restrict__ u_part, int splits,
+                    long long rows_pad, const int* __restrict__ n_rows_p, float inv_tau,
+                    int need_grad, float* __restrict__ grad_unit, float* __restrict__ block_part) {
+  const int n_rows = *n_rows_p;
+  float lsum = 0.f, lcnt = 0.f;
+  for (long long row = blockIdx.x; row < n_rows; row += gridDim.x) {
+    const float num = stats[2 * rows_pad + row];
+    float L = 0.f, T = 0.f;
+    for (int s = 0; s < splits; ++s) {
+      L += loss_part[(size_t)s * 2 * rows_pad + row];
+      T += loss_part[(size_t)s * 2 * rows_pad + rows_pad + row];
+    }
+    const bool valid = num != 0.f;
+    if (need_grad) {
+      float V = 0.f, U = 0.f;
+      for (int s = 0; s < splits; ++s) {
+        V += v_part[((size_t)s * rows_pad + row) * 256 + threadIdx.x];
+        U += u_part[((size_t)s * rows_pad + row) * 256 + threadIdx.x];
+      }
+      grad_unit[(size_t)row * 256 + threadIdx.x] = valid ? (inv_tau / num) * (T * V - U) : 0.f;
+    }
+    if (threadIdx.x == 0 && valid) {
+      lsum += -L / num;
+      lcnt += 1.f;
+    }
+  }
+  if (threadIdx.x == 0) {
+    block_part[blockIdx.x] = lsum;
+    block_part[gridDim.x + blockIdx.x] = lcnt;
+  }
+}
+
+__global__ void con_reduce_out_kernel(const float* __restrict__ block_part, int nblk, float* __restrict__ out) {
+  __shared__ float red[32];
+  for (int k = 0; k < 2; ++k) {
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < nblk; i += blockDim.x) acc += block_part[(size_t)k * nblk + i];
+    const float r = block_sum(acc, red);
+    if (threadIdx.x == 0) out[k] = r;
+  }
+}
+
+__global__ void con_bwd_kernel(const float* __restrict__ grad_unit, const float* __restrict__ out,
+                               const float* __restrict__ g_scalar, float g_mul, const int* __restrict__ n_rows_p,
+                               float* __restrict__ d_anchor, long long max_rows) {
+  const long long n_rows = min((long long)*n_rows_p, max_rows);
+  const float coef = (out[1] > 0.f) ? g_scalar[0] * g_mul / out[1] : 0.f;
+  const long long n4 = n_rows * 64;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 g = reinterpret_cast<const float4*>(grad_unit)[i];
+    g.x *= coef, g.y *= coef, g.z *= coef, g.w *= coef;
+    reinterpret_cast<float4*>(d_anchor)[i] = g;
+  }
+}
+
+constexpr int kFinalizeBlocks = kNumSMs * 4;
+
+struct ConPlan {
+  int splits;
+  long long rows_pad;
+  size_t off_stats_part, off_stats, off_loss_part, off_v, off_u, off_block, total;
+};
+
+static ConPlan make_plan(long long max_row_tiles, long long max_col_tiles) {
+  ConPlan p;
+  // choose the number of column splits that best fills 148 SMs without tiny per-CTA ranges
+  int best = 1;
+  double best_eff = 0.0;
+  for (int s = 1; s <= 16; ++s) {
+    if (s > 1 && max_col_tiles / s < 4) break;
+    const long long ctas = max_row_tiles * s;
+    const long long waves = (ctas + kNumSMs - 1) / kNumSMs;
+    const double eff = (double)ctas / (double)(waves * kNumSMs);
+    if (eff > best_eff + 0.03) {
+      best_eff = eff;
+      best = s;
+    }
+  }
+  p.splits = best;
+  p.rows_pad = max_row_tiles * 128;
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    size_t r = o;
+    o += (bytes + 255) & ~(size_t)255;
+    return r;
+  };
+  p.off_stats_part = take((size_t)p.splits * 3 * p.rows_pad * 4);
+  p.off_stats = take((size_t)3 * p.rows_pad * 4);
+  p.off_loss_part = take((size_t)p.splits * 2 * p.rows_pad * 4);
+  p.off_v = take((size_t)p.splits * p.rows_pad * 256 * 4);
+  p.off_u = take((size_t)p.splits * p.rows_pad * 256 * 4);
+  p.off_block = take((size_t)2 * kFinalizeBlocks * 4);
+  p.total = o;
+  return p;
+}
+
+template <int PHASE, int PMODE>
+static int launch_sweep(const ConArgs& a, long long max_row_tiles, cudaStream_t st) {
+  static bool configured = false;  // benign race: attribute set is idempotent
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(con_sweep_kernel<PHASE, PMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)kConSmem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(con_sweep_kernel)");
+    configured = true;
+  }
+  const unsigned grid = (unsigned)(max_row_tiles * a.splits);
+  con_sweep_kernel<PHASE, PMODE><<<grid, kConThreads, kConSmem, st>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "con_sweep_kernel launch");
+  return UCD_OK;
+}
+
+}  // namespace ucd
+
+using namespace ucd;
+
+extern "C" size_t ucd_con_workspace_bytes(int64_t max_row_tiles, int64_t max_col_tiles) {
+  if (max_row_tiles <= 0 || max_col_tiles <= 0) return 0;
+  return make_plan(max_row_tiles, max_col_tiles).total;
+}
+
+extern "C" int ucd_con_fwd(const void* feat_tiles, const void* prob_tiles, const int32_t* lab_tiles,
+                           const int32_t* chunk_counts, int n_chunks, int64_t chunk_tiles, const void* row_feat_tiles,
+                           const void* row_prob_tiles, const int32_t* row_lab_tiles, const int32_t* n_rows,
+                           int64_t self_tile0, const int32_t* min_new, int p_mode, int kpad, const float* dense_p,
+                           int64_t ldp,
+                           float inv_temperature, int need_grad, float* out, float* grad_unit, void* workspace,
+                           size_t workspace_bytes, int64_t max_row_tiles, void* stream) {
+  UCD_CHECK_ARG(feat_tiles && lab_tiles && chunk_counts && out && workspace, "ucd_con_fwd: null pointer");
+  UCD_CHECK_ARG(n_chunks >= 1 && n_chunks <= kMaxChunks, "ucd_con_fwd: n_chunks=%d outside [1,%d]", n_chunks, kMaxChunks);
+  UCD_CHECK_ARG(row_feat_tiles && row_lab_tiles && n_rows, "ucd_con_fwd: null row pointer");
+  UCD_CHECK_ARG(aligned16(row_feat_tiles) && (!row_prob_tiles || aligned16(row_prob_tiles)),
+                "ucd_con_fwd: row tiles must be 16 B aligned");
+  UCD_CHECK_ARG(self_tile0 >= -1 && self_tile0 < (int64_t)n_chunks * chunk_tiles, "ucd_con_fwd: bad self_tile0");
+  UCD_CHECK_ARG(chunk_tiles >= 1 && max_row_tiles >= 1, "ucd_con_fwd: bad tile counts");
+  UCD_CHECK_ARG(p_mode >= 0 && p_mode <= 2, "ucd_con_fwd: bad p_mode");
+  UCD_CHECK_ARG(p_mode != 1 || (prob_tiles && row_prob_tiles && min_new), "ucd_con_fwd: p_mode 1 needs prob tiles and min_new");
+  UCD_CHECK_ARG(p_mode != 2 || (dense_p && n_chunks == 1), "ucd_con_fwd: dense P needs a single chunk");
+  UCD_CHECK_ARG(!need_grad || grad_unit, "ucd_con_fwd: need_grad without grad_unit");
+  UCD_CHECK_ARG(aligned16(feat_tiles) && aligned16(lab_tiles) && (!prob_tiles || aligned16(prob_tiles)),
+                "ucd_con_fwd: tile buffers must be 16 B aligned");
+  UCD_CHECK_ARG(inv_temperature > 0.f, "ucd_con_fwd: bad temperature");
+  if (p_mode == 1 && (kpad < 16 || kpad > 32 || kpad % 16 != 0)) {
+    set_error("ucd_con_fwd: joint-probability width kpad=%d not supported yet (16 or 32, i.e. C_old <= 32)", kpad);
+    return UCD_ENOSUP;
+  }
+  const ConPlan plan = make_plan(max_row_tiles, (int64_t)n_chunks * chunk_tiles);
+  UCD_CHECK_ARG(workspace_bytes >= plan.total, "ucd_con_fwd: workspace too small (%zu < %zu)", workspace_bytes, plan.total);
+  UCD_CHECK_ARG(max_row_tiles * plan.splits < (1ll << 31), "ucd_con_fwd: grid too large");
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* ws = (uint8_t*)workspace;
+  ConArgs a;
+  a.feat_tiles = (const __nv_bfloat16*)feat_tiles;
+  a.prob_tiles = (const __nv_bfloat16*)prob_tiles;
+  a.lab_tiles = lab_tiles;
+  a.chunk_counts = chunk_counts;
+  a.n_chunks = n_chunks;
+  a.chunk_tiles = chunk_tiles;
+  a.row_feat = (const __nv_bfloat16*)row_feat_tiles;
+  a.row_prob = (const __nv_bfloat16*)row_prob_tiles;
+  a.row_lab = row_lab_tiles;
+  a.n_rows = n_rows;
+  a.self_tile0 = self_tile0;
+  a.min_new = min_new;
+  a.dense_p = dense_p;
+  a.ldp = ldp;
+  a.inv_tau = inv_temperature;
+  a.splits = plan.splits;
+  a.need_grad = need_grad;
+  a.kpad = kpad;
+  a.rows_pad = plan.rows_pad;
+  a.stats_part = (float*)(ws + plan.off_stats_part);
+  a.stats = (const float*)(ws + plan.off_stats);
+  a.loss_part = (float*)(ws + plan.off_loss_part);
+  // sweep 1
+  a.acc_part = (float*)(ws + plan.off_v);
+  int rc = launch_sweep<1, 0>(a, max_row_tiles, st);
+  if (rc != UCD_OK) return rc;
+  con_combine_kernel<<<(unsigned)((plan.rows_pad + 255) / 256), 256, 0, st>>>(a.stats_part, plan.splits, plan.rows_pad,
+                                                                               (float*)(ws + plan.off_stats));
+  UCD_CHECK_LAUNCH("con_combine_kernel");
+  // sweep 2
+  a.acc_part = (float*)(ws + plan.off_u);
+  if (p_mode == 0)
+    rc = launch_sweep<2, 0>(a, max_row_tiles, st);
+  else if (p_mode == 1)
+    rc = launch_sweep<2, 1>(a, max_row_tiles, st);
+  else
+    rc = launch_sweep<2, 2>(a, max_row_tiles, st);
+  if (rc != UCD_OK) return rc;
+  float* block_part = (float*)(ws + plan.off_block);
+  con_finalize_kernel<<<kFinalizeBlocks, 256, 0, st>>>(a.stats, a.loss_part, (const float*)(ws + plan.off_v),
+                                                       (const float*)(ws + plan.off_u), plan.splits, plan.rows_pad,
+                                                       n_rows, inv_temperature, need_grad, grad_unit, block_part);
+  UCD_CHECK_LAUNCH("con_finalize_kernel");
+  con_reduce_out_kernel<<<1, 256, 0, st>>>(block_part, kFinalizeBlocks, out);
+  UCD_CHECK_LAUNCH("con_reduce_out_kernel");
+  return UCD_OK;
+}
+
+extern "C" int ucd_con_bwd(const float* grad_unit, const float* out, const float* g_scalar, float g_mul,
+                           const int32_t* n_rows, float* d_anchor, int64_t max_rows, void* stream) {
+  UCD_CHECK_ARG(grad_unit && out && g_scalar && n_rows && d_anchor, "ucd_con_bwd: null pointer");
+  UCD_CHECK_ARG(aligned16(grad_unit) && aligned16(d_anchor), "ucd_con_bwd: 16 B alignment required");
+  if (max_rows <= 0) return UCD_OK;
+  long long blocks = (max_rows * 64 + 255) / 256;
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  con_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(grad_unit, out, g_scalar, g_mul, n_rows, d_anchor,
+                                                                     max_rows);
+  UCD_CHECK_LAUNCH("con_bwd_kernel");
+  return UCD_OK;
+}

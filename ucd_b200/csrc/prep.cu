@@ -1,0 +1,412 @@
+// Contrastive prep: label downsample / pseudo-label mixing / compaction / normalise / bf16 tile pack.
+// Reference: utils/loss.py:258-395 (pre_contrastive_pixel, v2 branch) == utils/utils.py:256-397;
+// exact semantics restated in SURVEY.md Appendix A.1 and oracle/ucd_oracle.py.
+//
+// Everything here is O(N_px * D) streaming work (HBM/L2 bound, tiny next to the N_a x N_c sweeps).
+// No host synchronisation: counts, ranks and offsets stay on the device.
+#include "common.cuh"
+
+namespace ucd {
+
+constexpr int kPrepBlock = 256;  // pixels per counting block
+
+// flags: bit0 anchor (mix>0), bit1 pseudo (anchor & !GT-new), bit2 GT-new (label_n>0)
+__global__ void __launch_bounds__(kPrepBlock)
+prep_labels_kernel(const long long* __restrict__ labels, const float* __restrict__ l_po, int B, int C_old, int h,
+                   int w, int H, int W, int max_label, float scale_h, float scale_w, int* __restrict__ label_n,
+                   int* __restrict__ mix, int* __restrict__ flags, int* __restrict__ rank_a,
+                   int* __restrict__ rank_o, int* __restrict__ block_cnt, int* __restrict__ counts) {
+  const int n_px = B * h * w;
+  const int p = blockIdx.x * kPrepBlock + threadIdx.x;
+  int is_a = 0, is_o = 0;
+  if (p < n_px) {
+    const int hw = h * w;
+    const int b = p / hw, q = p - b * hw;
+    const int y = q / w, x = q - y * w;
+    // --- bilinear label downsample, bit-exact with ATen's CPU kernel (oracle/_bilinear_eval_f32) ---
+    const Tap ty = bilinear_tap(y, scale_h, H, h);
+    const Tap tx = bilinear_tap(x, scale_w, W, w);
+    const long long* lb = labels + (size_t)b * H * W;
+    const float v00 = (float)lb[(size_t)ty.i0 * W + tx.i0], v01 = (float)lb[(size_t)ty.i0 * W + tx.i1];
+    const float v10 = (float)lb[(size_t)ty.i1 * W + tx.i0], v11 = (float)lb[(size_t)ty.i1 * W + tx.i1];
+    float acc = __fmul_rn(__fmul_rn(ty.w0, tx.w1), v01);
+    acc = __fmaf_rn(__fmul_rn(ty.w0, tx.w0), v00, acc);
+    acc = __fmaf_rn(__fmul_rn(ty.w1, tx.w0), v10, acc);
+    acc = __fmaf_rn(__fmul_rn(ty.w1, tx.w1), v11, acc);
+    int g = (int)truncf(acc);                 // .type(int8) + the two masked fills (loss.py:262,269-270)
+    if (g < 0 || g > max_label) g = 0;
+    // --- pseudo label: first maximal channel of the old model's low-res logits (loss.py:357) ---
+    const float* lp = l_po + (size_t)b * C_old * hw + q;
+    float best = lp[0];
+    int arg = 0;
+    for (int c = 1; c < C_old; ++c) {
+      const float v = lp[(size_t)c * hw];
+      if (v > best) {
+        best = v;
+        arg = c;
+      }
+    }
+    const int m = g > 0 ? g : arg;
+    is_a = m > 0;
+    is_o = is_a && !(g > 0);
+    label_n[p] = g;
+    mix[p] = m;
+    flags[p] = is_a | (is_o << 1) | ((g > 0) << 2);
+    if (g > 0) atomicMin(&counts[2], g);
+  }
+  // rank of this pixel among the block's anchors / pseudos
+  __shared__ int wsum_a[kPrepBlock / 32], wsum_o[kPrepBlock / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const unsigned ba = __ballot_sync(0xffffffffu, is_a), bo = __ballot_sync(0xffffffffu, is_o);
+  const unsigned lt = (1u << lane) - 1u;
+  int ra = __popc(ba & lt), ro = __popc(bo & lt);
+  if (lane == 0) {
+    wsum_a[wid] = __popc(ba);
+    wsum_o[wid] = __popc(bo);
+  }
+  __syncthreads();
+  int tot_a = 0, tot_o = 0;
+  for (int i = 0; i < kPrepBlock / 32; ++i) {
+    if (i < wid) {
+      ra += wsum_a[i];
+      ro += wsum_o[i];
+    }
+    tot_a += wsum_a[i];
+    tot_o += wsum_o[i];
+  }
+  if (p < n_px) {
+    rank_a[p] = ra;
+    rank_o[p] = ro;
+  }
+  if (threadIdx.x == 0) {
+    block_cnt[2 * blockIdx.x] = tot_a;
+    block_cnt[2 * blockIdx.x + 1] = tot_o;
+  }
+}
+
+// exclusive scan of the per-block counts (in place) + totals.  One block.
+__global__ void __launch_bounds__(1024)
+prep_scan_kernel(int* __restrict__ block_cnt, int nblk, int* __restrict__ counts, int n_px) {
+  __shared__ int sa[1024], so[1024];
+  __shared__ int carry_a, carry_o;
+  if (threadIdx.x == 0) carry_a = carry_o = 0;
+  __syncthreads();
+  for (int base = 0; base < nblk; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int va = i < nblk ? block_cnt[2 * i] : 0, vo = i < nblk ? block_cnt[2 * i + 1] : 0;
+    sa[threadIdx.x] = va;
+    so[threadIdx.x] = vo;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+      int ta = 0, to = 0;
+      if ((int)threadIdx.x >= off) {
+        ta = sa[threadIdx.x - off];
+        to = so[threadIdx.x - off];
+      }
+      __syncthreads();
+      sa[threadIdx.x] += ta;
+      so[threadIdx.x] += to;
+      __syncthreads();
+    }
+    if (i < nblk) {
+      block_cnt[2 * i] = carry_a + sa[threadIdx.x] - va;
+      block_cnt[2 * i + 1] = carry_o + so[threadIdx.x] - vo;
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) {
+      carry_a += sa[1023];
+      carry_o += so[1023];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    counts[0] = carry_a;
+    counts[1] = carry_o;
+    counts[3] = n_px;
+  }
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// tile layout: element (row r, feature k) of tile T at  ((T*(K/8) + k/8)*128 + r)*8 + k%8
+__device__ __forceinline__ size_t tile_chunk_off(long long tile, int chunks_per_tile, int chunk, int r) {
+  return (((size_t)tile * chunks_per_tile + chunk) * 128 + r) * 8;
+}
+
+// Pack kernel: block = 32 consecutive pixels, blockIdx.y = source (0: f_n -> anchors, 1: f_o -> pseudo columns)
+__global__ void __launch_bounds__(128)
+prep_pack_kernel(const float* __restrict__ f_n, const float* __restrict__ f_o, const int* __restrict__ mix,
+                 const int* __restrict__ flags, const int* __restrict__ rank_a, const int* __restrict__ rank_o,
+                 const int* __restrict__ block_off, const int* __restrict__ counts, int n_px, int hw,
+                 float* __restrict__ anchor_f32, float* __restrict__ contrast_f32, int* __restrict__ la,
+                 int* __restrict__ lc, __nv_bfloat16* __restrict__ feat_tiles, int* __restrict__ lab_tiles,
+                 int* __restrict__ row_pix, float* __restrict__ inv_norm) {
+  __shared__ float tile[256][33];
+  __shared__ float ss[4][32];
+  __shared__ int slot_s[32];
+  __shared__ float inv_s[32];
+  const int src = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int p = blockIdx.x * 32 + lane;
+  const int n_a = counts[0];
+  int slot = -1;
+  if (p < n_px) {
+    const int f = flags[p];
+    const int blk = p / kPrepBlock;
+    if (src == 0 && (f & 1)) slot = block_off[2 * blk] + rank_a[p];
+    if (src == 1 && (f & 2)) slot = block_off[2 * blk + 1] + rank_o[p];
+  }
+  if (!__syncthreads_or(slot >= 0)) return;
+  const float* f = src == 0 ? f_n : f_o;
+  float part = 0.f;
+  if (p < n_px) {
+    const int b = p / hw, q = p - b * hw;
+    const float* fp = f + ((size_t)b * 256 + warp * 64) * hw + q;
+#pragma unroll 8
+    for (int c = 0; c < 64; ++c) {
+      const float v = fp[(size_t)c * hw];
+      tile[warp * 64 + c][lane] = v;
+      part = fmaf(v, v, part);
+    }
+  } else {
+    for (int c = 0; c < 64; ++c) tile[warp * 64 + c][lane] = 0.f;
+  }
+  ss[warp][lane] = part;
+  __syncthreads();
+  if (warp == 0) {
+    const float tot = ss[0][lane] + ss[1][lane] + ss[2][lane] + ss[3][lane];
+    const float inv = 1.f / fmaxf(sqrtf(tot), 1e-12f);  // F.normalize eps
+    inv_s[lane] = inv;
+    slot_s[lane] = slot;
+    if (slot >= 0) {
+      const int m = mix[p];
+      const int cs = src == 0 ? slot : n_a + slot;  // column slot in [anchors ; pseudo]
+      lc[cs] = m;
+      lab_tiles[cs] = m;
+      if (src == 0) {
+        la[slot] = m;
+        row_pix[slot] = p;
+        inv_norm[slot] = inv;
+      }
+    }
+  }
+  __syncthreads();
+  // (a) fp32 rows in reference order: warp per pixel, lanes over channels (coalesced 128 B stores)
+  for (int pi = warp; pi < 32; pi += 4) {
+    const int s = slot_s[pi];
+    if (s < 0) continue;
+    const float inv = inv_s[pi];
+    const size_t crow = (size_t)(src == 0 ? s : n_a + s) * 256;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = lane + 32 * k;
+      const float v = tile[c][pi] * inv;
+      contrast_f32[crow + c] = v;
+      if (src == 0) anchor_f32[(size_t)s * 256 + c] = v;
+    }
+  }
+  // (b) bf16 tiles: lane = pixel, each warp writes 8 of the 32 k-chunks (16 B per lane, rows adjacent)
+  if (slot >= 0) {
+    const int cs = src == 0 ? slot : n_a + slot;
+    const long long T = cs >> 7;
+    const int r = cs & 127;
+    const float inv = inv_s[lane];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int chunk = warp * 8 + k;
+      uint4 o;
+      o.x = pack_bf16x2(tile[chunk * 8 + 0][lane] * inv, tile[chunk * 8 + 1][lane] * inv);
+      o.y = pack_bf16x2(tile[chunk * 8 + 2][lane] * inv, tile[chunk * 8 + 3][lane] * inv);
+      o.z = pack_bf16x2(tile[chunk * 8 + 4][lane] * inv, tile[chunk * 8 + 5][lane] * inv);
+      o.w = pack_bf16x2(tile[chunk * 8 + 6][lane] * inv, tile[chunk * 8 + 7][lane] * inv);
+      *reinterpret_cast<uint4*>(feat_tiles + tile_chunk_off(T, 32, chunk, r)) = o;
+    }
+  }
+}
+
+// softmax(l_po) per pixel -> bf16 prob tiles at the pixel's anchor slot and (if pseudo) pseudo slot
+__global__ void __launch_bounds__(256)
+prep_prob_kernel(const float* __restrict__ l_po, const int* __restrict__ flags, const int* __restrict__ rank_a,
+                 const int* __restrict__ rank_o, const int* __restrict__ block_off, const int* __restrict__ counts,
+                 int n_px, int hw, int C_old, int kpad, __nv_bfloat16* __restrict__ prob_tiles) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_px) return;
+  const int f = flags[p];
+  if (!(f & 1)) return;
+  const int n_a = counts[0];
+  const int blk = p / kPrepBlock;
+  const int b = p / hw, q = p - b * hw;
+  const float* lp = l_po + (size_t)b * C_old * hw + q;
+  float m = lp[0];
+  for (int c = 1; c < C_old; ++c) m = fmaxf(m, lp[(size_t)c * hw]);
+  float s = 0.f;
+  for (int c = 0; c < C_old; ++c) s += __expf(lp[(size_t)c * hw] - m);
+  const float inv = 1.f / s;
+  const int sa = block_off[2 * blk] + rank_a[p];
+  const int so = (f & 2) ? n_a + block_off[2 * blk + 1] + rank_o[p] : -1;
+  const int chunks = kpad / 8;
+  for (int ch = 0; ch < chunks; ++ch) {
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = ch * 8 + e;
+      v[e] = c < C_old ? __expf(lp[(size_t)c * hw] - m) * inv : 0.f;
+    }
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]);
+    o.y = pack_bf16x2(v[2], v[3]);
+    o.z = pack_bf16x2(v[4], v[5]);
+    o.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(prob_tiles + tile_chunk_off(sa >> 7, chunks, ch, sa & 127)) = o;
+    if (so >= 0) *reinterpret_cast<uint4*>(prob_tiles + tile_chunk_off(so >> 7, chunks, ch, so & 127)) = o;
+  }
+}
+
+// adjoint of gather + normalize; block = 32 consecutive pixels, writes all 256 channels (zeros for non-anchors)
+__global__ void __launch_bounds__(128)
+prep_bwd_kernel(const float* __restrict__ g_anchor, const float* __restrict__ anchor_f32,
+                const float* __restrict__ inv_norm, const int* __restrict__ flags, const int* __restrict__ rank_a,
+                const int* __restrict__ block_off, float* __restrict__ df_n, int n_px, int hw) {
+  __shared__ float tile[256][33];
+  __shared__ int slot_s[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int p = blockIdx.x * 32 + lane;
+  int slot = -1;
+  if (p < n_px && (flags[p] & 1)) slot = block_off[2 * (p / kPrepBlock)] + rank_a[p];
+  if (warp == 0) slot_s[lane] = slot;
+  __syncthreads();
+  for (int pi = warp; pi < 32; pi += 4) {
+    const int s = slot_s[pi];
+    if (s < 0) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) tile[lane + 32 * k][pi] = 0.f;
+      continue;
+    }
+    float g[8], a[8], dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      g[k] = g_anchor[(size_t)s * 256 + lane + 32 * k];
+      a[k] = anchor_f32[(size_t)s * 256 + lane + 32 * k];
+      dot = fmaf(g[k], a[k], dot);
+    }
+    dot = warp_sum(dot);
+    const float inv = inv_norm[s];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) tile[lane + 32 * k][pi] = (g[k] - dot * a[k]) * inv;
+  }
+  __syncthreads();
+  if (p < n_px) {
+    const int b = p / hw, q = p - b * hw;
+    float* dp = df_n + ((size_t)b * 256 + warp * 64) * hw + q;
+#pragma unroll 8
+    for (int c = 0; c < 64; ++c) dp[(size_t)c * hw] = tile[warp * 64 + c][lane];
+  }
+}
+
+// compat path: caller-supplied fp32 rows [n,256] (+labels) -> bf16 tiles.  warp per row.
+__global__ void __launch_bounds__(256)
+pack_rows_kernel(const float* __restrict__ rows, const int* __restrict__ labels, long long n,
+                 __nv_bfloat16* __restrict__ feat_tiles, int* __restrict__ lab_tiles) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const float4* src = reinterpret_cast<const float4*>(rows + row * 256 + lane * 8);
+  const float4 a = src[0], b = src[1];
+  uint4 o;
+  o.x = pack_bf16x2(a.x, a.y);
+  o.y = pack_bf16x2(a.z, a.w);
+  o.z = pack_bf16x2(b.x, b.y);
+  o.w = pack_bf16x2(b.z, b.w);
+  *reinterpret_cast<uint4*>(feat_tiles + tile_chunk_off(row >> 7, 32, lane, (int)(row & 127))) = o;
+  if (lane == 0 && lab_tiles != nullptr) lab_tiles[row] = labels[row];
+}
+
+}  // namespace ucd
+
+using namespace ucd;
+
+extern "C" int64_t ucd_con_max_tiles(int64_t n_px) { return (2 * n_px + 127) / 128 + 1; }
+extern "C" int ucd_con_prob_kpad(int C_old) { return (C_old + 15) / 16 * 16; }
+
+extern "C" int ucd_con_prep_labels(const int64_t* labels, const float* l_po, int B, int C_old, int h, int w, int H,
+                                   int W, int max_label, int32_t* label_n, int32_t* mix, int32_t* flags,
+                                   int32_t* rank_a, int32_t* rank_o, int32_t* block_cnt, int32_t* counts,
+                                   void* stream) {
+  UCD_CHECK_ARG(labels && l_po && label_n && mix && flags && rank_a && rank_o && block_cnt && counts,
+                "ucd_con_prep_labels: null pointer");
+  UCD_CHECK_ARG(B > 0 && C_old > 0 && h > 0 && w > 0 && H > 0 && W > 0, "ucd_con_prep_labels: bad shape");
+  UCD_CHECK_ARG((long long)B * h * w < (1ll << 30), "ucd_con_prep_labels: too many pixels");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n_px = B * h * w;
+  const int nblk = (n_px + kPrepBlock - 1) / kPrepBlock;
+  cudaError_t e = cudaMemsetAsync(counts, 0x7f, 4 * sizeof(int32_t), st);  // min_new starts at 0x7f7f7f7f
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(counts)");
+  prep_labels_kernel<<<nblk, kPrepBlock, 0, st>>>((const long long*)labels, l_po, B, C_old, h, w, H, W, max_label,
+                                                  (float)H / (float)h, (float)W / (float)w, label_n, mix, flags,
+                                                  rank_a, rank_o, block_cnt, counts);
+  UCD_CHECK_LAUNCH("prep_labels_kernel");
+  prep_scan_kernel<<<1, 1024, 0, st>>>(block_cnt, nblk, counts, n_px);
+  UCD_CHECK_LAUNCH("prep_scan_kernel");
+  return UCD_OK;
+}
+
+extern "C" int ucd_con_prep_pack(const float* f_n, const float* f_o, const float* l_po, const int32_t* mix,
+                                 const int32_t* flags, const int32_t* rank_a, const int32_t* rank_o,
+                                 const int32_t* block_off, const int32_t* counts, int B, int C_old, int h, int w,
+                                 float* anchor_f32, float* contrast_f32, int32_t* la, int32_t* lc, void* feat_tiles,
+                                 void* prob_tiles, int32_t* lab_tiles, int32_t* row_pix, float* inv_norm,
+                                 int64_t max_tiles, void* stream) {
+  UCD_CHECK_ARG(f_n && f_o && l_po && mix && flags && rank_a && rank_o && block_off && counts && anchor_f32 &&
+                    contrast_f32 && la && lc && feat_tiles && prob_tiles && lab_tiles && row_pix && inv_norm,
+                "ucd_con_prep_pack: null pointer");
+  UCD_CHECK_ARG(aligned16(feat_tiles) && aligned16(prob_tiles), "ucd_con_prep_pack: tiles must be 16 B aligned");
+  const int n_px = B * h * w;
+  UCD_CHECK_ARG(max_tiles >= ucd_con_max_tiles(n_px), "ucd_con_prep_pack: max_tiles too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int kpad = ucd_con_prob_kpad(C_old);
+  cudaError_t e = cudaMemsetAsync(feat_tiles, 0, (size_t)max_tiles * 128 * 256 * 2, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(prob_tiles, 0, (size_t)max_tiles * 128 * kpad * 2, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(lab_tiles, 0xff, (size_t)max_tiles * 128 * sizeof(int32_t), st);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(tiles)");
+  dim3 grid((n_px + 31) / 32, 2);
+  prep_pack_kernel<<<grid, 128, 0, st>>>(f_n, f_o, mix, flags, rank_a, rank_o, block_off, counts, n_px, h * w,
+                                         anchor_f32, contrast_f32, la, lc, (__nv_bfloat16*)feat_tiles, lab_tiles,
+                                         row_pix, inv_norm);
+  UCD_CHECK_LAUNCH("prep_pack_kernel");
+  prep_prob_kernel<<<(n_px + 255) / 256, 256, 0, st>>>(l_po, flags, rank_a, rank_o, block_off, counts, n_px, h * w,
+                                                       C_old, kpad, (__nv_bfloat16*)prob_tiles);
+  UCD_CHECK_LAUNCH("prep_prob_kernel");
+  return UCD_OK;
+}
+
+extern "C" int ucd_con_prep_bwd(const float* g_anchor, const float* anchor_f32, const float* inv_norm,
+                                const int32_t* flags, const int32_t* rank_a, const int32_t* block_off, float* df_n,
+                                int B, int h, int w, void* stream) {
+  UCD_CHECK_ARG(g_anchor && anchor_f32 && inv_norm && flags && rank_a && block_off && df_n,
+                "ucd_con_prep_bwd: null pointer");
+  const int n_px = B * h * w;
+  prep_bwd_kernel<<<(n_px + 31) / 32, 128, 0, (cudaStream_t)stream>>>(g_anchor, anchor_f32, inv_norm, flags, rank_a,
+                                                                       block_off, df_n, n_px, h * w);
+  UCD_CHECK_LAUNCH("prep_bwd_kernel");
+  return UCD_OK;
+}
+
+extern "C" int ucd_con_pack_rows(const float* rows, const int32_t* labels, int64_t n, void* feat_tiles,
+                                 int32_t* lab_tiles, int64_t max_tiles, void* stream) {
+  UCD_CHECK_ARG(rows && feat_tiles, "ucd_con_pack_rows: null pointer");
+  UCD_CHECK_ARG(labels || !lab_tiles, "ucd_con_pack_rows: lab_tiles without labels");
+  UCD_CHECK_ARG(aligned16(rows) && aligned16(feat_tiles), "ucd_con_pack_rows: 16 B alignment required");
+  UCD_CHECK_ARG(n >= 0 && max_tiles * 128 >= n, "ucd_con_pack_rows: max_tiles too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(feat_tiles, 0, (size_t)max_tiles * 128 * 256 * 2, st);
+  if (e == cudaSuccess && lab_tiles) e = cudaMemsetAsync(lab_tiles, 0xff, (size_t)max_tiles * 128 * 4, st);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(pack_rows)");
+  if (n > 0) {
+    pack_rows_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(rows, labels, n, (__nv_bfloat16*)feat_tiles, lab_tiles);
+    UCD_CHECK_LAUNCH("pack_rows_kernel");
+  }
+  return UCD_OK;
+}

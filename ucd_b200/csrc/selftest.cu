@@ -1,0 +1,153 @@
+// Self-test of the tcgen05 / TMEM / bulk-copy building blocks with the production tile layout.
+//   variant 0:  S[128,128] = A[128,256] * C[128,256]^T      (both operands K-major, like sweep MMA 1)
+//   variant 1:  V[128,256] = E[128,128] * C[128,256]        (A K-major from thread-written smem,
+//                                                             B = the same C tile read MN-major)
+// Used by tests/test_gpu_umma.py; not on the product path.
+#include "umma.cuh"
+
+#include <stdlib.h>
+#include <vector>
+
+namespace ucd {
+
+constexpr uint32_t ST_OFF_A = 0, ST_OFF_C = 65536, ST_OFF_E = 131072, ST_OFF_BAR = 163840, ST_SMEM = 163840 + 64;
+
+__global__ void __launch_bounds__(128, 1)
+selftest_kernel(int variant, const __nv_bfloat16* __restrict__ a_tile, const __nv_bfloat16* __restrict__ c_tile,
+                const float* __restrict__ e_rows /*[128][128] fp32*/, float* __restrict__ out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint32_t s_tmem;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar_ld = sbase + ST_OFF_BAR, bar_mma = sbase + ST_OFF_BAR + 8;
+  if (threadIdx.x == 0) {
+    mbar_init(bar_ld, 1);
+    mbar_init(bar_mma, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(&s_tmem), 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(bar_ld, 2 * 65536u);
+    for (int q = 0; q < 4; ++q) {
+      bulk_g2s(sbase + ST_OFF_A + q * 16384u, reinterpret_cast<const uint8_t*>(a_tile) + q * 16384u, 16384u, bar_ld);
+      bulk_g2s(sbase + ST_OFF_C + q * 16384u, reinterpret_cast<const uint8_t*>(c_tile) + q * 16384u, 16384u, bar_ld);
+    }
+  }
+  if (variant == 1) {
+    // every thread writes its row of E as bf16 into the K-major chunk layout, exactly like the sweep epilogue
+    const int r = threadIdx.x;
+    for (int kc = 0; kc < 16; ++kc) {
+      uint32_t pk[4];
+      for (int u = 0; u < 4; ++u) {
+        __nv_bfloat162 v = __floats2bfloat162_rn(e_rows[r * 128 + kc * 8 + 2 * u], e_rows[r * 128 + kc * 8 + 2 * u + 1]);
+        pk[u] = *reinterpret_cast<uint32_t*>(&v);
+      }
+      *reinterpret_cast<uint4*>(smem + ST_OFF_E + kc * 2048 + r * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+    fence_proxy_async();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_wait(bar_ld, 0);
+    tc_fence_after();
+    if (variant == 0) {
+      constexpr uint32_t idesc = umma_idesc(128, 128, 0, 0);
+      for (int ks = 0; ks < 16; ++ks)
+        umma_bf16(tmem, umma_desc(sbase + ST_OFF_A + ks * 4096, 2048, 128),
+                  umma_desc(sbase + ST_OFF_C + ks * 4096, 2048, 128), idesc, ks > 0);
+    } else {
+      constexpr uint32_t idesc = umma_idesc(128, 256, 0, 1);
+      for (int kk = 0; kk < 8; ++kk)
+        umma_bf16(tmem, umma_desc(sbase + ST_OFF_E + kk * 4096, 2048, 128),
+                  umma_desc(sbase + ST_OFF_C + kk * 16 * 16, 128, 2048), idesc, kk > 0);
+    }
+    umma_commit(bar_mma);
+  }
+  __syncwarp();
+  mbar_wait(bar_mma, 0);
+  tc_fence_after();
+  const int ncols = variant == 0 ? 128 : 256;
+  const int r = warp * 32 + lane;
+  for (int cc = 0; cc < ncols / 32; ++cc) {
+    uint32_t rv[32];
+    tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + cc * 32, rv);
+    tmem_ld_wait();
+    for (int j = 0; j < 32; ++j) out[r * ncols + cc * 32 + j] = __uint_as_float(rv[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
+static float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+}  // namespace ucd
+
+using namespace ucd;
+
+extern "C" int ucd_selftest_umma(int variant, float* max_err_host) {
+  UCD_CHECK_ARG(variant == 0 || variant == 1, "ucd_selftest_umma: variant must be 0 or 1");
+  UCD_CHECK_ARG(max_err_host, "ucd_selftest_umma: null pointer");
+  const int M = 128, D = 256;
+  std::vector<float> A(M * D), C(M * D), E(M * 128);
+  unsigned s = 12345u;
+  auto rnd = [&]() {
+    s = s * 1664525u + 1013904223u;
+    return ((s >> 8) & 0xffff) / 65536.f - 0.5f;
+  };
+  for (auto& v : A) v = bf16_round(rnd());
+  for (auto& v : C) v = bf16_round(rnd());
+  for (auto& v : E) v = bf16_round(rnd() * 4.f);
+  std::vector<__nv_bfloat16> At(M * D), Ct(M * D);
+  for (int r = 0; r < M; ++r)
+    for (int k = 0; k < D; ++k) {
+      const size_t o = ((size_t)(k / 8) * 128 + r) * 8 + k % 8;
+      At[o] = __float2bfloat16_rn(A[r * D + k]);
+      Ct[o] = __float2bfloat16_rn(C[r * D + k]);
+    }
+  const int ncols = variant == 0 ? 128 : 256;
+  std::vector<float> ref((size_t)M * ncols, 0.f), got((size_t)M * ncols, 0.f);
+  for (int i = 0; i < M; ++i)
+    for (int j = 0; j < ncols; ++j) {
+      double acc = 0;
+      if (variant == 0)
+        for (int k = 0; k < D; ++k) acc += (double)A[i * D + k] * C[j * D + k];
+      else
+        for (int k = 0; k < 128; ++k) acc += (double)E[i * 128 + k] * C[k * D + j];
+      ref[(size_t)i * ncols + j] = (float)acc;
+    }
+  __nv_bfloat16 *dA = nullptr, *dC = nullptr;
+  float *dE = nullptr, *dO = nullptr;
+  cudaError_t e;
+#define ST_TRY(x)                                   \
+  if ((e = (x)) != cudaSuccess) {                   \
+    cudaFree(dA), cudaFree(dC), cudaFree(dE), cudaFree(dO); \
+    return cuda_fail(e, #x);                        \
+  }
+  ST_TRY(cudaMalloc(&dA, At.size() * 2));
+  ST_TRY(cudaMalloc(&dC, Ct.size() * 2));
+  ST_TRY(cudaMalloc(&dE, E.size() * 4));
+  ST_TRY(cudaMalloc(&dO, got.size() * 4));
+  ST_TRY(cudaMemcpy(dA, At.data(), At.size() * 2, cudaMemcpyHostToDevice));
+  ST_TRY(cudaMemcpy(dC, Ct.data(), Ct.size() * 2, cudaMemcpyHostToDevice));
+  ST_TRY(cudaMemcpy(dE, E.data(), E.size() * 4, cudaMemcpyHostToDevice));
+  ST_TRY(cudaMemset(dO, 0, got.size() * 4));
+  ST_TRY(cudaFuncSetAttribute(selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM));
+  selftest_kernel<<<1, 128, ST_SMEM>>>(variant, dA, dC, dE, dO);
+  ST_TRY(cudaGetLastError());
+  ST_TRY(cudaDeviceSynchronize());
+  ST_TRY(cudaMemcpy(got.data(), dO, got.size() * 4, cudaMemcpyDeviceToHost));
+#undef ST_TRY
+  cudaFree(dA), cudaFree(dC), cudaFree(dE), cudaFree(dO);
+  float mx = 0.f;
+  for (size_t i = 0; i < ref.size(); ++i) mx = fmaxf(mx, fabsf(ref[i] - got[i]));
+  *max_err_host = mx;
+  return UCD_OK;
+}

@@ -1,0 +1,541 @@
+"""Host-side mirror of the reference loss interface for the UCD hot path.
+
+Same class names, constructor and ``forward`` signatures as the reference so that ``train.py`` and
+``segmentation_module.py`` can use this module as a drop-in:
+
+* ``UnbiasedCrossEntropy(old_cl=None, reduction='mean', ignore_index=255)``      utils/loss.py:89-109
+* ``UnbiasedKnowledgeDistillationLoss(reduction='mean', alpha=1.)``              utils/loss.py:139-184
+* ``PixelConLossV2(sample_method='none', temperature=0.07)``                     utils/loss.py:403-466
+* ``pre_contrastive_pixel(f_n, l_n, l_po=None, f_o=None)`` (alias ``pre_contractive_pixel``)
+                                                            utils/loss.py:258-399 / utils/utils.py:256-397
+* ``interpolate_bilinear(x, size)`` for ``F.interpolate(..., mode='bilinear')``   segmentation_module.py:133
+
+Everything runs in hand-written sm_100a CUDA kernels behind the C ABI of include/ucd_b200.h
+(ucd_b200/_lib.py).  PyTorch is used for device memory, streams, autograd glue and NCCL only.
+There is no CPU path: CPU tensors or a missing library raise.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import check, cur_stream, ptr
+
+FEAT_DIM = 256
+TILE = 128
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("ucd_b200: expected CUDA tensors (there is no CPU fallback for this path)")
+
+
+def _f32c(t):
+    """fp32 contiguous view/copy of a floating tensor (the reference runs this path in fp32, amp O0)."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _scalar_grad(g):
+    """A broadcast upstream gradient (e.g. from ``.mean()``) as a 1-element tensor, else None."""
+    if g.dim() == 0:
+        return g.reshape(1)
+    if all(s == 0 for s in g.stride()):
+        return g.as_strided((1,), (1,))
+    return None
+
+
+# ----------------------------------------------------------------------------------------------
+# bilinear logit upsample
+# ----------------------------------------------------------------------------------------------
+class _UpsampleFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, out_h, out_w):
+        _need_cuda(x)
+        x = _f32c(x)
+        lead, (h, w) = x.shape[:-2], x.shape[-2:]
+        planes = 1
+        for d in lead:
+            planes *= d
+        out = torch.empty(*lead, out_h, out_w, device=x.device, dtype=torch.float32)
+        if planes > 0:
+            check(_lib.lib().ucd_upsample_bilinear_fwd(ptr(x), ptr(out), planes, h, w, out_h, out_w, cur_stream()),
+                  "upsample_bilinear_fwd")
+        ctx.shape = (lead, h, w, out_h, out_w, planes)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lead, h, w, out_h, out_w, planes = ctx.shape
+        g = _f32c(g)
+        gin = torch.empty(*lead, h, w, device=g.device, dtype=torch.float32)
+        if planes > 0:
+            check(_lib.lib().ucd_upsample_bilinear_bwd(ptr(g), ptr(gin), planes, h, w, out_h, out_w, cur_stream()),
+                  "upsample_bilinear_bwd")
+        return gin, None, None
+
+
+def interpolate_bilinear(x, size):
+    """``F.interpolate(x, size=size, mode='bilinear', align_corners=False)`` (segmentation_module.py:133)."""
+    return _UpsampleFn.apply(x, int(size[0]), int(size[1]))
+
+
+# ----------------------------------------------------------------------------------------------
+# MiB unbiased cross-entropy
+# ----------------------------------------------------------------------------------------------
+class _UnceFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, inputs, targets, old_cl, ignore_index, reduction):
+        B, C = inputs.shape[0], inputs.shape[1]
+        HW = inputs[0, 0].numel()
+        x = _f32c(inputs)
+        dev = x.device
+        loss_px = torch.empty(targets.shape, device=dev, dtype=torch.float32)
+        lse = torch.empty((2,) + tuple(targets.shape), device=dev, dtype=torch.float32)
+        want_stats = reduction != "none"
+        stats = torch.empty(2, device=dev, dtype=torch.float32) if want_stats else None
+        scratch = (torch.empty(_lib.lib().ucd_reduce_scratch_floats(), device=dev, dtype=torch.float32)
+                   if want_stats else None)
+        check(_lib.lib().ucd_unce_fwd(ptr(x), ptr(targets), ptr(loss_px), ptr(lse[0]), ptr(lse[1]), ptr(stats),
+                                      ptr(scratch), B, C, old_cl, HW, ignore_index, cur_stream()), "unce_fwd")
+        ctx.save_for_backward(x, targets, lse, stats)
+        ctx.cfg = (B, C, HW, old_cl, ignore_index, reduction)
+        if reduction == "none":
+            return loss_px
+        if reduction == "sum":
+            return stats[0].clone()
+        return stats[0] / stats[1]
+
+    @staticmethod
+    def backward(ctx, g):
+        x, targets, lse, stats = ctx.saved_tensors
+        B, C, HW, old_cl, ignore_index, reduction = ctx.cfg
+        dx = torch.empty_like(x)
+        g_px, g_sc = None, None
+        if reduction == "none":
+            g_sc = _scalar_grad(g)
+            if g_sc is None:
+                g_px = _f32c(g)
+        else:
+            g_sc = g.reshape(1)
+        if g_sc is not None:
+            g_sc = _f32c(g_sc)
+        check(_lib.lib().ucd_unce_bwd(ptr(x), ptr(targets), ptr(lse[0]), ptr(lse[1]), ptr(g_px), ptr(g_sc), 1.0,
+                                      ptr(stats), 1 if reduction == "mean" else 0, ptr(dx), B, C, old_cl, HW,
+                                      ignore_index, cur_stream()), "unce_bwd")
+        return dx, None, None, None, None
+
+
+class UnbiasedCrossEntropy(nn.Module):
+    """MiB unbiased cross-entropy (utils/loss.py:89-109).  Like the reference it remaps ``targets`` in
+    place (labels below ``old_cl`` become 0, loss.py:104-105)."""
+
+    def __init__(self, old_cl=None, reduction='mean', ignore_index=255):
+        super().__init__()
+        self.reduction = reduction
+        self.ignore_index = ignore_index
+        self.old_cl = old_cl
+
+    def forward(self, inputs, targets):
+        _need_cuda(inputs, targets)
+        if self.reduction not in ("none", "mean", "sum"):
+            raise ValueError("reduction must be 'none', 'mean' or 'sum'")
+        if targets.dtype != torch.int64:
+            raise TypeError("UnbiasedCrossEntropy: targets must be int64 (train.py:98 casts labels to long)")
+        if inputs.dim() < 2 or targets.shape != inputs.shape[:1] + inputs.shape[2:]:
+            raise ValueError("UnbiasedCrossEntropy: inputs [B,C,...] and targets [B,...] shapes disagree")
+        old_cl = inputs.shape[1] if self.old_cl is None else int(self.old_cl)  # x[:, 0:None] == all channels
+        tgt = targets if targets.is_contiguous() else targets.contiguous()
+        out = _UnceFn.apply(inputs, tgt, old_cl, int(self.ignore_index), self.reduction)
+        if tgt is not targets:
+            targets.copy_(tgt)  # keep the in-place remap visible to the caller
+        return out
+
+
+# ----------------------------------------------------------------------------------------------
+# MiB unbiased knowledge distillation
+# ----------------------------------------------------------------------------------------------
+class _UnkdFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, inputs, targets, mask, alpha, reduction):
+        B, C, C_old = inputs.shape[0], inputs.shape[1], targets.shape[1]
+        HW = inputs[0, 0].numel()
+        x, t = _f32c(inputs), _f32c(targets)
+        m = None if mask is None else _f32c(mask)
+        dev = x.device
+        px_shape = (B,) + tuple(inputs.shape[2:])
+        out_px = torch.empty(px_shape, device=dev, dtype=torch.float32) if reduction == "none" else None
+        stats = torch.empty(1, device=dev, dtype=torch.float32)
+        lse3 = torch.empty((3,) + px_shape, device=dev, dtype=torch.float32)
+        scratch = torch.empty(_lib.lib().ucd_reduce_scratch_floats(), device=dev, dtype=torch.float32)
+        check(_lib.lib().ucd_unkd_fwd(ptr(x), ptr(t), ptr(m), float(alpha), ptr(out_px), ptr(stats), ptr(lse3),
+                                      ptr(scratch), B, C, C_old, HW, cur_stream()), "unkd_fwd")
+        ctx.save_for_backward(x, t, m, lse3)
+        ctx.cfg = (B, C, C_old, HW, float(alpha), reduction)
+        if reduction == "none":
+            return out_px
+        if reduction == "sum":
+            return -stats[0]
+        return -stats[0] / float(B * HW)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, t, m, lse3 = ctx.saved_tensors
+        B, C, C_old, HW, alpha, reduction = ctx.cfg
+        dx = torch.empty_like(x)
+        g_px, g_sc, g_mul = None, None, 1.0
+        if reduction == "none":
+            g_sc = _scalar_grad(g)
+            if g_sc is None:
+                g_px = _f32c(g)
+        else:
+            g_sc = g.reshape(1)
+            if reduction == "mean":
+                g_mul = 1.0 / float(B * HW)
+        if g_sc is not None:
+            g_sc = _f32c(g_sc)
+        check(_lib.lib().ucd_unkd_bwd(ptr(x), ptr(t), ptr(m), alpha, ptr(lse3), ptr(g_px), ptr(g_sc), g_mul, ptr(dx),
+                                      B, C, C_old, HW, cur_stream()), "unkd_bwd")
+        return dx, None, None, None, None
+
+
+class UnbiasedKnowledgeDistillationLoss(nn.Module):
+    """MiB unbiased KD (utils/loss.py:139-184).  ``targets`` (old-model logits) get no gradient, as in
+    the reference where they are produced under ``no_grad`` (train.py:100-102)."""
+
+    def __init__(self, reduction='mean', alpha=1.):
+        super().__init__()
+        self.reduction = reduction
+        self.alpha = alpha
+
+    def forward(self, inputs, targets, mask=None):
+        _need_cuda(inputs, targets, mask)
+        if inputs.shape[1] < targets.shape[1] or inputs.shape[2:] != targets.shape[2:]:
+            raise ValueError("UnbiasedKnowledgeDistillationLoss: inputs [B,C,...] / targets [B,C_old,...] disagree")
+        if mask is not None and tuple(mask.shape) != (inputs.shape[0],) + tuple(inputs.shape[2:]):
+            raise ValueError("UnbiasedKnowledgeDistillationLoss: mask must be [B,...]")
+        red = self.reduction if self.reduction in ("mean", "sum") else "none"
+        return _UnkdFn.apply(inputs, targets.detach(), mask, self.alpha, red)
+
+
+# ----------------------------------------------------------------------------------------------
+# contrastive prep
+# ----------------------------------------------------------------------------------------------
+class ContrastPack:
+    """Device-side product of the prep kernels for one batch: bf16 operand tiles for the tensor-core
+    sweeps plus the metadata the backward needs.  Shared by the 5 tuple slots."""
+
+    def __init__(self):
+        self.n_px = 0
+        self.shape = None          # (B, h, w)
+        self.c_old = 0
+        self.kpad = 0
+        self.max_tiles = 0
+        self.counts = None         # int32[4] device: N_a, N_o, min_new, n_px
+        self.n_a = self.n_o = self.min_new = None   # host copies (one sync)
+        self.label_n = self.mix = self.flags = None
+        self.rank_a = self.rank_o = self.block_off = None
+        self.anchor_f32 = self.contrast_f32 = None
+        self.la = self.lc = None
+        self.feat_tiles = self.prob_tiles = self.lab_tiles = None
+        self.row_pix = self.inv_norm = None
+        self.l_po = None
+
+    @property
+    def n_c(self):
+        return self.n_a + self.n_o
+
+
+def _build_pack(f_n, f_o, l_po, labels, max_label):
+    _need_cuda(f_n, f_o, l_po, labels)
+    if f_n.dim() != 4 or f_n.shape[1] != FEAT_DIM or f_o.shape != f_n.shape:
+        raise ValueError("pre_contrastive_pixel: f_n / f_o must be [B,%d,h,w]" % FEAT_DIM)
+    B, _, h, w = f_n.shape
+    if l_po.dim() != 4 or l_po.shape[0] != B or tuple(l_po.shape[2:]) != (h, w):
+        raise ValueError("pre_contrastive_pixel: l_po must be [B,C_old,h,w]")
+    if labels.dim() != 3 or labels.shape[0] != B:
+        raise ValueError("pre_contrastive_pixel: l_n must be [B,H,W]")
+    L = _lib.lib()
+    dev = f_n.device
+    labels = labels.to(torch.int64).contiguous()
+    f_n, f_o, l_po = _f32c(f_n), _f32c(f_o), _f32c(l_po)
+    H, W = labels.shape[-2:]
+    pk = ContrastPack()
+    pk.shape, pk.n_px, pk.c_old = (B, h, w), B * h * w, l_po.shape[1]
+    pk.kpad = L.ucd_con_prob_kpad(pk.c_old)
+    pk.max_tiles = L.ucd_con_max_tiles(pk.n_px)
+    n_px = pk.n_px
+    i32 = dict(device=dev, dtype=torch.int32)
+    meta = torch.empty(5, n_px, **i32)
+    pk.label_n, pk.mix, pk.flags, pk.rank_a, pk.rank_o = meta[0], meta[1], meta[2], meta[3], meta[4]
+    pk.block_off = torch.empty(2 * ((n_px + 255) // 256), **i32)
+    pk.counts = torch.empty(4, **i32)
+    st = cur_stream()
+    check(L.ucd_con_prep_labels(ptr(labels), ptr(l_po), B, pk.c_old, h, w, H, W, int(max_label), ptr(pk.label_n),
+                                ptr(pk.mix), ptr(pk.flags), ptr(pk.rank_a), ptr(pk.rank_o), ptr(pk.block_off),
+                                ptr(pk.counts), st), "con_prep_labels")
+    pk.anchor_f32 = torch.empty(n_px, FEAT_DIM, device=dev, dtype=torch.float32)
+    pk.contrast_f32 = torch.empty(2 * n_px, FEAT_DIM, device=dev, dtype=torch.float32)
+    pk.la = torch.empty(n_px, **i32)
+    pk.lc = torch.empty(2 * n_px, **i32)
+    pk.feat_tiles = torch.empty(pk.max_tiles, FEAT_DIM // 8, TILE, 8, device=dev, dtype=torch.bfloat16)
+    pk.prob_tiles = torch.empty(pk.max_tiles, pk.kpad // 8, TILE, 8, device=dev, dtype=torch.bfloat16)
+    pk.lab_tiles = torch.empty(pk.max_tiles, TILE, **i32)
+    pk.row_pix = torch.empty(n_px, **i32)
+    pk.inv_norm = torch.empty(n_px, device=dev, dtype=torch.float32)
+    check(L.ucd_con_prep_pack(ptr(f_n), ptr(f_o), ptr(l_po), ptr(pk.mix), ptr(pk.flags), ptr(pk.rank_a),
+                              ptr(pk.rank_o), ptr(pk.block_off), ptr(pk.counts), B, pk.c_old, h, w,
+                              ptr(pk.anchor_f32), ptr(pk.contrast_f32), ptr(pk.la), ptr(pk.lc), ptr(pk.feat_tiles),
+                              ptr(pk.prob_tiles), ptr(pk.lab_tiles), ptr(pk.row_pix), ptr(pk.inv_norm), pk.max_tiles,
+                              st), "con_prep_pack")
+    pk.l_po = l_po
+    # the one host sync of the tuple API: the 5-tuple's tensor shapes depend on N_a / N_o
+    pk.n_a, pk.n_o, pk.min_new, _ = (int(v) for v in pk.counts.tolist())
+    if pk.n_a > 0 and pk.min_new > max(int(max_label), 0):
+        # no GT new-class pixel in the batch: the reference raises at utils/loss.py:355 (min() of empty)
+        raise RuntimeError("pre_contrastive_pixel: no new-class pixel in the batch "
+                           "(the reference raises here too, utils/loss.py:355)")
+    return pk
+
+
+class _AnchorFn(torch.autograd.Function):
+    """Autograd link f_n -> Output_anchor (gather of anchor pixels + F.normalize, loss.py:363-365)."""
+
+    @staticmethod
+    def forward(ctx, f_n, pack):
+        ctx.pack = pack
+        ctx.in_dtype = f_n.dtype
+        return pack.anchor_f32[:pack.n_a]
+
+    @staticmethod
+    def backward(ctx, g):
+        pk = ctx.pack
+        B, h, w = pk.shape
+        g = _f32c(g)
+        df = torch.empty(B, FEAT_DIM, h, w, device=g.device, dtype=torch.float32)
+        check(_lib.lib().ucd_con_prep_bwd(ptr(g), ptr(pk.anchor_f32), ptr(pk.inv_norm), ptr(pk.flags), ptr(pk.rank_a),
+                                          ptr(pk.block_off), ptr(df), B, h, w, cur_stream()), "con_prep_bwd")
+        return df.to(ctx.in_dtype), None
+
+
+class JointProb:
+    """Lazy stand-in for the reference's dense ``JM_p`` [N_a, N_c] (utils/loss.py:369-395): it carries
+    the bf16 softmax tiles and the GT-new threshold so that ``PixelConLossV2`` evaluates
+    P_ij = p_i.p_j (or 1 for GT-new x GT-new pairs) tile by tile on the tensor cores.  ``dense()``
+    materialises the fp32 matrix for inspection / compatibility."""
+
+    def __init__(self, pack):
+        self.pack = pack
+
+    @property
+    def shape(self):
+        return (self.pack.n_a, self.pack.n_c)
+
+    def dense(self):
+        pk = self.pack
+        B, h, w = pk.shape
+        p = torch.softmax(pk.l_po.permute(0, 2, 3, 1).reshape(pk.n_px, pk.c_old), dim=1)
+        anchor = (pk.flags & 1).bool()
+        pseudo = (pk.flags & 2).bool()
+        pa = p[anchor]
+        pc = torch.cat([pa, p[pseudo]])
+        P = pa @ pc.T
+        la, lc = pk.la[:pk.n_a], pk.lc[:pk.n_c]
+        P[(la >= pk.min_new)[:, None] & (lc >= pk.min_new)[None, :]] = 1.0
+        return P
+
+    def detach(self):
+        return self
+
+
+def _label_dtype(max_label):
+    return torch.int8 if max_label <= 127 else torch.int32
+
+
+def pre_contrastive_pixel(f_n, l_n, l_po=None, f_o=None, max_label=20):
+    """Drop-in for utils/loss.py:258 ``pre_contrastive_pixel`` (v2 branch, the one ``train.py`` reaches).
+
+    Returns the 5-tuple ``(Output_anchor, Output_contrast, Lable_anchor, Lable_contrast, JM_p)`` in the
+    reference's row order; ``JM_p`` is a :class:`JointProb` handle (call ``.dense()`` for the matrix).
+    ``max_label`` generalises the reference's hard-coded VOC clamp ``label_n > 20 -> 0`` (loss.py:270).
+    """
+    if l_po is None or f_o is None:
+        raise NotImplementedError(
+            "ucd_b200.pre_contrastive_pixel implements the l_po+f_o (v2) branch used by the UCD trainer; "
+            "the single/double pixel-to-pixel branches (utils/loss.py:278-289) are outside this hot path")
+    pack = _build_pack(f_n.detach(), f_o.detach(), l_po.detach(), l_n, max_label)
+    anchor = _AnchorFn.apply(f_n, pack)
+    ldt = _label_dtype(max_label)
+    out = (anchor, pack.contrast_f32[:pack.n_c], pack.la[:pack.n_a].to(ldt), pack.lc[:pack.n_c].to(ldt),
+           JointProb(pack))
+    return out
+
+
+pre_contractive_pixel = pre_contrastive_pixel  # spelling used by utils/utils.py:256 and train.py:9
+
+
+# ----------------------------------------------------------------------------------------------
+# PixelConLossV2
+# ----------------------------------------------------------------------------------------------
+def _all_gather(t, group):
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    t = t.contiguous()
+    out = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), device=t.device, dtype=t.dtype)
+    dist.all_gather_into_tensor(out, t, group=group)      # concatenation along dim 0 (gloo and nccl agree)
+    return out.view((world,) + tuple(t.shape))
+
+
+def gather_contrast_columns(feat_tiles, prob_tiles, lab_tiles, counts, group):
+    """The one exchange step of the data-parallel path: every rank contributes its packed
+    contrast columns; rank r's tiles become chunk r of the gathered buffers.
+
+    feat_tiles [T,32,128,8] bf16, prob_tiles [T,Kp/8,128,8] bf16, lab_tiles [T,128] int32 and
+    counts int32[>=3] = {N_a, N_o, min_new} of this rank (T must be equal on all ranks).
+    Returns dict(feat, prob, lab, counts [W,2], min_new [1] (global MIN), n_chunks, chunk_tiles, self_tile0).
+    No gradient flows through the gathered columns (they are detached in the reference, loss.py:366,395),
+    so backward needs no collective.
+    """
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    min_new = counts[2:3].clone()
+    dist.all_reduce(min_new, op=dist.ReduceOp.MIN, group=group)
+    return dict(feat=_all_gather(feat_tiles, group), prob=_all_gather(prob_tiles, group),
+                lab=_all_gather(lab_tiles, group), counts=_all_gather(counts[:2], group), min_new=min_new,
+                n_chunks=world, chunk_tiles=feat_tiles.shape[0], self_tile0=rank * feat_tiles.shape[0])
+
+
+class _ConFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, anchor, cols, rows, inv_tau, p_mode, dense_p, group, ddp_scale):
+        """cols / rows: dicts of device buffers (see PixelConLossV2._run)."""
+        L = _lib.lib()
+        dev = anchor.device
+        max_row_tiles = rows["max_tiles"]
+        ws_bytes = L.ucd_con_workspace_bytes(max_row_tiles, cols["n_chunks"] * cols["chunk_tiles"])
+        ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+        out = torch.empty(2, device=dev, dtype=torch.float32)
+        need_grad = bool(ctx.needs_input_grad[0])
+        grad_unit = (torch.empty(max_row_tiles * TILE, FEAT_DIM, device=dev, dtype=torch.float32)
+                     if need_grad else None)
+        check(L.ucd_con_fwd(ptr(cols["feat"]), ptr(cols["prob"]), ptr(cols["lab"]), ptr(cols["counts"]),
+                            cols["n_chunks"], cols["chunk_tiles"], ptr(rows["feat"]), ptr(rows["prob"]),
+                            ptr(rows["lab"]), ptr(rows["n_rows"]), rows["self_tile0"], ptr(cols["min_new"]), p_mode,
+                            cols["kpad"], ptr(dense_p), 0 if dense_p is None else dense_p.shape[1], inv_tau,
+                            1 if need_grad else 0, ptr(out), ptr(grad_unit), ptr(ws), ws_bytes, max_row_tiles,
+                            cur_stream()), "con_fwd")
+        world = 1
+        if group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(out, group=group)      # {sum of row losses, #valid rows} over all ranks
+            world = dist.get_world_size(group)
+        ctx.save_for_backward(grad_unit, out, rows["n_rows"])
+        ctx.n_a = anchor.shape[0]
+        ctx.world = world if ddp_scale else 1
+        return out[0] / out[1]
+
+    @staticmethod
+    def backward(ctx, g):
+        grad_unit, out, n_rows = ctx.saved_tensors
+        d_anchor = torch.empty(ctx.n_a, FEAT_DIM, device=g.device, dtype=torch.float32)
+        # With DDP averaging parameter gradients over ranks, the exact gradient of the global-batch loss needs
+        # each rank's local contribution scaled by world (columns carry no gradient, loss.py:366,395).
+        check(_lib.lib().ucd_con_bwd(ptr(grad_unit), ptr(out), ptr(_f32c(g.reshape(1))), float(ctx.world),
+                                     ptr(n_rows), ptr(d_anchor), ctx.n_a, cur_stream()), "con_bwd")
+        return d_anchor, None, None, None, None, None, None, None
+
+
+class PixelConLossV2(nn.Module):
+    """Supervised pixel contrastive loss with uncertainty (joint-probability) weights
+    (utils/loss.py:403-466), evaluated by the fused sm_100a sweeps without materialising any
+    N_a x N_c matrix.
+
+    ``forward(anchor_features, contrast_feature, anchor_labels, contrast_labels, P=None)`` accepts the
+    tuple returned by :func:`pre_contrastive_pixel` (fast path: operands are already packed) or plain
+    dense tensors / ``P=None`` / a dense ``P`` matrix (compat path: packed on the fly).
+
+    Extension: with ``gather_negatives=True`` and an initialised process group the
+    contrast columns of all ranks are all-gathered over NCCL so negatives span the global batch.
+    """
+
+    def __init__(self, sample_method='none', temperature=0.07, *, gather_negatives=False, process_group=None,
+                 ddp_grad_scale=True):
+        super(PixelConLossV2, self).__init__()
+        self.temperature = temperature
+        self.sample_method = sample_method
+        self.gather_negatives = gather_negatives
+        self.process_group = process_group
+        # under DDP's gradient averaging the exact global-batch gradient needs the local part scaled by world
+        self.ddp_grad_scale = ddp_grad_scale
+        print(temperature)  # the reference prints it on construction (utils/loss.py:410)
+
+    # -- helpers ---------------------------------------------------------------------------------
+    def _group(self):
+        if not self.gather_negatives:
+            return None
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            return None
+        g = self.process_group if self.process_group is not None else dist.group.WORLD
+        return g if dist.get_world_size(g) > 1 else None
+
+    def forward(self, anchor_features, contrast_feature, anchor_labels, contrast_labels, P=None):
+        _need_cuda(anchor_features, contrast_feature)
+        inv_tau = 1.0 / float(self.temperature)
+        L = _lib.lib()
+        dev = anchor_features.device
+        pack = P.pack if isinstance(P, JointProb) else None
+        if pack is not None and not (anchor_features.data_ptr() == pack.anchor_f32.data_ptr()
+                                     and anchor_features.shape[0] == pack.n_a):
+            P, pack = P.dense(), None  # handle used with foreign features: fall back to its dense matrix
+        if pack is not None:
+            # ---- fast path: operands packed by pre_contrastive_pixel ----
+            group = self._group()
+            counts2 = pack.counts[:2]
+            rows = dict(feat=pack.feat_tiles, prob=pack.prob_tiles, lab=pack.lab_tiles, n_rows=pack.counts[0:1],
+                        max_tiles=(pack.n_a + TILE - 1) // TILE, self_tile0=0)
+            if group is None:
+                cols = dict(feat=pack.feat_tiles, prob=pack.prob_tiles, lab=pack.lab_tiles,
+                            counts=counts2.contiguous(), n_chunks=1, chunk_tiles=pack.max_tiles, kpad=pack.kpad,
+                            min_new=pack.counts[2:3])
+            else:
+                cols = gather_contrast_columns(pack.feat_tiles, pack.prob_tiles, pack.lab_tiles, pack.counts, group)
+                cols["kpad"] = pack.kpad
+                rows["self_tile0"] = cols["self_tile0"]
+            if pack.n_a == 0:
+                return anchor_features.sum() * 0.0
+            return _ConFn.apply(anchor_features, cols, rows, inv_tau, 1, None, group, self.ddp_grad_scale)
+
+        # ---- compat path: dense caller-supplied tensors ----
+        if anchor_features.dim() != 2 or anchor_features.shape[1] != FEAT_DIM or contrast_feature.shape[1] != FEAT_DIM:
+            raise ValueError("PixelConLossV2: features must be [N,%d]" % FEAT_DIM)
+        n_a, n_c = anchor_features.shape[0], contrast_feature.shape[0]
+        if n_a == 0 or n_c == 0:
+            return anchor_features.sum() * 0.0
+        a32, c32 = _f32c(anchor_features.detach()), _f32c(contrast_feature.detach())
+        la = anchor_labels.reshape(-1).to(device=dev, dtype=torch.int32).contiguous()
+        lc = contrast_labels.reshape(-1).to(device=dev, dtype=torch.int32).contiguous()
+        if la.numel() != n_a or lc.numel() != n_c:
+            raise ValueError("PixelConLossV2: label / feature counts disagree")
+        rt, ct = (n_a + TILE - 1) // TILE, (n_c + TILE - 1) // TILE
+        bf = dict(device=dev, dtype=torch.bfloat16)
+        rfeat = torch.empty(rt, FEAT_DIM // 8, TILE, 8, **bf)
+        cfeat = torch.empty(ct, FEAT_DIM // 8, TILE, 8, **bf)
+        rlab = torch.empty(rt, TILE, device=dev, dtype=torch.int32)
+        clab = torch.empty(ct, TILE, device=dev, dtype=torch.int32)
+        st = cur_stream()
+        check(L.ucd_con_pack_rows(ptr(a32), ptr(la), n_a, ptr(rfeat), ptr(rlab), rt, st), "con_pack_rows")
+        check(L.ucd_con_pack_rows(ptr(c32), ptr(lc), n_c, ptr(cfeat), ptr(clab), ct, st), "con_pack_rows")
+        counts = torch.tensor([[n_c, 0]], device=dev, dtype=torch.int32)
+        n_rows = torch.tensor([n_a], device=dev, dtype=torch.int32)
+        dense_p, p_mode = None, 0
+        if P is not None:
+            if tuple(P.shape) != (n_a, n_c):
+                raise ValueError("PixelConLossV2: P must be [N_a, N_c]")
+            dense_p, p_mode = _f32c(P.detach()), 2
+        cols = dict(feat=cfeat, prob=None, lab=clab, counts=counts, n_chunks=1, chunk_tiles=ct, kpad=16, min_new=None)
+        rows = dict(feat=rfeat, prob=None, lab=rlab, n_rows=n_rows, max_tiles=rt, self_tile0=0)
+        return _ConFn.apply(anchor_features, cols, rows, inv_tau, p_mode, dense_p, None, False)
