@@ -45,19 +45,30 @@ F32 = np.float32
 # ----------------------------------------------------------------------------
 # bilinear taps (ATen area_pixel_compute_source_index, align_corners=False)
 # ----------------------------------------------------------------------------
+def _fma(a, b, c, ft):
+    """fused multiply-add in float type ft (fp32 emulated through fp64: the product of two fp32 is
+    exact in fp64 and the single rounding back to fp32 then equals a hardware fma up to rare double
+    rounding; fp64 has no such emulation here and uses a*b+c)."""
+    if ft is F32:
+        return (np.asarray(a, F32).astype(np.float64) * np.asarray(b, F32).astype(np.float64)
+                + np.asarray(c, F32).astype(np.float64)).astype(F32)
+    return np.asarray(a, ft) * np.asarray(b, ft) + np.asarray(c, ft)
+
+
 def bilinear_taps(in_size: int, out_size: int, ft=F32):
     """Source indices and weights of ATen's bilinear kernel along one axis, computed in the
     tensor's own float type ``ft`` (fp32 for the label map and fp32 logits).
 
-    scale = ft(in)/out ; src = max(0, scale*(dst+0.5)-0.5) ; i0 = floor(src)
+    scale = ft(in)/out ; src = max(0, fma(scale, dst+0.5, -0.5)) ; i0 = floor(src)
     i1 = i0 + (i0 < in-1) ; w1 = src - i0 ; w0 = 1 - w1
+    (the x86 build contracts scale*(dst+0.5)-0.5 into one fma; verified against F.interpolate)
     """
     if in_size == out_size:
         idx = np.arange(out_size, dtype=np.int64)
         return idx, idx.copy(), np.ones(out_size, ft), np.zeros(out_size, ft)
     scale = ft(in_size) / ft(out_size)
     dst = np.arange(out_size, dtype=ft)
-    src = (scale * (dst + ft(0.5))).astype(ft) - ft(0.5)
+    src = _fma(np.full_like(dst, scale), dst + ft(0.5), np.full_like(dst, ft(-0.5)), ft)
     src = np.maximum(src, ft(0)).astype(ft)
     i0 = np.minimum(np.floor(src).astype(np.int64), in_size - 1)
     i1 = i0 + (i0 < in_size - 1)
@@ -67,16 +78,18 @@ def bilinear_taps(in_size: int, out_size: int, ft=F32):
 
 
 def _fma32(a, b, c):
-    """fp32 fused multiply-add emulated through fp64 (product of two fp32 is exact)."""
-    return (np.asarray(a, F32).astype(np.float64) * np.asarray(b, F32).astype(np.float64)
-            + np.asarray(c, F32).astype(np.float64)).astype(F32)
+    return _fma(a, b, c, F32)
 
 
 def _bilinear_eval_f32(x: np.ndarray, out_h: int, out_w: int) -> np.ndarray:
-    """Bit-exact restatement of ATen's CPU bilinear kernel on fp32 [..., H, W].
+    """Bit-exact restatement of ATen's CPU bilinear kernels on contiguous fp32 [..., H, W].
 
-    out = fma(h1*w1, x11, fma(h1*w0, x10, fma(h0*w0, x00, (h0*w1)*x01)))
-    with the four weight products rounded to fp32 first.
+    ATen picks one of two kernels (UpSampleKernel.cpp, _use_vectorized_kernel_cond_2d):
+      out_h + out_w <= 128 ("vectorized" kernel, the case of every UCD label map 32x32 .. 32x64):
+          out = fma(h1*w1, x11, fma(h1*w0, x10, fma(h0*w0, x00, (h0*w1)*x01)))   weight products rounded first
+      otherwise (generic N-d kernel, the case of the 512x512 logit upsample):
+          t0 = fma(x00, w0, x01*w1) ; t1 = fma(x10, w0, x11*w1) ; out = fma(t0, h0, t1*h1)
+    Both orders were found by exhaustive search and are verified bit-exact in tests/test_oracle.py.
     """
     x = np.asarray(x, F32)
     H, W = x.shape[-2:]
@@ -86,15 +99,20 @@ def _bilinear_eval_f32(x: np.ndarray, out_h: int, out_w: int) -> np.ndarray:
     v01 = x[..., y0[:, None], x1[None, :]]
     v10 = x[..., y1[:, None], x0[None, :]]
     v11 = x[..., y1[:, None], x1[None, :]]
-    k00 = (hy0[:, None] * wx0[None, :]).astype(F32)
-    k01 = (hy0[:, None] * wx1[None, :]).astype(F32)
-    k10 = (hy1[:, None] * wx0[None, :]).astype(F32)
-    k11 = (hy1[:, None] * wx1[None, :]).astype(F32)
-    acc = (k01 * v01).astype(F32)
-    acc = _fma32(np.broadcast_to(k00, v00.shape), v00, acc)
-    acc = _fma32(np.broadcast_to(k10, v10.shape), v10, acc)
-    acc = _fma32(np.broadcast_to(k11, v11.shape), v11, acc)
-    return acc
+    bc = lambda v: np.broadcast_to(v, v00.shape)  # noqa: E731
+    if out_h + out_w <= 128:
+        k00 = (hy0[:, None] * wx0[None, :]).astype(F32)
+        k01 = (hy0[:, None] * wx1[None, :]).astype(F32)
+        k10 = (hy1[:, None] * wx0[None, :]).astype(F32)
+        k11 = (hy1[:, None] * wx1[None, :]).astype(F32)
+        acc = (k01 * v01).astype(F32)
+        acc = _fma32(bc(k00), v00, acc)
+        acc = _fma32(bc(k10), v10, acc)
+        return _fma32(bc(k11), v11, acc)
+    w0, w1, h0, h1 = bc(wx0[None, :]), bc(wx1[None, :]), bc(hy0[:, None]), bc(hy1[:, None])
+    t0 = _fma32(v00, w0, (v01 * w1).astype(F32))
+    t1 = _fma32(v10, w0, (v11 * w1).astype(F32))
+    return _fma32(t0, h0, (t1 * h1).astype(F32))
 
 
 # ----------------------------------------------------------------------------

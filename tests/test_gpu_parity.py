@@ -63,10 +63,12 @@ def test_upsample_fwd_bwd(U, shape, size):
     xc = x.cuda().requires_grad_(True)
     out = U.interpolate_bilinear(xc, size)
     out.backward(go.cuda())
-    torch.testing.assert_close(out.cpu(), ref.detach(), rtol=1e-5, atol=1e-6)
+    # forward: same taps and the same fp32 operation order as ATen's CPU kernels -> bit exact
+    assert torch.equal(out.cpu(), ref.detach()), float((out.cpu() - ref.detach()).abs().max())
+    assert np.array_equal(out.detach().cpu().numpy(), O._bilinear_eval_f32(x.numpy(), *size))
+    # adjoint: fixed but different summation order -> fp32 tolerance
     torch.testing.assert_close(xc.grad.cpu(), xr.grad, rtol=1e-4, atol=1e-5)
-    # restated oracle agrees as well
-    torch.testing.assert_close(out.cpu(), O.upsample_bilinear(x, *size), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(out.cpu(), O.upsample_bilinear(x, *size), rtol=1e-5, atol=1e-5)
 
 
 @pytest.mark.parametrize("shape", [(2, 7, 9, 11), (2, 21, 64, 64), (1, 17, 33, 33), (3, 151, 16, 20)])
@@ -92,7 +94,7 @@ def test_unce(U, shape, reduction):
     if reduction == "none":
         assert (out.cpu()[y_ref == 255] == 0).all()
     assert cos(xc.grad, xr.grad) > 1 - 1e-6
-    torch.testing.assert_close(xc.grad.cpu().double(), xr.grad, rtol=1e-3, atol=1e-6 * float(xr.grad.abs().max()) + 1e-9)
+    torch.testing.assert_close(xc.grad.cpu().double(), xr.grad, rtol=1e-3, atol=5e-6 * float(xr.grad.abs().max()) + 1e-9)
 
 
 def test_unce_broadcast_grad_and_noncontiguous_targets(U):
@@ -130,7 +132,7 @@ def test_unkd(U, shape, c_old, reduction, alpha, use_mask):
     (out * w8.cuda().float()).sum().backward() if reduction == "none" else out.backward()
     torch.testing.assert_close(out.cpu().double(), ref.detach(), rtol=5e-5, atol=5e-5)
     assert cos(xc.grad, xr.grad) > 1 - 1e-6
-    torch.testing.assert_close(xc.grad.cpu().double(), xr.grad, rtol=1e-3, atol=1e-6 * float(xr.grad.abs().max()) + 1e-9)
+    torch.testing.assert_close(xc.grad.cpu().double(), xr.grad, rtol=1e-3, atol=5e-6 * float(xr.grad.abs().max()) + 1e-9)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -123,7 +123,7 @@ __device__ __forceinline__ Tap bilinear_tap(int dst, float scale, int in_size, i
     t.w1 = 0.f;
     return t;
   }
-  float src = __fsub_rn(__fmul_rn(scale, __fadd_rn((float)dst, 0.5f)), 0.5f);
+  float src = __fmaf_rn(scale, __fadd_rn((float)dst, 0.5f), -0.5f);  // ATen's x86 build contracts this to one fma
   src = src < 0.f ? 0.f : src;
   int i0 = (int)floorf(src);
   i0 = i0 < in_size - 1 ? i0 : in_size - 1;
@@ -134,6 +134,22 @@ __device__ __forceinline__ Tap bilinear_tap(int dst, float scale, int in_size, i
   t.w1 = l1;
   t.w0 = __fsub_rn(1.f, l1);
   return t;
+}
+
+// 4-tap blend with ATen's CPU operation order (oracle/ucd_oracle.py::_bilinear_eval_f32):
+//   small outputs (out_h + out_w <= 128, ATen's "vectorized" kernel): weight products first, then an fma chain
+//   otherwise (generic N-d kernel): blend along x, then along y
+__device__ __forceinline__ float bilinear_blend(bool small_out, float v00, float v01, float v10, float v11,
+                                                float h0, float h1, float w0, float w1) {
+  if (small_out) {
+    float acc = __fmul_rn(__fmul_rn(h0, w1), v01);
+    acc = __fmaf_rn(__fmul_rn(h0, w0), v00, acc);
+    acc = __fmaf_rn(__fmul_rn(h1, w0), v10, acc);
+    return __fmaf_rn(__fmul_rn(h1, w1), v11, acc);
+  }
+  const float t0 = __fmaf_rn(v00, w0, __fmul_rn(v01, w1));
+  const float t1 = __fmaf_rn(v10, w0, __fmul_rn(v11, w1));
+  return __fmaf_rn(t0, h0, __fmul_rn(t1, h1));
 }
 
 }  // namespace ucd

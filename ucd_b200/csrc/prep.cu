@@ -29,10 +29,7 @@ prep_labels_kernel(const long long* __restrict__ labels, const float* __restrict
     const long long* lb = labels + (size_t)b * H * W;
     const float v00 = (float)lb[(size_t)ty.i0 * W + tx.i0], v01 = (float)lb[(size_t)ty.i0 * W + tx.i1];
     const float v10 = (float)lb[(size_t)ty.i1 * W + tx.i0], v11 = (float)lb[(size_t)ty.i1 * W + tx.i1];
-    float acc = __fmul_rn(__fmul_rn(ty.w0, tx.w1), v01);
-    acc = __fmaf_rn(__fmul_rn(ty.w0, tx.w0), v00, acc);
-    acc = __fmaf_rn(__fmul_rn(ty.w1, tx.w0), v10, acc);
-    acc = __fmaf_rn(__fmul_rn(ty.w1, tx.w1), v11, acc);
+    const float acc = bilinear_blend(h + w <= 128, v00, v01, v10, v11, ty.w0, ty.w1, tx.w0, tx.w1);
     int g = (int)truncf(acc);                 // .type(int8) + the two masked fills (loss.py:262,269-270)
     if (g < 0 || g > max_label) g = 0;
     // --- pseudo label: first maximal channel of the old model's low-res logits (loss.py:357) ---
