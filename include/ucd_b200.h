@@ -94,26 +94,38 @@ int ucd_upsample_bilinear_bwd(const float* gout, float* gin, int64_t planes, int
  *   - unit-norm fp32 rows  anchor_f32 [N_a,256], contrast_f32 [N_a+N_o,256] (reference order b,y,x)
  *   - bf16 tiles for the tensor-core sweeps: feat_tiles [T][32][128][8], prob_tiles [T][Kp/8][128][8]
  *     (softmax of l_po), lab_tiles [T][128] (-1 = padding), T = ucd_con_max_tiles(n_px)
- *   - row metadata: row_pix [n_px] pixel index of each anchor, inv_norm [n_px]
+ *   - row metadata: row_ref [n_px] (class-sorted anchor row -> reference row), inv_norm [n_px]
  * Layout of a tile: element (row r, feature k) at ((k/8)*128 + r)*8 + k%8  (UMMA no-swizzle
  * canonical layout, K-major for S=A*C^T and MN-major for V=E*C from the same bytes).
  * ---------------------------------------------------------------------------------------- */
 int64_t ucd_con_max_tiles(int64_t n_px);          /* ceil(2*n_px/128)+1 */
 int ucd_con_prob_kpad(int C_old);                 /* C_old rounded up to a multiple of 16 */
+int ucd_con_num_bins(int max_label, int C_old);   /* label bins of the class sort: max(max_label, C_old-1)+1 */
+int64_t ucd_con_px_meta_ints(int64_t n_px);       /* int32 count of px_meta (7 planes of n_px) */
+int64_t ucd_con_blk_meta_ints(int64_t n_px, int nb);
+/* px_meta planes: 0 label_n | 1 mix | 2 flags | 3,4 rank of the pixel among the anchors / pseudos of its
+ * 256-pixel block in pixel order | 5,6 the same rank among pixels of the SAME label (class-sorted order).
+ * blk_meta: per-block exclusive offsets for both orders.  counts = {N_a, N_o, min_new, n_px}. */
 int ucd_con_prep_labels(const int64_t* labels, const float* l_po, int B, int C_old, int h, int w,
-                        int H, int W, int max_label, int32_t* label_n, int32_t* mix, int32_t* flags,
-                        int32_t* rank_a, int32_t* rank_o, int32_t* block_cnt, int32_t* counts,
+                        int H, int W, int max_label, int32_t* px_meta, int32_t* blk_meta, int32_t* counts,
                         void* stream);
-int ucd_con_prep_pack(const float* f_n, const float* f_o, const float* l_po, const int32_t* mix,
-                      const int32_t* flags, const int32_t* rank_a, const int32_t* rank_o,
-                      const int32_t* block_cnt, const int32_t* counts, int B, int C_old, int h, int w,
+/* fp32 rows / labels are written in the reference's row order (pixel order b,y,x); the bf16 tiles are
+ * written CLASS-SORTED (stable counting sort by label, anchors first, then pseudo columns) so that most
+ * tiles hold a single label; row_ref[sorted anchor row] = reference row.  tile_range [max_tiles][2] =
+ * min/max valid label per tile. */
+int ucd_con_prep_pack(const float* f_n, const float* f_o, const float* l_po, const int32_t* px_meta,
+                      int32_t* blk_meta, const int32_t* counts, int B, int C_old, int h, int w, int max_label,
                       float* anchor_f32, float* contrast_f32, int32_t* la, int32_t* lc,
-                      void* feat_tiles, void* prob_tiles, int32_t* lab_tiles, int32_t* row_pix,
-                      float* inv_norm, int64_t max_tiles, void* stream);
+                      void* feat_tiles, void* prob_tiles, int32_t* lab_tiles, int32_t* tile_range,
+                      int32_t* row_range /*[ceil(n_px/128)][2], anchors only*/, int32_t* row_ref, float* inv_norm,
+                      int64_t max_tiles, void* stream);
 /* adjoint of the anchor gather + F.normalize: df_n[b,:,y,x] = (g - (g.a)a) * inv_norm for anchors, 0 else */
 int ucd_con_prep_bwd(const float* g_anchor, const float* anchor_f32, const float* inv_norm,
-                     const int32_t* flags, const int32_t* rank_a, const int32_t* block_cnt,
-                     float* df_n, int B, int h, int w, void* stream);
+                     const int32_t* px_meta, const int32_t* blk_meta, float* df_n, int B, int h, int w,
+                     void* stream);
+/* min/max valid (>= 0) label of every 128-entry tile; with n_limit != NULL only entries [0, *n_limit) count */
+int ucd_con_tile_ranges(const int32_t* lab_tiles, int64_t n_tiles, const int32_t* n_limit, int32_t* tile_range,
+                        void* stream);
 /* compat path of PixelConLossV2.forward with caller-supplied dense tensors: fp32 rows -> bf16 tiles */
 int ucd_con_pack_rows(const float* rows, const int32_t* labels, int64_t n, void* feat_tiles,
                       int32_t* lab_tiles, int64_t max_tiles, void* stream);
@@ -125,6 +137,8 @@ int ucd_con_pack_rows(const float* rows, const int32_t* labels, int64_t n, void*
  * `chunk_tiles` tiles each; chunk_counts [n_chunks][2] = {N_a, N_o} of that rank (device), the chunk
  * holds N_a+N_o valid columns.  Rows (anchors) come as their own tile pointers (row block rb = tile rb;
  * in the fused path they alias the first tiles of the local chunk), *n_rows of them are valid.
+ * tile_range / row_range: [tile][2] min/max valid label per column tile / row tile (ucd_con_tile_ranges);
+ * sweep 2 skips column tiles whose range misses the row block's range (no equal-label pair possible).
  * self_tile0: column tile that holds row block 0 itself (row i of block rb is column i of tile
  * self_tile0+rb - the reference's `eye` on the first N_a columns, loss.py:437), or -1.
  * p_mode: 0 = P is None, 1 = joint probability pA.pC^T from the prob tiles with the GT-new override
@@ -139,12 +153,17 @@ size_t ucd_con_workspace_bytes(int64_t max_row_tiles, int64_t max_col_tiles);
 int ucd_con_fwd(const void* feat_tiles, const void* prob_tiles, const int32_t* lab_tiles,
                 const int32_t* chunk_counts, int n_chunks, int64_t chunk_tiles, const void* row_feat_tiles,
                 const void* row_prob_tiles, const int32_t* row_lab_tiles, const int32_t* n_rows,
-                int64_t self_tile0, const int32_t* min_new, int p_mode, int kpad, const float* dense_p,
+                const int32_t* tile_range, const int32_t* row_range, int64_t self_tile0, const int32_t* min_new, int p_mode, int kpad, const float* dense_p,
                 int64_t ldp, float inv_temperature, int need_grad, float* out, float* grad_unit,
                 void* workspace, size_t workspace_bytes, int64_t max_row_tiles, void* stream);
-/* d_anchor[i,:] = (*g_scalar) * g_mul / out[1] * grad_unit[i,:] for i < min(*n_rows, max_rows) */
+/* d_anchor[row_ref[i],:] = (*g_scalar) * g_mul / out[1] * grad_unit[i,:] for i < min(*n_rows, max_rows);
+ * row_ref NULL = identity */
 int ucd_con_bwd(const float* grad_unit, const float* out, const float* g_scalar, float g_mul,
-                const int32_t* n_rows, float* d_anchor, int64_t max_rows, void* stream);
+                const int32_t* n_rows, const int32_t* row_ref, float* d_anchor, int64_t max_rows, void* stream);
+
+/* Debug aids (never on the product path): per-role cycle counters of the sweep CTAs, see contrast.cu */
+int ucd_con_debug_trace(void* device_buffer_or_null);
+int ucd_con_debug_splits(int64_t max_row_tiles, int64_t max_col_tiles);
 
 /* Self-test of the tcgen05/TMEM/bulk-copy building blocks: C[M=128,N] = A[128,K] * B[N,K]^T in bf16
  * with the production tile layout, and D[128,256] = E[128,128] * Bt (MN-major B). Returns max abs

@@ -43,7 +43,9 @@ def _worker(rank, world, port, ret):
         lab = torch.full((T * TILE,), -1, dtype=torch.int32)
         lab[:lc.numel()] = lc.to(torch.int32)
         counts = torch.tensor([A.shape[0], Cst.shape[0] - A.shape[0], prep.min_new, n_px], dtype=torch.int32)
-        g = gather_contrast_columns(feat, prob, lab.view(T, TILE), counts, dist.group.WORLD)
+        rng = torch.stack([lab.view(T, TILE).clamp_min(0).amin(1), lab.view(T, TILE).amax(1)], 1).to(torch.int32)
+        g = gather_contrast_columns(feat, prob, lab.view(T, TILE), rng, counts, dist.group.WORLD)
+        assert g["range"].shape == (world, T, 2) and torch.equal(g["range"][rank], rng)
         # reference: the rank-sharded oracle on all ranks' inputs
         per_rank, Cg, lcg, min_new = O.pre_contrastive_pixel_global(
             [x["f_n"] for x in cases], [x["labels"] for x in cases], [x["l_po"] for x in cases], [x["f_o"] for x in cases])

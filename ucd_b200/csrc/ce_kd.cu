@@ -55,6 +55,44 @@ __global__ void reduce_partials_kernel(const float* __restrict__ part, int nblk,
   }
 }
 
+constexpr float kNegBig = -3.0e38f;
+constexpr int kLseChunk = 8;
+
+// Online log-sum-exp (log2 domain) of channels [c0,c1) of VEC adjacent pixels, kLseChunk channels at a time.
+// PICK: also fetch x[label] on the way.
+template <int VEC, bool PICK>
+__device__ __forceinline__ void lse_chunks(const float* __restrict__ xp, long long HW, int c0, int c1,
+                                           const long long (&lab)[VEC], float (&m)[VEC], float (&s)[VEC],
+                                           float (&picked)[VEC]) {
+  for (int c = c0; c < c1; c += kLseChunk) {
+    float v[kLseChunk][VEC];
+#pragma unroll
+    for (int k = 0; k < kLseChunk; ++k) {
+      if (c + k < c1) {
+        Vec<VEC>::load(xp + (long long)(c + k) * HW, v[k]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) v[k][i] = kNegBig;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      float cm = v[0][i];
+#pragma unroll
+      for (int k = 1; k < kLseChunk; ++k) cm = fmaxf(cm, v[k][i]);
+      const float nm = fmaxf(m[i], cm * kLog2e);
+      float acc = s[i] * ex2f(m[i] - nm);
+#pragma unroll
+      for (int k = 0; k < kLseChunk; ++k) {
+        acc += ex2f(fmaf(v[k][i], kLog2e, -nm));
+        if (PICK) picked[i] = (lab[i] == c + k) ? v[k][i] : picked[i];
+      }
+      m[i] = nm;
+      s[i] = acc;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // UNCE forward
 // ------------------------------------------------------------------------------------------
@@ -81,37 +119,19 @@ unce_fwd_kernel(const float* __restrict__ x, long long* __restrict__ y, float* _
       }
       lab[i] = t;
     }
+    // log-sum-exp over channel chunks: CH*VEC independent loads in flight, the chunk maximum rescales the
+    // running sum once per chunk (no per-element dependency chain), CH+1 exps per CH elements.
     float m[VEC], s[VEC], picked[VEC], lse_old2[VEC];
-    {
-      float v[VEC];
-      Vec<VEC>::load(xp, v);
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        m[i] = v[i] * kLog2e;
-        s[i] = 1.f;
-        picked[i] = (lab[i] == 0) ? v[i] : 0.f;
-        lse_old2[i] = m[i];
-      }
-    }
-#pragma unroll 4
-    for (int c = 1; c < C; ++c) {
-      float v[VEC];
-      Vec<VEC>::load(xp + (long long)c * HW, v);
-      if (c == old_cl) {
+    for (int i = 0; i < VEC; ++i) m[i] = kNegBig, s[i] = 0.f, picked[i] = 0.f, lse_old2[i] = kNegBig;
+    lse_chunks<VEC, true>(xp, HW, 0, (old_cl < C ? old_cl : C), lab, m, s, picked);
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) lse_old2[i] = m[i] + lg2f(s[i]);
-      }
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        lse_push(m[i], s[i], v[i] * kLog2e);
-        picked[i] = (lab[i] == c) ? v[i] : picked[i];
-      }
-    }
+    for (int i = 0; i < VEC; ++i) lse_old2[i] = m[i] + lg2f(s[i]);
+    lse_chunks<VEC, true>(xp, HW, (old_cl < C ? old_cl : C), C, lab, m, s, picked);
     float out[VEC], la[VEC], lo[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
       const float lse2 = m[i] + lg2f(s[i]);
-      if (old_cl >= C) lse_old2[i] = lse2;
       la[i] = lse2 * kLn2;
       lo[i] = lse_old2[i] * kLn2;
       const bool ign = lab[i] == ignore_index;
@@ -201,7 +221,7 @@ unce_bwd_kernel(const float* __restrict__ x, const long long* __restrict__ y, co
 //   loss_px = [ q0 (lse_b - lse) + sum_{1<=c<C_old} q_c (x_c - lse) ] / C_old
 // ------------------------------------------------------------------------------------------
 template <int VEC>
-__global__ void __launch_bounds__(kStreamThreads)
+__global__ void __launch_bounds__(kStreamThreads, 2)
 unkd_fwd_kernel(const float* __restrict__ x, const float* __restrict__ t, const float* __restrict__ mask,
                 float alpha, float* __restrict__ out_px, float* __restrict__ lse3, float* __restrict__ part,
                 int B, int C, int C_old, long long HW) {
@@ -217,50 +237,77 @@ unkd_fwd_kernel(const float* __restrict__ x, const float* __restrict__ t, const 
     const float* xp = x + (b * C) * HW + p;
     const float* tp = t + (b * C_old) * HW + p;
     // x: lse over all channels (m,s) and over S_b (mb,sb); t: lse (mt,st) and weighted sum wx = sum_{c>=1} 2^(t_c-mt) x_c
+    // all in channel chunks (see lse_chunks): 2*CH*VEC loads in flight, no per-element dependency chain.
     float m[VEC], s[VEC], mb[VEC], sb[VEC], mt[VEC], st[VEC], wx[VEC], t0[VEC];
-    {
-      float v[VEC], u[VEC];
-      Vec<VEC>::load(xp, v);
-      Vec<VEC>::load(tp, u);
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        m[i] = mb[i] = v[i] * kLog2e;
-        s[i] = sb[i] = 1.f;
-        mt[i] = t0[i] = u[i] * a2;
-        st[i] = 1.f;
-        wx[i] = 0.f;
-      }
-    }
-#pragma unroll 4
-    for (int c = 1; c < C_old; ++c) {
-      float v[VEC], u[VEC];
-      Vec<VEC>::load(xp + (long long)c * HW, v);
-      Vec<VEC>::load(tp + (long long)c * HW, u);
+    for (int i = 0; i < VEC; ++i) m[i] = mb[i] = mt[i] = kNegBig, s[i] = sb[i] = st[i] = wx[i] = 0.f, t0[i] = 0.f;
+    for (int c = 0; c < C_old; c += kLseChunk) {
+      float v[kLseChunk][VEC], u[kLseChunk][VEC];
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        lse_push(m[i], s[i], v[i] * kLog2e);
-        const float tv = u[i] * a2;
-        const float d = tv - mt[i];
-        const float e = ex2f(-fabsf(d));
-        if (d > 0.f) {
-          st[i] = fmaf(st[i], e, 1.f);
-          wx[i] = fmaf(wx[i], e, v[i]);
-          mt[i] = tv;
+      for (int k = 0; k < kLseChunk; ++k) {
+        if (c + k < C_old) {
+          Vec<VEC>::load(xp + (long long)(c + k) * HW, v[k]);
+          Vec<VEC>::load(tp + (long long)(c + k) * HW, u[k]);
         } else {
-          st[i] += e;
-          wx[i] = fmaf(e, v[i], wx[i]);
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) v[k][i] = kNegBig, u[k][i] = kNegBig;
         }
       }
-    }
-#pragma unroll 4
-    for (int c = C_old; c < C; ++c) {
-      float v[VEC];
-      Vec<VEC>::load(xp + (long long)c * HW, v);
 #pragma unroll
       for (int i = 0; i < VEC; ++i) {
-        const float v2 = v[i] * kLog2e;
-        lse_push(m[i], s[i], v2);
-        lse_push(mb[i], sb[i], v2);
+        float cm = v[0][i], ct = u[0][i] * a2;
+#pragma unroll
+        for (int k = 1; k < kLseChunk; ++k) cm = fmaxf(cm, v[k][i]), ct = fmaxf(ct, u[k][i] * a2);
+        if (a2 < 0.f) {  // negative alpha flips the order of t
+          ct = u[0][i] * a2;
+#pragma unroll
+          for (int k = 1; k < kLseChunk; ++k) ct = fmaxf(ct, (c + k < C_old) ? u[k][i] * a2 : kNegBig);
+        }
+        const float nm = fmaxf(m[i], cm * kLog2e), nt = fmaxf(mt[i], ct);
+        float acc = s[i] * ex2f(m[i] - nm);
+        const float rs = ex2f(mt[i] - nt);
+        float tacc = st[i] * rs, wacc = wx[i] * rs;
+#pragma unroll
+        for (int k = 0; k < kLseChunk; ++k) {
+          acc += ex2f(fmaf(v[k][i], kLog2e, -nm));
+          const bool live = (c + k < C_old);
+          const float e = live ? ex2f(fmaf(u[k][i], a2, -nt)) : 0.f;
+          tacc += e;
+          if (c + k >= 1) wacc = fmaf(e, live ? v[k][i] : 0.f, wacc);
+        }
+        if (c == 0) {
+          mb[i] = v[0][i] * kLog2e;
+          sb[i] = 1.f;
+          t0[i] = u[0][i] * a2;
+        }
+        m[i] = nm, s[i] = acc, mt[i] = nt, st[i] = tacc, wx[i] = wacc;
+      }
+    }
+    for (int c = C_old; c < C; c += kLseChunk) {
+      float v[kLseChunk][VEC];
+#pragma unroll
+      for (int k = 0; k < kLseChunk; ++k) {
+        if (c + k < C) {
+          Vec<VEC>::load(xp + (long long)(c + k) * HW, v[k]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) v[k][i] = kNegBig;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        float cm = v[0][i];
+#pragma unroll
+        for (int k = 1; k < kLseChunk; ++k) cm = fmaxf(cm, v[k][i]);
+        const float nm = fmaxf(m[i], cm * kLog2e), nb = fmaxf(mb[i], cm * kLog2e);
+        float acc = s[i] * ex2f(m[i] - nm), bacc = sb[i] * ex2f(mb[i] - nb);
+#pragma unroll
+        for (int k = 0; k < kLseChunk; ++k) {
+          const float x2 = v[k][i] * kLog2e;
+          acc += ex2f(x2 - nm);
+          bacc += ex2f(x2 - nb);
+        }
+        m[i] = nm, s[i] = acc, mb[i] = nb, sb[i] = bacc;
       }
     }
     float o[VEC], l_all[VEC], l_bkg[VEC], l_t[VEC];

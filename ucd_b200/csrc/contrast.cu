@@ -22,9 +22,12 @@
 // warps 2-5 are the epilogue (one thread per row, accumulators read with tcgen05.ld).
 #include "umma.cuh"
 
+#include <stdlib.h>
+
 namespace ucd {
 
-constexpr int kConThreads = 192;
+constexpr int kEpiWarps = 8;                       // 2 per SM sub-partition: one hides the other's stalls
+constexpr int kConThreads = 64 + 32 * kEpiWarps;   // producer warp + MMA warp + epilogue warps
 constexpr uint32_t kTileBytes = 65536;  // 128 rows x 256 bf16
 constexpr uint32_t kChunkB = 2048;      // one 8-element k-chunk for 128 rows
 constexpr uint32_t kESub = 16384;       // 128 rows x 64 columns bf16
@@ -38,7 +41,8 @@ constexpr uint32_t OFF_PC = 221184;   // sweep 2: column probabilities, <= 8 KB,
 constexpr uint32_t OFF_LAB = 229376;  // 2 x 128 int32
 constexpr uint32_t OFF_BAR = 230400;
 constexpr uint32_t kConSmem = OFF_BAR + 256;
-constexpr int kMaxChunks = 64;
+constexpr int kMaxChunks = 16;        // ranks whose columns are gathered (one 8-GPU box: 8)
+constexpr int kMaxTilesPerCta = 8192;  // column tiles one CTA walks (bit mask in shared memory)
 
 enum { BAR_A = 0, BAR_CF = 1, BAR_CE = 3, BAR_SF = 5, BAR_SE = 7, BAR_EF = 9, BAR_EE = 11, BAR_PF = 13, BAR_PE = 14, BAR_V = 15 };
 
@@ -53,6 +57,8 @@ struct ConArgs {
   const __nv_bfloat16* row_prob;  // [row_block][kpad/8][128][8]
   const int* row_lab;             // [row_block][128]
   const int* n_rows;              // device scalar: number of valid rows
+  const int* tile_range;          // [tiles][2] min/max valid label of every column tile (sweep 2 skip test)
+  const int* row_range;           // [row_block][2] same for the row tiles
   long long self_tile0;           // column tile holding row block 0 itself (block rb <-> self_tile0 + rb), -1: none
   const int* min_new;
   const float* dense_p;
@@ -66,7 +72,15 @@ struct ConArgs {
   float* acc_part;     // [splits][rows_pad][256] sweep 1: V ; sweep 2: U
   const float* stats;  // [3][rows_pad]           sweep 2 in (combined)
   float* loss_part;    // [splits][2][rows_pad]   sweep 2 out: L_i, T_i
+  long long* trace;    // debug: [grid][16] cycle counters per role (ucd_con_debug_trace), or NULL
 };
+
+// mbar_wait that also accumulates the cycles spent waiting (debug tracing of the role pipelines)
+__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, long long& acc) {
+  const long long c0 = clock64();
+  mbar_wait(bar, parity);
+  acc += clock64() - c0;
+}
 
 struct TileLoc {
   long long gtile;  // tile index in the gathered buffers
@@ -126,6 +140,21 @@ __device__ __forceinline__ void sweep1_cols(const uint32_t (&r)[32], const int* 
   }
 }
 
+// Sweep-1 fast path: the tile's label range misses the row block's, so every pair is a negative - no label
+// compare, no positive count: exp, row sum, row max, pack (about 4.5 instructions per pair).
+__device__ __forceinline__ void sweep1_cols_neg(const uint32_t (&r)[32], float sc, float& mx, float& neg,
+                                                uint32_t (&pk)[16]) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+    const float a0 = __uint_as_float(r[j]), a1 = __uint_as_float(r[j + 1]);
+    const float e0 = ex2f(a0 * sc), e1 = ex2f(a1 * sc);
+    mx = fmaxf(mx, fmaxf(a0, a1));
+    neg += e0;
+    neg += e1;
+    pk[j / 2] = bf16x2_bits(e0, e1);
+  }
+}
+
 // ---- sweep 2 epilogue on 32 columns ---------------------------------------------------------
 // PMODE 0: P == 1 ; 1: P from the prob GEMM with GT-new override ; 2: dense P in global memory
 template <bool FULL, bool SELF, int PMODE>
@@ -166,10 +195,11 @@ __device__ __forceinline__ void sweep2_cols(const uint32_t (&r)[32], const uint3
 
 template <int PHASE, int PMODE>
 __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs a) {
-  extern __shared__ __align__(1024) uint8_t smem[];
+  extern __shared__ __align__(128) uint8_t smem[];  // no-swizzle operands: 16 B alignment suffices
   __shared__ int s_pre[kMaxChunks + 1];
   __shared__ int s_ncols[kMaxChunks];
   __shared__ uint32_t s_tmem;
+  __shared__ uint32_t s_mask[kMaxTilesPerCta / 32];  // bit tt: column tile k0+tt can hold an equal-label pair (or self)
 
   constexpr int NE = (PHASE == 1) ? 2 : 1;  // E sub-tile buffers
   constexpr int NS = (PHASE == 1) ? 2 : 1;  // S accumulator buffers in TMEM
@@ -194,9 +224,9 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
     mbar_init(BAR(BAR_A), 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(BAR(BAR_CF + i), 1);
-      mbar_init(BAR(BAR_CE + i), 5);  // tcgen05.commit + the 4 epilogue warps (they read the stage's labels)
+      mbar_init(BAR(BAR_CE + i), 1 + kEpiWarps);  // tcgen05.commit + the epilogue warps (they read the stage's labels)
       mbar_init(BAR(BAR_SF + i), 1);
-      mbar_init(BAR(BAR_SE + i), 4);
+      mbar_init(BAR(BAR_SE + i), kEpiWarps);
       mbar_init(BAR(BAR_EF + i), 4);
       mbar_init(BAR(BAR_EE + i), 1);
     }
@@ -218,6 +248,29 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
   const int n = max(0, k1 - k0);
   const long long self_tile = a.self_tile0 >= 0 ? a.self_tile0 + rb : -1;  // the anchors' own column tile
   const int pchunks = a.kpad >> 3;
+  // Sweep 2 only touches pairs with equal labels (w_ij = 0 otherwise): a column tile whose label range misses the
+  // row block's range contributes nothing and is skipped by all three roles (class-sorted tiles make this common).
+  // Label-overlap mask of this CTA's column tiles, evaluated once by all threads (the range lookups are L2
+  // round trips: doing them per tile inside the role loops would put ~1.5k cycles of latency on every tile).
+  // Sweep 2 only walks the set bits (w_ij = 0 for unequal labels); sweep 1 uses the clear bits to pick the
+  // all-negative fast path.  Class-sorted tiles make clear bits the common case.
+  {
+    const int row_lo = __ldg(a.row_range + 2 * rb), row_hi = __ldg(a.row_range + 2 * rb + 1);
+    for (int base = 0; base < n; base += kConThreads) {
+      const int tt = base + (int)threadIdx.x;
+      bool ov = false;
+      if (tt < n) {
+        const TileLoc loc = locate_tile(k0 + tt, s_pre, s_ncols, a.n_chunks, a.chunk_tiles);
+        const int lo = __ldg(a.tile_range + 2 * loc.gtile), hi = __ldg(a.tile_range + 2 * loc.gtile + 1);
+        ov = loc.gtile == self_tile || !(hi < row_lo || lo > row_hi);
+      }
+      const unsigned bits = __ballot_sync(0xffffffffu, ov);
+      if (lane == 0 && base + warp * 32 < n) s_mask[(base >> 5) + warp] = bits;
+    }
+    __syncthreads();
+  }
+  auto tile_overlaps = [&](int tt) -> bool { return (s_mask[tt >> 5] >> (tt & 31)) & 1u; };
+  auto tile_active = [&](int tt) -> bool { return PHASE == 1 || tile_overlaps(tt); };
 
   if (warp == 0) {
     // ===================== producer: bulk async copies =====================
@@ -231,20 +284,29 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
       for (int q = 0; q < 4; ++q)
         bulk_g2s(sbase + OFF_A + q * 16384u, rft + (size_t)rb * kTileBytes + q * 16384u, 16384u, BAR(BAR_A));
       if (PHASE == 2 && PMODE == 1) bulk_g2s(sbase + OFF_PA, rpt + (size_t)rb * pbytes, pbytes, BAR(BAR_A));
-      for (int t = 0; t < n; ++t) {
+      long long w_ce = 0, w_pe = 0;
+      const long long c_start = clock64();
+      int t = 0;
+      for (int tt = 0; tt < n; ++tt) {
+        if (!tile_active(tt)) continue;
+        const TileLoc loc = locate_tile(k0 + tt, s_pre, s_ncols, a.n_chunks, a.chunk_tiles);
         const int stage = t & 1;
-        const TileLoc loc = locate_tile(k0 + t, s_pre, s_ncols, a.n_chunks, a.chunk_tiles);
-        mbar_wait(BAR(BAR_CE + stage), ((t >> 1) & 1) ^ 1);
+        mbar_wait_t(BAR(BAR_CE + stage), ((t >> 1) & 1) ^ 1, w_ce);
         mbar_arrive_expect_tx(BAR(BAR_CF + stage), kTileBytes + 512u);
         const uint32_t dst = sbase + OFF_C + stage * kTileBytes;
         for (int q = 0; q < 4; ++q)
           bulk_g2s(dst + q * 16384u, ft + (size_t)loc.gtile * kTileBytes + q * 16384u, 16384u, BAR(BAR_CF + stage));
         bulk_g2s(sbase + OFF_LAB + stage * 512u, a.lab_tiles + loc.gtile * 128, 512u, BAR(BAR_CF + stage));
         if (PHASE == 2 && PMODE == 1) {
-          mbar_wait(BAR(BAR_PE), (t & 1) ^ 1);
+          mbar_wait_t(BAR(BAR_PE), (t & 1) ^ 1, w_pe);
           mbar_arrive_expect_tx(BAR(BAR_PF), pbytes);
           bulk_g2s(sbase + OFF_PC, pt + (size_t)loc.gtile * pbytes, pbytes, BAR(BAR_PF));
         }
+        ++t;
+      }
+      if (a.trace) {
+        long long* tr = a.trace + (size_t)blockIdx.x * 16;
+        tr[0] = clock64() - c_start, tr[1] = w_ce, tr[2] = w_pe, tr[3] = t;
       }
     }
   } else if (warp == 1) {
@@ -256,11 +318,15 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
       const uint32_t tP = tmem + 128;       // sweep 2: P at [128,256)
       const uint32_t tV = tmem + 256;       // V / U accumulator at [256,512)
       mbar_wait(BAR(BAR_A), 0);
-      auto issue_s = [&](int t) {
+      auto ready_s = [&](int t) -> bool {
         const int stage = t & 1, sb = t % NS;
-        mbar_wait(BAR(BAR_CF + stage), (t >> 1) & 1);
-        mbar_wait(BAR(BAR_SE + sb), ((t / NS) & 1) ^ 1);
-        if (PHASE == 2 && PMODE == 1) mbar_wait(BAR(BAR_PF), t & 1);
+        if (!mbar_test_wait(BAR(BAR_CF + stage), (t >> 1) & 1)) return false;
+        if (!mbar_test_wait(BAR(BAR_SE + sb), ((t / NS) & 1) ^ 1)) return false;
+        if (PHASE == 2 && PMODE == 1 && !mbar_test_wait(BAR(BAR_PF), t & 1)) return false;
+        return true;
+      };
+      auto issue_s = [&](int t) {  // S (and P) for the t-th active tile; operands are in stage t&1
+        const int stage = t & 1, sb = t % NS;
         tc_fence_after();
         const uint32_t sc = sbase + OFF_C + stage * kTileBytes;
 #pragma unroll
@@ -275,40 +341,63 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
         }
         umma_commit(BAR(BAR_SF + sb));
       };
-      auto issue_v = [&](int t) {
-        const int stage = t & 1;
-        const uint32_t sc = sbase + OFF_C + stage * kTileBytes;
-        for (int h = 0; h < 2; ++h) {
-          const int q = 2 * t + h, buf = q % NE;
-          mbar_wait(BAR(BAR_EF + buf), (q / NE) & 1);
-          tc_fence_after();
+      auto ready_v = [&](int q) -> bool { return mbar_test_wait(BAR(BAR_EF + q % NE), (q / NE) & 1); };
+      auto issue_v = [&](int q) {  // V/U += E sub-tile q (tile q/2, column half q&1) x C
+        const int t = q >> 1, h = q & 1, buf = q % NE;
+        const uint32_t sc = sbase + OFF_C + (t & 1) * kTileBytes;
+        tc_fence_after();
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            umma_bf16(tV, umma_desc(sbase + OFF_E + buf * kESub + kk * 2 * kChunkB, kChunkB, 128),
-                      umma_desc(sc + (uint32_t)(h * 64 + kk * 16) * 16u, 128, kChunkB), idesc_v,
-                      (t > 0 || h > 0 || kk > 0) ? 1u : 0u);
-          umma_commit(BAR(BAR_EE + buf));
-        }
+        for (int kk = 0; kk < 4; ++kk)
+          umma_bf16(tV, umma_desc(sbase + OFF_E + buf * kESub + kk * 2 * kChunkB, kChunkB, 128),
+                    umma_desc(sc + (uint32_t)(h * 64 + kk * 16) * 16u, 128, kChunkB), idesc_v,
+                    (q > 0 || kk > 0) ? 1u : 0u);
+        umma_commit(BAR(BAR_EE + buf));
+        if (h == 1) umma_commit(BAR(BAR_CE + (t & 1)));  // both MMAs of tile t are done with its C stage
       };
-      if (PHASE == 1) {
-        for (int it = 0; it <= n; ++it) {
-          if (it < n) issue_s(it);
-          if (it >= 1) {
-            if (a.need_grad) issue_v(it - 1);
-            umma_commit(BAR(BAR_CE + ((it - 1) & 1)));
-          }
-        }
-      } else {
-        for (int t = 0; t < n; ++t) {
-          issue_s(t);
-          if (a.need_grad) issue_v(t);
-          umma_commit(BAR(BAR_CE + (t & 1)));
+      // number of active tiles of this CTA (sweep 1: all; sweep 2: those that can hold an equal-label pair)
+      int n_act = n;
+      if (PHASE == 2) {
+        n_act = 0;
+        for (int tt = 0; tt < n; ++tt)
+          n_act += tile_active(tt) ? 1 : 0;
+      }
+      // Issue whatever is ready, preferring the V/U accumulation (it releases the C stage for the next load);
+      // a fixed S(t+1)-then-V(t) order would expose the full load latency of every tile.
+      const int n_v = a.need_grad ? 2 * n_act : 0;
+      int s_next = 0, v_next = 0;
+      const unsigned long long t0 = globaltimer_ns();
+      uint32_t spins = 0;
+      const long long c_start = clock64();
+      long long c_idle = 0, c_mark = c_start;
+      bool idle = false;
+      while (s_next < n_act || v_next < n_v) {
+        if (v_next < n_v && (v_next >> 1) < s_next && ready_v(v_next)) {
+          if (idle) c_idle += clock64() - c_mark, idle = false;
+          issue_v(v_next++);
+        } else if (s_next < n_act && ready_s(s_next)) {
+          if (idle) c_idle += clock64() - c_mark, idle = false;
+          issue_s(s_next);
+          if (!a.need_grad) umma_commit(BAR(BAR_CE + (s_next & 1)));
+          ++s_next;
+        } else if (!idle) {
+          idle = true;
+          c_mark = clock64();
+        } else if ((++spins & 0xfffff) == 0 && globaltimer_ns() - t0 > 8000000000ull) {
+          printf("ucd_b200: MMA issue loop timed out (block %d s=%d/%d v=%d/%d)\n", blockIdx.x, s_next, n_act, v_next, n_v);
+          __trap();
         }
       }
       umma_commit(BAR(BAR_V));
+      if (a.trace) {
+        long long* tr = a.trace + (size_t)blockIdx.x * 16;
+        tr[4] = clock64() - c_start, tr[5] = c_idle, tr[6] = n_act;
+      }
     }
   } else {
     // ===================== epilogue: one thread per row =====================
+    // warps 2-5 own columns [0,64) of every tile (E sub-tile 0), warps 6-9 columns [64,128) (sub-tile 1);
+    // within a half, warp w reads TMEM lanes 32*(w%4).. (hardware restriction) = rows of the block.
+    const int half = (warp - 2) >> 2;
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;  // row within the block == TMEM lane
     const long long grow = (long long)rb * 128 + r;
@@ -328,48 +417,70 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
         gt_row = la >= min_new;
       }
     }
-    for (int t = 0; t < n; ++t) {
+    int t = 0;  // number of active tiles processed so far (drives stage / parity bookkeeping)
+    long long w_sf = 0, w_ee = 0;
+    const long long c_start = clock64();
+    for (int tt = 0; tt < n; ++tt) {
+      if (!tile_active(tt)) continue;
+      const TileLoc loc = locate_tile(k0 + tt, s_pre, s_ncols, a.n_chunks, a.chunk_tiles);
       const int stage = t & 1, sb = t % NS;
-      const TileLoc loc = locate_tile(k0 + t, s_pre, s_ncols, a.n_chunks, a.chunk_tiles);
       const bool full = loc.nvalid == 128;
       const bool self = loc.gtile == self_tile;
       const int* lab = reinterpret_cast<const int*>(smem + OFF_LAB + stage * 512);
       const float* dp = (PMODE == 2) ? a.dense_p + (size_t)min(grow, (long long)n_rows - 1) * a.ldp + loc.dcol0 : nullptr;
-      mbar_wait(BAR(BAR_SF + sb), (t / NS) & 1);
+      const bool all_neg = PHASE == 1 && full && !tile_overlaps(tt);
+      mbar_wait_t(BAR(BAR_SF + sb), (t / NS) & 1, w_sf);
       tc_fence_after();
-#pragma unroll 1
-      for (int cc = 0; cc < 4; ++cc) {
-        uint32_t rv[32], pk[16];
-        tmem_ld32(tmem + lane_addr + sb * 128 + cc * 32, rv);
-        if (PHASE == 1) {
-          tmem_ld_wait();
-          if (full && !self)
-            sweep1_cols<true, false>(rv, lab, cc * 32, 128, la, r, sc, mx, neg, num, pk);
-          else
-            sweep1_cols<false, true>(rv, lab, cc * 32, loc.nvalid, la, self ? r : -1, sc, mx, neg, num, pk);
-        } else {
-          uint32_t pv[32];
-          if (PMODE == 1) tmem_ld32(tmem + lane_addr + 128 + cc * 32, pv);
-          tmem_ld_wait();
-          if (full && !self)
-            sweep2_cols<true, false, PMODE>(rv, pv, lab, cc * 32, 128, la, r, sc, mraw, negi, gt_row, min_new, dp,
-                                            lacc, tacc, pk);
-          else
-            sweep2_cols<false, true, PMODE>(rv, pv, lab, cc * 32, loc.nvalid, la, self ? r : -1, sc, mraw, negi,
-                                            gt_row, min_new, dp, lacc, tacc, pk);
-        }
-        if (a.need_grad) {
-          const int q = 2 * t + (cc >> 1), buf = q % NE;
-          if ((cc & 1) == 0) mbar_wait(BAR(BAR_EE + buf), ((q / NE) & 1) ^ 1);
-          uint8_t* eb = smem + OFF_E + buf * kESub + (uint32_t)((cc & 1) * 4) * kChunkB + (uint32_t)r * 16u;
+      // E / Ucoef sub-tile hand-off to the MMA warp: 32 packed bf16 of this row go to k-chunks (cc&1)*4..+3
+      auto emit = [&](int cc, const uint32_t (&pk)[16]) {  // cc = chunk 0/1 within this thread's column half
+        if (!a.need_grad) return;
+        const int q = 2 * t + half, buf = q % NE;
+        if (cc == 0) mbar_wait_t(BAR(BAR_EE + buf), ((q / NE) & 1) ^ 1, w_ee);
+        uint8_t* eb = smem + OFF_E + buf * kESub + (uint32_t)(cc * 4) * kChunkB + (uint32_t)r * 16u;
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            *reinterpret_cast<uint4*>(eb + k * kChunkB) = make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
-          if (cc & 1) {
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(BAR(BAR_EF + buf));
-          }
+        for (int k = 0; k < 4; ++k)
+          *reinterpret_cast<uint4*>(eb + k * kChunkB) = make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
+        if (cc == 1) {
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(BAR(BAR_EF + buf));
+        }
+      };
+      const int c0 = half * 64;  // first column of this thread's half
+      if (PHASE == 1) {
+        // software-pipelined TMEM reads: the second chunk is in flight while the first is processed
+        uint32_t r0[32], r1[32];
+        auto proc = [&](int cc, const uint32_t (&rv)[32]) {
+          uint32_t pk[16];
+          if (all_neg)
+            sweep1_cols_neg(rv, sc, mx, neg, pk);
+          else if (full && !self)
+            sweep1_cols<true, false>(rv, lab, c0 + cc * 32, 128, la, r, sc, mx, neg, num, pk);
+          else
+            sweep1_cols<false, true>(rv, lab, c0 + cc * 32, loc.nvalid, la, self ? r : -1, sc, mx, neg, num, pk);
+          emit(cc, pk);
+        };
+        const uint32_t tb = tmem + lane_addr + sb * 128 + c0;
+        tmem_ld32(tb, r0);
+        tmem_ld_wait();
+        tmem_ld32(tb + 32, r1);
+        proc(0, r0);
+        tmem_ld_wait();
+        proc(1, r1);
+      } else {
+#pragma unroll 1
+        for (int cc = 0; cc < 2; ++cc) {
+          uint32_t rv[32], pv[32], pk[16];
+          tmem_ld32(tmem + lane_addr + sb * 128 + c0 + cc * 32, rv);
+          if (PMODE == 1) tmem_ld32(tmem + lane_addr + 128 + c0 + cc * 32, pv);
+          tmem_ld_wait();
+          if (full && !self)
+            sweep2_cols<true, false, PMODE>(rv, pv, lab, c0 + cc * 32, 128, la, r, sc, mraw, negi, gt_row, min_new,
+                                            dp, lacc, tacc, pk);
+          else
+            sweep2_cols<false, true, PMODE>(rv, pv, lab, c0 + cc * 32, loc.nvalid, la, self ? r : -1, sc, mraw, negi,
+                                            gt_row, min_new, dp, lacc, tacc, pk);
+          emit(cc, pk);
         }
       }
       tc_fence_before();
@@ -378,26 +489,42 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
         mbar_arrive(BAR(BAR_SE + sb));
         mbar_arrive(BAR(BAR_CE + stage));
       }
+      ++t;
     }
-    // ---- per-row outputs ----
-    const size_t prow = (size_t)split * a.rows_pad + grow;
-    if (PHASE == 1) {
-      a.stats_part[(size_t)split * 3 * a.rows_pad + grow] = mx;
-      a.stats_part[(size_t)split * 3 * a.rows_pad + a.rows_pad + grow] = neg;
-      a.stats_part[(size_t)split * 3 * a.rows_pad + 2 * a.rows_pad + grow] = num;
-    } else {
-      a.loss_part[(size_t)split * 2 * a.rows_pad + grow] = lacc * kLn2;
-      a.loss_part[(size_t)split * 2 * a.rows_pad + a.rows_pad + grow] = tacc;
+    if (a.trace && warp == 2 && lane == 0) {  // one representative epilogue thread
+      long long* tr = a.trace + (size_t)blockIdx.x * 16;
+      tr[8] = clock64() - c_start, tr[9] = w_sf, tr[10] = w_ee, tr[11] = t;
     }
-    if (a.need_grad) {
-      float4* dst = reinterpret_cast<float4*>(a.acc_part + prow * 256);
-      if (n > 0) {
-        mbar_wait(BAR(BAR_V), 0);
-        tc_fence_after();
+    // ---- per-row outputs: the two column halves of a row combine through shared memory ----
+    if (a.need_grad && t > 0) {  // all MMAs retired: accumulator final, E buffers free for reuse below
+      mbar_wait(BAR(BAR_V), 0);
+      tc_fence_after();
+    }
+    float* comb = reinterpret_cast<float*>(smem + OFF_E);  // [128][3]
+    if (half == 1) {
+      comb[r * 3 + 0] = PHASE == 1 ? mx : lacc;
+      comb[r * 3 + 1] = PHASE == 1 ? neg : tacc;
+      comb[r * 3 + 2] = num;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+    if (half == 0) {
+      if (PHASE == 1) {
+        a.stats_part[(size_t)split * 3 * a.rows_pad + grow] = fmaxf(mx, comb[r * 3 + 0]);
+        a.stats_part[(size_t)split * 3 * a.rows_pad + a.rows_pad + grow] = neg + comb[r * 3 + 1];
+        a.stats_part[(size_t)split * 3 * a.rows_pad + 2 * a.rows_pad + grow] = num + comb[r * 3 + 2];
+      } else {
+        a.loss_part[(size_t)split * 2 * a.rows_pad + grow] = (lacc + comb[r * 3 + 0]) * kLn2;
+        a.loss_part[(size_t)split * 2 * a.rows_pad + a.rows_pad + grow] = tacc + comb[r * 3 + 1];
+      }
+    }
+    if (a.need_grad) {  // each half writes 128 of the row's 256 accumulator columns
+      const size_t prow = (size_t)split * a.rows_pad + grow;
+      float4* dst = reinterpret_cast<float4*>(a.acc_part + prow * 256 + half * 128);
+      if (t > 0) {
 #pragma unroll 1
-        for (int cc = 0; cc < 8; ++cc) {
+        for (int cc = 0; cc < 4; ++cc) {
           uint32_t rv[32];
-          tmem_ld32(tmem + lane_addr + 256 + cc * 32, rv);
+          tmem_ld32(tmem + lane_addr + 256 + half * 128 + cc * 32, rv);
           tmem_ld_wait();
 #pragma unroll
           for (int k = 0; k < 8; ++k)
@@ -405,7 +532,7 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
                                           __uint_as_float(rv[4 * k + 2]), __uint_as_float(rv[4 * k + 3]));
         }
       } else {
-        for (int k = 0; k < 64; ++k) dst[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < 32; ++k) dst[k] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
     tc_fence_before();
@@ -437,7 +564,7 @@ __global__ void con_combine_kernel(const float* __restrict__ part, int splits, l
 // finalize: per-row loss terms, unit gradient, per-block partial sums.  block = 256 threads (one per feature)
 __global__ void __launch_bounds__(256)
 con_finalize_kernel(const float* __restrict__ stats, const float* __restrict__ loss_part,
-                    const float* __restrict__ v_part, const float* __restrict__ u_part, int splits,
+                    const float* __restrict__ v_part, const float* __restrict__ u_part, int splits, int splits2,
                     long long rows_pad, const int* __restrict__ n_rows_p, float inv_tau,
                     int need_grad, float* __restrict__ grad_unit, float* __restrict__ block_part) {
   const int n_rows = *n_rows_p;
@@ -445,17 +572,15 @@ con_finalize_kernel(const float* __restrict__ stats, const float* __restrict__ l
   for (long long row = blockIdx.x; row < n_rows; row += gridDim.x) {
     const float num = stats[2 * rows_pad + row];
     float L = 0.f, T = 0.f;
-    for (int s = 0; s < splits; ++s) {
+    for (int s = 0; s < splits2; ++s) {
       L += loss_part[(size_t)s * 2 * rows_pad + row];
       T += loss_part[(size_t)s * 2 * rows_pad + rows_pad + row];
     }
     const bool valid = num != 0.f;
     if (need_grad) {
       float V = 0.f, U = 0.f;
-      for (int s = 0; s < splits; ++s) {
-        V += v_part[((size_t)s * rows_pad + row) * 256 + threadIdx.x];
-        U += u_part[((size_t)s * rows_pad + row) * 256 + threadIdx.x];
-      }
+      for (int s = 0; s < splits; ++s) V += v_part[((size_t)s * rows_pad + row) * 256 + threadIdx.x];
+      for (int s = 0; s < splits2; ++s) U += u_part[((size_t)s * rows_pad + row) * 256 + threadIdx.x];
       grad_unit[(size_t)row * 256 + threadIdx.x] = valid ? (inv_tau / num) * (T * V - U) : 0.f;
     }
     if (threadIdx.x == 0 && valid) {
@@ -481,21 +606,25 @@ __global__ void con_reduce_out_kernel(const float* __restrict__ block_part, int 
 
 __global__ void con_bwd_kernel(const float* __restrict__ grad_unit, const float* __restrict__ out,
                                const float* __restrict__ g_scalar, float g_mul, const int* __restrict__ n_rows_p,
-                               float* __restrict__ d_anchor, long long max_rows) {
+                               const int* __restrict__ row_ref, float* __restrict__ d_anchor, long long max_rows) {
   const long long n_rows = min((long long)*n_rows_p, max_rows);
   const float coef = (out[1] > 0.f) ? g_scalar[0] * g_mul / out[1] : 0.f;
   const long long n4 = n_rows * 64;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 g = reinterpret_cast<const float4*>(grad_unit)[i];
     g.x *= coef, g.y *= coef, g.z *= coef, g.w *= coef;
-    reinterpret_cast<float4*>(d_anchor)[i] = g;
+    const long long row = i >> 6;
+    const long long dst = row_ref ? (long long)row_ref[row] : row;  // tile (class-sorted) row -> reference row
+    reinterpret_cast<float4*>(d_anchor)[dst * 64 + (i & 63)] = g;
   }
 }
 
 constexpr int kFinalizeBlocks = kNumSMs * 4;
+static long long* g_trace = nullptr;  // debug only (ucd_con_debug_trace)
 
 struct ConPlan {
-  int splits;
+  int splits;   // column splits of sweep 1
+  int splits2;  // column splits of sweep 2 (few active tiles per CTA: fewer, longer CTAs amortise the fixed cost)
   long long rows_pad;
   size_t off_stats_part, off_stats, off_loss_part, off_v, off_u, off_block, total;
 };
@@ -515,7 +644,13 @@ static ConPlan make_plan(long long max_row_tiles, long long max_col_tiles) {
       best = s;
     }
   }
+  while ((max_col_tiles + best - 1) / best > kMaxTilesPerCta) ++best;
   p.splits = best;
+  p.splits2 = best > 1 ? (best + 1) / 2 : 1;
+  if (const char* e = getenv("UCD_SPLITS1")) p.splits = atoi(e) > 0 ? atoi(e) : p.splits;    // tuning knobs
+  if (const char* e = getenv("UCD_SPLITS2")) p.splits2 = atoi(e) > 0 ? atoi(e) : p.splits2;
+  while ((max_col_tiles + p.splits - 1) / p.splits > kMaxTilesPerCta) ++p.splits;
+  while ((max_col_tiles + p.splits2 - 1) / p.splits2 > kMaxTilesPerCta) ++p.splits2;
   p.rows_pad = max_row_tiles * 128;
   size_t o = 0;
   auto take = [&](size_t bytes) {
@@ -525,9 +660,9 @@ static ConPlan make_plan(long long max_row_tiles, long long max_col_tiles) {
   };
   p.off_stats_part = take((size_t)p.splits * 3 * p.rows_pad * 4);
   p.off_stats = take((size_t)3 * p.rows_pad * 4);
-  p.off_loss_part = take((size_t)p.splits * 2 * p.rows_pad * 4);
+  p.off_loss_part = take((size_t)p.splits2 * 2 * p.rows_pad * 4);
   p.off_v = take((size_t)p.splits * p.rows_pad * 256 * 4);
-  p.off_u = take((size_t)p.splits * p.rows_pad * 256 * 4);
+  p.off_u = take((size_t)p.splits2 * p.rows_pad * 256 * 4);
   p.off_block = take((size_t)2 * kFinalizeBlocks * 4);
   p.total = o;
   return p;
@@ -561,13 +696,14 @@ extern "C" size_t ucd_con_workspace_bytes(int64_t max_row_tiles, int64_t max_col
 extern "C" int ucd_con_fwd(const void* feat_tiles, const void* prob_tiles, const int32_t* lab_tiles,
                            const int32_t* chunk_counts, int n_chunks, int64_t chunk_tiles, const void* row_feat_tiles,
                            const void* row_prob_tiles, const int32_t* row_lab_tiles, const int32_t* n_rows,
-                           int64_t self_tile0, const int32_t* min_new, int p_mode, int kpad, const float* dense_p,
+                           const int32_t* tile_range, const int32_t* row_range, int64_t self_tile0, const int32_t* min_new, int p_mode, int kpad, const float* dense_p,
                            int64_t ldp,
                            float inv_temperature, int need_grad, float* out, float* grad_unit, void* workspace,
                            size_t workspace_bytes, int64_t max_row_tiles, void* stream) {
   UCD_CHECK_ARG(feat_tiles && lab_tiles && chunk_counts && out && workspace, "ucd_con_fwd: null pointer");
   UCD_CHECK_ARG(n_chunks >= 1 && n_chunks <= kMaxChunks, "ucd_con_fwd: n_chunks=%d outside [1,%d]", n_chunks, kMaxChunks);
   UCD_CHECK_ARG(row_feat_tiles && row_lab_tiles && n_rows, "ucd_con_fwd: null row pointer");
+  UCD_CHECK_ARG(tile_range && row_range, "ucd_con_fwd: null tile range pointer");
   UCD_CHECK_ARG(aligned16(row_feat_tiles) && (!row_prob_tiles || aligned16(row_prob_tiles)),
                 "ucd_con_fwd: row tiles must be 16 B aligned");
   UCD_CHECK_ARG(self_tile0 >= -1 && self_tile0 < (int64_t)n_chunks * chunk_tiles, "ucd_con_fwd: bad self_tile0");
@@ -585,7 +721,8 @@ extern "C" int ucd_con_fwd(const void* feat_tiles, const void* prob_tiles, const
   }
   const ConPlan plan = make_plan(max_row_tiles, (int64_t)n_chunks * chunk_tiles);
   UCD_CHECK_ARG(workspace_bytes >= plan.total, "ucd_con_fwd: workspace too small (%zu < %zu)", workspace_bytes, plan.total);
-  UCD_CHECK_ARG(max_row_tiles * plan.splits < (1ll << 31), "ucd_con_fwd: grid too large");
+  UCD_CHECK_ARG(max_row_tiles * (plan.splits > plan.splits2 ? plan.splits : plan.splits2) < (1ll << 31),
+                "ucd_con_fwd: grid too large");
   cudaStream_t st = (cudaStream_t)stream;
   uint8_t* ws = (uint8_t*)workspace;
   ConArgs a;
@@ -599,6 +736,8 @@ extern "C" int ucd_con_fwd(const void* feat_tiles, const void* prob_tiles, const
   a.row_prob = (const __nv_bfloat16*)row_prob_tiles;
   a.row_lab = row_lab_tiles;
   a.n_rows = n_rows;
+  a.tile_range = tile_range;
+  a.row_range = row_range;
   a.self_tile0 = self_tile0;
   a.min_new = min_new;
   a.dense_p = dense_p;
@@ -611,15 +750,18 @@ extern "C" int ucd_con_fwd(const void* feat_tiles, const void* prob_tiles, const
   a.stats_part = (float*)(ws + plan.off_stats_part);
   a.stats = (const float*)(ws + plan.off_stats);
   a.loss_part = (float*)(ws + plan.off_loss_part);
+  a.trace = g_trace;
   // sweep 1
   a.acc_part = (float*)(ws + plan.off_v);
   int rc = launch_sweep<1, 0>(a, max_row_tiles, st);
   if (rc != UCD_OK) return rc;
+  if (a.trace) a.trace += (size_t)max_row_tiles * plan.splits * 16;  // sweep 2 counters follow sweep 1's
   con_combine_kernel<<<(unsigned)((plan.rows_pad + 255) / 256), 256, 0, st>>>(a.stats_part, plan.splits, plan.rows_pad,
                                                                                (float*)(ws + plan.off_stats));
   UCD_CHECK_LAUNCH("con_combine_kernel");
   // sweep 2
   a.acc_part = (float*)(ws + plan.off_u);
+  a.splits = plan.splits2;
   if (p_mode == 0)
     rc = launch_sweep<2, 0>(a, max_row_tiles, st);
   else if (p_mode == 1)
@@ -629,7 +771,8 @@ extern "C" int ucd_con_fwd(const void* feat_tiles, const void* prob_tiles, const
   if (rc != UCD_OK) return rc;
   float* block_part = (float*)(ws + plan.off_block);
   con_finalize_kernel<<<kFinalizeBlocks, 256, 0, st>>>(a.stats, a.loss_part, (const float*)(ws + plan.off_v),
-                                                       (const float*)(ws + plan.off_u), plan.splits, plan.rows_pad,
+                                                       (const float*)(ws + plan.off_u), plan.splits, plan.splits2,
+                                                       plan.rows_pad,
                                                        n_rows, inv_temperature, need_grad, grad_unit, block_part);
   UCD_CHECK_LAUNCH("con_finalize_kernel");
   con_reduce_out_kernel<<<1, 256, 0, st>>>(block_part, kFinalizeBlocks, out);
@@ -638,14 +781,28 @@ extern "C" int ucd_con_fwd(const void* feat_tiles, const void* prob_tiles, const
 }
 
 extern "C" int ucd_con_bwd(const float* grad_unit, const float* out, const float* g_scalar, float g_mul,
-                           const int32_t* n_rows, float* d_anchor, int64_t max_rows, void* stream) {
+                           const int32_t* n_rows, const int32_t* row_ref, float* d_anchor, int64_t max_rows,
+                           void* stream) {
   UCD_CHECK_ARG(grad_unit && out && g_scalar && n_rows && d_anchor, "ucd_con_bwd: null pointer");
   UCD_CHECK_ARG(aligned16(grad_unit) && aligned16(d_anchor), "ucd_con_bwd: 16 B alignment required");
   if (max_rows <= 0) return UCD_OK;
   long long blocks = (max_rows * 64 + 255) / 256;
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-  con_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(grad_unit, out, g_scalar, g_mul, n_rows, d_anchor,
-                                                                     max_rows);
+  con_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(grad_unit, out, g_scalar, g_mul, n_rows, row_ref,
+                                                                     d_anchor, max_rows);
   UCD_CHECK_LAUNCH("con_bwd_kernel");
   return UCD_OK;
+}
+
+// Debug aid (not part of the product path): when set to a device buffer of
+// 2 * max_row_tiles * splits * 16 int64, every CTA of the two sweeps records per-role cycle counters:
+//   [0] producer total, [1] wait for a free C stage, [2] wait for the P stage, [3] tiles loaded
+//   [4] MMA issuer total, [5] idle (nothing ready), [6] active tiles
+//   [8] epilogue total, [9] wait for S, [10] wait for the E buffer, [11] tiles
+extern "C" int ucd_con_debug_trace(void* device_buffer) {
+  g_trace = (long long*)device_buffer;
+  return UCD_OK;
+}
+extern "C" int ucd_con_debug_splits(int64_t max_row_tiles, int64_t max_col_tiles) {
+  return make_plan(max_row_tiles, max_col_tiles).splits;
 }

@@ -10,15 +10,34 @@ namespace ucd {
 
 constexpr int kPrepBlock = 256;  // pixels per counting block
 
-// flags: bit0 anchor (mix>0), bit1 pseudo (anchor & !GT-new), bit2 GT-new (label_n>0)
+// Per-pixel metadata planes (int32 [n_px] each) and per-block offset tables.
+//   px_meta: 0 label_n | 1 mix | 2 flags | 3 rank_a | 4 rank_o | 5 srank_a | 6 srank_o
+//     flags: bit0 anchor (mix>0), bit1 pseudo (anchor & !GT-new), bit2 GT-new (label_n>0)
+//     rank_*: rank among the block's anchors / pseudos in pixel order (reference row order)
+//     srank_*: rank among the block's anchors / pseudos OF THE SAME LABEL (class-sorted tile order)
+//   blk_meta: ref_off[2][nblk] | cls_off[2][nb][nblk]   (counts after the label kernel, exclusive offsets after the scan)
+enum { PX_LABEL_N = 0, PX_MIX, PX_FLAGS, PX_RANK_A, PX_RANK_O, PX_SRANK_A, PX_SRANK_O, PX_PLANES };
+
+struct BlkMeta {
+  int* ref;  // [2][nblk]
+  int* cls;  // [2][nb][nblk]
+  int nblk, nb;
+  __host__ __device__ BlkMeta(int* base, int nblk_, int nb_) : ref(base), cls(base + 2 * nblk_), nblk(nblk_), nb(nb_) {}
+  __device__ int& ref_at(int set, int blk) const { return ref[set * nblk + blk]; }
+  __device__ int& cls_at(int set, int c, int blk) const { return cls[((size_t)set * nb + c) * nblk + blk]; }
+};
+
 __global__ void __launch_bounds__(kPrepBlock)
 prep_labels_kernel(const long long* __restrict__ labels, const float* __restrict__ l_po, int B, int C_old, int h,
-                   int w, int H, int W, int max_label, float scale_h, float scale_w, int* __restrict__ label_n,
-                   int* __restrict__ mix, int* __restrict__ flags, int* __restrict__ rank_a,
-                   int* __restrict__ rank_o, int* __restrict__ block_cnt, int* __restrict__ counts) {
+                   int w, int H, int W, int max_label, float scale_h, float scale_w, int* __restrict__ px_meta,
+                   int* __restrict__ blk_base, int nb, int* __restrict__ counts) {
+  extern __shared__ int wcnt[];  // [2][8 warps][nb] per-warp class counts
   const int n_px = B * h * w;
+  const int nblk = gridDim.x;
+  const BlkMeta bm(blk_base, nblk, nb);
   const int p = blockIdx.x * kPrepBlock + threadIdx.x;
-  int is_a = 0, is_o = 0;
+  for (int i = threadIdx.x; i < 2 * 8 * nb; i += kPrepBlock) wcnt[i] = 0;
+  int is_a = 0, is_o = 0, m = 0;
   if (p < n_px) {
     const int hw = h * w;
     const int b = p / hw, q = p - b * hw;
@@ -43,82 +62,100 @@ prep_labels_kernel(const long long* __restrict__ labels, const float* __restrict
         arg = c;
       }
     }
-    const int m = g > 0 ? g : arg;
+    m = g > 0 ? g : arg;
     is_a = m > 0;
     is_o = is_a && !(g > 0);
-    label_n[p] = g;
-    mix[p] = m;
-    flags[p] = is_a | (is_o << 1) | ((g > 0) << 2);
+    px_meta[(size_t)PX_LABEL_N * n_px + p] = g;
+    px_meta[(size_t)PX_MIX * n_px + p] = m;
+    px_meta[(size_t)PX_FLAGS * n_px + p] = is_a | (is_o << 1) | ((g > 0) << 2);
     if (g > 0) atomicMin(&counts[2], g);
   }
-  // rank of this pixel among the block's anchors / pseudos
-  __shared__ int wsum_a[kPrepBlock / 32], wsum_o[kPrepBlock / 32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const unsigned ba = __ballot_sync(0xffffffffu, is_a), bo = __ballot_sync(0xffffffffu, is_o);
   const unsigned lt = (1u << lane) - 1u;
+  // pixel-order ranks (reference row order)
+  __shared__ int wsum_a[kPrepBlock / 32], wsum_o[kPrepBlock / 32];
+  const unsigned ba = __ballot_sync(0xffffffffu, is_a), bo = __ballot_sync(0xffffffffu, is_o);
   int ra = __popc(ba & lt), ro = __popc(bo & lt);
+  // same-label ranks (class-sorted order): lanes holding the same label form a match group
+  const unsigned ma = __match_any_sync(0xffffffffu, is_a ? m : (0x40000000 | lane));
+  const unsigned mo = __match_any_sync(0xffffffffu, is_o ? m : (0x40000000 | lane));
+  int sra = __popc(ma & lt), sro = __popc(mo & lt);
+  __syncthreads();  // wcnt zeroed
   if (lane == 0) {
     wsum_a[wid] = __popc(ba);
     wsum_o[wid] = __popc(bo);
   }
+  if (is_a && sra == 0) wcnt[(0 * 8 + wid) * nb + m] = __popc(ma);
+  if (is_o && sro == 0) wcnt[(1 * 8 + wid) * nb + m] = __popc(mo);
   __syncthreads();
   int tot_a = 0, tot_o = 0;
   for (int i = 0; i < kPrepBlock / 32; ++i) {
     if (i < wid) {
       ra += wsum_a[i];
       ro += wsum_o[i];
+      if (is_a) sra += wcnt[(0 * 8 + i) * nb + m];
+      if (is_o) sro += wcnt[(1 * 8 + i) * nb + m];
     }
     tot_a += wsum_a[i];
     tot_o += wsum_o[i];
   }
   if (p < n_px) {
-    rank_a[p] = ra;
-    rank_o[p] = ro;
+    px_meta[(size_t)PX_RANK_A * n_px + p] = ra;
+    px_meta[(size_t)PX_RANK_O * n_px + p] = ro;
+    px_meta[(size_t)PX_SRANK_A * n_px + p] = sra;
+    px_meta[(size_t)PX_SRANK_O * n_px + p] = sro;
   }
   if (threadIdx.x == 0) {
-    block_cnt[2 * blockIdx.x] = tot_a;
-    block_cnt[2 * blockIdx.x + 1] = tot_o;
+    bm.ref_at(0, blockIdx.x) = tot_a;
+    bm.ref_at(1, blockIdx.x) = tot_o;
+  }
+  for (int i = threadIdx.x; i < 2 * nb; i += kPrepBlock) {
+    const int set = i / nb, c = i - set * nb;
+    int t = 0;
+    for (int k = 0; k < 8; ++k) t += wcnt[(set * 8 + k) * nb + c];
+    bm.cls_at(set, c, blockIdx.x) = t;
   }
 }
 
-// exclusive scan of the per-block counts (in place) + totals.  One block.
-__global__ void __launch_bounds__(1024)
-prep_scan_kernel(int* __restrict__ block_cnt, int nblk, int* __restrict__ counts, int n_px) {
-  __shared__ int sa[1024], so[1024];
-  __shared__ int carry_a, carry_o;
-  if (threadIdx.x == 0) carry_a = carry_o = 0;
+// in-place exclusive scan of data[0..n) by one 1024-thread block; returns the total (valid in all threads)
+__device__ int block_excl_scan(int* __restrict__ data, int n, int* sh /*[1024]*/) {
+  const int t = threadIdx.x;
+  const int per = (n + 1023) / 1024;
+  const int lo = min(t * per, n), hi = min(lo + per, n);
+  int sum = 0;
+  for (int i = lo; i < hi; ++i) sum += data[i];
   __syncthreads();
-  for (int base = 0; base < nblk; base += 1024) {
-    const int i = base + threadIdx.x;
-    const int va = i < nblk ? block_cnt[2 * i] : 0, vo = i < nblk ? block_cnt[2 * i + 1] : 0;
-    sa[threadIdx.x] = va;
-    so[threadIdx.x] = vo;
+  sh[t] = sum;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {
+    const int v = t >= off ? sh[t - off] : 0;
     __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {
-      int ta = 0, to = 0;
-      if ((int)threadIdx.x >= off) {
-        ta = sa[threadIdx.x - off];
-        to = so[threadIdx.x - off];
-      }
-      __syncthreads();
-      sa[threadIdx.x] += ta;
-      so[threadIdx.x] += to;
-      __syncthreads();
-    }
-    if (i < nblk) {
-      block_cnt[2 * i] = carry_a + sa[threadIdx.x] - va;
-      block_cnt[2 * i + 1] = carry_o + so[threadIdx.x] - vo;
-    }
-    __syncthreads();
-    if (threadIdx.x == 1023) {
-      carry_a += sa[1023];
-      carry_o += so[1023];
-    }
+    sh[t] += v;
     __syncthreads();
   }
+  int run = sh[t] - sum;
+  const int total = sh[1023];
+  for (int i = lo; i < hi; ++i) {
+    const int v = data[i];
+    data[i] = run;
+    run += v;
+  }
+  __syncthreads();
+  return total;
+}
+
+// counts -> exclusive offsets for the four tables; totals into counts[0..1]
+__global__ void __launch_bounds__(1024)
+prep_scan_kernel(int* __restrict__ blk_base, int nblk, int nb, int* __restrict__ counts, int n_px) {
+  __shared__ int sh[1024];
+  const BlkMeta bm(blk_base, nblk, nb);
+  const int ta = block_excl_scan(bm.ref, nblk, sh);
+  const int to = block_excl_scan(bm.ref + nblk, nblk, sh);
+  block_excl_scan(bm.cls, nb * nblk, sh);                        // class-major: sorted by label, then by pixel
+  block_excl_scan(bm.cls + (size_t)nb * nblk, nb * nblk, sh);
   if (threadIdx.x == 0) {
-    counts[0] = carry_a;
-    counts[1] = carry_o;
+    counts[0] = ta;
+    counts[1] = to;
     counts[3] = n_px;
   }
 }
@@ -133,28 +170,32 @@ __device__ __forceinline__ size_t tile_chunk_off(long long tile, int chunks_per_
   return (((size_t)tile * chunks_per_tile + chunk) * 128 + r) * 8;
 }
 
-// Pack kernel: block = 32 consecutive pixels, blockIdx.y = source (0: f_n -> anchors, 1: f_o -> pseudo columns)
+// Pack kernel: block = 32 consecutive pixels, blockIdx.y = source (0: f_n -> anchors, 1: f_o -> pseudo columns).
+// fp32 rows / labels go to the REFERENCE slot (pixel order); bf16 tiles go to the CLASS-SORTED slot.
 __global__ void __launch_bounds__(128)
-prep_pack_kernel(const float* __restrict__ f_n, const float* __restrict__ f_o, const int* __restrict__ mix,
-                 const int* __restrict__ flags, const int* __restrict__ rank_a, const int* __restrict__ rank_o,
-                 const int* __restrict__ block_off, const int* __restrict__ counts, int n_px, int hw,
+prep_pack_kernel(const float* __restrict__ f_n, const float* __restrict__ f_o, const int* __restrict__ px_meta,
+                 int* __restrict__ blk_base, int nblk, int nb, const int* __restrict__ counts, int n_px, int hw,
                  float* __restrict__ anchor_f32, float* __restrict__ contrast_f32, int* __restrict__ la,
                  int* __restrict__ lc, __nv_bfloat16* __restrict__ feat_tiles, int* __restrict__ lab_tiles,
-                 int* __restrict__ row_pix, float* __restrict__ inv_norm) {
+                 int* __restrict__ row_ref, float* __restrict__ inv_norm) {
   __shared__ float tile[256][33];
   __shared__ float ss[4][32];
   __shared__ int slot_s[32];
   __shared__ float inv_s[32];
+  const BlkMeta bm(blk_base, nblk, nb);
   const int src = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int p = blockIdx.x * 32 + lane;
   const int n_a = counts[0];
-  int slot = -1;
+  int slot = -1, sslot = -1;  // reference slot, class-sorted slot (within the anchor / pseudo section)
   if (p < n_px) {
-    const int f = flags[p];
+    const int f = px_meta[(size_t)PX_FLAGS * n_px + p];
     const int blk = p / kPrepBlock;
-    if (src == 0 && (f & 1)) slot = block_off[2 * blk] + rank_a[p];
-    if (src == 1 && (f & 2)) slot = block_off[2 * blk + 1] + rank_o[p];
+    if ((src == 0 && (f & 1)) || (src == 1 && (f & 2))) {
+      const int m = px_meta[(size_t)PX_MIX * n_px + p];
+      slot = bm.ref_at(src, blk) + px_meta[(size_t)(src == 0 ? PX_RANK_A : PX_RANK_O) * n_px + p];
+      sslot = bm.cls_at(src, m, blk) + px_meta[(size_t)(src == 0 ? PX_SRANK_A : PX_SRANK_O) * n_px + p];
+    }
   }
   if (!__syncthreads_or(slot >= 0)) return;
   const float* f = src == 0 ? f_n : f_o;
@@ -179,13 +220,12 @@ prep_pack_kernel(const float* __restrict__ f_n, const float* __restrict__ f_o, c
     inv_s[lane] = inv;
     slot_s[lane] = slot;
     if (slot >= 0) {
-      const int m = mix[p];
-      const int cs = src == 0 ? slot : n_a + slot;  // column slot in [anchors ; pseudo]
-      lc[cs] = m;
-      lab_tiles[cs] = m;
+      const int m = px_meta[(size_t)PX_MIX * n_px + p];
+      lc[src == 0 ? slot : n_a + slot] = m;
+      lab_tiles[src == 0 ? sslot : n_a + sslot] = m;
       if (src == 0) {
         la[slot] = m;
-        row_pix[slot] = p;
+        row_ref[sslot] = slot;
         inv_norm[slot] = inv;
       }
     }
@@ -205,9 +245,9 @@ prep_pack_kernel(const float* __restrict__ f_n, const float* __restrict__ f_o, c
       if (src == 0) anchor_f32[(size_t)s * 256 + c] = v;
     }
   }
-  // (b) bf16 tiles: lane = pixel, each warp writes 8 of the 32 k-chunks (16 B per lane, rows adjacent)
+  // (b) bf16 tiles in class-sorted order: lane = pixel, each warp writes 8 of the 32 k-chunks (16 B per lane)
   if (slot >= 0) {
-    const int cs = src == 0 ? slot : n_a + slot;
+    const int cs = src == 0 ? sslot : n_a + sslot;
     const long long T = cs >> 7;
     const int r = cs & 127;
     const float inv = inv_s[lane];
@@ -224,17 +264,19 @@ prep_pack_kernel(const float* __restrict__ f_n, const float* __restrict__ f_o, c
   }
 }
 
-// softmax(l_po) per pixel -> bf16 prob tiles at the pixel's anchor slot and (if pseudo) pseudo slot
+// softmax(l_po) per pixel -> bf16 prob tiles at the pixel's (class-sorted) anchor slot and, if pseudo, pseudo slot
 __global__ void __launch_bounds__(256)
-prep_prob_kernel(const float* __restrict__ l_po, const int* __restrict__ flags, const int* __restrict__ rank_a,
-                 const int* __restrict__ rank_o, const int* __restrict__ block_off, const int* __restrict__ counts,
-                 int n_px, int hw, int C_old, int kpad, __nv_bfloat16* __restrict__ prob_tiles) {
+prep_prob_kernel(const float* __restrict__ l_po, const int* __restrict__ px_meta, int* __restrict__ blk_base, int nblk,
+                 int nb, const int* __restrict__ counts, int n_px, int hw, int C_old, int kpad,
+                 __nv_bfloat16* __restrict__ prob_tiles) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_px) return;
-  const int f = flags[p];
+  const int f = px_meta[(size_t)PX_FLAGS * n_px + p];
   if (!(f & 1)) return;
+  const BlkMeta bm(blk_base, nblk, nb);
   const int n_a = counts[0];
   const int blk = p / kPrepBlock;
+  const int mlab = px_meta[(size_t)PX_MIX * n_px + p];
   const int b = p / hw, q = p - b * hw;
   const float* lp = l_po + (size_t)b * C_old * hw + q;
   float m = lp[0];
@@ -242,8 +284,8 @@ prep_prob_kernel(const float* __restrict__ l_po, const int* __restrict__ flags, 
   float s = 0.f;
   for (int c = 0; c < C_old; ++c) s += __expf(lp[(size_t)c * hw] - m);
   const float inv = 1.f / s;
-  const int sa = block_off[2 * blk] + rank_a[p];
-  const int so = (f & 2) ? n_a + block_off[2 * blk + 1] + rank_o[p] : -1;
+  const int sa = bm.cls_at(0, mlab, blk) + px_meta[(size_t)PX_SRANK_A * n_px + p];
+  const int so = (f & 2) ? n_a + bm.cls_at(1, mlab, blk) + px_meta[(size_t)PX_SRANK_O * n_px + p] : -1;
   const int chunks = kpad / 8;
   for (int ch = 0; ch < chunks; ++ch) {
     float v[8];
@@ -262,17 +304,46 @@ prep_prob_kernel(const float* __restrict__ l_po, const int* __restrict__ flags, 
   }
 }
 
+// label range of every tile (valid labels are >= 0): lets sweep 2 skip tiles that cannot hold a positive pair
+__global__ void __launch_bounds__(256)
+tile_range_kernel(const int* __restrict__ lab_tiles, long long n_tiles, const int* __restrict__ n_limit,
+                  int* __restrict__ range /*[n_tiles][2]*/) {
+  const long long t = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (t >= n_tiles) return;
+  const long long limit = n_limit ? (long long)*n_limit : (1ll << 62);  // only entries [0, limit) count
+  const int4 v = reinterpret_cast<const int4*>(lab_tiles + t * 128)[lane];
+  int lo = 0x7fffffff, hi = -1;
+  const int ls[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (ls[i] >= 0 && t * 128 + lane * 4 + i < limit) {
+      lo = min(lo, ls[i]);
+      hi = max(hi, ls[i]);
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if (lane == 0) {
+    range[2 * t] = lo;
+    range[2 * t + 1] = hi;
+  }
+}
+
 // adjoint of gather + normalize; block = 32 consecutive pixels, writes all 256 channels (zeros for non-anchors)
 __global__ void __launch_bounds__(128)
 prep_bwd_kernel(const float* __restrict__ g_anchor, const float* __restrict__ anchor_f32,
-                const float* __restrict__ inv_norm, const int* __restrict__ flags, const int* __restrict__ rank_a,
-                const int* __restrict__ block_off, float* __restrict__ df_n, int n_px, int hw) {
+                const float* __restrict__ inv_norm, const int* __restrict__ px_meta, const int* __restrict__ blk_base,
+                float* __restrict__ df_n, int n_px, int hw) {
   __shared__ float tile[256][33];
   __shared__ int slot_s[32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int p = blockIdx.x * 32 + lane;
   int slot = -1;
-  if (p < n_px && (flags[p] & 1)) slot = block_off[2 * (p / kPrepBlock)] + rank_a[p];
+  if (p < n_px && (px_meta[(size_t)PX_FLAGS * n_px + p] & 1))
+    slot = blk_base[p / kPrepBlock] + px_meta[(size_t)PX_RANK_A * n_px + p];  // ref_off[0][blk]
   if (warp == 0) slot_s[lane] = slot;
   __syncthreads();
   for (int pi = warp; pi < 32; pi += 4) {
@@ -327,66 +398,93 @@ using namespace ucd;
 
 extern "C" int64_t ucd_con_max_tiles(int64_t n_px) { return (2 * n_px + 127) / 128 + 1; }
 extern "C" int ucd_con_prob_kpad(int C_old) { return (C_old + 15) / 16 * 16; }
+extern "C" int ucd_con_num_bins(int max_label, int C_old) { return (max_label > C_old - 1 ? max_label : C_old - 1) + 1; }
+extern "C" int64_t ucd_con_px_meta_ints(int64_t n_px) { return (int64_t)PX_PLANES * n_px; }
+extern "C" int64_t ucd_con_blk_meta_ints(int64_t n_px, int nb) {
+  const int64_t nblk = (n_px + kPrepBlock - 1) / kPrepBlock;
+  return 2 * nblk * (1 + (int64_t)nb);
+}
 
 extern "C" int ucd_con_prep_labels(const int64_t* labels, const float* l_po, int B, int C_old, int h, int w, int H,
-                                   int W, int max_label, int32_t* label_n, int32_t* mix, int32_t* flags,
-                                   int32_t* rank_a, int32_t* rank_o, int32_t* block_cnt, int32_t* counts,
+                                   int W, int max_label, int32_t* px_meta, int32_t* blk_meta, int32_t* counts,
                                    void* stream) {
-  UCD_CHECK_ARG(labels && l_po && label_n && mix && flags && rank_a && rank_o && block_cnt && counts,
-                "ucd_con_prep_labels: null pointer");
+  UCD_CHECK_ARG(labels && l_po && px_meta && blk_meta && counts, "ucd_con_prep_labels: null pointer");
   UCD_CHECK_ARG(B > 0 && C_old > 0 && h > 0 && w > 0 && H > 0 && W > 0, "ucd_con_prep_labels: bad shape");
   UCD_CHECK_ARG((long long)B * h * w < (1ll << 30), "ucd_con_prep_labels: too many pixels");
+  const int nb = ucd_con_num_bins(max_label, C_old);
+  UCD_CHECK_ARG(max_label >= 0 && nb <= 1024, "ucd_con_prep_labels: %d label bins not supported (max 1024)", nb);
   cudaStream_t st = (cudaStream_t)stream;
   const int n_px = B * h * w;
   const int nblk = (n_px + kPrepBlock - 1) / kPrepBlock;
   cudaError_t e = cudaMemsetAsync(counts, 0x7f, 4 * sizeof(int32_t), st);  // min_new starts at 0x7f7f7f7f
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(counts)");
-  prep_labels_kernel<<<nblk, kPrepBlock, 0, st>>>((const long long*)labels, l_po, B, C_old, h, w, H, W, max_label,
-                                                  (float)H / (float)h, (float)W / (float)w, label_n, mix, flags,
-                                                  rank_a, rank_o, block_cnt, counts);
+  const size_t smem = (size_t)2 * 8 * nb * sizeof(int);
+  if (smem > 48 * 1024) {
+    e = cudaFuncSetAttribute(prep_labels_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(prep_labels_kernel)");
+  }
+  prep_labels_kernel<<<nblk, kPrepBlock, smem, st>>>((const long long*)labels, l_po, B, C_old, h, w, H, W, max_label,
+                                                     (float)H / (float)h, (float)W / (float)w, px_meta, blk_meta, nb,
+                                                     counts);
   UCD_CHECK_LAUNCH("prep_labels_kernel");
-  prep_scan_kernel<<<1, 1024, 0, st>>>(block_cnt, nblk, counts, n_px);
+  prep_scan_kernel<<<1, 1024, 0, st>>>(blk_meta, nblk, nb, counts, n_px);
   UCD_CHECK_LAUNCH("prep_scan_kernel");
   return UCD_OK;
 }
 
-extern "C" int ucd_con_prep_pack(const float* f_n, const float* f_o, const float* l_po, const int32_t* mix,
-                                 const int32_t* flags, const int32_t* rank_a, const int32_t* rank_o,
-                                 const int32_t* block_off, const int32_t* counts, int B, int C_old, int h, int w,
-                                 float* anchor_f32, float* contrast_f32, int32_t* la, int32_t* lc, void* feat_tiles,
-                                 void* prob_tiles, int32_t* lab_tiles, int32_t* row_pix, float* inv_norm,
-                                 int64_t max_tiles, void* stream) {
-  UCD_CHECK_ARG(f_n && f_o && l_po && mix && flags && rank_a && rank_o && block_off && counts && anchor_f32 &&
-                    contrast_f32 && la && lc && feat_tiles && prob_tiles && lab_tiles && row_pix && inv_norm,
+extern "C" int ucd_con_tile_ranges(const int32_t* lab_tiles, int64_t n_tiles, const int32_t* n_limit,
+                                   int32_t* tile_range, void* stream) {
+  UCD_CHECK_ARG(lab_tiles && tile_range && n_tiles >= 0, "ucd_con_tile_ranges: bad argument");
+  UCD_CHECK_ARG(aligned16(lab_tiles), "ucd_con_tile_ranges: lab_tiles must be 16 B aligned");
+  if (n_tiles == 0) return UCD_OK;
+  tile_range_kernel<<<(unsigned)((n_tiles + 7) / 8), 256, 0, (cudaStream_t)stream>>>(lab_tiles, n_tiles, n_limit,
+                                                                                      tile_range);
+  UCD_CHECK_LAUNCH("tile_range_kernel");
+  return UCD_OK;
+}
+
+extern "C" int ucd_con_prep_pack(const float* f_n, const float* f_o, const float* l_po, const int32_t* px_meta,
+                                 int32_t* blk_meta, const int32_t* counts, int B, int C_old, int h, int w,
+                                 int max_label, float* anchor_f32, float* contrast_f32, int32_t* la, int32_t* lc,
+                                 void* feat_tiles, void* prob_tiles, int32_t* lab_tiles, int32_t* tile_range,
+                                 int32_t* row_range, int32_t* row_ref, float* inv_norm, int64_t max_tiles, void* stream) {
+  UCD_CHECK_ARG(f_n && f_o && l_po && px_meta && blk_meta && counts && anchor_f32 && contrast_f32 && la && lc &&
+                    feat_tiles && prob_tiles && lab_tiles && tile_range && row_range && row_ref && inv_norm,
                 "ucd_con_prep_pack: null pointer");
-  UCD_CHECK_ARG(aligned16(feat_tiles) && aligned16(prob_tiles), "ucd_con_prep_pack: tiles must be 16 B aligned");
+  UCD_CHECK_ARG(aligned16(feat_tiles) && aligned16(prob_tiles) && aligned16(lab_tiles),
+                "ucd_con_prep_pack: tiles must be 16 B aligned");
   const int n_px = B * h * w;
   UCD_CHECK_ARG(max_tiles >= ucd_con_max_tiles(n_px), "ucd_con_prep_pack: max_tiles too small");
   cudaStream_t st = (cudaStream_t)stream;
   const int kpad = ucd_con_prob_kpad(C_old);
+  const int nb = ucd_con_num_bins(max_label, C_old);
+  const int nblk = (n_px + kPrepBlock - 1) / kPrepBlock;
   cudaError_t e = cudaMemsetAsync(feat_tiles, 0, (size_t)max_tiles * 128 * 256 * 2, st);
   if (e == cudaSuccess) e = cudaMemsetAsync(prob_tiles, 0, (size_t)max_tiles * 128 * kpad * 2, st);
   if (e == cudaSuccess) e = cudaMemsetAsync(lab_tiles, 0xff, (size_t)max_tiles * 128 * sizeof(int32_t), st);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(tiles)");
   dim3 grid((n_px + 31) / 32, 2);
-  prep_pack_kernel<<<grid, 128, 0, st>>>(f_n, f_o, mix, flags, rank_a, rank_o, block_off, counts, n_px, h * w,
-                                         anchor_f32, contrast_f32, la, lc, (__nv_bfloat16*)feat_tiles, lab_tiles,
-                                         row_pix, inv_norm);
+  prep_pack_kernel<<<grid, 128, 0, st>>>(f_n, f_o, px_meta, blk_meta, nblk, nb, counts, n_px, h * w, anchor_f32,
+                                         contrast_f32, la, lc, (__nv_bfloat16*)feat_tiles, lab_tiles, row_ref,
+                                         inv_norm);
   UCD_CHECK_LAUNCH("prep_pack_kernel");
-  prep_prob_kernel<<<(n_px + 255) / 256, 256, 0, st>>>(l_po, flags, rank_a, rank_o, block_off, counts, n_px, h * w,
-                                                       C_old, kpad, (__nv_bfloat16*)prob_tiles);
+  prep_prob_kernel<<<(n_px + 255) / 256, 256, 0, st>>>(l_po, px_meta, blk_meta, nblk, nb, counts, n_px, h * w, C_old,
+                                                       kpad, (__nv_bfloat16*)prob_tiles);
   UCD_CHECK_LAUNCH("prep_prob_kernel");
-  return UCD_OK;
+  int rc = ucd_con_tile_ranges(lab_tiles, max_tiles, nullptr, tile_range, stream);
+  if (rc != UCD_OK) return rc;
+  // rows are the first N_a (= counts[0]) columns: the last anchor tile also holds pseudo columns, which must not
+  // widen the ROW range (it would make every column tile "active" for that row block in sweep 2)
+  return ucd_con_tile_ranges(lab_tiles, (n_px + 127) / 128, counts, row_range, stream);
 }
 
 extern "C" int ucd_con_prep_bwd(const float* g_anchor, const float* anchor_f32, const float* inv_norm,
-                                const int32_t* flags, const int32_t* rank_a, const int32_t* block_off, float* df_n,
-                                int B, int h, int w, void* stream) {
-  UCD_CHECK_ARG(g_anchor && anchor_f32 && inv_norm && flags && rank_a && block_off && df_n,
-                "ucd_con_prep_bwd: null pointer");
+                                const int32_t* px_meta, const int32_t* blk_meta, float* df_n, int B, int h, int w,
+                                void* stream) {
+  UCD_CHECK_ARG(g_anchor && anchor_f32 && inv_norm && px_meta && blk_meta && df_n, "ucd_con_prep_bwd: null pointer");
   const int n_px = B * h * w;
-  prep_bwd_kernel<<<(n_px + 31) / 32, 128, 0, (cudaStream_t)stream>>>(g_anchor, anchor_f32, inv_norm, flags, rank_a,
-                                                                       block_off, df_n, n_px, h * w);
+  prep_bwd_kernel<<<(n_px + 31) / 32, 128, 0, (cudaStream_t)stream>>>(g_anchor, anchor_f32, inv_norm, px_meta,
+                                                                       blk_meta, df_n, n_px, h * w);
   UCD_CHECK_LAUNCH("prep_bwd_kernel");
   return UCD_OK;
 }

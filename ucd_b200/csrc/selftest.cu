@@ -2,6 +2,8 @@
 //   variant 0:  S[128,128] = A[128,256] * C[128,256]^T      (both operands K-major, like sweep MMA 1)
 //   variant 1:  V[128,256] = E[128,128] * C[128,256]        (A K-major from thread-written smem,
 //                                                             B = the same C tile read MN-major)
+//   variant 2:  same product, but E is written to TENSOR MEMORY with tcgen05.st and the MMA reads its A
+//               operand from there (the production path of the sweeps)
 // Used by tests/test_gpu_umma.py; not on the product path.
 #include "umma.cuh"
 
@@ -25,7 +27,7 @@ selftest_kernel(int variant, const __nv_bfloat16* __restrict__ a_tile, const __n
     mbar_init(bar_mma, 1);
     fence_mbar_init();
   }
-  if (warp == 0) tmem_alloc(smem_u32(&s_tmem), 256);
+  if (warp == 0) tmem_alloc(smem_u32(&s_tmem), 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -50,6 +52,20 @@ selftest_kernel(int variant, const __nv_bfloat16* __restrict__ a_tile, const __n
     }
     fence_proxy_async();
   }
+  if (variant == 2) {
+    // row r of E as packed bf16 pairs -> 64 TMEM columns at [256, 320) of this thread's lane
+    const int r = threadIdx.x;
+    for (int c16 = 0; c16 < 4; ++c16) {
+      uint32_t pk[16];
+      for (int u = 0; u < 16; ++u) {
+        __nv_bfloat162 v = __floats2bfloat162_rn(e_rows[r * 128 + c16 * 32 + 2 * u], e_rows[r * 128 + c16 * 32 + 2 * u + 1]);
+        pk[u] = *reinterpret_cast<uint32_t*>(&v);
+      }
+      tmem_st16(tmem + ((uint32_t)(warp * 32) << 16) + 256 + c16 * 16, pk);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     mbar_wait(bar_ld, 0);
@@ -59,11 +75,15 @@ selftest_kernel(int variant, const __nv_bfloat16* __restrict__ a_tile, const __n
       for (int ks = 0; ks < 16; ++ks)
         umma_bf16(tmem, umma_desc(sbase + ST_OFF_A + ks * 4096, 2048, 128),
                   umma_desc(sbase + ST_OFF_C + ks * 4096, 2048, 128), idesc, ks > 0);
-    } else {
+    } else if (variant == 1) {
       constexpr uint32_t idesc = umma_idesc(128, 256, 0, 1);
       for (int kk = 0; kk < 8; ++kk)
         umma_bf16(tmem, umma_desc(sbase + ST_OFF_E + kk * 4096, 2048, 128),
                   umma_desc(sbase + ST_OFF_C + kk * 16 * 16, 128, 2048), idesc, kk > 0);
+    } else {
+      constexpr uint32_t idesc = umma_idesc(128, 256, 0, 1);
+      for (int kk = 0; kk < 8; ++kk)
+        umma_bf16_ts(tmem, tmem + 256 + kk * 8, umma_desc(sbase + ST_OFF_C + kk * 16 * 16, 128, 2048), idesc, kk > 0);
     }
     umma_commit(bar_mma);
   }
@@ -82,7 +102,7 @@ selftest_kernel(int variant, const __nv_bfloat16* __restrict__ a_tile, const __n
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem, 256);
+    tmem_dealloc(tmem, 512);
   }
 }
 
@@ -93,7 +113,7 @@ static float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x
 using namespace ucd;
 
 extern "C" int ucd_selftest_umma(int variant, float* max_err_host) {
-  UCD_CHECK_ARG(variant == 0 || variant == 1, "ucd_selftest_umma: variant must be 0 or 1");
+  UCD_CHECK_ARG(variant >= 0 && variant <= 2, "ucd_selftest_umma: variant must be 0, 1 or 2");
   UCD_CHECK_ARG(max_err_host, "ucd_selftest_umma: null pointer");
   const int M = 128, D = 256;
   std::vector<float> A(M * D), C(M * D), E(M * 128);

@@ -14,7 +14,8 @@ namespace ucd {
 
 constexpr int kUpThreads = 256;
 
-// grid: x = ceil(W/(4*kUpThreads_x)) ... we flatten (Y, X4) into one index; blockIdx.y = plane group
+// Forward.  A thread owns VEC consecutive output x of one output row and loops over the planes of its
+// plane group.  blockIdx.x covers (Y, X/VEC) flattened, blockIdx.y the plane group.
 template <int VEC>
 __global__ void __launch_bounds__(kUpThreads)
 upsample_fwd_kernel(const float* __restrict__ in, float* __restrict__ out, long long planes, int h, int w, int H,
@@ -25,57 +26,59 @@ upsample_fwd_kernel(const float* __restrict__ in, float* __restrict__ out, long 
   const int Y = (int)(idx / wv);
   const int X = (int)(idx - (long long)Y * wv) * VEC;
   const Tap ty = bilinear_tap(Y, scale_h, h, H);
-  int o00[VEC], o01[VEC], o10[VEC], o11[VEC];
+  int x0[VEC], x1[VEC];
   float wx0[VEC], wx1[VEC];
   const bool small_out = H + W <= 128;  // selects ATen's operation order (bit-exact parity with the CPU reference)
+  bool uniform = true;
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
-    const int xx = (X + i < W) ? X + i : W - 1;
-    const Tap tx = bilinear_tap(xx, scale_w, w, W);
-    o00[i] = ty.i0 * w + tx.i0;
-    o01[i] = ty.i0 * w + tx.i1;
-    o10[i] = ty.i1 * w + tx.i0;
-    o11[i] = ty.i1 * w + tx.i1;
-    wx0[i] = tx.w0;
-    wx1[i] = tx.w1;
+    const Tap tx = bilinear_tap(X + i, scale_w, w, W);
+    x0[i] = tx.i0, x1[i] = tx.i1, wx0[i] = tx.w0, wx1[i] = tx.w1;
+    uniform = uniform && tx.i0 == x0[0] && tx.i1 == x1[0];
   }
   const long long p0 = (long long)blockIdx.y * planes_per_block;
   const long long p1 = (p0 + planes_per_block < planes) ? p0 + planes_per_block : planes;
   const size_t in_plane = (size_t)h * w, out_plane = (size_t)H * W;
-  // Fast path (any upscale factor >= ~4): the VEC outputs draw on at most 3 adjacent source columns,
-  // so 6 loads per plane instead of 4*VEC keep the LSU below the store rate.
-  const int xmin = o00[0] - ty.i0 * w;
-  bool narrow = true;
+  float* dst = out + p0 * out_plane + (size_t)Y * W + X;
+  if (uniform) {
+    // All VEC outputs read the same 2x2 source cell (always the case for upscale factors that are a multiple of
+    // 2*VEC, e.g. the 16x of DeepLab): 4 loads per plane, UP planes in flight.
+    const float* s00 = in + p0 * in_plane + ty.i0 * w + x0[0];
+    const int d01 = x1[0] - x0[0], d10 = (ty.i1 - ty.i0) * w;
+    constexpr int UP = 4;
+    long long p = p0;
+    for (; p + UP <= p1; p += UP) {
+      float v[UP][4];
 #pragma unroll
-  for (int i = 0; i < VEC; ++i) narrow = narrow && (o01[i] - ty.i0 * w - xmin <= 2) && (o00[i] - ty.i0 * w >= xmin);
-  if (narrow) {
-    int d0[VEC], d1[VEC];
+      for (int u = 0; u < UP; ++u) {
+        const float* s = s00 + u * in_plane;
+        v[u][0] = __ldg(s), v[u][1] = __ldg(s + d01), v[u][2] = __ldg(s + d10), v[u][3] = __ldg(s + d10 + d01);
+      }
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-      d0[i] = o00[i] - ty.i0 * w - xmin;
-      d1[i] = o01[i] - ty.i0 * w - xmin;
+      for (int u = 0; u < UP; ++u) {
+        float r[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i)
+          r[i] = bilinear_blend(small_out, v[u][0], v[u][1], v[u][2], v[u][3], ty.w0, ty.w1, wx0[i], wx1[i]);
+        if (VEC == 4)
+          stg_stream4(dst + u * out_plane, make_float4(r[0], r[1], r[2], r[3]));
+        else
+          stg_stream1(dst + u * out_plane, r[0]);
+      }
+      s00 += UP * in_plane;
+      dst += UP * out_plane;
     }
-    const int c0 = xmin, c1 = min(xmin + 1, w - 1), c2 = min(xmin + 2, w - 1);
-    const int ra = ty.i0 * w, rb = ty.i1 * w;
-    for (long long p = p0; p < p1; ++p) {
-      const float* src = in + p * in_plane;
-      const float a0 = __ldg(src + ra + c0), a1 = __ldg(src + ra + c1), a2 = __ldg(src + ra + c2);
-      const float b0 = __ldg(src + rb + c0), b1 = __ldg(src + rb + c1), b2 = __ldg(src + rb + c2);
+    for (; p < p1; ++p) {
+      const float a = __ldg(s00), b = __ldg(s00 + d01), c = __ldg(s00 + d10), d = __ldg(s00 + d10 + d01);
       float r[VEC];
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        const float v00 = d0[i] == 0 ? a0 : (d0[i] == 1 ? a1 : a2);
-        const float v01 = d1[i] == 0 ? a0 : (d1[i] == 1 ? a1 : a2);
-        const float v10 = d0[i] == 0 ? b0 : (d0[i] == 1 ? b1 : b2);
-        const float v11 = d1[i] == 0 ? b0 : (d1[i] == 1 ? b1 : b2);
-        r[i] = bilinear_blend(small_out, v00, v01, v10, v11, ty.w0, ty.w1, wx0[i], wx1[i]);
-      }
-      float* dst = out + p * out_plane + (size_t)Y * W + X;
-      if (VEC == 4) {
+      for (int i = 0; i < VEC; ++i) r[i] = bilinear_blend(small_out, a, b, c, d, ty.w0, ty.w1, wx0[i], wx1[i]);
+      if (VEC == 4)
         stg_stream4(dst, make_float4(r[0], r[1], r[2], r[3]));
-      } else {
+      else
         stg_stream1(dst, r[0]);
-      }
+      s00 += in_plane;
+      dst += out_plane;
     }
     return;
   }
@@ -84,23 +87,28 @@ upsample_fwd_kernel(const float* __restrict__ in, float* __restrict__ out, long 
     float r[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i)
-      r[i] = bilinear_blend(small_out, __ldg(src + o00[i]), __ldg(src + o01[i]), __ldg(src + o10[i]),
-                            __ldg(src + o11[i]), ty.w0, ty.w1, wx0[i], wx1[i]);
-    float* dst = out + p * out_plane + (size_t)Y * W + X;
-    if (VEC == 4) {
+      r[i] = bilinear_blend(small_out, __ldg(src + ty.i0 * w + x0[i]), __ldg(src + ty.i0 * w + x1[i]),
+                            __ldg(src + ty.i1 * w + x0[i]), __ldg(src + ty.i1 * w + x1[i]), ty.w0, ty.w1, wx0[i],
+                            wx1[i]);
+    if (VEC == 4)
       stg_stream4(dst, make_float4(r[0], r[1], r[2], r[3]));
-    } else {
+    else
       stg_stream1(dst, r[0]);
-    }
+    dst += out_plane;
   }
 }
 
-// Adjoint.  block = (plane, group of RY low-res rows).  smem: colsum[RY][W].
-template <int RY>
+// Adjoint.  block = (plane, group of RY low-res rows).  Dynamic smem: colsum[RY][W] | wrow[ny_cap][RY].
+//   step 0: per full-res row Y of the group's footprint, its weight towards each of the RY low-res rows
+//   step 1: stream the footprint rows once (VEC=4: 128-bit loads), reduce along y in registers -> colsum
+//   step 2: reduce colsum along x into the RY*w outputs
+template <int RY, int VEC>
 __global__ void __launch_bounds__(kUpThreads)
 upsample_bwd_kernel(const float* __restrict__ gout, float* __restrict__ gin, int h, int w, int H, int W,
-                    float scale_h, float scale_w, float inv_scale_h, float inv_scale_w) {
-  extern __shared__ float colsum[];  // [RY][W]
+                    float scale_h, float scale_w, float inv_scale_h, float inv_scale_w, int ny_cap) {
+  extern __shared__ __align__(16) float up_smem[];
+  float* colsum = up_smem;                 // [RY][W]
+  float* wrow = up_smem + (size_t)RY * W;  // [ny_cap][RY]
   const long long plane = blockIdx.y;
   const int ybase = blockIdx.x * RY;
   const int ylast = min(ybase + RY, h) - 1;
@@ -114,43 +122,68 @@ upsample_bwd_kernel(const float* __restrict__ gout, float* __restrict__ gin, int
     Ylo = ybase;
     Yhi = ylast;
   }
-  constexpr int KX = 4;  // columns per thread per pass
-  for (int x0 = 0; x0 < W; x0 += KX * kUpThreads) {
-    float acc[RY][KX];
+  Yhi = min(Yhi, Ylo + ny_cap - 1);  // ny_cap is sized by the host to cover the footprint
+  const int ny = Yhi - Ylo + 1;
+  for (int i = threadIdx.x; i < ny; i += kUpThreads) {
+    const Tap ty = bilinear_tap(Ylo + i, scale_h, h, H);
+#pragma unroll
+    for (int r = 0; r < RY; ++r) {
+      float wgt = 0.f;
+      if (ty.i0 - ybase == r) wgt += ty.w0;
+      if (ty.i1 - ybase == r) wgt += ty.w1;
+      wrow[i * RY + r] = wgt;
+    }
+  }
+  for (int i = threadIdx.x; i < RY * W; i += kUpThreads) colsum[i] = 0.f;
+  __syncthreads();
+  const int ngroups = (W + VEC - 1) / VEC;                  // column groups per row
+  const int nsplit = max(1, min(kUpThreads / ngroups, 8));  // row-interleaved thread teams per column group
+  const int team = threadIdx.x / ngroups;
+  const bool working = team < nsplit || ngroups >= kUpThreads;
+  for (int g0 = 0; g0 < ngroups; g0 += kUpThreads) {
+    const int xg = g0 + (ngroups >= kUpThreads ? threadIdx.x : threadIdx.x - team * ngroups);
+    float acc[RY][VEC];
 #pragma unroll
     for (int r = 0; r < RY; ++r)
 #pragma unroll
-      for (int k = 0; k < KX; ++k) acc[r][k] = 0.f;
-#pragma unroll 2
-    for (int Y = Ylo; Y <= Yhi; ++Y) {
-      const Tap ty = bilinear_tap(Y, scale_h, h, H);
-      const int r0 = ty.i0 - ybase, r1 = ty.i1 - ybase;
-      const bool in0 = (r0 >= 0 && r0 < RY), in1 = (r1 >= 0 && r1 < RY);
-      if (!in0 && !in1) continue;
-      float v[KX];
+      for (int k = 0; k < VEC; ++k) acc[r][k] = 0.f;
+    if (working && xg < ngroups) {
+      const int ystep = ngroups >= kUpThreads ? 1 : nsplit;
+      const float* gp = g + (size_t)Ylo * W + (size_t)xg * VEC;
+#pragma unroll 4
+      for (int i = (ngroups >= kUpThreads ? 0 : team); i < ny; i += ystep) {
+        float v[VEC];
+        if (VEC == 4) {
+          const float4 t = ldg_stream4(gp + (size_t)i * W);
+          v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
+        } else {
+          v[0] = ldg_stream1(gp + (size_t)i * W);
+        }
+        float wr[RY];
+        if (RY == 4) {
+          const float4 t = *reinterpret_cast<const float4*>(wrow + i * RY);
+          wr[0] = t.x, wr[1] = t.y, wr[2] = t.z, wr[3] = t.w;
+        } else {
 #pragma unroll
-      for (int k = 0; k < KX; ++k) {
-        const int X = x0 + k * kUpThreads + threadIdx.x;
-        v[k] = (X < W) ? ldg_stream1(g + (size_t)Y * W + X) : 0.f;
-      }
+          for (int r = 0; r < RY; ++r) wr[r] = wrow[i * RY + r];
+        }
 #pragma unroll
-      for (int r = 0; r < RY; ++r) {
-        float wgt = 0.f;
-        if (in0 && r == r0) wgt += ty.w0;
-        if (in1 && r == r1) wgt += ty.w1;
+        for (int r = 0; r < RY; ++r)
 #pragma unroll
-        for (int k = 0; k < KX; ++k) acc[r][k] = fmaf(wgt, v[k], acc[r][k]);
+          for (int k = 0; k < VEC; ++k) acc[r][k] = fmaf(wr[r], v[k], acc[r][k]);
       }
     }
+    // fixed-order combination of the teams (deterministic)
+    for (int s = 0; s < (ngroups >= kUpThreads ? 1 : nsplit); ++s) {
+      if (working && xg < ngroups && (ngroups >= kUpThreads || team == s)) {
 #pragma unroll
-    for (int r = 0; r < RY; ++r)
+        for (int r = 0; r < RY; ++r)
 #pragma unroll
-      for (int k = 0; k < KX; ++k) {
-        const int X = x0 + k * kUpThreads + threadIdx.x;
-        if (X < W) colsum[r * W + X] = acc[r][k];
+          for (int k = 0; k < VEC; ++k) colsum[r * W + xg * VEC + k] += acc[r][k];
       }
+      __syncthreads();
+    }
   }
-  __syncthreads();
   // reduce along x: out[y][x] = sum_X wx(X,x) colsum[y][X]
   const int n_out = RY * w;
   for (int o = threadIdx.x; o < n_out; o += kUpThreads) {
@@ -208,25 +241,25 @@ extern "C" int ucd_upsample_bilinear_bwd(const float* gout, float* gin, int64_t 
                                          void* stream) {
   UCD_CHECK_ARG(gout && gin, "ucd_upsample_bilinear_bwd: null pointer");
   UCD_CHECK_ARG(planes > 0 && h > 0 && w > 0 && H > 0 && W > 0, "ucd_upsample_bilinear_bwd: bad shape");
-  UCD_CHECK_ARG(planes <= 65535ll * 32768, "ucd_upsample_bilinear_bwd: too many planes");
   cudaStream_t st = (cudaStream_t)stream;
   constexpr int RY = 4;
-  const size_t smem = (size_t)RY * W * sizeof(float);
-  UCD_CHECK_ARG(smem <= 200 * 1024, "ucd_upsample_bilinear_bwd: W=%d too wide", W);
+  // full-res rows that can touch RY consecutive low-res rows (+ the slack the kernel adds around its estimate)
+  const int ny_cap = (h == H) ? RY : (int)((double)(RY + 2) * H / h) + 8;
+  const size_t smem = ((size_t)RY * W + (size_t)ny_cap * RY) * sizeof(float);
+  UCD_CHECK_ARG(smem <= 200 * 1024, "ucd_upsample_bilinear_bwd: W=%d / scale too large for one block", W);
   const float sh = (float)h / (float)H, sw = (float)w / (float)W;
+  const bool v4 = (W % 4 == 0) && aligned16(gout);
+  auto kern = v4 ? upsample_bwd_kernel<RY, 4> : upsample_bwd_kernel<RY, 1>;
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(upsample_bwd_kernel<RY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(upsample_bwd)");
   }
-  // planes on grid.y is limited to 65535: fold the excess into grid.z-free loop by chunking launches
   const int gyb = (h + RY - 1) / RY;
-  for (int64_t p0 = 0; p0 < planes; p0 += 65535) {
+  for (int64_t p0 = 0; p0 < planes; p0 += 65535) {  // grid.y limit
     const int np = (int)((planes - p0 < 65535) ? planes - p0 : 65535);
     dim3 grid(gyb, np);
-    upsample_bwd_kernel<RY><<<grid, kUpThreads, smem, st>>>(gout + (size_t)p0 * H * W, gin + (size_t)p0 * h * w, h,
-                                                             w, H, W, sh, sw, (float)H / (float)h,
-                                                             (float)W / (float)w);
+    kern<<<grid, kUpThreads, smem, st>>>(gout + (size_t)p0 * H * W, gin + (size_t)p0 * h * w, h, w, H, W, sh, sw,
+                                         (float)H / (float)h, (float)W / (float)w, ny_cap);
     UCD_CHECK_LAUNCH("upsample_bwd_kernel");
   }
   return UCD_OK;

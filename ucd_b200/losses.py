@@ -236,12 +236,15 @@ class ContrastPack:
         self.max_tiles = 0
         self.counts = None         # int32[4] device: N_a, N_o, min_new, n_px
         self.n_a = self.n_o = self.min_new = None   # host copies (one sync)
-        self.label_n = self.mix = self.flags = None
-        self.rank_a = self.rank_o = self.block_off = None
-        self.anchor_f32 = self.contrast_f32 = None
+        self.px_meta = self.blk_meta = None         # see include/ucd_b200.h (ucd_con_prep_labels)
+        self.label_n = self.mix = self.flags = None  # views of px_meta planes 0..2
+        self.anchor_f32 = self.contrast_f32 = None   # reference row order (b,y,x)
         self.la = self.lc = None
-        self.feat_tiles = self.prob_tiles = self.lab_tiles = None
-        self.row_pix = self.inv_norm = None
+        self.feat_tiles = self.prob_tiles = self.lab_tiles = None   # class-sorted bf16 / int32 tiles
+        self.tile_range = None                       # [T,2] min/max label per column tile
+        self.row_range = None                        # [ceil(n_px/128),2] same over the anchor rows only
+        self.row_ref = self.inv_norm = None          # sorted anchor row -> reference row
+        self.max_label = 20
         self.l_po = None
 
     @property
@@ -269,14 +272,15 @@ def _build_pack(f_n, f_o, l_po, labels, max_label):
     pk.max_tiles = L.ucd_con_max_tiles(pk.n_px)
     n_px = pk.n_px
     i32 = dict(device=dev, dtype=torch.int32)
-    meta = torch.empty(5, n_px, **i32)
-    pk.label_n, pk.mix, pk.flags, pk.rank_a, pk.rank_o = meta[0], meta[1], meta[2], meta[3], meta[4]
-    pk.block_off = torch.empty(2 * ((n_px + 255) // 256), **i32)
+    pk.max_label = int(max_label)
+    nb = L.ucd_con_num_bins(pk.max_label, pk.c_old)
+    pk.px_meta = torch.empty(7, n_px, **i32)
+    pk.label_n, pk.mix, pk.flags = pk.px_meta[0], pk.px_meta[1], pk.px_meta[2]
+    pk.blk_meta = torch.empty(L.ucd_con_blk_meta_ints(n_px, nb), **i32)
     pk.counts = torch.empty(4, **i32)
     st = cur_stream()
-    check(L.ucd_con_prep_labels(ptr(labels), ptr(l_po), B, pk.c_old, h, w, H, W, int(max_label), ptr(pk.label_n),
-                                ptr(pk.mix), ptr(pk.flags), ptr(pk.rank_a), ptr(pk.rank_o), ptr(pk.block_off),
-                                ptr(pk.counts), st), "con_prep_labels")
+    check(L.ucd_con_prep_labels(ptr(labels), ptr(l_po), B, pk.c_old, h, w, H, W, pk.max_label, ptr(pk.px_meta),
+                                ptr(pk.blk_meta), ptr(pk.counts), st), "con_prep_labels")
     pk.anchor_f32 = torch.empty(n_px, FEAT_DIM, device=dev, dtype=torch.float32)
     pk.contrast_f32 = torch.empty(2 * n_px, FEAT_DIM, device=dev, dtype=torch.float32)
     pk.la = torch.empty(n_px, **i32)
@@ -284,13 +288,16 @@ def _build_pack(f_n, f_o, l_po, labels, max_label):
     pk.feat_tiles = torch.empty(pk.max_tiles, FEAT_DIM // 8, TILE, 8, device=dev, dtype=torch.bfloat16)
     pk.prob_tiles = torch.empty(pk.max_tiles, pk.kpad // 8, TILE, 8, device=dev, dtype=torch.bfloat16)
     pk.lab_tiles = torch.empty(pk.max_tiles, TILE, **i32)
-    pk.row_pix = torch.empty(n_px, **i32)
+    pk.tile_range = torch.empty(pk.max_tiles, 2, **i32)
+    pk.row_range = torch.empty((n_px + TILE - 1) // TILE, 2, **i32)
+    pk.row_ref = torch.empty(n_px, **i32)
     pk.inv_norm = torch.empty(n_px, device=dev, dtype=torch.float32)
-    check(L.ucd_con_prep_pack(ptr(f_n), ptr(f_o), ptr(l_po), ptr(pk.mix), ptr(pk.flags), ptr(pk.rank_a),
-                              ptr(pk.rank_o), ptr(pk.block_off), ptr(pk.counts), B, pk.c_old, h, w,
-                              ptr(pk.anchor_f32), ptr(pk.contrast_f32), ptr(pk.la), ptr(pk.lc), ptr(pk.feat_tiles),
-                              ptr(pk.prob_tiles), ptr(pk.lab_tiles), ptr(pk.row_pix), ptr(pk.inv_norm), pk.max_tiles,
-                              st), "con_prep_pack")
+    check(L.ucd_con_prep_pack(ptr(f_n), ptr(f_o), ptr(l_po), ptr(pk.px_meta), ptr(pk.blk_meta), ptr(pk.counts), B,
+                              pk.c_old, h, w, pk.max_label, ptr(pk.anchor_f32), ptr(pk.contrast_f32), ptr(pk.la),
+                              ptr(pk.lc), ptr(pk.feat_tiles), ptr(pk.prob_tiles), ptr(pk.lab_tiles),
+                              ptr(pk.tile_range), ptr(pk.row_range), ptr(pk.row_ref), ptr(pk.inv_norm),
+                              pk.max_tiles, st),
+          "con_prep_pack")
     pk.l_po = l_po
     # the one host sync of the tuple API: the 5-tuple's tensor shapes depend on N_a / N_o
     pk.n_a, pk.n_o, pk.min_new, _ = (int(v) for v in pk.counts.tolist())
@@ -316,8 +323,8 @@ class _AnchorFn(torch.autograd.Function):
         B, h, w = pk.shape
         g = _f32c(g)
         df = torch.empty(B, FEAT_DIM, h, w, device=g.device, dtype=torch.float32)
-        check(_lib.lib().ucd_con_prep_bwd(ptr(g), ptr(pk.anchor_f32), ptr(pk.inv_norm), ptr(pk.flags), ptr(pk.rank_a),
-                                          ptr(pk.block_off), ptr(df), B, h, w, cur_stream()), "con_prep_bwd")
+        check(_lib.lib().ucd_con_prep_bwd(ptr(g), ptr(pk.anchor_f32), ptr(pk.inv_norm), ptr(pk.px_meta),
+                                          ptr(pk.blk_meta), ptr(df), B, h, w, cur_stream()), "con_prep_bwd")
         return df.to(ctx.in_dtype), None
 
 
@@ -389,13 +396,13 @@ def _all_gather(t, group):
     return out.view((world,) + tuple(t.shape))
 
 
-def gather_contrast_columns(feat_tiles, prob_tiles, lab_tiles, counts, group):
+def gather_contrast_columns(feat_tiles, prob_tiles, lab_tiles, tile_range, counts, group):
     """The one exchange step of the data-parallel path: every rank contributes its packed
     contrast columns; rank r's tiles become chunk r of the gathered buffers.
 
-    feat_tiles [T,32,128,8] bf16, prob_tiles [T,Kp/8,128,8] bf16, lab_tiles [T,128] int32 and
-    counts int32[>=3] = {N_a, N_o, min_new} of this rank (T must be equal on all ranks).
-    Returns dict(feat, prob, lab, counts [W,2], min_new [1] (global MIN), n_chunks, chunk_tiles, self_tile0).
+    feat_tiles [T,32,128,8] bf16, prob_tiles [T,Kp/8,128,8] bf16, lab_tiles [T,128] int32, tile_range [T,2]
+    int32 and counts int32[>=3] = {N_a, N_o, min_new} of this rank (T must be equal on all ranks).
+    Returns dict(feat, prob, lab, range, counts [W,2], min_new [1] (global MIN), n_chunks, chunk_tiles, self_tile0).
     No gradient flows through the gathered columns (they are detached in the reference, loss.py:366,395),
     so backward needs no collective.
     """
@@ -404,7 +411,8 @@ def gather_contrast_columns(feat_tiles, prob_tiles, lab_tiles, counts, group):
     min_new = counts[2:3].clone()
     dist.all_reduce(min_new, op=dist.ReduceOp.MIN, group=group)
     return dict(feat=_all_gather(feat_tiles, group), prob=_all_gather(prob_tiles, group),
-                lab=_all_gather(lab_tiles, group), counts=_all_gather(counts[:2], group), min_new=min_new,
+                lab=_all_gather(lab_tiles, group), range=_all_gather(tile_range, group),
+                counts=_all_gather(counts[:2], group), min_new=min_new,
                 n_chunks=world, chunk_tiles=feat_tiles.shape[0], self_tile0=rank * feat_tiles.shape[0])
 
 
@@ -423,7 +431,8 @@ class _ConFn(torch.autograd.Function):
                      if need_grad else None)
         check(L.ucd_con_fwd(ptr(cols["feat"]), ptr(cols["prob"]), ptr(cols["lab"]), ptr(cols["counts"]),
                             cols["n_chunks"], cols["chunk_tiles"], ptr(rows["feat"]), ptr(rows["prob"]),
-                            ptr(rows["lab"]), ptr(rows["n_rows"]), rows["self_tile0"], ptr(cols["min_new"]), p_mode,
+                            ptr(rows["lab"]), ptr(rows["n_rows"]), ptr(cols["range"]), ptr(rows["range"]),
+                            rows["self_tile0"], ptr(cols["min_new"]), p_mode,
                             cols["kpad"], ptr(dense_p), 0 if dense_p is None else dense_p.shape[1], inv_tau,
                             1 if need_grad else 0, ptr(out), ptr(grad_unit), ptr(ws), ws_bytes, max_row_tiles,
                             cur_stream()), "con_fwd")
@@ -432,19 +441,19 @@ class _ConFn(torch.autograd.Function):
             import torch.distributed as dist
             dist.all_reduce(out, group=group)      # {sum of row losses, #valid rows} over all ranks
             world = dist.get_world_size(group)
-        ctx.save_for_backward(grad_unit, out, rows["n_rows"])
+        ctx.save_for_backward(grad_unit, out, rows["n_rows"], rows.get("row_ref"))
         ctx.n_a = anchor.shape[0]
         ctx.world = world if ddp_scale else 1
         return out[0] / out[1]
 
     @staticmethod
     def backward(ctx, g):
-        grad_unit, out, n_rows = ctx.saved_tensors
+        grad_unit, out, n_rows, row_ref = ctx.saved_tensors
         d_anchor = torch.empty(ctx.n_a, FEAT_DIM, device=g.device, dtype=torch.float32)
         # With DDP averaging parameter gradients over ranks, the exact gradient of the global-batch loss needs
         # each rank's local contribution scaled by world (columns carry no gradient, loss.py:366,395).
         check(_lib.lib().ucd_con_bwd(ptr(grad_unit), ptr(out), ptr(_f32c(g.reshape(1))), float(ctx.world),
-                                     ptr(n_rows), ptr(d_anchor), ctx.n_a, cur_stream()), "con_bwd")
+                                     ptr(n_rows), ptr(row_ref), ptr(d_anchor), ctx.n_a, cur_stream()), "con_bwd")
         return d_anchor, None, None, None, None, None, None, None
 
 
@@ -496,13 +505,15 @@ class PixelConLossV2(nn.Module):
             group = self._group()
             counts2 = pack.counts[:2]
             rows = dict(feat=pack.feat_tiles, prob=pack.prob_tiles, lab=pack.lab_tiles, n_rows=pack.counts[0:1],
-                        max_tiles=(pack.n_a + TILE - 1) // TILE, self_tile0=0)
+                        range=pack.row_range, row_ref=pack.row_ref, max_tiles=(pack.n_a + TILE - 1) // TILE,
+                        self_tile0=0)
             if group is None:
-                cols = dict(feat=pack.feat_tiles, prob=pack.prob_tiles, lab=pack.lab_tiles,
+                cols = dict(feat=pack.feat_tiles, prob=pack.prob_tiles, lab=pack.lab_tiles, range=pack.tile_range,
                             counts=counts2.contiguous(), n_chunks=1, chunk_tiles=pack.max_tiles, kpad=pack.kpad,
                             min_new=pack.counts[2:3])
             else:
-                cols = gather_contrast_columns(pack.feat_tiles, pack.prob_tiles, pack.lab_tiles, pack.counts, group)
+                cols = gather_contrast_columns(pack.feat_tiles, pack.prob_tiles, pack.lab_tiles, pack.tile_range,
+                                               pack.counts, group)
                 cols["kpad"] = pack.kpad
                 rows["self_tile0"] = cols["self_tile0"]
             if pack.n_a == 0:
@@ -529,6 +540,10 @@ class PixelConLossV2(nn.Module):
         st = cur_stream()
         check(L.ucd_con_pack_rows(ptr(a32), ptr(la), n_a, ptr(rfeat), ptr(rlab), rt, st), "con_pack_rows")
         check(L.ucd_con_pack_rows(ptr(c32), ptr(lc), n_c, ptr(cfeat), ptr(clab), ct, st), "con_pack_rows")
+        rrange = torch.empty(rt, 2, device=dev, dtype=torch.int32)
+        crange = torch.empty(ct, 2, device=dev, dtype=torch.int32)
+        check(L.ucd_con_tile_ranges(ptr(rlab), rt, None, ptr(rrange), st), "con_tile_ranges")
+        check(L.ucd_con_tile_ranges(ptr(clab), ct, None, ptr(crange), st), "con_tile_ranges")
         counts = torch.tensor([[n_c, 0]], device=dev, dtype=torch.int32)
         n_rows = torch.tensor([n_a], device=dev, dtype=torch.int32)
         dense_p, p_mode = None, 0
@@ -536,6 +551,7 @@ class PixelConLossV2(nn.Module):
             if tuple(P.shape) != (n_a, n_c):
                 raise ValueError("PixelConLossV2: P must be [N_a, N_c]")
             dense_p, p_mode = _f32c(P.detach()), 2
-        cols = dict(feat=cfeat, prob=None, lab=clab, counts=counts, n_chunks=1, chunk_tiles=ct, kpad=16, min_new=None)
-        rows = dict(feat=rfeat, prob=None, lab=rlab, n_rows=n_rows, max_tiles=rt, self_tile0=0)
+        cols = dict(feat=cfeat, prob=None, lab=clab, range=crange, counts=counts, n_chunks=1, chunk_tiles=ct, kpad=16,
+                    min_new=None)
+        rows = dict(feat=rfeat, prob=None, lab=rlab, range=rrange, n_rows=n_rows, max_tiles=rt, self_tile0=0)
         return _ConFn.apply(anchor_features, cols, rows, inv_tau, p_mode, dense_p, None, False)
