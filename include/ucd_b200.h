@@ -169,6 +169,8 @@ int ucd_con_debug_splits(int64_t max_row_tiles, int64_t max_col_tiles);
  * with the production tile layout, and D[128,256] = E[128,128] * Bt (MN-major B). Returns max abs
  * error through *max_err_host (synchronises). */
 int ucd_selftest_umma(int variant, float* max_err_host);
+/* tcgen05.mma issue-rate probe (cycles per instruction for a chain of `iters` MMAs; modes in selftest.cu) */
+int ucd_selftest_mma_rate(int mode, int iters, float* cycles_per_instr_host);
 
 #ifdef __cplusplus
 }

@@ -43,6 +43,7 @@ _PROTOS = {
     "ucd_con_debug_trace": (c_int, [P]),
     "ucd_con_debug_splits": (c_int, [c_int64, c_int64]),
     "ucd_selftest_umma": (c_int, [c_int, ctypes.POINTER(c_float)]),
+    "ucd_selftest_mma_rate": (c_int, [c_int, c_int, ctypes.POINTER(c_float)]),
 }
 EXPORTED = tuple(_PROTOS)
 

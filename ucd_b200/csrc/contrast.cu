@@ -27,7 +27,7 @@
 namespace ucd {
 
 constexpr int kEpiWarps = 8;                       // 2 per SM sub-partition: one hides the other's stalls
-constexpr int kConThreads = 64 + 32 * kEpiWarps;   // producer warp + MMA warp + epilogue warps
+constexpr int kConThreads = 96 + 32 * kEpiWarps;   // producer warp + two MMA-issuing warps + epilogue warps
 constexpr uint32_t kTileBytes = 65536;  // 128 rows x 256 bf16
 constexpr uint32_t kChunkB = 2048;      // one 8-element k-chunk for 128 rows
 constexpr uint32_t kESub = 16384;       // 128 rows x 64 columns bf16
@@ -44,7 +44,9 @@ constexpr uint32_t kConSmem = OFF_BAR + 256;
 constexpr int kMaxChunks = 16;        // ranks whose columns are gathered (one 8-GPU box: 8)
 constexpr int kMaxTilesPerCta = 8192;  // column tiles one CTA walks (bit mask in shared memory)
 
-enum { BAR_A = 0, BAR_CF = 1, BAR_CE = 3, BAR_SF = 5, BAR_SE = 7, BAR_EF = 9, BAR_EE = 11, BAR_PF = 13, BAR_PE = 14, BAR_V = 15 };
+// A: row tile loaded | CF/CE: column stage full/empty | SF: S accumulator ready | SE: S buffer free (no-grad runs)
+// EF[2*buf+half]: E/Ucoef half written to TMEM | PF/PE: probability stage full/empty | V: all MMAs retired
+enum { BAR_A = 0, BAR_CF = 1, BAR_CE = 3, BAR_SF = 5, BAR_SE = 7, BAR_EF = 9, BAR_PF = 13, BAR_PE = 14, BAR_V = 15 };
 
 struct ConArgs {
   const __nv_bfloat16* feat_tiles;
@@ -201,7 +203,6 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
   __shared__ uint32_t s_tmem;
   __shared__ uint32_t s_mask[kMaxTilesPerCta / 32];  // bit tt: column tile k0+tt can hold an equal-label pair (or self)
 
-  constexpr int NE = (PHASE == 1) ? 2 : 1;  // E sub-tile buffers
   constexpr int NS = (PHASE == 1) ? 2 : 1;  // S accumulator buffers in TMEM
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rb = blockIdx.x / a.splits, split = blockIdx.x - rb * a.splits;
@@ -226,9 +227,9 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
       mbar_init(BAR(BAR_CF + i), 1);
       mbar_init(BAR(BAR_CE + i), 1 + kEpiWarps);  // tcgen05.commit + the epilogue warps (they read the stage's labels)
       mbar_init(BAR(BAR_SF + i), 1);
-      mbar_init(BAR(BAR_SE + i), kEpiWarps);
-      mbar_init(BAR(BAR_EF + i), 4);
-      mbar_init(BAR(BAR_EE + i), 1);
+      mbar_init(BAR(BAR_SE + i), a.need_grad ? 1 : kEpiWarps);  // S buffer free: V MMAs retired / epilogue done
+      mbar_init(BAR(BAR_EF + 2 * i), 4);
+      mbar_init(BAR(BAR_EF + 2 * i + 1), 4);
     }
     mbar_init(BAR(BAR_PF), 1);
     mbar_init(BAR(BAR_PE), 1);
@@ -310,23 +311,22 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
+    // ===================== S issuer: S = A C^T (and P = pA pC^T in sweep 2), one thread =====================
+    // A single thread sustains one tcgen05.mma per ~110-120 clk (measured, scripts/mma_rate.py), more than the
+    // 64 clk an N=128 K step occupies the tensor pipe; S and V/U are therefore issued by two different warps.
     if (lane == 0 && n > 0) {
-      constexpr uint32_t idesc_s = umma_idesc(128, 128, 0, 0);   // S / P : A K-major, B K-major
-      constexpr uint32_t idesc_v = umma_idesc(128, 256, 0, 1);   // V / U : A K-major, B MN-major
-      const uint32_t tS = tmem;             // S buffers at columns [0,128) and [128,256)
-      const uint32_t tP = tmem + 128;       // sweep 2: P at [128,256)
-      const uint32_t tV = tmem + 256;       // V / U accumulator at [256,512)
+      constexpr uint32_t idesc_s = umma_idesc(128, 128, 0, 0);   // A K-major, B K-major
+      const uint32_t tS = tmem, tP = tmem + 128;
       mbar_wait(BAR(BAR_A), 0);
-      auto ready_s = [&](int t) -> bool {
+      long long c_idle = 0;
+      const long long c_start = clock64();
+      int t = 0;
+      for (int tt = 0; tt < n; ++tt) {
+        if (!tile_active(tt)) continue;
         const int stage = t & 1, sb = t % NS;
-        if (!mbar_test_wait(BAR(BAR_CF + stage), (t >> 1) & 1)) return false;
-        if (!mbar_test_wait(BAR(BAR_SE + sb), ((t / NS) & 1) ^ 1)) return false;
-        if (PHASE == 2 && PMODE == 1 && !mbar_test_wait(BAR(BAR_PF), t & 1)) return false;
-        return true;
-      };
-      auto issue_s = [&](int t) {  // S (and P) for the t-th active tile; operands are in stage t&1
-        const int stage = t & 1, sb = t % NS;
+        mbar_wait_t(BAR(BAR_CF + stage), (t >> 1) & 1, c_idle);
+        mbar_wait_t(BAR(BAR_SE + sb), ((t / NS) & 1) ^ 1, c_idle);
+        if (PHASE == 2 && PMODE == 1) mbar_wait_t(BAR(BAR_PF), t & 1, c_idle);
         tc_fence_after();
         const uint32_t sc = sbase + OFF_C + stage * kTileBytes;
 #pragma unroll
@@ -340,64 +340,51 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
           umma_commit(BAR(BAR_PE));
         }
         umma_commit(BAR(BAR_SF + sb));
-      };
-      auto ready_v = [&](int q) -> bool { return mbar_test_wait(BAR(BAR_EF + q % NE), (q / NE) & 1); };
-      auto issue_v = [&](int q) {  // V/U += E sub-tile q (tile q/2, column half q&1) x C
-        const int t = q >> 1, h = q & 1, buf = q % NE;
-        const uint32_t sc = sbase + OFF_C + (t & 1) * kTileBytes;
-        tc_fence_after();
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-          umma_bf16(tV, umma_desc(sbase + OFF_E + buf * kESub + kk * 2 * kChunkB, kChunkB, 128),
-                    umma_desc(sc + (uint32_t)(h * 64 + kk * 16) * 16u, 128, kChunkB), idesc_v,
-                    (q > 0 || kk > 0) ? 1u : 0u);
-        umma_commit(BAR(BAR_EE + buf));
-        if (h == 1) umma_commit(BAR(BAR_CE + (t & 1)));  // both MMAs of tile t are done with its C stage
-      };
-      // number of active tiles of this CTA (sweep 1: all; sweep 2: those that can hold an equal-label pair)
-      int n_act = n;
-      if (PHASE == 2) {
-        n_act = 0;
-        for (int tt = 0; tt < n; ++tt)
-          n_act += tile_active(tt) ? 1 : 0;
+        if (!a.need_grad) umma_commit(BAR(BAR_CE + stage));  // no V/U pass: the stage is free once S is done
+        ++t;
       }
-      // Issue whatever is ready, preferring the V/U accumulation (it releases the C stage for the next load);
-      // a fixed S(t+1)-then-V(t) order would expose the full load latency of every tile.
-      const int n_v = a.need_grad ? 2 * n_act : 0;
-      int s_next = 0, v_next = 0;
-      const unsigned long long t0 = globaltimer_ns();
-      uint32_t spins = 0;
+      if (!a.need_grad) umma_commit(BAR(BAR_V));
+      if (a.trace) {
+        long long* tr = a.trace + (size_t)blockIdx.x * 16;
+        tr[4] = clock64() - c_start, tr[5] = c_idle, tr[6] = t;
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== V/U issuer: acc += E x C with E (bf16) read from tensor memory, one thread ============
+    if (lane == 0 && n > 0 && a.need_grad) {
+      constexpr uint32_t idesc_v = umma_idesc(128, 256, 0, 1);   // A from TMEM, B MN-major
+      const uint32_t tS = tmem, tV = tmem + 256;
+      long long c_idle = 0;
       const long long c_start = clock64();
-      long long c_idle = 0, c_mark = c_start;
-      bool idle = false;
-      while (s_next < n_act || v_next < n_v) {
-        if (v_next < n_v && (v_next >> 1) < s_next && ready_v(v_next)) {
-          if (idle) c_idle += clock64() - c_mark, idle = false;
-          issue_v(v_next++);
-        } else if (s_next < n_act && ready_s(s_next)) {
-          if (idle) c_idle += clock64() - c_mark, idle = false;
-          issue_s(s_next);
-          if (!a.need_grad) umma_commit(BAR(BAR_CE + (s_next & 1)));
-          ++s_next;
-        } else if (!idle) {
-          idle = true;
-          c_mark = clock64();
-        } else if ((++spins & 0xfffff) == 0 && globaltimer_ns() - t0 > 8000000000ull) {
-          printf("ucd_b200: MMA issue loop timed out (block %d s=%d/%d v=%d/%d)\n", blockIdx.x, s_next, n_act, v_next, n_v);
-          __trap();
+      int t = 0;
+      for (int tt = 0; tt < n; ++tt) {
+        if (!tile_active(tt)) continue;
+        const int stage = t & 1, sb = t % NS;
+        const uint32_t sc = sbase + OFF_C + stage * kTileBytes;
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait_t(BAR(BAR_EF + 2 * sb + h), (t / NS) & 1, c_idle);
+          tc_fence_after();
+          const uint32_t te = tS + sb * 128 + h * 64;  // 32 columns of packed bf16 pairs = 64 K values
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_bf16_ts(tV, te + kk * 8, umma_desc(sc + (uint32_t)(h * 64 + kk * 16) * 16u, 128, kChunkB), idesc_v,
+                         (t > 0 || h > 0 || kk > 0) ? 1u : 0u);
         }
+        umma_commit(BAR(BAR_CE + stage));  // tile t no longer needs its C stage ...
+        umma_commit(BAR(BAR_SE + sb));     // ... nor its S buffer (E lived there)
+        ++t;
       }
       umma_commit(BAR(BAR_V));
       if (a.trace) {
         long long* tr = a.trace + (size_t)blockIdx.x * 16;
-        tr[4] = clock64() - c_start, tr[5] = c_idle, tr[6] = n_act;
+        tr[12] = clock64() - c_start, tr[13] = c_idle, tr[14] = t;
       }
     }
   } else {
     // ===================== epilogue: one thread per row =====================
-    // warps 2-5 own columns [0,64) of every tile (E sub-tile 0), warps 6-9 columns [64,128) (sub-tile 1);
+    // warps 3-6 own columns [0,64) of every tile (E half 0), warps 7-10 columns [64,128) (half 1);
     // within a half, warp w reads TMEM lanes 32*(w%4).. (hardware restriction) = rows of the block.
-    const int half = (warp - 2) >> 2;
+    const int half = (warp - 3) >> 2;
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;  // row within the block == TMEM lane
     const long long grow = (long long)rb * 128 + r;
@@ -418,7 +405,7 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
       }
     }
     int t = 0;  // number of active tiles processed so far (drives stage / parity bookkeeping)
-    long long w_sf = 0, w_ee = 0;
+    long long w_sf = 0, w_ee = 0;  // w_ee: unused since E moved to tensor memory
     const long long c_start = clock64();
     for (int tt = 0; tt < n; ++tt) {
       if (!tile_active(tt)) continue;
@@ -432,18 +419,16 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
       mbar_wait_t(BAR(BAR_SF + sb), (t / NS) & 1, w_sf);
       tc_fence_after();
       // E / Ucoef sub-tile hand-off to the MMA warp: 32 packed bf16 of this row go to k-chunks (cc&1)*4..+3
+      // E / Ucoef hand-off to the MMA warp: the 32 bf16 of this chunk overwrite the first columns of the thread's
+      // own (already consumed) S range in tensor memory; the V/U MMA reads its A operand from there.
       auto emit = [&](int cc, const uint32_t (&pk)[16]) {  // cc = chunk 0/1 within this thread's column half
         if (!a.need_grad) return;
-        const int q = 2 * t + half, buf = q % NE;
-        if (cc == 0) mbar_wait_t(BAR(BAR_EE + buf), ((q / NE) & 1) ^ 1, w_ee);
-        uint8_t* eb = smem + OFF_E + buf * kESub + (uint32_t)(cc * 4) * kChunkB + (uint32_t)r * 16u;
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          *reinterpret_cast<uint4*>(eb + k * kChunkB) = make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
+        tmem_st16(tmem + lane_addr + sb * 128 + half * 64 + cc * 16, pk);
         if (cc == 1) {
-          fence_proxy_async();
+          tmem_st_wait();
+          tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(BAR(BAR_EF + buf));
+          if (lane == 0) mbar_arrive(BAR(BAR_EF + 2 * sb + half));
         }
       };
       const int c0 = half * 64;  // first column of this thread's half
@@ -486,12 +471,12 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(BAR(BAR_SE + sb));
+        if (!a.need_grad) mbar_arrive(BAR(BAR_SE + sb));
         mbar_arrive(BAR(BAR_CE + stage));
       }
       ++t;
     }
-    if (a.trace && warp == 2 && lane == 0) {  // one representative epilogue thread
+    if (a.trace && warp == 3 && lane == 0) {  // one representative epilogue thread
       long long* tr = a.trace + (size_t)blockIdx.x * 16;
       tr[8] = clock64() - c_start, tr[9] = w_sf, tr[10] = w_ee, tr[11] = t;
     }

@@ -106,6 +106,96 @@ selftest_kernel(int variant, const __nv_bfloat16* __restrict__ a_tile, const __n
   }
 }
 
+// MMA issue-rate probe: `iters` back-to-back tcgen05.mma of one shape onto one accumulator (K-step chain, like
+// the sweeps), timed with clock64 from the first issue to the commit's arrival.
+//   mode: 0 SS N=64 | 1 SS N=128 | 2 SS N=256 (B MN-major) | 3 TS N=64 | 4 TS N=128 | 5 TS N=256 (B MN-major)
+//         6 SS N=256 K-major B | 7 TS N=128 alternating two accumulators | 8 SS N=128 alternating two accumulators
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int mode, int iters, long long* __restrict__ cycles) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint32_t s_tmem;
+  const int warp = threadIdx.x >> 5;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar = sbase + ST_OFF_BAR;
+  for (int i = threadIdx.x; i < (int)(ST_OFF_E / 4); i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    mbar_init(bar + 8, 1);
+    fence_mbar_init();
+  }
+  fence_proxy_async();
+  if (warp == 0) tmem_alloc(smem_u32(&s_tmem), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+  if (threadIdx.x == 0 && mode <= 8) {
+    const bool ts = (mode >= 3 && mode <= 5) || mode == 7;
+    const int N = (mode == 0 || mode == 3) ? 64 : ((mode == 1 || mode == 4 || mode == 7 || mode == 8) ? 128 : 256);
+    const bool mn = (mode == 2 || mode == 5);
+    const uint32_t idesc = umma_idesc(128, N, 0, mn ? 1 : 0);
+    const long long c0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+      const int ks = i & 15;
+      const uint64_t bdesc = mn ? umma_desc(sbase + ST_OFF_C + (ks & 7) * 256, 128, 2048)
+                                : umma_desc(sbase + ST_OFF_C + ks * 4096, 2048, 128);
+      const uint32_t d = tmem + 256 + (((mode == 7 || mode == 8) && (i & 1)) ? 128 : 0);
+      if (ts)
+        umma_bf16_ts(d, tmem + ks * 8, bdesc, idesc, 1u);
+      else
+        umma_bf16(d, umma_desc(sbase + ST_OFF_A + ks * 4096, 2048, 128), bdesc, idesc, 1u);
+    }
+    umma_commit(bar);
+    mbar_wait(bar, 0);
+    cycles[0] = clock64() - c0;
+  }
+  // modes 12..13: ONE warp, warp-uniform loop, MMA issued by the elected lane: 12 SS N=128 | 13 TS N=128
+  if ((mode == 12 || mode == 13) && warp == 0) {
+    const uint32_t idesc = umma_idesc(128, 128, 0, 0);
+    const long long c0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+      const int ks = i & 15;
+      const uint64_t bdesc = umma_desc(sbase + ST_OFF_C + ks * 4096, 2048, 128);
+      const uint64_t adesc = umma_desc(sbase + ST_OFF_A + ks * 4096, 2048, 128);
+      if (elect_one()) {
+        if (mode == 13)
+          umma_bf16_ts(tmem + 256, tmem + ks * 8, bdesc, idesc, 1u);
+        else
+          umma_bf16(tmem + 256, adesc, bdesc, idesc, 1u);
+      }
+      __syncwarp();
+    }
+    if (elect_one()) umma_commit(bar);
+    __syncwarp();
+    mbar_wait(bar, 0);
+    if (threadIdx.x == 0) cycles[0] = clock64() - c0;
+  }
+  // modes 9..11: TWO issuing threads (warps 0 and 1), each its own accumulator: 9 SS N=128 | 10 TS N=128 | 11 SS N=64
+  if (mode >= 9 && mode <= 11 && (threadIdx.x == 0 || threadIdx.x == 32)) {
+    const bool ts = mode == 10;
+    const int N = mode == 11 ? 64 : 128;
+    const uint32_t idesc = umma_idesc(128, N, 0, 0);
+    const uint32_t d = tmem + 256 + (threadIdx.x == 32 ? 128 : 0);
+    const uint32_t mybar = bar + (threadIdx.x == 32 ? 8 : 0);
+    const long long c0 = clock64();
+    for (int i = 0; i < iters / 2; ++i) {
+      const int ks = i & 15;
+      const uint64_t bdesc = umma_desc(sbase + ST_OFF_C + ks * 4096, 2048, 128);
+      if (ts)
+        umma_bf16_ts(d, tmem + ks * 8, bdesc, idesc, 1u);
+      else
+        umma_bf16(d, umma_desc(sbase + ST_OFF_A + ks * 4096, 2048, 128), bdesc, idesc, 1u);
+    }
+    umma_commit(mybar);
+    mbar_wait(mybar, 0);
+    if (threadIdx.x == 0) cycles[0] = clock64() - c0;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
 static float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
 }  // namespace ucd
@@ -169,5 +259,26 @@ extern "C" int ucd_selftest_umma(int variant, float* max_err_host) {
   float mx = 0.f;
   for (size_t i = 0; i < ref.size(); ++i) mx = fmaxf(mx, fabsf(ref[i] - got[i]));
   *max_err_host = mx;
+  return UCD_OK;
+}
+
+extern "C" int ucd_selftest_mma_rate(int mode, int iters, float* cycles_per_instr_host) {
+  UCD_CHECK_ARG(mode >= 0 && mode <= 13 && iters > 0 && cycles_per_instr_host, "ucd_selftest_mma_rate: bad argument");
+  long long* d = nullptr;
+  cudaError_t e;
+  if ((e = cudaMalloc(&d, 8)) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+  if ((e = cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM)) != cudaSuccess)
+    return cuda_fail(e, "cudaFuncSetAttribute(mma_rate_kernel)");
+  long long h = 0;
+  for (int rep = 0; rep < 2; ++rep) {  // second run is warm
+    mma_rate_kernel<<<1, 128, ST_SMEM>>>(mode, iters, d);
+    if ((e = cudaDeviceSynchronize()) != cudaSuccess) {
+      cudaFree(d);
+      return cuda_fail(e, "mma_rate_kernel");
+    }
+  }
+  cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  *cycles_per_instr_host = (float)h / (float)iters;
   return UCD_OK;
 }

@@ -108,6 +108,13 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// one lane of a converged warp (warp-uniform control flow around it keeps MMA operands in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred P1;\nelect.sync _|P1, 0xffffffff;\nselp.b32 %0, 1, 0, P1;\n}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- UMMA descriptors ---------------------------------------------------------------------
 // Shared-memory matrix descriptor, SWIZZLE_NONE ("interleaved" canonical layout built from 8x16 B core
 // matrices).  K-major:  LBO = byte distance between the two 8-element K halves of one K=16 step,
