@@ -61,49 +61,67 @@ def make_inputs(rank, B, wl):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region (NVML every 5 ms in a thread; the
+    nvidia-smi query of the profiling recipe is the fallback)."""
+    REASONS = (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40))
 
     def __init__(self, gpu_index):
-        self.idx, self.proc, self.rows = gpu_index, None, []
-
-    def start(self):
+        self.idx, self.rows, self.stop_flag, self.thr, self.max_mhz = gpu_index, [], False, None, None
+        self.nvml = None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thr = threading.Thread(target=self._read, daemon=True)
-            self.thr.start()
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[gpu_index]) if visible and visible.split(",")[gpu_index].isdigit() else gpu_index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
         except Exception:
-            self.proc = None
+            self.nvml = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self):
-        if self.proc is None:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
+    def _loop(self):
+        nv = self.nvml
+        while not self.stop_flag:
             try:
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.rows.append((mhz, rs))
             except Exception:
                 pass
-        sm.sort()
-        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=(max(mx) if mx else None),
-                    reasons=sorted(reasons), samples=len(sm))
+            time.sleep(0.005)
+
+    def start(self):
+        if self.nvml is not None:
+            self.thr = threading.Thread(target=self._loop, daemon=True)
+            self.thr.start()
+
+    def stop(self):
+        if self.nvml is None:
+            return self._smi_once()
+        self.stop_flag = True
+        self.thr.join(timeout=1)
+        sm = sorted(r[0] for r in self.rows)
+        bits = 0
+        for _, rs in self.rows:
+            bits |= rs
+        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=self.max_mhz,
+                    reasons=[n for n, b in self.REASONS if bits & b], samples=len(sm), source="nvml, 5 ms period")
+
+    def _smi_once(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            out = subprocess.run(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                 capture_output=True, text=True, timeout=10).stdout.strip().split(",")
+            names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+            return dict(sm_mhz=float(out[0]), sm_max_mhz=float(out[1]),
+                        reasons=[n for n, v in zip(names, out[2:6]) if v.strip().lower().startswith("active")],
+                        samples=1, source="nvidia-smi after the timed region (NVML unavailable)")
+        except Exception:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["clock query unavailable"], samples=0)
 
 
 class CallTimer:
@@ -205,7 +223,9 @@ def main():
     wl = dict(WORKLOAD, B=args.batch)
     B, H, W, C_old = wl["B"], wl["H"], wl["W"], wl["C_old"]
     host = make_inputs(rank, B, wl)
-    pinned = {k: v.pin_memory() for k, v in host.items()}
+    # the dataloader hands labels over as uint8 and the trainer casts them on the device (train.py:97-98,
+    # dataset/transform.py:350): the end-to-end leg copies uint8 labels and casts after the copy, like the reference
+    pinned = {k: (v.to(torch.uint8) if k == "labels" else v).pin_memory() for k, v in host.items()}
     devin = {k: v.to(dev) for k, v in host.items()}
     conloss = U.PixelConLossV2(temperature=0.07, gather_negatives=world > 1)
     unce = U.UnbiasedCrossEntropy(old_cl=C_old, ignore_index=255, reduction="none")
@@ -254,24 +274,52 @@ def main():
     launches = sum(KERNELS_PER_CALL.get(k, 1) * v for k, v in timer.counts.items())
 
     # ---- end-to-end through the public API with host buffers (e2e) ----
+    # Every step copies its inputs from pinned host memory and copies losses + both gradients back.  Like a
+    # DataLoader with pin_memory / non_blocking prefetch, the copies of step i+1 / i-1 run on a side stream while
+    # step i computes; all of them are inside the timed region.
     out_host = dict(losses=torch.empty(3).pin_memory(), g_fn=torch.empty_like(host["f_n"]).pin_memory(),
                     g_lr=torch.empty_like(host["logits_lr"]).pin_memory())
+    copy_stream = torch.cuda.Stream()
+    main = torch.cuda.current_stream()
+    slots = [dict() for _ in range(2)]
 
-    def e2e_step():
-        inp = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
-        step(inp)
-        out_host["losses"].copy_(torch.stack([state["con"], state["ce"], state["kd"]]), non_blocking=True)
-        out_host["g_fn"].copy_(state["g_fn"], non_blocking=True)
-        out_host["g_lr"].copy_(state["g_lr"], non_blocking=True)
+    def prefetch(slot):
+        with torch.cuda.stream(copy_stream):
+            for k, v in pinned.items():
+                slot[k] = v.to(dev, non_blocking=True)
+            slot["ready"] = torch.cuda.Event()
+            slot["ready"].record(copy_stream)
 
-    for _ in range(max(3, args.warmup // 2)):
-        e2e_step()
+    def e2e_run(n_steps):
+        prefetch(slots[0])
+        for i in range(n_steps):
+            cur = slots[i % 2]
+            main.wait_event(cur["ready"])
+            if i + 1 < n_steps:
+                prefetch(slots[(i + 1) % 2])
+            inp = {k: cur[k] for k in pinned}
+            inp["labels"] = inp["labels"].to(torch.long)          # train.py:98
+            for v in inp.values():
+                v.record_stream(main)
+            step(inp)
+            losses = torch.stack([state["con"], state["ce"], state["kd"]])
+            done = torch.cuda.Event()
+            done.record(main)
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(done)
+                out_host["losses"].copy_(losses, non_blocking=True)
+                out_host["g_fn"].copy_(state["g_fn"], non_blocking=True)
+                out_host["g_lr"].copy_(state["g_lr"], non_blocking=True)
+                for t_ in (losses, state["g_fn"], state["g_lr"]):
+                    t_.record_stream(copy_stream)
+        main.wait_stream(copy_stream)
+
+    e2e_run(max(3, args.warmup // 2))
     barrier()
     t0 = time.perf_counter()
     e2a, e2b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2a.record()
-    for _ in range(args.steps):
-        e2e_step()
+    e2e_run(args.steps)
     e2b.record()
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t0) / args.steps

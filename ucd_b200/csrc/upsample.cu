@@ -10,6 +10,8 @@
 // registers, then along x out of shared memory.  No atomics; summation order is fixed.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace ucd {
 
 constexpr int kUpThreads = 256;
@@ -221,9 +223,12 @@ extern "C" int ucd_upsample_bilinear_fwd(const float* in, float* out, int64_t pl
   const int wv = v4 ? W / 4 : W;
   const long long work = (long long)H * wv;
   const int gx = (int)((work + kUpThreads - 1) / kUpThreads);
-  // enough blocks in y to fill the machine a few times over, while amortising the tap computation
-  long long want_y = (4ll * kNumSMs + gx - 1) / gx;
+  // planes per block: enough to amortise the tap computation (>= 16 planes when there are that many), few enough
+  // that the grid is many waves deep (blocks finish at different times; a 2-3 wave grid left SMs idle)
+  long long want_y = (32ll * kNumSMs + gx - 1) / gx;
   if (want_y < 1) want_y = 1;
+  if (want_y > (planes + 15) / 16) want_y = (planes + 15) / 16;
+  if (const char* e = getenv("UCD_UP_GY")) want_y = atoi(e) > 0 ? atoi(e) : want_y;  // tuning knob
   if (want_y > planes) want_y = planes;
   const int ppb = (int)((planes + want_y - 1) / want_y);
   const int gy = (int)((planes + ppb - 1) / ppb);

@@ -252,6 +252,18 @@ class ContrastPack:
         return self.n_a + self.n_o
 
 
+_PINNED = {}
+
+
+def _pinned_counts(dev):
+    """Per-device pinned int32[4] staging buffer for the {N_a, N_o, min_new, n_px} read-back."""
+    key = (dev.type, dev.index)
+    buf = _PINNED.get(key)
+    if buf is None:
+        buf = _PINNED[key] = torch.empty(4, dtype=torch.int32).pin_memory()
+    return buf
+
+
 def _build_pack(f_n, f_o, l_po, labels, max_label):
     _need_cuda(f_n, f_o, l_po, labels)
     if f_n.dim() != 4 or f_n.shape[1] != FEAT_DIM or f_o.shape != f_n.shape:
@@ -281,6 +293,12 @@ def _build_pack(f_n, f_o, l_po, labels, max_label):
     st = cur_stream()
     check(L.ucd_con_prep_labels(ptr(labels), ptr(l_po), B, pk.c_old, h, w, H, W, pk.max_label, ptr(pk.px_meta),
                                 ptr(pk.blk_meta), ptr(pk.counts), st), "con_prep_labels")
+    # The tuple API needs N_a / N_o on the host (tensor shapes).  Start the 16-byte copy now and wait for it only
+    # after the pack kernels are queued, so the GPU has work while the host catches up.
+    counts_host = _pinned_counts(dev)
+    counts_host.copy_(pk.counts, non_blocking=True)
+    copied = torch.cuda.Event()
+    copied.record()
     pk.anchor_f32 = torch.empty(n_px, FEAT_DIM, device=dev, dtype=torch.float32)
     pk.contrast_f32 = torch.empty(2 * n_px, FEAT_DIM, device=dev, dtype=torch.float32)
     pk.la = torch.empty(n_px, **i32)
@@ -300,7 +318,8 @@ def _build_pack(f_n, f_o, l_po, labels, max_label):
           "con_prep_pack")
     pk.l_po = l_po
     # the one host sync of the tuple API: the 5-tuple's tensor shapes depend on N_a / N_o
-    pk.n_a, pk.n_o, pk.min_new, _ = (int(v) for v in pk.counts.tolist())
+    copied.synchronize()
+    pk.n_a, pk.n_o, pk.min_new, _ = (int(v) for v in counts_host.tolist())
     if pk.n_a > 0 and pk.min_new > max(int(max_label), 0):
         # no GT new-class pixel in the batch: the reference raises at utils/loss.py:355 (min() of empty)
         raise RuntimeError("pre_contrastive_pixel: no new-class pixel in the batch "
