@@ -238,6 +238,28 @@ def test_pixelconloss_compat_dense_inputs(U, n_a, n_c, with_p):
     assert cos(Ac.grad, Ar.grad) >= COS
 
 
+@pytest.mark.parametrize("c_tot,c_old,max_label", [(151, 101, 150), (40, 30, 39), (70, 60, 69)])
+def test_contrastive_wide_joint_probability(U, c_tot, c_old, max_label):
+    """ADE-like class counts (BASELINE config 3): joint-probability width > 16 (K-chunked P GEMM) and labels > 20.
+    The reference itself cannot run this (hard-coded VOC clamp + int8 cast), so the bar is the oracle
+    with ``max_label`` (the "patched oracle")."""
+    case = O.synthetic_case(2, 16, 16, 256, 256, c_tot, c_old, correlated=True)
+    f_ref = case["f_n"].double().requires_grad_(True)
+    A, Cst, la, lc, P, prep = O.pre_contrastive_pixel(f_ref, case["labels"], case["l_po"].double(), case["f_o"].double(),
+                                                       max_label=max_label)
+    ref = O.pixel_con_loss(A, Cst, la, lc, P)
+    ref.backward()
+    f_n = case["f_n"].cuda().requires_grad_(True)
+    tup = U.pre_contrastive_pixel(f_n, case["labels"].cuda(), l_po=case["l_po"].cuda(), f_o=case["f_o"].cuda(),
+                                  max_label=max_label)
+    assert np.array_equal(tup[2].cpu().numpy(), la.numpy()) and np.array_equal(tup[3].cpu().numpy(), lc.numpy())
+    assert tup[4].pack.min_new == prep.min_new
+    loss = U.PixelConLossV2(temperature=0.07)(*tup)
+    loss.backward()
+    assert loss.item() == pytest.approx(ref.item(), rel=REL)
+    assert cos(f_n.grad, f_ref.grad) >= COS
+
+
 @pytest.mark.parametrize("name", ["voc15-5_b2_513", "voc15-5s_b3_512"])
 def test_whole_hot_path_matches_reference(U, golden_dir, name):
     """train.py:115-116,133: UNCE(outputs,labels).mean() + con/100 + 10*UNKD(outputs, outputs_old)."""

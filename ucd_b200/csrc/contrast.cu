@@ -35,9 +35,9 @@ constexpr uint32_t kESub = 16384;       // 128 rows x 64 columns bf16
 // shared memory map (bytes)
 constexpr uint32_t OFF_A = 0;
 constexpr uint32_t OFF_C = 65536;     // 2 stages
-constexpr uint32_t OFF_E = 196608;    // sweep 1: 2 x 16 KB ; sweep 2: 1 x 16 KB
-constexpr uint32_t OFF_PA = 212992;   // sweep 2: row probabilities, <= 8 KB
-constexpr uint32_t OFF_PC = 221184;   // sweep 2: column probabilities, <= 8 KB, single stage
+constexpr uint32_t OFF_E = 196608;    // 32 KB: sweep 2 probability operands; reused at the end to combine the column halves
+constexpr uint32_t OFF_PA = OFF_E;    // sweep 2: row probabilities [kpad/8][128][8] bf16 (kpad*256 B <= 28 KB)
+constexpr uint32_t kProbBytes = 32768;  // OFF_PA .. OFF_LAB: the column probabilities use what pA leaves, in K chunks
 constexpr uint32_t OFF_LAB = 229376;  // 2 x 128 int32
 constexpr uint32_t OFF_BAR = 230400;
 constexpr uint32_t kConSmem = OFF_BAR + 256;
@@ -248,7 +248,12 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
   const int k1 = min(n_total, k0 + per);
   const int n = max(0, k1 - k0);
   const long long self_tile = a.self_tile0 >= 0 ? a.self_tile0 + rb : -1;  // the anchors' own column tile
-  const int pchunks = a.kpad >> 3;
+  // sweep 2 probability operands: pA (kpad*256 B) stays resident; pC of a tile comes in K chunks of pc_k values
+  // (all of it when it fits: kpad <= 64; 16 at a time for kpad = 112, i.e. ADE's 101 old classes)
+  const uint32_t pa_bytes = (uint32_t)a.kpad * 256u;
+  const int pc_k = min(a.kpad, (int)((kProbBytes - pa_bytes) / 256u) & ~15);
+  const int n_pc = (PHASE == 2 && PMODE == 1) ? (a.kpad + pc_k - 1) / pc_k : 0;
+  const uint32_t off_pc = OFF_PA + pa_bytes;
   // Sweep 2 only touches pairs with equal labels (w_ij = 0 otherwise): a column tile whose label range misses the
   // row block's range contributes nothing and is skipped by all three roles (class-sorted tiles make this common).
   // Label-overlap mask of this CTA's column tiles, evaluated once by all threads (the range lookups are L2
@@ -280,7 +285,7 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
       const uint8_t* pt = reinterpret_cast<const uint8_t*>(a.prob_tiles);
       const uint8_t* rft = reinterpret_cast<const uint8_t*>(a.row_feat);
       const uint8_t* rpt = reinterpret_cast<const uint8_t*>(a.row_prob);
-      const uint32_t pbytes = (uint32_t)a.kpad * 256u;
+      const uint32_t pbytes = pa_bytes;
       mbar_arrive_expect_tx(BAR(BAR_A), kTileBytes + ((PHASE == 2 && PMODE == 1) ? pbytes : 0u));
       for (int q = 0; q < 4; ++q)
         bulk_g2s(sbase + OFF_A + q * 16384u, rft + (size_t)rb * kTileBytes + q * 16384u, 16384u, BAR(BAR_A));
@@ -298,10 +303,12 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
         for (int q = 0; q < 4; ++q)
           bulk_g2s(dst + q * 16384u, ft + (size_t)loc.gtile * kTileBytes + q * 16384u, 16384u, BAR(BAR_CF + stage));
         bulk_g2s(sbase + OFF_LAB + stage * 512u, a.lab_tiles + loc.gtile * 128, 512u, BAR(BAR_CF + stage));
-        if (PHASE == 2 && PMODE == 1) {
-          mbar_wait_t(BAR(BAR_PE), (t & 1) ^ 1, w_pe);
-          mbar_arrive_expect_tx(BAR(BAR_PF), pbytes);
-          bulk_g2s(sbase + OFF_PC, pt + (size_t)loc.gtile * pbytes, pbytes, BAR(BAR_PF));
+        for (int c = 0; c < n_pc; ++c) {  // column probabilities, one K chunk at a time through a single buffer
+          const int u = t * n_pc + c;
+          const uint32_t kb = (uint32_t)min(pc_k, a.kpad - c * pc_k) * 256u;
+          mbar_wait_t(BAR(BAR_PE), (u & 1) ^ 1, w_pe);
+          mbar_arrive_expect_tx(BAR(BAR_PF), kb);
+          bulk_g2s(sbase + off_pc, pt + (size_t)loc.gtile * pbytes + (size_t)c * pc_k * 256u, kb, BAR(BAR_PF));
         }
         ++t;
       }
@@ -326,17 +333,20 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
         const int stage = t & 1, sb = t % NS;
         mbar_wait_t(BAR(BAR_CF + stage), (t >> 1) & 1, c_idle);
         mbar_wait_t(BAR(BAR_SE + sb), ((t / NS) & 1) ^ 1, c_idle);
-        if (PHASE == 2 && PMODE == 1) mbar_wait_t(BAR(BAR_PF), t & 1, c_idle);
         tc_fence_after();
         const uint32_t sc = sbase + OFF_C + stage * kTileBytes;
 #pragma unroll
         for (int ks = 0; ks < 16; ++ks)
           umma_bf16(tS + sb * 128, umma_desc(sbase + OFF_A + ks * 2 * kChunkB, kChunkB, 128),
                     umma_desc(sc + ks * 2 * kChunkB, kChunkB, 128), idesc_s, ks > 0);
-        if (PHASE == 2 && PMODE == 1) {
-          for (int ks = 0; ks < (pchunks >> 1); ++ks)
-            umma_bf16(tP, umma_desc(sbase + OFF_PA + ks * 2 * kChunkB, kChunkB, 128),
-                      umma_desc(sbase + OFF_PC + ks * 2 * kChunkB, kChunkB, 128), idesc_s, ks > 0);
+        for (int c = 0; c < n_pc; ++c) {  // P = pA pC^T accumulated over the K chunks of pC
+          const int u = t * n_pc + c;
+          mbar_wait_t(BAR(BAR_PF), u & 1, c_idle);
+          tc_fence_after();
+          const int ksteps = min(pc_k, a.kpad - c * pc_k) >> 4;
+          for (int ks = 0; ks < ksteps; ++ks)
+            umma_bf16(tP, umma_desc(sbase + OFF_PA + (uint32_t)(c * (pc_k >> 3) + ks * 2) * kChunkB, kChunkB, 128),
+                      umma_desc(sbase + off_pc + ks * 2 * kChunkB, kChunkB, 128), idesc_s, (c > 0 || ks > 0) ? 1u : 0u);
           umma_commit(BAR(BAR_PE));
         }
         umma_commit(BAR(BAR_SF + sb));
@@ -700,8 +710,8 @@ extern "C" int ucd_con_fwd(const void* feat_tiles, const void* prob_tiles, const
   UCD_CHECK_ARG(aligned16(feat_tiles) && aligned16(lab_tiles) && (!prob_tiles || aligned16(prob_tiles)),
                 "ucd_con_fwd: tile buffers must be 16 B aligned");
   UCD_CHECK_ARG(inv_temperature > 0.f, "ucd_con_fwd: bad temperature");
-  if (p_mode == 1 && (kpad < 16 || kpad > 32 || kpad % 16 != 0)) {
-    set_error("ucd_con_fwd: joint-probability width kpad=%d not supported yet (16 or 32, i.e. C_old <= 32)", kpad);
+  if (p_mode == 1 && (kpad < 16 || kpad > 112 || kpad % 16 != 0)) {
+    set_error("ucd_con_fwd: joint-probability width kpad=%d not supported (multiple of 16 up to 112, i.e. C_old <= 112)", kpad);
     return UCD_ENOSUP;
   }
   const ConPlan plan = make_plan(max_row_tiles, (int64_t)n_chunks * chunk_tiles);
