@@ -316,3 +316,95 @@ def test_full_size_properties(U):
     prep = O.prep_labels(case["labels"].numpy(), case["l_po"].numpy())
     gz = g1.permute(0, 2, 3, 1).reshape(-1, 256)[torch.from_numpy(~prep.anchor).cuda()]
     assert gz.numel() == 0 or float(gz.abs().max()) == 0.0
+
+
+# ------------------------------------------------------------------------------------------------
+# edge cases and randomised shapes
+# ------------------------------------------------------------------------------------------------
+def _compare_contrastive(U, case, max_label=20, rel=REL):
+    f_ref = case["f_n"].double().requires_grad_(True)
+    A, Cst, la, lc, P, prep = O.pre_contrastive_pixel(f_ref, case["labels"], case["l_po"].double(), case["f_o"].double(),
+                                                       max_label=max_label)
+    ref = O.pixel_con_loss(A, Cst, la, lc, P)
+    ref.backward()
+    f_n = case["f_n"].cuda().requires_grad_(True)
+    tup = U.pre_contrastive_pixel(f_n, case["labels"].cuda(), l_po=case["l_po"].cuda(), f_o=case["f_o"].cuda(),
+                                  max_label=max_label)
+    pk = tup[4].pack
+    assert np.array_equal(pk.label_n.cpu().numpy(), prep.label_n.reshape(-1))
+    assert np.array_equal(tup[2].cpu().numpy(), la.numpy()) and np.array_equal(tup[3].cpu().numpy(), lc.numpy())
+    loss = U.PixelConLossV2(temperature=0.07)(*tup)
+    loss.backward()
+    if torch.isnan(ref):                      # no row with a positive: the reference's mean of an empty set
+        assert torch.isnan(loss)
+        return
+    assert loss.item() == pytest.approx(ref.item(), rel=rel)
+    if float(f_ref.grad.norm()) > 0:
+        assert cos(f_n.grad, f_ref.grad) >= COS
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_contrastive_random_shapes(U, seed):
+    g = torch.Generator().manual_seed(100 + seed)
+    ri = lambda lo, hi: int(torch.randint(lo, hi + 1, (1,), generator=g))  # noqa: E731
+    B, h, w = ri(1, 3), ri(3, 20), ri(3, 20)
+    scale = (8, 16)[ri(0, 1)]
+    H, W = h * scale + ri(0, 1), w * scale + ri(0, 1)
+    c_old, n_new = ri(2, 20), ri(1, 5)
+    c_tot = min(c_old + n_new, 21)
+    c_old = c_tot - n_new
+    case = dict(f_n=torch.randn(B, 256, h, w, generator=g), f_o=torch.randn(B, 256, h, w, generator=g),
+                l_po=torch.randn(B, c_old, h, w, generator=g) * 3)
+    lab = torch.zeros(B, H, W, dtype=torch.int64)
+    for _ in range(ri(1, 4)):                  # random rectangles of new-class labels, plus an ignore band
+        y0, x0 = ri(0, H - 2), ri(0, W - 2)
+        lab[ri(0, B - 1), y0:y0 + ri(1, H), x0:x0 + ri(1, W)] = ri(c_old, c_tot - 1)
+    lab[:, :ri(0, H // 8)] = 255
+    lab[0, H // 2:H // 2 + max(2 * scale, 2), W // 2:W // 2 + max(2 * scale, 2)] = c_old   # guarantee a new-class pixel
+    case["labels"] = lab
+    _compare_contrastive(U, case)
+
+
+def test_contrastive_no_pseudo_pixels(U):
+    """Old model predicts background everywhere: N_o = 0, the contrast set is the anchors themselves."""
+    case = O.synthetic_case(2, 12, 12, 192, 192, 8, 6)
+    case["l_po"][:, 0] = 100.0
+    _compare_contrastive(U, case)
+
+
+def test_contrastive_single_image_and_tiny_sets(U):
+    """B = 1 (the reference's squeeze() breaks there; the oracle and the kernels do not), N_a below one tile."""
+    case = O.synthetic_case(1, 6, 7, 96, 112, 8, 6)
+    _compare_contrastive(U, case)
+
+
+def test_contrastive_raises_without_new_class_pixel(U):
+    case = O.synthetic_case(2, 8, 8, 128, 128, 6, 4)
+    lab = torch.zeros_like(case["labels"])
+    with pytest.raises(RuntimeError, match="no new-class pixel"):
+        U.pre_contrastive_pixel(case["f_n"].cuda(), lab.cuda(), l_po=case["l_po"].cuda(), f_o=case["f_o"].cuda())
+    with pytest.raises(ValueError):
+        O.prep_labels(lab.numpy(), case["l_po"].numpy())
+
+
+def test_contrastive_no_grad_mode(U, golden_dir):
+    """validation-style call under no_grad: sweeps run without the V/U accumulation, same loss."""
+    fx, case, _ = load_case(golden_dir, "voc15-5s_b3_512")
+    with torch.no_grad():
+        tup = U.pre_contrastive_pixel(case["f_n"].cuda(), case["labels"].cuda(), l_po=case["l_po"].cuda(), f_o=case["f_o"].cuda())
+        loss = U.PixelConLossV2(temperature=0.07)(*tup)
+    assert not loss.requires_grad
+    assert loss.item() == pytest.approx(fx["con"][1], rel=REL)
+
+
+def test_unce_all_ignored_and_old_only_labels(U):
+    x = torch.randn(1, 5, 8, 8, device="cuda", requires_grad=True)
+    y = torch.full((1, 8, 8), 255, dtype=torch.int64, device="cuda")
+    out = U.UnbiasedCrossEntropy(old_cl=3, reduction="none")(x, y)
+    out.sum().backward()
+    assert float(out.abs().max()) == 0.0 and float(x.grad.abs().max()) == 0.0
+    y2 = torch.randint(0, 3, (1, 8, 8), device="cuda")            # only old labels: all remapped to 0
+    out2 = U.UnbiasedCrossEntropy(old_cl=3, reduction="mean")(x, y2)
+    assert int(y2.abs().max()) == 0
+    ref = O.unbiased_ce(x.detach().cpu().double(), torch.zeros(1, 8, 8, dtype=torch.int64), 3, 255, "mean")
+    assert out2.item() == pytest.approx(ref.item(), rel=1e-5)
