@@ -30,3 +30,15 @@ res["unkd_fwd+bwd"] = (timeit(lambda: torch.autograd.grad(unkd(x, old), x)), npx
 print("shape B=%d C=%d C_old=%d %dx%d" % (B, C, C_old, H, W))
 for k, (ms, by) in res.items():
     print("  %-14s %8.3f ms  %7.1f GB/s (%.2f of 6454)" % (k, ms, by / ms / 1e6, by / ms / 1e6 / 6454))
+# ---- N1 fused path: same losses from the low-res logits ----
+fused = U.FusedUnbiasedLosses(old_cl=C_old)
+def unfused():
+    o = U.interpolate_bilinear(lr, (H, W))
+    with torch.no_grad():
+        oo = U.interpolate_bilinear(lpo, (H, W))
+    l = unce(o, lab).mean() + 10 * unkd(o, oo)
+    return torch.autograd.grad(l, lr)
+def fused_run():
+    ce, kd = fused(lr, lpo, lab)
+    return torch.autograd.grad(ce + 10 * kd, lr)
+print("  unfused upsample+CE+KD fwd+bwd: %.3f ms   fused (N1): %.3f ms" % (timeit(unfused), timeit(fused_run)))

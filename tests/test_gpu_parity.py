@@ -408,3 +408,39 @@ def test_unce_all_ignored_and_old_only_labels(U):
     assert int(y2.abs().max()) == 0
     ref = O.unbiased_ce(x.detach().cpu().double(), torch.zeros(1, 8, 8, dtype=torch.int64), 3, 255, "mean")
     assert out2.item() == pytest.approx(ref.item(), rel=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------
+# N1: fused upsample + UNCE + UNKD from the low-res logits
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,C,c_old,h,w,scale", [(2, 21, 16, 9, 11, 16), (2, 17, 16, 32, 32, 16), (1, 8, 6, 5, 7, 8),
+                                                 (2, 151, 101, 6, 5, 16), (1, 6, 6, 4, 4, 16), (2, 20, 14, 8, 16, 16)])
+def test_fused_unbiased_losses(U, B, C, c_old, h, w, scale):
+    H, W = h * scale + (1 if (h + w) % 2 else 0), w * scale + (1 if (h + w) % 2 else 0)   # also 513-style sizes
+    g = torch.Generator().manual_seed(B * 1000 + C)
+    lr = torch.randn(B, C, h, w, generator=g) * 3
+    lo = torch.randn(B, c_old, h, w, generator=g) * 3
+    lab = torch.randint(0, C, (B, H, W), generator=g)
+    lab[:, : max(1, H // 20)] = 255
+    # reference: the three separate reference ops (oracle restatements), fp64
+    lr_ref = lr.double().requires_grad_(True)
+    out = O.upsample_bilinear(lr_ref, H, W)
+    old = O.upsample_bilinear(lo.double(), H, W)
+    lab_ref = lab.clone()
+    ce_ref = O.unbiased_ce(out, lab_ref, c_old, 255, "none").mean()
+    kd_ref = O.unbiased_kd(out, old, 1.0)
+    (ce_ref + 10 * kd_ref).backward()
+    lr_c, lab_c = lr.cuda().requires_grad_(True), lab.cuda()
+    ce, kd = U.FusedUnbiasedLosses(old_cl=c_old, alpha=1.0)(lr_c, lo.cuda(), lab_c)
+    (ce + 10 * kd).backward()
+    assert torch.equal(lab_c.cpu(), lab_ref), "in-place label remap"
+    assert ce.item() == pytest.approx(ce_ref.item(), rel=REL)
+    assert kd.item() == pytest.approx(kd_ref.item(), rel=REL)
+    assert cos(lr_c.grad, lr_ref.grad) >= COS
+    torch.testing.assert_close(lr_c.grad.cpu().double(), lr_ref.grad, rtol=2e-3, atol=2e-5 * float(lr_ref.grad.abs().max()))
+    # and equal to the unfused drop-in modules
+    lr_d = lr.cuda().requires_grad_(True)
+    o = U.interpolate_bilinear(lr_d, (H, W))
+    ce_d = U.UnbiasedCrossEntropy(old_cl=c_old, reduction="none")(o, lab.cuda()).mean()
+    kd_d = U.UnbiasedKnowledgeDistillationLoss()(o, U.interpolate_bilinear(lo.cuda(), (H, W)))
+    assert ce.item() == pytest.approx(ce_d.item(), rel=1e-4) and kd.item() == pytest.approx(kd_d.item(), rel=1e-4)

@@ -25,6 +25,8 @@ _PROTOS = {
     "ucd_unkd_bwd": (c_int, [P, P, P, c_float, P, P, P, c_float, P, c_int, c_int, c_int, c_int64, P]),
     "ucd_upsample_bilinear_fwd": (c_int, [P, P, c_int64, c_int, c_int, c_int, c_int, P]),
     "ucd_upsample_bilinear_bwd": (c_int, [P, P, c_int64, c_int, c_int, c_int, c_int, P]),
+    "ucd_seg_fused_fwd": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                  c_float, c_int, P]),
     "ucd_con_max_tiles": (c_int64, [c_int64]),
     "ucd_con_prob_kpad": (c_int, [c_int]),
     "ucd_con_num_bins": (c_int, [c_int, c_int]),

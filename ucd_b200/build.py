@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libucd_b200.so")
-SOURCES = ["capi.cu", "ce_kd.cu", "upsample.cu", "prep.cu", "contrast.cu", "selftest.cu"]
+SOURCES = ["capi.cu", "ce_kd.cu", "upsample.cu", "prep.cu", "contrast.cu", "seg_fused.cu", "selftest.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

@@ -1,0 +1,343 @@
+// N1: upsample + unbiased CE + unbiased KD fused, straight from the LOW-RES logits.
+//
+// Reference path being fused (train.py:108,116,133 with segmentation_module.py:133):
+//   outputs     = interpolate(sem_logits    [B,C,h,w])      -> [B,C,H,W]      (grad)
+//   outputs_old = interpolate(sem_logits_old[B,C_old,h,w])  -> [B,C_old,H,W]  (no grad)
+//   ce = UnbiasedCrossEntropy(old_cl, 'none')(outputs, labels).mean() ; kd = UnbiasedKD(alpha)(outputs, outputs_old)
+// The full-resolution logits exist only to feed these two reductions, so this kernel never writes them: every
+// full-res pixel is interpolated on the fly from a low-res tile in shared memory, both losses and both
+// gradients w.r.t. the full-res logits are formed in registers, and the gradients go straight through the
+// adjoint of the bilinear interpolation into two small [B,C,h,w] tensors.  HBM traffic drops from
+// ~(32C+12C_old+28) B per full-res pixel to the 8 B label read; the kernel is exp/issue bound.
+//
+// Work decomposition: block = (image b, low-res row interval k, column tile): all full-res rows Y whose upper tap
+// is low-res row k (they share the y taps), TX consecutive columns, one thread per column.  For a fixed column the
+// x-blend of the two tap rows, u0[c] and u1[c], is computed once per block and kept in shared memory; then
+// x_c(Y) = hy0(Y) u0[c] + hy1(Y) u1[c] costs two FMAs per pixel and channel.
+//   phase A (per pixel): online log-sum-exps (all / old / bkg set, old-model softmax) -> per-pixel stats in registers
+//     (4 threads share a column and own every 4th row)
+//   phase B (per channel, pixels of the column in the inner loop): dCE/dx_c and dKD/dx_c, accumulated over the
+//     rows with the y-tap weights; then multiplied by the x-tap weights, segment-reduced over the lanes that
+//     share a low-res column, and added to the four low-res cells.
+// The cross-block sums (a low-res cell collects from <= 2 row intervals x <= 3 column tiles) use float atomicAdd:
+// results can differ in the last bits between runs (unlike the rest of the library, which is deterministic).
+#include "common.cuh"
+
+namespace ucd {
+
+constexpr int kRG = 4;        // row groups: threads (x, g) share column x, thread g owns rows g, g+4, ...
+constexpr int kRPT = 8;       // rows per thread  => up to 32 full-res rows per low-res interval (upscale <= 19)
+constexpr float kNeg = -3.0e38f;
+
+struct FusedArgs {
+  const float* lr;      // [B,C,h,w]
+  const float* lo;      // [B,C_old,h,w]
+  long long* labels;    // [B,H,W] (remapped in place like UnbiasedCrossEntropy)
+  float* g_ce;          // [B,C,h,w]  d(sum_px ce_px)/d lr        (zero-initialised by the host)
+  float* g_kd;          // [B,C,h,w]  d(sum_px kd_px)/d lr, kd_px = -loss_px
+  float* sums;          // [3] {sum ce_px, #non-ignored, sum kd_px}  (zero-initialised)
+  int B, C, C_old, h, w, H, W, old_cl, ignore_index;
+  float alpha, scale_h, scale_w;
+  int need_grad;
+};
+
+// dynamic smem: u[(C + C_old)][2][TX] | cell[nwarps][2][ncx][C][2]
+template <int TX>
+__global__ void __launch_bounds__(TX * kRG) seg_fused_kernel(const FusedArgs a, int ncx_cap) {
+  extern __shared__ __align__(16) float fs[];
+  constexpr int NW = TX * kRG / 32;
+  const int C = a.C, Co = a.C_old, CT = C + Co;
+  float* u = fs;                          // [CT][2][TX]  x-blended tap rows per column
+  float* cell = u + (size_t)CT * 2 * TX;  // [NW][2][ncx_cap][C][2]
+  __shared__ float red[3][NW];
+
+  const int b = blockIdx.z, k = blockIdx.y, X0 = blockIdx.x * TX;
+  const int xl = threadIdx.x % TX, rg = threadIdx.x / TX;
+  const int X = X0 + xl;
+  const bool colok = X < a.W;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  // rows of this interval: all Y with tap.i0 == k (contiguous).  Found by scanning a conservative range.
+  int Ya = a.H, Yb = -1;
+  {
+    const float inv = (float)a.H / (float)a.h;
+    int lo_ = (int)floorf(((float)k - 0.5f) * inv) - 2, hi_ = (int)ceilf(((float)k + 1.5f) * inv) + 2;
+    lo_ = max(lo_, 0), hi_ = min(hi_, a.H - 1);
+    if (a.h == a.H) lo_ = hi_ = k;
+    for (int Y = lo_; Y <= hi_; ++Y) {
+      if (bilinear_tap(Y, a.scale_h, a.h, a.H).i0 == k) {
+        Ya = min(Ya, Y);
+        Yb = max(Yb, Y);
+      }
+    }
+  }
+  const int nrow = Yb - Ya + 1;
+  if (nrow <= 0) return;               // uniform per block
+  const int k1 = min(k + 1, a.h - 1);  // lower tap row (weight 0 when clamped)
+
+  const Tap tx = bilinear_tap(colok ? X : a.W - 1, a.scale_w, a.w, a.W);
+  // x-blended tap rows for every channel of this column (channels split over the row groups)
+  {
+    const float* pn = a.lr + (size_t)b * C * a.h * a.w;
+    const float* po = a.lo + (size_t)b * Co * a.h * a.w;
+    for (int c = rg; c < CT; c += kRG) {
+      const float* p = (c < C) ? pn + (size_t)c * a.h * a.w : po + (size_t)(c - C) * a.h * a.w;
+      const float v00 = __ldg(p + k * a.w + tx.i0), v01 = __ldg(p + k * a.w + tx.i1);
+      const float v10 = __ldg(p + k1 * a.w + tx.i0), v11 = __ldg(p + k1 * a.w + tx.i1);
+      // ATen's generic kernel order: t = fma(v0, w0, v1*w1), out = fma(t0, h0, t1*h1)
+      u[((size_t)c * 2 + 0) * TX + xl] = __fmaf_rn(v00, tx.w0, __fmul_rn(v01, tx.w1));
+      u[((size_t)c * 2 + 1) * TX + xl] = __fmaf_rn(v10, tx.w0, __fmul_rn(v11, tx.w1));
+    }
+  }
+  const int ncell = 2 * ncx_cap * C * 2;
+  for (int i = threadIdx.x; i < NW * ncell; i += TX * kRG) cell[i] = 0.f;
+  __syncthreads();
+
+  const float a2 = a.alpha * kLog2e;
+  const float inv_co = 1.f / (float)Co;
+  float ce_acc = 0.f, valid_acc = 0.f, kd_acc = 0.f;
+  // per-pixel statistics of this thread's rows (registers)
+  float s_lse2[kRPT], s_fold[kRPT], s_fb[kRPT], s_lt2[kRPT], s_h0[kRPT], s_h1[kRPT];
+  int s_lab[kRPT];
+  // ---------------- phase A: channels in the outer loop, 4 rows of the thread in flight (independent chains) ----
+#pragma unroll
+  for (int j = 0; j < kRPT; ++j) {
+    s_lab[j] = -1;
+    s_lse2[j] = 0.f, s_fold[j] = 0.f, s_fb[j] = 0.f, s_lt2[j] = 0.f, s_h0[j] = 0.f, s_h1[j] = 0.f;
+  }
+#pragma unroll
+  for (int jb = 0; jb < kRPT; jb += 4) {
+    if (rg + jb * kRG >= nrow) break;
+    long long lab[4];
+    float h0[4], h1[4];
+    bool live[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int r = rg + (jb + q) * kRG;
+      live[q] = r < nrow;
+      const int Y = Ya + (live[q] ? r : 0);
+      const Tap ty = bilinear_tap(Y, a.scale_h, a.h, a.H);
+      h0[q] = ty.w0, h1[q] = ty.w1;
+      lab[q] = 0;
+      if (live[q] && colok) {
+        long long* lp = a.labels + ((size_t)b * a.H + Y) * a.W + X;
+        lab[q] = *lp;
+        if (lab[q] < a.old_cl) {  // utils/loss.py:104-105
+          if (lab[q] != 0) *lp = 0;
+          lab[q] = 0;
+        }
+      }
+    }
+    float m[4], s[4], mo[4], so[4], mb[4], sb[4], picked[4], mt[4], stt[4], wx[4], t0v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      m[q] = mo[q] = mb[q] = mt[q] = kNeg, s[q] = so[q] = sb[q] = stt[q] = 0.f, picked[q] = wx[q] = t0v[q] = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float u0 = u[((size_t)c * 2) * TX + xl], u1 = u[((size_t)c * 2 + 1) * TX + xl];
+      const bool bkg = (c == 0 || c >= Co);
+      float v0 = 0.f, v1 = 0.f;
+      if (c < Co) v0 = u[((size_t)(C + c) * 2) * TX + xl], v1 = u[((size_t)(C + c) * 2 + 1) * TX + xl];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float x = __fmaf_rn(u0, h0[q], __fmul_rn(u1, h1[q]));
+        const float x2 = x * kLog2e;
+        if (c == a.old_cl) mo[q] = m[q], so[q] = s[q];  // snapshot: log-sum-exp over the first old_cl channels
+        lse_push(m[q], s[q], x2);
+        if (bkg) lse_push(mb[q], sb[q], x2);
+        picked[q] = (lab[q] == c) ? x : picked[q];
+        if (c < Co) {
+          const float tv = __fmaf_rn(v0, h0[q], __fmul_rn(v1, h1[q])) * a2;
+          if (c == 0) t0v[q] = tv;
+          const float d = tv - mt[q];
+          const float e = ex2f(-fabsf(d));
+          const float xc = c >= 1 ? x : 0.f;
+          stt[q] = d > 0.f ? fmaf(stt[q], e, 1.f) : stt[q] + e;
+          wx[q] = d > 0.f ? fmaf(wx[q], e, xc) : fmaf(e, xc, wx[q]);
+          mt[q] = fmaxf(mt[q], tv);
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int j = jb + q;
+      if (!live[q]) continue;
+      if (a.old_cl >= C) mo[q] = m[q], so[q] = s[q];
+      const float lse2 = m[q] + lg2f(s[q]), lseo2 = mo[q] + lg2f(so[q]), lseb2 = mb[q] + lg2f(sb[q]);
+      const float lset2 = mt[q] + lg2f(stt[q]);
+      const float lse = lse2 * kLn2;
+      const bool ign = lab[q] == a.ignore_index;
+      const bool dead = ign || lab[q] < 0 || lab[q] >= C;
+      float l = (lab[q] == 0 && a.old_cl > 0) ? (lse - lseo2 * kLn2) : (lse - picked[q]);
+      if (dead) l = 0.f;
+      const float q0 = ex2f(t0v[q] - lset2);
+      const float kdpx = -((q0 * (lseb2 * kLn2 - lse) + wx[q] / stt[q] - (1.f - q0) * lse) * inv_co);
+      if (colok) {
+        ce_acc += l;
+        valid_acc += ign ? 0.f : 1.f;
+        kd_acc += kdpx;
+      }
+      s_lse2[j] = lse2;
+      s_fold[j] = ex2f(lse2 - lseo2);       // exp(lse - lse_old)
+      s_fb[j] = q0 * ex2f(lse2 - lseb2);    // q0 exp(lse - lse_bkg)
+      s_lt2[j] = lset2;
+      s_lab[j] = (dead || !colok) ? -1 : (int)lab[q];
+      s_h0[j] = colok ? h0[q] : 0.f;        // out-of-image columns contribute nothing
+      s_h1[j] = colok ? h1[q] : 0.f;
+    }
+  }
+  {
+    float v0 = warp_sum(ce_acc), v1 = warp_sum(valid_acc), v2 = warp_sum(kd_acc);
+    if (lane == 0) red[0][warp] = v0, red[1][warp] = v1, red[2][warp] = v2;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    for (int i = 0; i < NW; ++i) s0 += red[0][i], s1 += red[1][i], s2 += red[2][i];
+    atomicAdd(a.sums + 0, s0);
+    atomicAdd(a.sums + 1, s1);
+    atomicAdd(a.sums + 2, s2);
+  }
+  if (!a.need_grad) return;
+
+  // ---------------- phase B: gradients, one channel at a time ----------------
+  const int cx_lo = bilinear_tap(min(X0, a.W - 1), a.scale_w, a.w, a.W).i0;  // first low-res column of this tile
+  float* mycell = cell + (size_t)warp * ncell;
+  // lanes of a warp hold consecutive X of one row group, so tx.i0 is non-decreasing along the warp
+  const int key = colok ? tx.i0 : -1 - lane;
+  const int key_prev = __shfl_up_sync(0xffffffffu, key, 1);
+  const bool head = (lane == 0) || (key != key_prev);
+  for (int c = 0; c < C; ++c) {
+    const float u0 = u[((size_t)c * 2) * TX + xl], u1 = u[((size_t)c * 2 + 1) * TX + xl];
+    float v0 = 0.f, v1 = 0.f;
+    if (c < Co) v0 = u[((size_t)(C + c) * 2) * TX + xl], v1 = u[((size_t)(C + c) * 2 + 1) * TX + xl];
+    const bool in_sb = (c == 0) || (c >= Co);
+    const bool old_fg = (c >= 1) && (c < Co);
+    float ce0 = 0.f, ce1 = 0.f, kd0 = 0.f, kd1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < kRPT; ++j) {
+      const float h0 = s_h0[j], h1 = s_h1[j];  // zero for rows this thread does not own
+      const float x = __fmaf_rn(u0, h0, __fmul_rn(u1, h1));
+      const int lab = s_lab[j];
+      const float p = ex2f(fmaf(x, kLog2e, -s_lse2[j]));
+      float sub;
+      if (lab == 0 && a.old_cl > 0)
+        sub = (c < a.old_cl) ? p * s_fold[j] : 0.f;
+      else
+        sub = (c == lab) ? 1.f : 0.f;
+      const float dce = (lab < 0) ? 0.f : (p - sub);
+      float dkd = p;
+      if (in_sb) dkd -= p * s_fb[j];
+      if (old_fg) dkd -= ex2f(fmaf(__fmaf_rn(v0, h0, __fmul_rn(v1, h1)), a2, -s_lt2[j]));
+      dkd *= inv_co;
+      ce0 = fmaf(h0, dce, ce0);
+      ce1 = fmaf(h1, dce, ce1);
+      kd0 = fmaf(h0, dkd, kd0);
+      kd1 = fmaf(h1, dkd, kd1);
+    }
+    // x taps: 8 values (2 tap rows x 2 terms x {x0, x1}); segmented sum over lanes with the same tx.i0
+    float vals[8] = {ce0 * tx.w0, ce0 * tx.w1, ce1 * tx.w0, ce1 * tx.w1, kd0 * tx.w0, kd0 * tx.w1, kd1 * tx.w0, kd1 * tx.w1};
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int ko = __shfl_down_sync(0xffffffffu, key, off);
+      const bool same = (lane + off < 32) && (ko == key);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float o = __shfl_down_sync(0xffffffffu, vals[i], off);
+        if (same) vals[i] += o;
+      }
+    }
+    // Segment heads add to this warp's private cells.  Two passes separated by __syncwarp: in pass 1 every head
+    // owns a distinct cell (its x0), in pass 2 its x1 - which is the NEXT head's x0, hence the ordering; at the
+    // right image border x1 == x0 and the x1 part is folded into pass 1.
+    const int c0x = tx.i0 - cx_lo, c1x = tx.i1 - cx_lo;  // tile-local low-res columns
+    const bool clamp = tx.i1 == tx.i0;
+    auto at = [&](int yy, int cx, int term) -> float& { return mycell[(((size_t)yy * ncx_cap + cx) * C + c) * 2 + term]; };
+    if (head && colok) {
+      at(0, c0x, 0) += vals[0] + (clamp ? vals[1] : 0.f);
+      at(1, c0x, 0) += vals[2] + (clamp ? vals[3] : 0.f);
+      at(0, c0x, 1) += vals[4] + (clamp ? vals[5] : 0.f);
+      at(1, c0x, 1) += vals[6] + (clamp ? vals[7] : 0.f);
+    }
+    __syncwarp();
+    if (head && colok && !clamp) {
+      at(0, c1x, 0) += vals[1];
+      at(1, c1x, 0) += vals[3];
+      at(0, c1x, 1) += vals[5];
+      at(1, c1x, 1) += vals[7];
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  // combine the warps in fixed order and add the tile's cells to the low-res gradients
+  for (int i = threadIdx.x; i < ncell; i += TX * kRG) {
+    float v = 0.f;
+    for (int wq = 0; wq < NW; ++wq) v += cell[(size_t)wq * ncell + i];
+    if (v == 0.f) continue;
+    const int term = i & 1;
+    const int c = (i >> 1) % C;
+    const int cx = ((i >> 1) / C) % ncx_cap;
+    const int yy = ((i >> 1) / C) / ncx_cap;
+    const int gy = yy == 0 ? k : k1, gx = cx_lo + cx;
+    if (gx >= a.w) continue;
+    float* dst = (term == 0 ? a.g_ce : a.g_kd) + (((size_t)b * C + c) * a.h + gy) * a.w + gx;
+    atomicAdd(dst, v);
+  }
+}
+
+}  // namespace ucd
+
+using namespace ucd;
+
+extern "C" int ucd_seg_fused_fwd(const float* lr, const float* lr_old, int64_t* labels, float* g_ce, float* g_kd,
+                                 float* sums, int B, int C, int C_old, int h, int w, int H, int W, int old_cl,
+                                 int ignore_index, float alpha, int need_grad, void* stream) {
+  UCD_CHECK_ARG(lr && lr_old && labels && sums, "ucd_seg_fused_fwd: null pointer");
+  UCD_CHECK_ARG(!need_grad || (g_ce && g_kd), "ucd_seg_fused_fwd: need_grad without gradient buffers");
+  UCD_CHECK_ARG(B > 0 && C > 0 && C_old >= 1 && C >= C_old && h > 0 && w > 0 && H >= h && W >= w,
+                "ucd_seg_fused_fwd: bad shape (upsampling only)");
+  UCD_CHECK_ARG(old_cl >= 0 && old_cl <= C, "ucd_seg_fused_fwd: old_cl outside [0,C]");
+  UCD_CHECK_ARG(B <= 65535 && h <= 65535, "ucd_seg_fused_fwd: batch / rows too large for the grid");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(sums, 0, 3 * sizeof(float), st);
+  if (e == cudaSuccess && need_grad) e = cudaMemsetAsync(g_ce, 0, (size_t)B * C * h * w * sizeof(float), st);
+  if (e == cudaSuccess && need_grad) e = cudaMemsetAsync(g_kd, 0, (size_t)B * C * h * w * sizeof(float), st);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(seg_fused)");
+  const int rows_cap = (int)(1.5 * (double)H / h) + 3;  // the first interval also owns the clamped rows above row 0
+  UCD_CHECK_ARG(rows_cap <= kRG * kRPT, "ucd_seg_fused_fwd: upscale factor %d too large for the fused kernel (max 19)", H / h);
+  FusedArgs a;
+  a.lr = lr, a.lo = lr_old, a.labels = (long long*)labels, a.g_ce = g_ce, a.g_kd = g_kd, a.sums = sums;
+  a.B = B, a.C = C, a.C_old = C_old, a.h = h, a.w = w, a.H = H, a.W = W, a.old_cl = old_cl, a.ignore_index = ignore_index;
+  a.alpha = alpha, a.scale_h = (float)h / (float)H, a.scale_w = (float)w / (float)W, a.need_grad = need_grad;
+  // column tile: the widest of {128, 64, 32} whose shared memory fits
+  const int CT = C + C_old;
+  int TX = 0;
+  size_t smem = 0;
+  int ncx = 0;
+  for (int cand : {128, 64, 32}) {
+    ncx = (int)((double)cand * w / W) + 3;
+    const size_t need = ((size_t)CT * 2 * cand + (size_t)(cand * kRG / 32) * 2 * ncx * C * 2) * sizeof(float);
+    if (need <= 72 * 1024 || (cand == 32 && need <= 200 * 1024)) {  // prefer >= 3 blocks per SM
+      TX = cand, smem = need;
+      break;
+    }
+  }
+  UCD_CHECK_ARG(TX != 0, "ucd_seg_fused_fwd: C + C_old = %d too large for one block", CT);
+  dim3 grid((W + TX - 1) / TX, h, B);
+#define UCD_LAUNCH_FUSED(T)                                                                                          \
+  do {                                                                                                               \
+    if (smem > 48 * 1024) {                                                                                          \
+      e = cudaFuncSetAttribute(seg_fused_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
+      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(seg_fused_kernel)");                           \
+    }                                                                                                                \
+    seg_fused_kernel<T><<<grid, T * kRG, smem, st>>>(a, ncx);                                                    \
+  } while (0)
+  if (TX == 128)
+    UCD_LAUNCH_FUSED(128);
+  else if (TX == 64)
+    UCD_LAUNCH_FUSED(64);
+  else
+    UCD_LAUNCH_FUSED(32);
+#undef UCD_LAUNCH_FUSED
+  UCD_CHECK_LAUNCH("seg_fused_kernel");
+  return UCD_OK;
+}

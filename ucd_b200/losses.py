@@ -574,3 +574,67 @@ class PixelConLossV2(nn.Module):
                     min_new=None)
         rows = dict(feat=rfeat, prob=None, lab=rlab, range=rrange, n_rows=n_rows, max_tiles=rt, self_tile0=0)
         return _ConFn.apply(anchor_features, cols, rows, inv_tau, p_mode, dense_p, None, False)
+
+
+# ----------------------------------------------------------------------------------------------
+# N1 (opt-in): upsample + unbiased CE + unbiased KD fused, from the low-res logits
+# ----------------------------------------------------------------------------------------------
+class _SegFusedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, lr, lr_old, labels, old_cl, ignore_index, alpha):
+        _need_cuda(lr, lr_old, labels)
+        x, t = _f32c(lr), _f32c(lr_old)
+        B, C, h, w = x.shape
+        C_old = t.shape[1]
+        H, W = labels.shape[-2:]
+        dev = x.device
+        need_grad = bool(ctx.needs_input_grad[0])
+        sums = torch.empty(3, device=dev, dtype=torch.float32)
+        g = torch.empty(2, B, C, h, w, device=dev, dtype=torch.float32) if need_grad else None
+        check(_lib.lib().ucd_seg_fused_fwd(ptr(x), ptr(t), ptr(labels), ptr(g[0]) if need_grad else None,
+                                           ptr(g[1]) if need_grad else None, ptr(sums), B, C, C_old, h, w, H, W,
+                                           old_cl, ignore_index, float(alpha), 1 if need_grad else 0, cur_stream()),
+              "seg_fused_fwd")
+        ctx.save_for_backward(g)
+        ctx.n_px = float(B * H * W)
+        ctx.in_dtype = lr.dtype
+        return sums[0] / ctx.n_px, sums[2] / ctx.n_px, sums[1]
+
+    @staticmethod
+    def backward(ctx, g_ce, g_kd, _g_cnt):
+        (g,) = ctx.saved_tensors
+        d = g[0] * (g_ce / ctx.n_px) + g[1] * (g_kd / ctx.n_px)   # two [B,C,h,w] tensors: negligible
+        return d.to(ctx.in_dtype), None, None, None, None, None
+
+
+class FusedUnbiasedLosses(nn.Module):
+    """Opt-in fusion of ``interpolate`` (segmentation_module.py:133), ``UnbiasedCrossEntropy(reduction='none')
+    (...).mean()`` (train.py:116) and ``UnbiasedKnowledgeDistillationLoss`` (train.py:133), computed straight from
+    the LOW-RES logits of the new and the old model: the full-resolution logits are never materialised
+    (SURVEY.md 8f, row N1).
+
+        ce, kd = FusedUnbiasedLosses(old_cl, alpha=opts.alpha)(out_lowres, out_old_lowres, labels)
+        loss = ce + con / 100 + opts.loss_kd * kd
+
+    ``ce`` averages over ALL pixels of the batch (the trainer's ``.mean()`` of the 'none'-reduced loss);
+    ``ce_reduction='valid'`` divides by the number of non-ignored pixels instead (nll_loss 'mean').
+    Labels are remapped in place like ``UnbiasedCrossEntropy`` does.
+    """
+
+    def __init__(self, old_cl, ignore_index=255, alpha=1., ce_reduction='mean'):
+        super().__init__()
+        self.old_cl, self.ignore_index, self.alpha, self.ce_reduction = int(old_cl), int(ignore_index), alpha, ce_reduction
+
+    def forward(self, logits_lr, logits_old_lr, labels):
+        if labels.dtype != torch.int64 or labels.dim() != 3:
+            raise TypeError("FusedUnbiasedLosses: labels must be int64 [B,H,W]")
+        if logits_lr.dim() != 4 or logits_old_lr.dim() != 4 or logits_lr.shape[0] != labels.shape[0] \
+                or logits_lr.shape[2:] != logits_old_lr.shape[2:] or logits_old_lr.shape[1] > logits_lr.shape[1]:
+            raise ValueError("FusedUnbiasedLosses: logits [B,C,h,w] / old logits [B,C_old,h,w] / labels [B,H,W] disagree")
+        tgt = labels if labels.is_contiguous() else labels.contiguous()
+        ce, kd, cnt = _SegFusedFn.apply(logits_lr, logits_old_lr.detach(), tgt, self.old_cl, self.ignore_index, self.alpha)
+        if tgt is not labels:
+            labels.copy_(tgt)
+        if self.ce_reduction == 'valid':
+            ce = ce * (float(labels.numel()) / cnt)
+        return ce, kd
