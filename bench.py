@@ -273,6 +273,28 @@ def main():
     call_ms = {k: v / args.steps for k, v in timer.totals_ms().items()}
     launches = sum(KERNELS_PER_CALL.get(k, 1) * v for k, v in timer.counts.items())
 
+    # ---- the same step with the opt-in N1 fusion (FusedUnbiasedLosses: no full-res logits), for information ----
+    fused = U.FusedUnbiasedLosses(old_cl=C_old, ignore_index=255, alpha=1.0)
+
+    def step_fused(inp):
+        f_n = inp["f_n"].detach().requires_grad_(True)
+        lr = inp["logits_lr"].detach().requires_grad_(True)
+        tup = U.pre_contrastive_pixel(f_n, inp["labels"], l_po=inp["l_po"], f_o=inp["f_o"])
+        con = conloss(*tup)
+        ce, kd = fused(lr, inp["l_po"], inp["labels"])
+        (ce + con / 100 + 10 * kd).backward()
+
+    for _ in range(3):
+        step_fused(devin)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        step_fused(devin)
+    f1.record()
+    barrier()
+    ms_fused = f0.elapsed_time(f1) / args.steps
+
     # ---- end-to-end through the public API with host buffers (e2e) ----
     # Every step copies its inputs from pinned host memory and copies losses + both gradients back.  Like a
     # DataLoader with pin_memory / non_blocking prefetch, the copies of step i+1 / i-1 run on a side stream while
@@ -329,14 +351,14 @@ def main():
 
     # ---- aggregate over ranks: max time, sum of pairs ----
     n_a = state["n_a"]
-    stats = torch.tensor([ms_dev, ms_e2e, float(n_a), float(state["n_c"])], device=dev, dtype=torch.float64)
+    stats = torch.tensor([ms_dev, ms_e2e, float(n_a), float(state["n_c"]), ms_fused], device=dev, dtype=torch.float64)
     if world > 1:
         allst = [torch.zeros_like(stats) for _ in range(world)]
         dist.all_gather(allst, stats)
     else:
         allst = [stats]
     allst = torch.stack(allst).cpu()
-    ms_dev_max, ms_e2e_max = float(allst[:, 0].max()), float(allst[:, 1].max())
+    ms_dev_max, ms_e2e_max, ms_fused_max = float(allst[:, 0].max()), float(allst[:, 1].max()), float(allst[:, 4].max())
     n_c_global = float(allst[:, 3].sum())
     pairs_total = float((allst[:, 2] * n_c_global).sum())
     pairs_local = float(n_a) * n_c_global
@@ -377,12 +399,16 @@ def main():
                         parallelism="dp%d, all-gathered contrast columns" % world),
             roofline=dict(bound="tensor", kernel="ucd_con_fwd (sweep 1 + combine + sweep 2 + finalize)",
                           achieved=con_tflops, peak=bf16_peak, unit="TFLOP/s", frac=con_tflops / bf16_peak,
-                          traffic=None, flop_per_pair=f_pair, ms=con_ms, peak_source=peak_src),
+                          traffic=(8.93e7 if (world == 1 and B == WORKLOAD["B"]) else None),
+                          traffic_note="dram read+write of the two sweep kernels per step, ncu --set full, profiles/r01d_ncu_full.md",
+                          flop_per_pair=f_pair, ms=con_ms, peak_source=peak_src),
             roofline_hbm=hbm,
             call_ms={k: round(v, 4) for k, v in sorted(call_ms.items())},
             cpu_baseline=cpu_baseline,
             e2e=dict(value=pairs_total / (ms_e2e_max * 1e-3) / 1e6, unit=UNIT, ms_per_step=ms_e2e_max,
                      h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
+            n1_fused=dict(note="same step with the opt-in FusedUnbiasedLosses (upsample+CE+KD from low-res logits)",
+                          ms_per_step=ms_fused_max, value=pairs_total / (ms_fused_max * 1e-3) / 1e6, unit=UNIT),
             gpu_launches=int(launches), clocks=clocks,
             losses=dict(con=float(state["con"]), ce=float(state["ce"]), kd=float(state["kd"])),
         )
