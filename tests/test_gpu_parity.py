@@ -387,6 +387,25 @@ def test_contrastive_raises_without_new_class_pixel(U):
         O.prep_labels(lab.numpy(), case["l_po"].numpy())
 
 
+def test_contrastive_bit_identical_reruns(U):
+    """Fixed-order reductions and race-free role pipelines: 20 reruns of a multi-row-block case are bit-identical
+    (this caught a shared-memory scratch that aliased an in-flight bulk copy)."""
+    case = O.synthetic_case(3, 32, 64, 512, 1024, 20, 14)
+    inp = {k: v.cuda() for k, v in case.items()}
+    con = U.PixelConLossV2(temperature=0.07)
+
+    def run():
+        f_n = inp["f_n"].clone().requires_grad_(True)
+        loss = con(*U.pre_contrastive_pixel(f_n, inp["labels"], l_po=inp["l_po"], f_o=inp["f_o"]))
+        loss.backward()
+        return loss.detach().clone(), f_n.grad.clone()
+
+    l0, g0 = run()
+    for _ in range(20):
+        l, g = run()
+        assert torch.equal(l, l0) and torch.equal(g, g0)
+
+
 def test_contrastive_no_grad_mode(U, golden_dir):
     """validation-style call under no_grad: sweeps run without the V/U accumulation, same loss."""
     fx, case, _ = load_case(golden_dir, "voc15-5s_b3_512")

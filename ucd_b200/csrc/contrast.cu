@@ -35,7 +35,7 @@ constexpr uint32_t kESub = 16384;       // 128 rows x 64 columns bf16
 // shared memory map (bytes)
 constexpr uint32_t OFF_A = 0;
 constexpr uint32_t OFF_C = 65536;     // 2 stages
-constexpr uint32_t OFF_E = 196608;    // 32 KB: sweep 2 probability operands; reused at the end to combine the column halves
+constexpr uint32_t OFF_E = 196608;    // 32 KB: sweep 2 probability operands
 constexpr uint32_t OFF_PA = OFF_E;    // sweep 2: row probabilities [kpad/8][128][8] bf16 (kpad*256 B <= 28 KB)
 constexpr uint32_t kProbBytes = 32768;  // OFF_PA .. OFF_LAB: the column probabilities use what pA leaves, in K chunks
 constexpr uint32_t OFF_LAB = 229376;  // 2 x 128 int32
@@ -159,10 +159,19 @@ __device__ __forceinline__ void sweep1_cols_neg(const uint32_t (&r)[32], float s
 
 // ---- sweep 2 epilogue on 32 columns ---------------------------------------------------------
 // PMODE 0: P == 1 ; 1: P from the prob GEMM with GT-new override ; 2: dense P in global memory
+// Row constants of sweep 2.  den_ij = exp(s_ij - m_i) + neg_i with exp(.) <= 1; when neg_i >= 4096 (the usual case:
+// thousands of negatives with exp(s) up to e^14) x = exp(.)/neg_i <= 2.5e-4 and
+//   log2(den) = log2(neg_i) + x log2(e) - O(x^2),   1/den = (1 - x)/neg_i + O(x^2),   |O(x^2)| <= 3e-8,
+// so the log and the reciprocal leave the MUFU (one ex2 per pair remains).  Small neg_i takes the exact path.
+struct RowC {
+  float mraw, negi, inv_neg, lneg2;
+  bool series;
+};
+
 template <bool FULL, bool SELF, int PMODE>
 __device__ __forceinline__ void sweep2_cols(const uint32_t (&r)[32], const uint32_t (&pr)[32],
                                             const int* __restrict__ lab, int cbase, int nv, int la, int rself,
-                                            float sc, float mraw, float negi, bool gt_row, int min_new,
+                                            float sc, const RowC rc, bool gt_row, int min_new,
                                             const float* __restrict__ dp, float& lacc, float& tacc,
                                             uint32_t (&pk)[16]) {
 #pragma unroll
@@ -174,10 +183,18 @@ __device__ __forceinline__ void sweep2_cols(const uint32_t (&r)[32], const uint3
     for (int u = 0; u < 4; ++u) {
       const int col = cbase + j4 + u;
       const float acc = __uint_as_float(r[j4 + u]);
-      const float sh2 = (acc - mraw) * sc;  // (s - m) * log2(e)
-      const float den = ex2f(sh2) + negi;
-      const float l2 = lg2f(den);
-      const float rd = rcpf(den);
+      const float sh2 = (acc - rc.mraw) * sc;  // (s - m) * log2(e)
+      const float e = ex2f(sh2);
+      float l2, rd;
+      if (rc.series) {
+        const float x = e * rc.inv_neg;
+        l2 = fmaf(x, kLog2e, rc.lneg2);
+        rd = fmaf(-x, rc.inv_neg, rc.inv_neg);
+      } else {
+        const float den = e + rc.negi;
+        l2 = lg2f(den);
+        rd = rcpf(den);
+      }
       float mp = (ls[u] == la) ? 1.f : 0.f;
       if (SELF) mp -= (col == rself) ? 1.f : 0.f;
       if (!FULL) mp = (col < nv) ? mp : 0.f;
@@ -188,7 +205,7 @@ __device__ __forceinline__ void sweep2_cols(const uint32_t (&r)[32], const uint3
       lacc = fmaf(w, sh2 - l2, lacc);
       const float wr = w * rd;
       tacc += wr;
-      uo[u] = wr * negi;
+      uo[u] = wr * rc.negi;
     }
     pk[j4 / 2] = bf16x2_bits(uo[0], uo[1]);
     pk[j4 / 2 + 1] = bf16x2_bits(uo[2], uo[3]);
@@ -276,7 +293,16 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
     __syncthreads();
   }
   auto tile_overlaps = [&](int tt) -> bool { return (s_mask[tt >> 5] >> (tt & 31)) & 1u; };
-  auto tile_active = [&](int tt) -> bool { return PHASE == 1 || tile_overlaps(tt); };
+  // next tile index >= tt that this sweep has to process (sweep 1: every tile; sweep 2: next set mask bit)
+  auto next_active = [&](int tt) -> int {
+    if (PHASE == 1) return tt;
+    while (tt < n) {
+      const uint32_t bits = s_mask[tt >> 5] >> (tt & 31);
+      if (bits) return tt + __ffs(bits) - 1;
+      tt = (tt | 31) + 1;
+    }
+    return n;
+  };
 
   if (warp == 0) {
     // ===================== producer: bulk async copies =====================
@@ -293,8 +319,7 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
       long long w_ce = 0, w_pe = 0;
       const long long c_start = clock64();
       int t = 0;
-      for (int tt = 0; tt < n; ++tt) {
-        if (!tile_active(tt)) continue;
+      for (int tt = next_active(0); tt < n; tt = next_active(tt + 1)) {
         const TileLoc loc = locate_tile(k0 + tt, s_pre, s_ncols, a.n_chunks, a.chunk_tiles);
         const int stage = t & 1;
         mbar_wait_t(BAR(BAR_CE + stage), ((t >> 1) & 1) ^ 1, w_ce);
@@ -328,8 +353,7 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
       long long c_idle = 0;
       const long long c_start = clock64();
       int t = 0;
-      for (int tt = 0; tt < n; ++tt) {
-        if (!tile_active(tt)) continue;
+      for (int tt = next_active(0); tt < n; tt = next_active(tt + 1)) {
         const int stage = t & 1, sb = t % NS;
         mbar_wait_t(BAR(BAR_CF + stage), (t >> 1) & 1, c_idle);
         mbar_wait_t(BAR(BAR_SE + sb), ((t / NS) & 1) ^ 1, c_idle);
@@ -367,8 +391,7 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
       long long c_idle = 0;
       const long long c_start = clock64();
       int t = 0;
-      for (int tt = 0; tt < n; ++tt) {
-        if (!tile_active(tt)) continue;
+      for (int tt = next_active(0); tt < n; tt = next_active(tt + 1)) {
         const int stage = t & 1, sb = t % NS;
         const uint32_t sc = sbase + OFF_C + stage * kTileBytes;
         for (int h = 0; h < 2; ++h) {
@@ -403,12 +426,15 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
     const float sc = a.inv_tau * kLog2e;
     float mx = -3.0e38f, neg = 0.f, num = 0.f;   // sweep 1
     float lacc = 0.f, tacc = 0.f;                // sweep 2
-    float mraw = 0.f, negi = 0.f;
+    RowC rc = {0.f, 0.f, 0.f, 0.f, false};
     int min_new = 0;
     bool gt_row = false;
     if (PHASE == 2) {
-      mraw = a.stats[grow];
-      negi = a.stats[a.rows_pad + grow];
+      rc.mraw = a.stats[grow];
+      rc.negi = a.stats[a.rows_pad + grow];
+      rc.series = rc.negi >= 4096.f;
+      rc.inv_neg = rc.series ? 1.f / rc.negi : 0.f;
+      rc.lneg2 = rc.series ? log2f(rc.negi) : 0.f;
       if (PMODE == 1) {
         min_new = *a.min_new;
         gt_row = la >= min_new;
@@ -417,8 +443,7 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
     int t = 0;  // number of active tiles processed so far (drives stage / parity bookkeeping)
     long long w_sf = 0, w_ee = 0;  // w_ee: unused since E moved to tensor memory
     const long long c_start = clock64();
-    for (int tt = 0; tt < n; ++tt) {
-      if (!tile_active(tt)) continue;
+    for (int tt = next_active(0); tt < n; tt = next_active(tt + 1)) {
       const TileLoc loc = locate_tile(k0 + tt, s_pre, s_ncols, a.n_chunks, a.chunk_tiles);
       const int stage = t & 1, sb = t % NS;
       const bool full = loc.nvalid == 128;
@@ -458,9 +483,11 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
         const uint32_t tb = tmem + lane_addr + sb * 128 + c0;
         tmem_ld32(tb, r0);
         tmem_ld_wait();
+        tmem_ld_fence(r0);
         tmem_ld32(tb + 32, r1);
         proc(0, r0);
         tmem_ld_wait();
+        tmem_ld_fence(r1);
         proc(1, r1);
       } else {
 #pragma unroll 1
@@ -469,11 +496,13 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
           tmem_ld32(tmem + lane_addr + sb * 128 + c0 + cc * 32, rv);
           if (PMODE == 1) tmem_ld32(tmem + lane_addr + 128 + c0 + cc * 32, pv);
           tmem_ld_wait();
+          tmem_ld_fence(rv);
+          if (PMODE == 1) tmem_ld_fence(pv);
           if (full && !self)
-            sweep2_cols<true, false, PMODE>(rv, pv, lab, c0 + cc * 32, 128, la, r, sc, mraw, negi, gt_row, min_new,
+            sweep2_cols<true, false, PMODE>(rv, pv, lab, c0 + cc * 32, 128, la, r, sc, rc, gt_row, min_new,
                                             dp, lacc, tacc, pk);
           else
-            sweep2_cols<false, true, PMODE>(rv, pv, lab, c0 + cc * 32, loc.nvalid, la, self ? r : -1, sc, mraw, negi,
+            sweep2_cols<false, true, PMODE>(rv, pv, lab, c0 + cc * 32, loc.nvalid, la, self ? r : -1, sc, rc,
                                             gt_row, min_new, dp, lacc, tacc, pk);
           emit(cc, pk);
         }
@@ -495,7 +524,9 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
       mbar_wait(BAR(BAR_V), 0);
       tc_fence_after();
     }
-    float* comb = reinterpret_cast<float*>(smem + OFF_E);  // [128][3]
+    // [128][3] scratch in C stage 0: every tile load has landed and every MMA that reads the stages has retired
+    // by now.  (NOT the probability region: with no active tile the row-probability copy may still be in flight.)
+    float* comb = reinterpret_cast<float*>(smem + OFF_C);
     if (half == 1) {
       comb[r * 3 + 0] = PHASE == 1 ? mx : lacc;
       comb[r * 3 + 1] = PHASE == 1 ? neg : tacc;
@@ -521,6 +552,7 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
           uint32_t rv[32];
           tmem_ld32(tmem + lane_addr + 256 + half * 128 + cc * 32, rv);
           tmem_ld_wait();
+          tmem_ld_fence(rv);
 #pragma unroll
           for (int k = 0; k < 8; ++k)
             dst[cc * 8 + k] = make_float4(__uint_as_float(rv[4 * k]), __uint_as_float(rv[4 * k + 1]),

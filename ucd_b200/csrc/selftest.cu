@@ -96,6 +96,7 @@ selftest_kernel(int variant, const __nv_bfloat16* __restrict__ a_tile, const __n
     uint32_t rv[32];
     tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + cc * 32, rv);
     tmem_ld_wait();
+    tmem_ld_fence(rv);
     for (int j = 0; j < 32; ++j) out[r * ncols + cc * 32 + j] = __uint_as_float(rv[j]);
   }
   tc_fence_before();
