@@ -75,6 +75,21 @@ int ucd_unkd_bwd(const float* x, const float* t, const float* mask, float alpha,
                  int C_old, int64_t HW, void* stream);
 size_t ucd_reduce_scratch_floats(void);
 
+/* Sibling distillation losses on the same kernels.  `variant`:
+ *   0  UnbiasedKnowledgeDistillationLoss (identical to ucd_unkd_*)
+ *   1  KnowledgeDistillationLoss (utils/loss.py:112-136): log-softmax over the first C_old of the C channels of x,
+ *      mean over those channels; dx of the remaining channels is written as 0
+ *   2  MaskKnowledgeDistillationLoss (utils/loss.py:218-256): variant 0 with the pixel weight [mask == 0] */
+int ucd_kd_fwd(const float* x, const float* t, const float* mask, float alpha, float* out_px, float* stats,
+               float* lse3, float* scratch, int B, int C, int C_old, int64_t HW, int variant, void* stream);
+int ucd_kd_bwd(const float* x, const float* t, const float* mask, float alpha, const float* lse3,
+               const float* g_px, const float* g_scalar, float g_mul, float* dx, int B, int C, int C_old,
+               int64_t HW, int variant, void* stream);
+/* MaskCrossEntropy's pixel weight (utils/loss.py:207-211): mask[b,p] = 1 if argmax_c t_old[b,c,p] == 0 or
+ * labels[b,p] > old_cl, else 0.  t_old [B,C_old,HW] fp32, labels [B,HW] int64, mask [B,HW] fp32. */
+int ucd_bkg_mask(const float* t_old, const int64_t* labels, float* mask, int B, int C_old, int64_t HW,
+                 int old_cl, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Bilinear logit upsample, align_corners=False   (segmentation_module.py:133)
  *   in [N,h,w] -> out [N,H,W]   (N = B*C planes), and its adjoint.
@@ -183,6 +198,8 @@ int ucd_con_debug_splits(int64_t max_row_tiles, int64_t max_col_tiles);
 int ucd_selftest_umma(int variant, float* max_err_host);
 /* tcgen05.mma issue-rate probe (cycles per instruction for a chain of `iters` MMAs; modes in selftest.cu) */
 int ucd_selftest_mma_rate(int mode, int iters, float* cycles_per_instr_host);
+/* CUDA-core pipe probe behind the sweep epilogue's design (ex2 / bf16 pack rates; modes in selftest.cu) */
+int ucd_selftest_pipe_rate(int mode, int warps, int iters, float* cycles_per_iter_host);
 
 #ifdef __cplusplus
 }

@@ -66,8 +66,43 @@ def run_reference(case, dtype):
                 outputs=outputs.detach())
 
 
+def gen_sibling():
+    """KnowledgeDistillationLoss, MaskKnowledgeDistillationLoss, MaskCrossEntropy (utils/loss.py) on stored inputs."""
+    from utils.loss import KnowledgeDistillationLoss, MaskCrossEntropy, MaskKnowledgeDistillationLoss
+    g = torch.Generator().manual_seed(4242)
+    B, C, C_old, H, W = 2, 7, 4, 20, 24
+    x = (torch.randn(B, C, H, W, generator=g) * 2.0).float()
+    t = (torch.randn(B, C_old, H, W, generator=g) * 2.0).float()
+    y = torch.randint(0, C, (B, H, W), generator=g)
+    y[:, :2] = 255
+    mask = torch.randint(0, 3, (B, H, W), generator=g)
+    fx = dict(x=x.numpy(), t=t.numpy(), y=y.numpy().astype(np.int64), mask=mask.numpy().astype(np.int64),
+              old_cl=np.array([C_old]), alpha=np.array([0.7]))
+
+    def run(tag, fn):
+        xd = x.double().requires_grad_(True)
+        out = fn(xd)
+        w = torch.linspace(0.5, 1.5, out.numel(), dtype=torch.float64).reshape(out.shape) if out.dim() else None
+        (out if w is None else (out * w).sum()).backward()
+        fx[tag + "_out"] = out.detach().numpy()
+        fx[tag + "_grad"] = xd.grad.numpy()
+
+    for red in ("mean", "sum", "none"):
+        run("kd_" + red, lambda xd: KnowledgeDistillationLoss(reduction=red, alpha=0.7)(xd, t.double()))
+        run("kd_mask_" + red, lambda xd: KnowledgeDistillationLoss(reduction=red, alpha=0.7)(xd, t.double(), (mask > 0)))
+        run("mkd_" + red, lambda xd: MaskKnowledgeDistillationLoss(reduction=red, alpha=0.7)(xd, t.double()))
+        run("mkd_mask_" + red, lambda xd: MaskKnowledgeDistillationLoss(reduction=red, alpha=0.7)(xd, t.double(), mask))
+        run("mce_" + red, lambda xd: MaskCrossEntropy(old_cl=C_old, reduction=red)(xd, y.clone()))
+        run("mce_old_" + red, lambda xd: MaskCrossEntropy(old_cl=C_old, reduction=red)(xd, y.clone(), t.double()))
+    np.savez_compressed(os.path.join(OUT, "sibling_losses.npz"), **fx)
+    print("sibling_losses:", {k: float(v) for k, v in fx.items() if k.endswith("_out") and v.ndim == 0})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "sibling":
+        return gen_sibling()
+    gen_sibling()
     for name, (B, h, w, H, W, C, C_old, corr) in CASES.items():
         case = synthetic_case(B, h, w, H, W, C, C_old, correlated=corr)
         r32 = run_reference(case, torch.float32)

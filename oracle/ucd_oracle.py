@@ -290,6 +290,58 @@ def unbiased_kd(x: torch.Tensor, t: torch.Tensor, alpha: float = 1.0, reduction:
 
 
 # ----------------------------------------------------------------------------
+# sibling losses on the same kernels
+# ----------------------------------------------------------------------------
+def _reduce_neg(per_px: torch.Tensor, reduction: str) -> torch.Tensor:
+    if reduction == "mean":
+        return -per_px.mean()
+    if reduction == "sum":
+        return -per_px.sum()
+    return -per_px
+
+
+def plain_kd(x: torch.Tensor, t: torch.Tensor, alpha: float = 1.0, reduction: str = "mean",
+             mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """utils/loss.py:112-136 (KnowledgeDistillationLoss): only the first C_old channels of x take part."""
+    c_old = t.shape[1]
+    xo = x[:, :c_old]
+    q = torch.softmax(t * alpha, dim=1)
+    per_px = (q * (xo - torch.logsumexp(xo, dim=1, keepdim=True))).sum(dim=1) / c_old
+    if mask is not None:
+        per_px = per_px * mask.to(per_px.dtype)
+    return _reduce_neg(per_px, reduction)
+
+
+def mask_kd(x: torch.Tensor, t: torch.Tensor, alpha: float = 1.0, reduction: str = "mean",
+            mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """utils/loss.py:218-256 (MaskKnowledgeDistillationLoss): the unbiased KD of :148-184 on pixels with mask == 0."""
+    sel = None if mask is None else (mask == 0)
+    return unbiased_kd(x, t, alpha=alpha, reduction=reduction, mask=sel)
+
+
+def mask_ce(x: torch.Tensor, y: torch.Tensor, old_cl: int, t_old: Optional[torch.Tensor] = None,
+            ignore_index: int = 255, reduction: str = "mean") -> torch.Tensor:
+    """utils/loss.py:186-216 (MaskCrossEntropy).  Labels are not remapped: a label in [1, old_cl) selects a
+    zero-filled channel (contributes 0); pixel weight 1 where argmax(t_old) == 0 or label > old_cl.
+    'mean'/'sum' come back negated, as the reference does (:213-215)."""
+    lse_all = torch.logsumexp(x, dim=1)
+    lse_old = torch.logsumexp(x[:, :old_cl], dim=1)
+    y_safe = y.clamp(0, x.shape[1] - 1)
+    picked = torch.gather(x, 1, y_safe.unsqueeze(1)).squeeze(1)
+    per_px = torch.where(y == 0, lse_all - lse_old, lse_all - picked)
+    dead = (y == ignore_index) | ((y >= 1) & (y < old_cl))
+    per_px = torch.where(dead, torch.zeros_like(per_px), per_px)
+    if t_old is not None:
+        w = (torch.argmax(t_old, dim=1) == 0) | (y > old_cl)
+        per_px = per_px * w.to(per_px.dtype)
+    if reduction == "mean":
+        return -per_px.mean()
+    if reduction == "sum":
+        return -per_px.sum()
+    return per_px
+
+
+# ----------------------------------------------------------------------------
 # bilinear logit upsample (differentiable restatement)
 # ----------------------------------------------------------------------------
 def upsample_bilinear(x: torch.Tensor, out_h: int, out_w: int) -> torch.Tensor:

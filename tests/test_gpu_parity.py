@@ -421,7 +421,7 @@ def test_unce_all_ignored_and_old_only_labels(U):
     y = torch.full((1, 8, 8), 255, dtype=torch.int64, device="cuda")
     out = U.UnbiasedCrossEntropy(old_cl=3, reduction="none")(x, y)
     out.sum().backward()
-    assert float(out.abs().max()) == 0.0 and float(x.grad.abs().max()) == 0.0
+    assert float(out.detach().abs().max()) == 0.0 and float(x.grad.abs().max()) == 0.0
     y2 = torch.randint(0, 3, (1, 8, 8), device="cuda")            # only old labels: all remapped to 0
     out2 = U.UnbiasedCrossEntropy(old_cl=3, reduction="mean")(x, y2)
     assert int(y2.abs().max()) == 0
@@ -463,3 +463,61 @@ def test_fused_unbiased_losses(U, B, C, c_old, h, w, scale):
     ce_d = U.UnbiasedCrossEntropy(old_cl=c_old, reduction="none")(o, lab.cuda()).mean()
     kd_d = U.UnbiasedKnowledgeDistillationLoss()(o, U.interpolate_bilinear(lo.cuda(), (H, W)))
     assert ce.item() == pytest.approx(ce_d.item(), rel=1e-4) and kd.item() == pytest.approx(kd_d.item(), rel=1e-4)
+
+
+# ------------------------------------------------------------------------------------------------
+# sibling losses on the same kernels
+@pytest.mark.parametrize("red", ["mean", "sum", "none"])
+def test_sibling_losses_vs_reference_fixture(U, golden_dir, red):
+    fx = np.load(os.path.join(golden_dir, "sibling_losses.npz"))
+    x0, t = torch.from_numpy(fx["x"]), torch.from_numpy(fx["t"]).cuda()
+    y, mask = torch.from_numpy(fx["y"]).cuda(), torch.from_numpy(fx["mask"]).cuda()
+    old_cl, alpha = int(fx["old_cl"][0]), float(fx["alpha"][0])
+    runs = {
+        "kd": lambda x: U.KnowledgeDistillationLoss(reduction=red, alpha=alpha)(x, t),
+        "kd_mask": lambda x: U.KnowledgeDistillationLoss(reduction=red, alpha=alpha)(x, t, mask > 0),
+        "mkd": lambda x: U.MaskKnowledgeDistillationLoss(reduction=red, alpha=alpha)(x, t),
+        "mkd_mask": lambda x: U.MaskKnowledgeDistillationLoss(reduction=red, alpha=alpha)(x, t, mask),
+        "mce": lambda x: U.MaskCrossEntropy(old_cl=old_cl, reduction=red)(x, y),
+        "mce_old": lambda x: U.MaskCrossEntropy(old_cl=old_cl, reduction=red)(x, y, t),
+    }
+    y_before = y.clone()
+    for tag, fn in runs.items():
+        x = x0.cuda().requires_grad_(True)
+        out = fn(x)
+        want = torch.from_numpy(np.asarray(fx[f"{tag}_{red}_out"]))
+        torch.testing.assert_close(out.detach().cpu().double(), want, rtol=1e-4, atol=1e-5, msg=lambda m: f"{tag}: {m}")
+        w = torch.linspace(0.5, 1.5, out.numel(), dtype=torch.float64).reshape(out.shape) if out.dim() else None
+        (out if w is None else (out * w.float().cuda()).sum()).backward()
+        gw = torch.from_numpy(fx[f"{tag}_{red}_grad"])
+        assert cos(x.grad, gw) > 1 - 1e-6, tag
+        torch.testing.assert_close(x.grad.cpu().double(), gw, rtol=1e-3, atol=5e-6 * float(gw.abs().max()) + 1e-9,
+                                   msg=lambda m: f"{tag} grad: {m}")
+    assert torch.equal(y, y_before)  # MaskCrossEntropy leaves the caller's labels alone (unlike UNCE)
+
+
+@pytest.mark.parametrize("shape,c_old", [((2, 21, 33, 35), 16), ((1, 17, 64, 64), 16), ((2, 151, 16, 20), 101)])
+def test_sibling_losses_vs_oracle(U, shape, c_old):
+    """Odd plane sizes (scalar path), many channels, NaN-free ties in the old model's argmax."""
+    B, C, H, W = shape
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(B, C, H, W, generator=g) * 3
+    t = torch.randn(B, c_old, H, W, generator=g) * 3
+    t[:, :, 0] = 0.0                                    # ties: argmax must pick index 0
+    y = torch.randint(0, C, (B, H, W), generator=g)
+    y[:, -1] = 255
+    mask = torch.randint(0, 2, (B, H, W), generator=g)
+    for tag, ofn, mfn in [
+        ("kd", lambda v: O.plain_kd(v, t.double(), 1.3, "mean", mask), lambda v: U.KnowledgeDistillationLoss(alpha=1.3)(v, t.cuda(), mask.cuda())),
+        ("mkd", lambda v: O.mask_kd(v, t.double(), 1.3, "mean", mask), lambda v: U.MaskKnowledgeDistillationLoss(alpha=1.3)(v, t.cuda(), mask.cuda())),
+        ("mce", lambda v: O.mask_ce(v, y, c_old, t.double(), 255, "mean"), lambda v: U.MaskCrossEntropy(old_cl=c_old)(v, y.cuda(), t.cuda())),
+    ]:
+        xr = x.double().requires_grad_(True)
+        ref = ofn(xr)
+        ref.backward()
+        xc = x.cuda().requires_grad_(True)
+        out = mfn(xc)
+        out.backward()
+        torch.testing.assert_close(out.cpu().double(), ref.detach(), rtol=5e-5, atol=5e-6, msg=lambda m: f"{tag}: {m}")
+        assert cos(xc.grad, xr.grad) > 1 - 1e-6, tag
+

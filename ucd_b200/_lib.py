@@ -23,6 +23,9 @@ _PROTOS = {
     "ucd_unce_bwd": (c_int, [P, P, P, P, P, P, c_float, P, c_int, P, c_int, c_int, c_int, c_int64, c_int, P]),
     "ucd_unkd_fwd": (c_int, [P, P, P, c_float, P, P, P, P, c_int, c_int, c_int, c_int64, P]),
     "ucd_unkd_bwd": (c_int, [P, P, P, c_float, P, P, P, c_float, P, c_int, c_int, c_int, c_int64, P]),
+    "ucd_kd_fwd": (c_int, [P, P, P, c_float, P, P, P, P, c_int, c_int, c_int, c_int64, c_int, P]),
+    "ucd_kd_bwd": (c_int, [P, P, P, c_float, P, P, P, c_float, P, c_int, c_int, c_int, c_int64, c_int, P]),
+    "ucd_bkg_mask": (c_int, [P, P, P, c_int, c_int, c_int64, c_int, P]),
     "ucd_upsample_bilinear_fwd": (c_int, [P, P, c_int64, c_int, c_int, c_int, c_int, P]),
     "ucd_upsample_bilinear_bwd": (c_int, [P, P, c_int64, c_int, c_int, c_int, c_int, P]),
     "ucd_seg_fused_fwd": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
@@ -46,6 +49,7 @@ _PROTOS = {
     "ucd_con_debug_splits": (c_int, [c_int64, c_int64]),
     "ucd_selftest_umma": (c_int, [c_int, ctypes.POINTER(c_float)]),
     "ucd_selftest_mma_rate": (c_int, [c_int, c_int, ctypes.POINTER(c_float)]),
+    "ucd_selftest_pipe_rate": (c_int, [c_int, c_int, c_int, ctypes.POINTER(c_float)]),
 }
 EXPORTED = tuple(_PROTOS)
 

@@ -224,7 +224,9 @@ template <int VEC>
 __global__ void __launch_bounds__(kStreamThreads, 2)
 unkd_fwd_kernel(const float* __restrict__ x, const float* __restrict__ t, const float* __restrict__ mask,
                 float alpha, float* __restrict__ out_px, float* __restrict__ lse3, float* __restrict__ part,
-                int B, int C, int C_old, long long HW) {
+                int B, int C, int Cs, int C_old, int mask_zero, long long HW) {
+  // C: channels of x that take part; Cs >= C: channels per image in memory (plain KD narrows x to C = C_old)
+  // mask_zero: the weight of a pixel is [mask == 0] (MaskKnowledgeDistillationLoss) instead of mask itself
   const long long gpi = HW / VEC;
   const long long n_groups = gpi * B;
   const long long plane = (long long)B * HW;
@@ -234,7 +236,7 @@ unkd_fwd_kernel(const float* __restrict__ x, const float* __restrict__ t, const 
   for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n_groups;
        g += (long long)gridDim.x * blockDim.x) {
     const long long b = g / gpi, p = (g - b * gpi) * VEC;
-    const float* xp = x + (b * C) * HW + p;
+    const float* xp = x + (b * Cs) * HW + p;
     const float* tp = t + (b * C_old) * HW + p;
     // x: lse over all channels (m,s) and over S_b (mb,sb); t: lse (mt,st) and weighted sum wx = sum_{c>=1} 2^(t_c-mt) x_c
     // all in channel chunks (see lse_chunks): 2*CH*VEC loads in flight, no per-element dependency chain.
@@ -324,7 +326,7 @@ unkd_fwd_kernel(const float* __restrict__ x, const float* __restrict__ t, const 
       const float q0 = ex2f(t0[i] - lset2);
       const float dot = wx[i] / st[i];  // sum_{c>=1} q_c x_c
       float l = (q0 * (l_bkg[i] - l_all[i]) + dot - (1.f - q0) * l_all[i]) * inv_cold;
-      if (mask != nullptr) l *= mk[i];
+      if (mask != nullptr) l *= mask_zero ? (mk[i] == 0.f ? 1.f : 0.f) : mk[i];
       o[i] = -l;
       acc += l;
     }
@@ -343,8 +345,8 @@ template <int VEC>
 __global__ void __launch_bounds__(kStreamThreads)
 unkd_bwd_kernel(const float* __restrict__ x, const float* __restrict__ t, const float* __restrict__ mask,
                 float alpha, const float* __restrict__ lse3, const float* __restrict__ g_px,
-                const float* __restrict__ g_scalar, float g_mul, float* __restrict__ dx, int B, int C,
-                int C_old, long long HW) {
+                const float* __restrict__ g_scalar, float g_mul, float* __restrict__ dx, int B, int C, int Cs,
+                int C_old, int mask_zero, long long HW) {
   const long long gpi = HW / VEC;
   const long long n_groups = gpi * B;
   const long long plane = (long long)B * HW;
@@ -354,9 +356,9 @@ unkd_bwd_kernel(const float* __restrict__ x, const float* __restrict__ t, const 
   for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n_groups;
        g += (long long)gridDim.x * blockDim.x) {
     const long long b = g / gpi, p = (g - b * gpi) * VEC;
-    const float* xp = x + (b * C) * HW + p;
+    const float* xp = x + (b * Cs) * HW + p;
     const float* tp = t + (b * C_old) * HW + p;
-    float* dp = dx + (b * C) * HW + p;
+    float* dp = dx + (b * Cs) * HW + p;
     float la2[VEC], lt2[VEC], up[VEC], fb[VEC];  // fb = q0 * exp(lse_all - lse_bkg)
     {
       float la[VEC], lb[VEC], lt[VEC], gp[VEC], mk[VEC], u0[VEC];
@@ -371,7 +373,7 @@ unkd_bwd_kernel(const float* __restrict__ x, const float* __restrict__ t, const 
         la2[i] = la[i] * kLog2e;
         lt2[i] = lt[i] * kLog2e;
         float u = (g_px != nullptr ? gp[i] : gs) * inv_cold;
-        if (mask != nullptr) u *= mk[i];
+        if (mask != nullptr) u *= mask_zero ? (mk[i] == 0.f ? 1.f : 0.f) : mk[i];
         up[i] = u;
         const float q0 = ex2f(fmaf(u0[i], a2, -lt2[i]));
         fb[i] = q0 * ex2f((la[i] - lb[i]) * kLog2e);
@@ -411,6 +413,32 @@ unkd_bwd_kernel(const float* __restrict__ x, const float* __restrict__ t, const 
       }
       Vec<VEC>::store_stream(dp + (long long)c * HW, o);
     }
+    for (int c = C; c < Cs; ++c) {  // channels outside the narrowed view get no gradient
+      float o[VEC];
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) o[i] = 0.f;
+      Vec<VEC>::store_stream(dp + (long long)c * HW, o);
+    }
+  }
+}
+
+// MaskCrossEntropy's pixel weight (utils/loss.py:207-211): 1 where the old model predicts background
+// (argmax over channels == 0; ties resolve to the first index like torch.argmax) or the label is > old_cl.
+__global__ void __launch_bounds__(kStreamThreads)
+bkg_mask_kernel(const float* __restrict__ t, const long long* __restrict__ y, float* __restrict__ mask, int B,
+                int C_old, long long HW, int old_cl) {
+  const long long n = (long long)B * HW;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n; g += (long long)gridDim.x * blockDim.x) {
+    const long long b = g / HW, p = g - b * HW;
+    const float* tp = t + (b * C_old) * HW + p;
+    const float t0 = ldg_stream1(tp);
+    const bool t0_nan = t0 != t0;  // torch.argmax: NaN is the maximum, the first maximum wins
+    bool bkg = true;
+    for (int c = 1; c < C_old; ++c) {
+      const float v = ldg_stream1(tp + (long long)c * HW);
+      if (!t0_nan && (v > t0 || v != v)) bkg = false;
+    }
+    mask[g] = (bkg || y[g] > old_cl) ? 1.f : 0.f;
   }
 }
 
@@ -482,39 +510,78 @@ extern "C" int ucd_unce_bwd(const float* x, const int64_t* y, const float* lse_a
   return UCD_OK;
 }
 
-extern "C" int ucd_unkd_fwd(const float* x, const float* t, const float* mask, float alpha, float* out_px,
-                            float* stats, float* lse3, float* scratch, int B, int C, int C_old, int64_t HW,
-                            void* stream) {
-  UCD_CHECK_ARG(x && t && stats && lse3 && scratch, "ucd_unkd_fwd: null pointer");
-  UCD_CHECK_ARG(B > 0 && HW > 0 && C_old >= 1 && C >= C_old, "ucd_unkd_fwd: bad shape C=%d C_old=%d", C, C_old);
+// variant 0: unbiased KD (loss.py:139-184); 1: plain KD on the first C_old channels (loss.py:112-136);
+// 2: unbiased KD with the pixel weight [mask == 0] (MaskKnowledgeDistillationLoss, loss.py:218-256)
+static int kd_fwd_impl(const float* x, const float* t, const float* mask, float alpha, float* out_px, float* stats,
+                       float* lse3, float* scratch, int B, int C, int C_old, int64_t HW, int variant, void* stream) {
+  UCD_CHECK_ARG(x && t && stats && lse3 && scratch, "ucd_kd_fwd: null pointer");
+  UCD_CHECK_ARG(B > 0 && HW > 0 && C_old >= 1 && C >= C_old, "ucd_kd_fwd: bad shape C=%d C_old=%d", C, C_old);
+  UCD_CHECK_ARG(variant >= 0 && variant <= 2, "ucd_kd_fwd: bad variant %d", variant);
   cudaStream_t st = (cudaStream_t)stream;
+  const int Cu = variant == 1 ? C_old : C, mz = variant == 2 ? 1 : 0;
   const bool v4 = can_vec4(HW, {x, t, mask, out_px, lse3}) && ((long long)B * HW) % 4 == 0;
   const int grid = stream_grid((long long)B * HW / (v4 ? 4 : 1));
   if (v4)
-    unkd_fwd_kernel<4><<<grid, kStreamThreads, 0, st>>>(x, t, mask, alpha, out_px, lse3, scratch, B, C, C_old, HW);
+    unkd_fwd_kernel<4><<<grid, kStreamThreads, 0, st>>>(x, t, mask, alpha, out_px, lse3, scratch, B, Cu, C, C_old, mz, HW);
   else
-    unkd_fwd_kernel<1><<<grid, kStreamThreads, 0, st>>>(x, t, mask, alpha, out_px, lse3, scratch, B, C, C_old, HW);
+    unkd_fwd_kernel<1><<<grid, kStreamThreads, 0, st>>>(x, t, mask, alpha, out_px, lse3, scratch, B, Cu, C, C_old, mz, HW);
   UCD_CHECK_LAUNCH("unkd_fwd_kernel");
   reduce_partials_kernel<<<1, 256, 0, st>>>(scratch, grid, 1, stats);
   UCD_CHECK_LAUNCH("reduce_partials_kernel");
   return UCD_OK;
 }
 
-extern "C" int ucd_unkd_bwd(const float* x, const float* t, const float* mask, float alpha, const float* lse3,
-                            const float* g_px, const float* g_scalar, float g_mul, float* dx, int B, int C,
-                            int C_old, int64_t HW, void* stream) {
-  UCD_CHECK_ARG(x && t && lse3 && dx, "ucd_unkd_bwd: null pointer");
-  UCD_CHECK_ARG(g_px || g_scalar, "ucd_unkd_bwd: need g_px or g_scalar");
-  UCD_CHECK_ARG(B > 0 && HW > 0 && C_old >= 1 && C >= C_old, "ucd_unkd_bwd: bad shape");
+static int kd_bwd_impl(const float* x, const float* t, const float* mask, float alpha, const float* lse3,
+                       const float* g_px, const float* g_scalar, float g_mul, float* dx, int B, int C, int C_old,
+                       int64_t HW, int variant, void* stream) {
+  UCD_CHECK_ARG(x && t && lse3 && dx, "ucd_kd_bwd: null pointer");
+  UCD_CHECK_ARG(g_px || g_scalar, "ucd_kd_bwd: need g_px or g_scalar");
+  UCD_CHECK_ARG(B > 0 && HW > 0 && C_old >= 1 && C >= C_old, "ucd_kd_bwd: bad shape");
+  UCD_CHECK_ARG(variant >= 0 && variant <= 2, "ucd_kd_bwd: bad variant %d", variant);
   cudaStream_t st = (cudaStream_t)stream;
+  const int Cu = variant == 1 ? C_old : C, mz = variant == 2 ? 1 : 0;
   const bool v4 = can_vec4(HW, {x, t, mask, g_px, lse3, dx}) && ((long long)B * HW) % 4 == 0;
   const int grid = stream_grid((long long)B * HW / (v4 ? 4 : 1));
   if (v4)
-    unkd_bwd_kernel<4><<<grid, kStreamThreads, 0, st>>>(x, t, mask, alpha, lse3, g_px, g_scalar, g_mul, dx, B, C,
-                                                        C_old, HW);
+    unkd_bwd_kernel<4><<<grid, kStreamThreads, 0, st>>>(x, t, mask, alpha, lse3, g_px, g_scalar, g_mul, dx, B, Cu, C,
+                                                        C_old, mz, HW);
   else
-    unkd_bwd_kernel<1><<<grid, kStreamThreads, 0, st>>>(x, t, mask, alpha, lse3, g_px, g_scalar, g_mul, dx, B, C,
-                                                        C_old, HW);
+    unkd_bwd_kernel<1><<<grid, kStreamThreads, 0, st>>>(x, t, mask, alpha, lse3, g_px, g_scalar, g_mul, dx, B, Cu, C,
+                                                        C_old, mz, HW);
   UCD_CHECK_LAUNCH("unkd_bwd_kernel");
+  return UCD_OK;
+}
+
+extern "C" int ucd_unkd_fwd(const float* x, const float* t, const float* mask, float alpha, float* out_px,
+                            float* stats, float* lse3, float* scratch, int B, int C, int C_old, int64_t HW,
+                            void* stream) {
+  return kd_fwd_impl(x, t, mask, alpha, out_px, stats, lse3, scratch, B, C, C_old, HW, 0, stream);
+}
+
+extern "C" int ucd_unkd_bwd(const float* x, const float* t, const float* mask, float alpha, const float* lse3,
+                            const float* g_px, const float* g_scalar, float g_mul, float* dx, int B, int C,
+                            int C_old, int64_t HW, void* stream) {
+  return kd_bwd_impl(x, t, mask, alpha, lse3, g_px, g_scalar, g_mul, dx, B, C, C_old, HW, 0, stream);
+}
+
+extern "C" int ucd_kd_fwd(const float* x, const float* t, const float* mask, float alpha, float* out_px,
+                          float* stats, float* lse3, float* scratch, int B, int C, int C_old, int64_t HW,
+                          int variant, void* stream) {
+  return kd_fwd_impl(x, t, mask, alpha, out_px, stats, lse3, scratch, B, C, C_old, HW, variant, stream);
+}
+
+extern "C" int ucd_kd_bwd(const float* x, const float* t, const float* mask, float alpha, const float* lse3,
+                          const float* g_px, const float* g_scalar, float g_mul, float* dx, int B, int C,
+                          int C_old, int64_t HW, int variant, void* stream) {
+  return kd_bwd_impl(x, t, mask, alpha, lse3, g_px, g_scalar, g_mul, dx, B, C, C_old, HW, variant, stream);
+}
+
+extern "C" int ucd_bkg_mask(const float* t_old, const int64_t* labels, float* mask, int B, int C_old, int64_t HW,
+                            int old_cl, void* stream) {
+  UCD_CHECK_ARG(t_old && labels && mask, "ucd_bkg_mask: null pointer");
+  UCD_CHECK_ARG(B > 0 && C_old >= 1 && HW > 0, "ucd_bkg_mask: bad shape");
+  bkg_mask_kernel<<<stream_grid((long long)B * HW), kStreamThreads, 0, (cudaStream_t)stream>>>(
+      t_old, (const long long*)labels, mask, B, C_old, HW, old_cl);
+  UCD_CHECK_LAUNCH("bkg_mask_kernel");
   return UCD_OK;
 }

@@ -283,3 +283,69 @@ extern "C" int ucd_selftest_mma_rate(int mode, int iters, float* cycles_per_inst
   *cycles_per_instr_host = (float)h / (float)iters;
   return UCD_OK;
 }
+
+// ---- CUDA-core pipe probe for the sweep epilogue: which instructions share the MUFU's issue rate? ----
+// One block of `warps` warps, 8 independent values per thread; cycles per loop iteration are reported.
+//   mode 0: 8 ex2            1: 4 cvt.rn.bf16x2.f32 (+8 FADD)     2: 8 ex2 + 4 cvt
+//   mode 3: 8 ex2 + integer round-half-up pack (8 IADD + 4 PRMT)  4: 8 FADD only (loop overhead reference)
+namespace ucd {
+__global__ void pipe_rate_kernel(int mode, int iters, long long* out, unsigned* sink_out) {
+  float x[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = 0.001f * (float)(threadIdx.x + i);
+  unsigned sink = 0;
+  __syncthreads();
+  const long long c0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    if (mode == 0 || mode == 2 || mode == 3) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = ex2f(x[i] * -0.75f);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] += 1.0f;
+    }
+    if (mode == 1 || mode == 2) {
+#pragma unroll
+      for (int i = 0; i < 8; i += 2) {
+        __nv_bfloat162 v = __floats2bfloat162_rn(x[i], x[i + 1]);
+        sink ^= *reinterpret_cast<unsigned*>(&v);
+      }
+    }
+    if (mode == 3) {
+#pragma unroll
+      for (int i = 0; i < 8; i += 2)
+        sink ^= __byte_perm(__float_as_uint(x[i]) + 0x8000u, __float_as_uint(x[i + 1]) + 0x8000u, 0x7632);
+    }
+  }
+  const long long c1 = clock64();
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc += x[i];
+  if (acc == 123.456f) sink ^= 1u;
+  sink_out[threadIdx.x] = sink;
+  if (threadIdx.x == 0) out[0] = c1 - c0;
+}
+}  // namespace ucd
+
+extern "C" int ucd_selftest_pipe_rate(int mode, int warps, int iters, float* cycles_per_iter_host) {
+  UCD_CHECK_ARG(mode >= 0 && mode <= 4 && warps >= 1 && warps <= 32 && iters > 0 && cycles_per_iter_host,
+                "ucd_selftest_pipe_rate: bad argument");
+  long long* d = nullptr;
+  unsigned* sink = nullptr;
+  cudaError_t e;
+  if ((e = cudaMalloc(&d, 8)) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+  if ((e = cudaMalloc(&sink, 4096)) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+  for (int rep = 0; rep < 2; ++rep) {
+    pipe_rate_kernel<<<1, warps * 32>>>(mode, iters, d, sink);
+    if ((e = cudaDeviceSynchronize()) != cudaSuccess) {
+      cudaFree(d), cudaFree(sink);
+      return cuda_fail(e, "pipe_rate_kernel");
+    }
+  }
+  long long h = 0;
+  cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
+  cudaFree(d), cudaFree(sink);
+  *cycles_per_iter_host = (float)h / (float)iters;
+  return UCD_OK;
+}
+

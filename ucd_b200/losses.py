@@ -160,7 +160,7 @@ class UnbiasedCrossEntropy(nn.Module):
 # ----------------------------------------------------------------------------------------------
 class _UnkdFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, inputs, targets, mask, alpha, reduction):
+    def forward(ctx, inputs, targets, mask, alpha, reduction, variant=0):
         B, C, C_old = inputs.shape[0], inputs.shape[1], targets.shape[1]
         HW = inputs[0, 0].numel()
         x, t = _f32c(inputs), _f32c(targets)
@@ -171,10 +171,10 @@ class _UnkdFn(torch.autograd.Function):
         stats = torch.empty(1, device=dev, dtype=torch.float32)
         lse3 = torch.empty((3,) + px_shape, device=dev, dtype=torch.float32)
         scratch = torch.empty(_lib.lib().ucd_reduce_scratch_floats(), device=dev, dtype=torch.float32)
-        check(_lib.lib().ucd_unkd_fwd(ptr(x), ptr(t), ptr(m), float(alpha), ptr(out_px), ptr(stats), ptr(lse3),
-                                      ptr(scratch), B, C, C_old, HW, cur_stream()), "unkd_fwd")
+        check(_lib.lib().ucd_kd_fwd(ptr(x), ptr(t), ptr(m), float(alpha), ptr(out_px), ptr(stats), ptr(lse3),
+                                    ptr(scratch), B, C, C_old, HW, variant, cur_stream()), "kd_fwd")
         ctx.save_for_backward(x, t, m, lse3)
-        ctx.cfg = (B, C, C_old, HW, float(alpha), reduction)
+        ctx.cfg = (B, C, C_old, HW, float(alpha), reduction, variant)
         if reduction == "none":
             return out_px
         if reduction == "sum":
@@ -184,7 +184,7 @@ class _UnkdFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         x, t, m, lse3 = ctx.saved_tensors
-        B, C, C_old, HW, alpha, reduction = ctx.cfg
+        B, C, C_old, HW, alpha, reduction, variant = ctx.cfg
         dx = torch.empty_like(x)
         g_px, g_sc, g_mul = None, None, 1.0
         if reduction == "none":
@@ -197,9 +197,9 @@ class _UnkdFn(torch.autograd.Function):
                 g_mul = 1.0 / float(B * HW)
         if g_sc is not None:
             g_sc = _f32c(g_sc)
-        check(_lib.lib().ucd_unkd_bwd(ptr(x), ptr(t), ptr(m), alpha, ptr(lse3), ptr(g_px), ptr(g_sc), g_mul, ptr(dx),
-                                      B, C, C_old, HW, cur_stream()), "unkd_bwd")
-        return dx, None, None, None, None
+        check(_lib.lib().ucd_kd_bwd(ptr(x), ptr(t), ptr(m), alpha, ptr(lse3), ptr(g_px), ptr(g_sc), g_mul, ptr(dx),
+                                    B, C, C_old, HW, variant, cur_stream()), "kd_bwd")
+        return dx, None, None, None, None, None
 
 
 class UnbiasedKnowledgeDistillationLoss(nn.Module):
@@ -219,6 +219,83 @@ class UnbiasedKnowledgeDistillationLoss(nn.Module):
             raise ValueError("UnbiasedKnowledgeDistillationLoss: mask must be [B,...]")
         red = self.reduction if self.reduction in ("mean", "sum") else "none"
         return _UnkdFn.apply(inputs, targets.detach(), mask, self.alpha, red)
+
+
+def _kd_forward(name, variant, self, inputs, targets, mask):
+    _need_cuda(inputs, targets, mask)
+    if inputs.shape[1] < targets.shape[1] or inputs.shape[2:] != targets.shape[2:]:
+        raise ValueError("%s: inputs [B,C,...] / targets [B,C_old,...] disagree" % name)
+    if mask is not None and tuple(mask.shape) != (inputs.shape[0],) + tuple(inputs.shape[2:]):
+        raise ValueError("%s: mask must be [B,...]" % name)
+    red = self.reduction if self.reduction in ("mean", "sum") else "none"
+    return _UnkdFn.apply(inputs, targets.detach(), mask, self.alpha, red, variant)
+
+
+class KnowledgeDistillationLoss(nn.Module):
+    """Plain KD of the LwF-style baselines (utils/loss.py:112-136): log-softmax over the first C_old channels of
+    ``inputs`` against softmax(alpha * targets), averaged over those channels.  Same kernels as the unbiased loss
+    (SURVEY section 8(f) N3); the narrowed view is read in place, never copied."""
+
+    def __init__(self, reduction='mean', alpha=1.):
+        super().__init__()
+        self.reduction = reduction
+        self.alpha = alpha
+
+    def forward(self, inputs, targets, mask=None):
+        return _kd_forward("KnowledgeDistillationLoss", 1, self, inputs, targets, mask)
+
+
+class MaskKnowledgeDistillationLoss(nn.Module):
+    """Unbiased KD restricted to the pixels where ``mask == 0`` (utils/loss.py:218-256)."""
+
+    def __init__(self, reduction='mean', alpha=1.):
+        super().__init__()
+        self.reduction = reduction
+        self.alpha = alpha
+
+    def forward(self, inputs, targets, mask=None):
+        return _kd_forward("MaskKnowledgeDistillationLoss", 2, self, inputs, targets, mask)
+
+
+class MaskCrossEntropy(nn.Module):
+    """utils/loss.py:186-216: unbiased log-probabilities (background = all old classes), labels NOT remapped -
+    a label in [1, old_cl) picks the zero-filled channel, i.e. contributes 0 - and, when ``outputs_old`` is given,
+    only pixels the old model calls background or whose label is > old_cl count.  Keeps the reference's sign:
+    'mean' / 'sum' return the NEGATED reduction (loss.py:213-215), 'none' the positive map."""
+
+    def __init__(self, old_cl=None, reduction='mean', ignore_index=255):
+        super().__init__()
+        self.reduction = reduction
+        self.ignore_index = ignore_index
+        self.old_cl = old_cl
+
+    def forward(self, inputs, targets, outputs_old=None):
+        _need_cuda(inputs, targets, outputs_old)
+        if targets.dtype != torch.int64:
+            raise TypeError("MaskCrossEntropy: targets must be int64")
+        if inputs.dim() < 2 or targets.shape != inputs.shape[:1] + inputs.shape[2:]:
+            raise ValueError("MaskCrossEntropy: inputs [B,C,...] and targets [B,...] shapes disagree")
+        if outputs_old is not None and self.old_cl is None:
+            raise TypeError("MaskCrossEntropy: old_cl=None cannot be compared with the labels (loss.py:210)")
+        old_cl = 0 if self.old_cl is None else int(self.old_cl)  # None: every channel is a plain log-softmax
+        ign = int(self.ignore_index)
+        tgt = targets.clone()  # the reference leaves `targets` untouched here
+        if old_cl > 1:
+            tgt[(targets >= 1) & (targets < old_cl)] = ign  # zero loss and zero gradient, as the zero channel gives
+        loss = _UnceFn.apply(inputs, tgt, old_cl, ign, "none")
+        if outputs_old is not None:
+            t = _f32c(outputs_old.detach())
+            B, C_old = t.shape[0], t.shape[1]
+            mask = torch.empty(targets.shape, device=t.device, dtype=torch.float32)
+            lab = targets if targets.is_contiguous() else targets.contiguous()
+            check(_lib.lib().ucd_bkg_mask(ptr(t), ptr(lab), ptr(mask), B, C_old, t[0, 0].numel(), old_cl,
+                                          cur_stream()), "bkg_mask")
+            loss = loss * mask
+        if self.reduction == 'mean':
+            return -torch.mean(loss)
+        if self.reduction == 'sum':
+            return -torch.sum(loss)
+        return loss
 
 
 # ----------------------------------------------------------------------------------------------
