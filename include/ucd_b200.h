@@ -105,11 +105,14 @@ int ucd_upsample_bilinear_bwd(const float* gout, float* gin, int64_t planes, int
  * The full-resolution logits are never written.  lr [B,C,h,w], lr_old [B,C_old,h,w], labels [B,H,W] int64
  * (remapped in place like ucd_unce_fwd).  Outputs: sums[3] = {sum_px ce_px, #non-ignored pixels, sum_px kd_px}
  * with kd_px = -loss_px of the KD term, and (need_grad) the unit gradients g_ce, g_kd [B,C,h,w] of the two sums
- * with respect to lr.  Cross-block sums use float atomics (last-bit run-to-run differences).
+ * with respect to lr.  Cross-block sums go through `workspace` (ucd_seg_fused_workspace_floats floats, 16 B
+ * aligned) and are added in a fixed order: bit-identical from run to run.
  * ---------------------------------------------------------------------------------------- */
+size_t ucd_seg_fused_workspace_floats(int B, int C, int C_old, int h, int w, int H, int W);
 int ucd_seg_fused_fwd(const float* lr, const float* lr_old, int64_t* labels, float* g_ce, float* g_kd,
-                      float* sums, int B, int C, int C_old, int h, int w, int H, int W, int old_cl,
-                      int ignore_index, float alpha, int need_grad, void* stream);
+                      float* sums, float* workspace, size_t workspace_floats, int B, int C, int C_old, int h,
+                      int w, int H, int W, int old_cl, int ignore_index, float alpha, int need_grad,
+                      void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Contrastive prep   (utils/loss.py:258-395 v2 branch == utils/utils.py:256-397)

@@ -463,6 +463,12 @@ def test_fused_unbiased_losses(U, B, C, c_old, h, w, scale):
     ce_d = U.UnbiasedCrossEntropy(old_cl=c_old, reduction="none")(o, lab.cuda()).mean()
     kd_d = U.UnbiasedKnowledgeDistillationLoss()(o, U.interpolate_bilinear(lo.cuda(), (H, W)))
     assert ce.item() == pytest.approx(ce_d.item(), rel=1e-4) and kd.item() == pytest.approx(kd_d.item(), rel=1e-4)
+    # fixed-order cross-block sums: reruns are bit-identical
+    for _ in range(5):
+        lr_r = lr.cuda().requires_grad_(True)
+        ce_r, kd_r = U.FusedUnbiasedLosses(old_cl=c_old, alpha=1.0)(lr_r, lo.cuda(), lab.cuda())
+        (ce_r + 10 * kd_r).backward()
+        assert torch.equal(ce_r, ce) and torch.equal(kd_r, kd) and torch.equal(lr_r.grad, lr_c.grad)
 
 
 # ------------------------------------------------------------------------------------------------

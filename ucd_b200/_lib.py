@@ -28,8 +28,9 @@ _PROTOS = {
     "ucd_bkg_mask": (c_int, [P, P, P, c_int, c_int, c_int64, c_int, P]),
     "ucd_upsample_bilinear_fwd": (c_int, [P, P, c_int64, c_int, c_int, c_int, c_int, P]),
     "ucd_upsample_bilinear_bwd": (c_int, [P, P, c_int64, c_int, c_int, c_int, c_int, P]),
-    "ucd_seg_fused_fwd": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
-                                  c_float, c_int, P]),
+    "ucd_seg_fused_workspace_floats": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
+    "ucd_seg_fused_fwd": (c_int, [P, P, P, P, P, P, P, c_size_t, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                  c_int, c_int, c_float, c_int, P]),
     "ucd_con_max_tiles": (c_int64, [c_int64]),
     "ucd_con_prob_kpad": (c_int, [c_int]),
     "ucd_con_num_bins": (c_int, [c_int, c_int]),

@@ -19,8 +19,9 @@
 //   phase B (per channel, pixels of the column in the inner loop): dCE/dx_c and dKD/dx_c, accumulated over the
 //     rows with the y-tap weights; then multiplied by the x-tap weights, segment-reduced over the lanes that
 //     share a low-res column, and added to the four low-res cells.
-// The cross-block sums (a low-res cell collects from <= 2 row intervals x <= 3 column tiles) use float atomicAdd:
-// results can differ in the last bits between runs (unlike the rest of the library, which is deterministic).
+// Cross-block sums (a low-res cell collects from <= 3 (interval, tap row) sources x <= 3 column tiles; the three loss
+// sums from every block) go through per-block slabs and a second kernel that adds them in a fixed order: like the
+// rest of the library the results are bit-identical from run to run (no atomics).
 #include "common.cuh"
 
 namespace ucd {
@@ -33,9 +34,11 @@ struct FusedArgs {
   const float* lr;      // [B,C,h,w]
   const float* lo;      // [B,C_old,h,w]
   long long* labels;    // [B,H,W] (remapped in place like UnbiasedCrossEntropy)
-  float* g_ce;          // [B,C,h,w]  d(sum_px ce_px)/d lr        (zero-initialised by the host)
+  float* g_ce;          // [B,C,h,w]  d(sum_px ce_px)/d lr
   float* g_kd;          // [B,C,h,w]  d(sum_px kd_px)/d lr, kd_px = -loss_px
-  float* sums;          // [3] {sum ce_px, #non-ignored, sum kd_px}  (zero-initialised)
+  float* sums;          // [3] {sum ce_px, #non-ignored, sum kd_px}
+  float* psum;          // workspace [3][nblk]: per-block partial sums
+  float* slab;          // workspace [nblk][ncell]: per-block gradient cells (need_grad)
   int B, C, C_old, h, w, H, W, old_cl, ignore_index;
   float alpha, scale_h, scale_w;
   int need_grad;
@@ -72,7 +75,15 @@ __global__ void __launch_bounds__(TX * kRG) seg_fused_kernel(const FusedArgs a, 
     }
   }
   const int nrow = Yb - Ya + 1;
-  if (nrow <= 0) return;               // uniform per block
+  const int blk = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  const int nblk = gridDim.x * gridDim.y * gridDim.z;
+  const int ncell = 2 * ncx_cap * C * 2;
+  if (nrow <= 0) {  // uniform per block (cannot happen when upsampling; kept for safety): contributes zeros
+    if (threadIdx.x < 3) a.psum[(size_t)threadIdx.x * nblk + blk] = 0.f;
+    if (a.need_grad)
+      for (int i = threadIdx.x; i < ncell; i += TX * kRG) a.slab[(size_t)blk * ncell + i] = 0.f;
+    return;
+  }
   const int k1 = min(k + 1, a.h - 1);  // lower tap row (weight 0 when clamped)
 
   const Tap tx = bilinear_tap(colok ? X : a.W - 1, a.scale_w, a.w, a.W);
@@ -89,7 +100,6 @@ __global__ void __launch_bounds__(TX * kRG) seg_fused_kernel(const FusedArgs a, 
       u[((size_t)c * 2 + 1) * TX + xl] = __fmaf_rn(v10, tx.w0, __fmul_rn(v11, tx.w1));
     }
   }
-  const int ncell = 2 * ncx_cap * C * 2;
   for (int i = threadIdx.x; i < NW * ncell; i += TX * kRG) cell[i] = 0.f;
   __syncthreads();
 
@@ -193,9 +203,9 @@ __global__ void __launch_bounds__(TX * kRG) seg_fused_kernel(const FusedArgs a, 
   if (threadIdx.x == 0) {
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
     for (int i = 0; i < NW; ++i) s0 += red[0][i], s1 += red[1][i], s2 += red[2][i];
-    atomicAdd(a.sums + 0, s0);
-    atomicAdd(a.sums + 1, s1);
-    atomicAdd(a.sums + 2, s2);
+    a.psum[blk] = s0;
+    a.psum[(size_t)nblk + blk] = s1;
+    a.psum[2 * (size_t)nblk + blk] = s2;
   }
   if (!a.need_grad) return;
 
@@ -268,61 +278,121 @@ __global__ void __launch_bounds__(TX * kRG) seg_fused_kernel(const FusedArgs a, 
     __syncwarp();
   }
   __syncthreads();
-  // combine the warps in fixed order and add the tile's cells to the low-res gradients
+  // combine the warps in fixed order; the block's cells go to its slab ([yy][cx][c][term])
   for (int i = threadIdx.x; i < ncell; i += TX * kRG) {
     float v = 0.f;
     for (int wq = 0; wq < NW; ++wq) v += cell[(size_t)wq * ncell + i];
-    if (v == 0.f) continue;
-    const int term = i & 1;
-    const int c = (i >> 1) % C;
-    const int cx = ((i >> 1) / C) % ncx_cap;
-    const int yy = ((i >> 1) / C) / ncx_cap;
-    const int gy = yy == 0 ? k : k1, gx = cx_lo + cx;
-    if (gx >= a.w) continue;
-    float* dst = (term == 0 ? a.g_ce : a.g_kd) + (((size_t)b * C + c) * a.h + gy) * a.w + gx;
-    atomicAdd(dst, v);
+    a.slab[(size_t)blk * ncell + i] = v;
   }
+}
+
+// Second stage: fixed-order sums of the per-block slabs.  One thread per low-res element (b, c, gy, gx), both terms.
+// Sources of row gy: interval gy as its upper tap row (yy = 0), interval gy-1 as its lower tap row (yy = 1), and - at
+// the bottom border, where the lower tap is clamped - interval h-1's lower tap row again.
+__global__ void __launch_bounds__(256)
+seg_fused_gather_kernel(const FusedArgs a, int TX, int ntx, int ncx_cap) {
+  const int C = a.C;
+  const size_t ncell = (size_t)2 * ncx_cap * C * 2;
+  const long long n = (long long)a.B * C * a.h * a.w;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int gx = (int)(i % a.w), gy = (int)((i / a.w) % a.h);
+    const int c = (int)((i / ((long long)a.w * a.h)) % C), b = (int)(i / ((long long)a.w * a.h * C));
+    float ce = 0.f, kd = 0.f;
+    for (int src = 0; src < 3; ++src) {
+      int k, yy;
+      if (src == 0) k = gy, yy = 0;
+      else if (src == 1) k = gy - 1, yy = 1;
+      else k = a.h - 1, yy = 1;
+      if (k < 0 || (src == 2 && gy != a.h - 1)) continue;
+      for (int t = 0; t < ntx; ++t) {
+        const int cx = gx - bilinear_tap(min(t * TX, a.W - 1), a.scale_w, a.w, a.W).i0;
+        if (cx < 0 || cx >= ncx_cap) continue;
+        const size_t blk = ((size_t)b * a.h + k) * ntx + t;
+        const float2 v = *reinterpret_cast<const float2*>(a.slab + blk * ncell + (((size_t)yy * ncx_cap + cx) * C + c) * 2);
+        ce += v.x, kd += v.y;
+      }
+    }
+    a.g_ce[i] = ce;
+    a.g_kd[i] = kd;
+  }
+}
+
+__global__ void seg_fused_sums_kernel(const float* __restrict__ psum, int nblk, float* __restrict__ sums) {
+  __shared__ float red[32];
+  for (int k = 0; k < 3; ++k) {
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < nblk; i += blockDim.x) acc += psum[(size_t)k * nblk + i];
+    const float r = block_sum(acc, red);
+    if (threadIdx.x == 0) sums[k] = r;
+  }
+}
+
+struct FusedPlan {
+  int TX, ncx, ntx;
+  size_t smem;
+  long long nblk;
+  size_t ncell, floats;  // workspace: psum [3][nblk] (padded to 4 floats) then slab [nblk][ncell]
+};
+
+static bool fused_plan(int B, int C, int C_old, int h, int w, int W, FusedPlan& p) {
+  // column tile: the widest of {128, 64, 32} whose shared memory fits
+  const int CT = C + C_old;
+  p.TX = 0;
+  for (int cand : {128, 64, 32}) {
+    const int ncx = (int)((double)cand * w / W) + 3;
+    const size_t need = ((size_t)CT * 2 * cand + (size_t)(cand * kRG / 32) * 2 * ncx * C * 2) * sizeof(float);
+    if (need <= 72 * 1024 || (cand == 32 && need <= 200 * 1024)) {  // prefer >= 3 blocks per SM
+      p.TX = cand, p.smem = need, p.ncx = ncx;
+      break;
+    }
+  }
+  if (p.TX == 0) return false;
+  p.ntx = (W + p.TX - 1) / p.TX;
+  p.nblk = (long long)B * h * p.ntx;
+  p.ncell = (size_t)2 * p.ncx * C * 2;
+  p.floats = (((size_t)3 * p.nblk + 3) & ~(size_t)3) + (size_t)p.nblk * p.ncell;
+  return true;
 }
 
 }  // namespace ucd
 
 using namespace ucd;
 
+extern "C" size_t ucd_seg_fused_workspace_floats(int B, int C, int C_old, int h, int w, int H, int W) {
+  (void)H;
+  FusedPlan p;
+  if (B <= 0 || C <= 0 || C_old <= 0 || h <= 0 || w <= 0 || W < w || !fused_plan(B, C, C_old, h, w, W, p)) return 0;
+  return p.floats;
+}
+
 extern "C" int ucd_seg_fused_fwd(const float* lr, const float* lr_old, int64_t* labels, float* g_ce, float* g_kd,
-                                 float* sums, int B, int C, int C_old, int h, int w, int H, int W, int old_cl,
-                                 int ignore_index, float alpha, int need_grad, void* stream) {
-  UCD_CHECK_ARG(lr && lr_old && labels && sums, "ucd_seg_fused_fwd: null pointer");
+                                 float* sums, float* workspace, size_t workspace_floats, int B, int C, int C_old, int h,
+                                 int w, int H, int W, int old_cl, int ignore_index, float alpha, int need_grad,
+                                 void* stream) {
+  UCD_CHECK_ARG(lr && lr_old && labels && sums && workspace, "ucd_seg_fused_fwd: null pointer");
   UCD_CHECK_ARG(!need_grad || (g_ce && g_kd), "ucd_seg_fused_fwd: need_grad without gradient buffers");
   UCD_CHECK_ARG(B > 0 && C > 0 && C_old >= 1 && C >= C_old && h > 0 && w > 0 && H >= h && W >= w,
                 "ucd_seg_fused_fwd: bad shape (upsampling only)");
   UCD_CHECK_ARG(old_cl >= 0 && old_cl <= C, "ucd_seg_fused_fwd: old_cl outside [0,C]");
   UCD_CHECK_ARG(B <= 65535 && h <= 65535, "ucd_seg_fused_fwd: batch / rows too large for the grid");
+  UCD_CHECK_ARG(aligned16(workspace), "ucd_seg_fused_fwd: workspace must be 16 B aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  cudaError_t e = cudaMemsetAsync(sums, 0, 3 * sizeof(float), st);
-  if (e == cudaSuccess && need_grad) e = cudaMemsetAsync(g_ce, 0, (size_t)B * C * h * w * sizeof(float), st);
-  if (e == cudaSuccess && need_grad) e = cudaMemsetAsync(g_kd, 0, (size_t)B * C * h * w * sizeof(float), st);
-  if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(seg_fused)");
   const int rows_cap = (int)(1.5 * (double)H / h) + 3;  // the first interval also owns the clamped rows above row 0
   UCD_CHECK_ARG(rows_cap <= kRG * kRPT, "ucd_seg_fused_fwd: upscale factor %d too large for the fused kernel (max 19)", H / h);
+  FusedPlan p;
+  UCD_CHECK_ARG(fused_plan(B, C, C_old, h, w, W, p), "ucd_seg_fused_fwd: C + C_old = %d too large for one block", C + C_old);
+  UCD_CHECK_ARG(workspace_floats >= p.floats, "ucd_seg_fused_fwd: workspace too small (%zu < %zu floats)",
+                workspace_floats, p.floats);
+  UCD_CHECK_ARG(p.nblk < (1ll << 31), "ucd_seg_fused_fwd: too many blocks");
   FusedArgs a;
   a.lr = lr, a.lo = lr_old, a.labels = (long long*)labels, a.g_ce = g_ce, a.g_kd = g_kd, a.sums = sums;
+  a.psum = workspace, a.slab = workspace + (((size_t)3 * p.nblk + 3) & ~(size_t)3);
   a.B = B, a.C = C, a.C_old = C_old, a.h = h, a.w = w, a.H = H, a.W = W, a.old_cl = old_cl, a.ignore_index = ignore_index;
   a.alpha = alpha, a.scale_h = (float)h / (float)H, a.scale_w = (float)w / (float)W, a.need_grad = need_grad;
-  // column tile: the widest of {128, 64, 32} whose shared memory fits
-  const int CT = C + C_old;
-  int TX = 0;
-  size_t smem = 0;
-  int ncx = 0;
-  for (int cand : {128, 64, 32}) {
-    ncx = (int)((double)cand * w / W) + 3;
-    const size_t need = ((size_t)CT * 2 * cand + (size_t)(cand * kRG / 32) * 2 * ncx * C * 2) * sizeof(float);
-    if (need <= 72 * 1024 || (cand == 32 && need <= 200 * 1024)) {  // prefer >= 3 blocks per SM
-      TX = cand, smem = need;
-      break;
-    }
-  }
-  UCD_CHECK_ARG(TX != 0, "ucd_seg_fused_fwd: C + C_old = %d too large for one block", CT);
-  dim3 grid((W + TX - 1) / TX, h, B);
+  const int TX = p.TX, ncx = p.ncx;
+  const size_t smem = p.smem;
+  cudaError_t e;
+  dim3 grid(p.ntx, h, B);
 #define UCD_LAUNCH_FUSED(T)                                                                                          \
   do {                                                                                                               \
     if (smem > 48 * 1024) {                                                                                          \
@@ -339,5 +409,14 @@ extern "C" int ucd_seg_fused_fwd(const float* lr, const float* lr_old, int64_t* 
     UCD_LAUNCH_FUSED(32);
 #undef UCD_LAUNCH_FUSED
   UCD_CHECK_LAUNCH("seg_fused_kernel");
+  seg_fused_sums_kernel<<<1, 256, 0, st>>>(a.psum, (int)p.nblk, sums);
+  UCD_CHECK_LAUNCH("seg_fused_sums_kernel");
+  if (need_grad) {
+    const long long n = (long long)B * C * h * w;
+    long long blocks = (n + 255) / 256;
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    seg_fused_gather_kernel<<<(unsigned)blocks, 256, 0, st>>>(a, TX, p.ntx, ncx);
+    UCD_CHECK_LAUNCH("seg_fused_gather_kernel");
+  }
   return UCD_OK;
 }

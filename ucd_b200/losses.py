@@ -668,10 +668,14 @@ class _SegFusedFn(torch.autograd.Function):
         need_grad = bool(ctx.needs_input_grad[0])
         sums = torch.empty(3, device=dev, dtype=torch.float32)
         g = torch.empty(2, B, C, h, w, device=dev, dtype=torch.float32) if need_grad else None
+        n_ws = int(_lib.lib().ucd_seg_fused_workspace_floats(B, C, C_old, h, w, H, W))
+        if n_ws == 0:
+            raise ValueError("FusedUnbiasedLosses: shapes not supported (%s)" % ((B, C, C_old, h, w, H, W),))
+        ws = torch.empty(n_ws, device=dev, dtype=torch.float32)
         check(_lib.lib().ucd_seg_fused_fwd(ptr(x), ptr(t), ptr(labels), ptr(g[0]) if need_grad else None,
-                                           ptr(g[1]) if need_grad else None, ptr(sums), B, C, C_old, h, w, H, W,
-                                           old_cl, ignore_index, float(alpha), 1 if need_grad else 0, cur_stream()),
-              "seg_fused_fwd")
+                                           ptr(g[1]) if need_grad else None, ptr(sums), ptr(ws), n_ws, B, C, C_old,
+                                           h, w, H, W, old_cl, ignore_index, float(alpha), 1 if need_grad else 0,
+                                           cur_stream()), "seg_fused_fwd")
         ctx.save_for_backward(g)
         ctx.n_px = float(B * H * W)
         ctx.in_dtype = lr.dtype
