@@ -238,9 +238,10 @@ def main():
         outputs = U.interpolate_bilinear(lr, (H, W))
         with torch.no_grad():
             outputs_old = U.interpolate_bilinear(inp["l_po"], (H, W))
+        # evaluation order of train.py:115-116,133: prep, criterion, contrastive loss, distillation
         tup = U.pre_contrastive_pixel(f_n, inp["labels"], l_po=inp["l_po"], f_o=inp["f_o"])
-        con = conloss(*tup)
         ce = unce(outputs, inp["labels"]).mean()
+        con = conloss(*tup)
         kd = unkd(outputs, outputs_old)
         loss = ce + con / 100 + 10 * kd
         loss.backward()

@@ -81,7 +81,8 @@ size_t ucd_reduce_scratch_floats(void);
  *      mean over those channels; dx of the remaining channels is written as 0
  *   2  MaskKnowledgeDistillationLoss (utils/loss.py:218-256): variant 0 with the pixel weight [mask == 0] */
 int ucd_kd_fwd(const float* x, const float* t, const float* mask, float alpha, float* out_px, float* stats,
-               float* lse3, float* scratch, int B, int C, int C_old, int64_t HW, int variant, void* stream);
+               float* lse3, float* scratch, int B, int C, int C_old, int64_t HW, int variant, float stats_scale,
+               void* stream);   /* stats[0] = stats_scale * sum_px(weight * l_px): -1/(B*HW) gives the 'mean' loss */
 int ucd_kd_bwd(const float* x, const float* t, const float* mask, float alpha, const float* lse3,
                const float* g_px, const float* g_scalar, float g_mul, float* dx, int B, int C, int C_old,
                int64_t HW, int variant, void* stream);
@@ -176,7 +177,7 @@ int ucd_con_pack_rows(const float* rows, const int32_t* labels, int64_t n, void*
  *
  * ucd_con_fwd runs sweep 1 (row max, negative sum, positive count, V = sum_neg exp(s) c), the
  * combine, sweep 2 (loss terms, T, U) and the finalize; it writes
- *   out float[2]  = {sum_i loss_i over rows with num_i != 0, number of such rows}
+ *   out float[3]  = {sum_i loss_i over rows with num_i != 0, number of such rows, their ratio (= the loss)}
  *   grad_unit [max_row_tiles*128, 256] = d(sum_i loss_i)/d a_i   (scaled by g/M in ucd_con_bwd)
  * ---------------------------------------------------------------------------------------- */
 size_t ucd_con_workspace_bytes(int64_t max_row_tiles, int64_t max_col_tiles);

@@ -1,0 +1,66 @@
+"""GPU timeline of one drop-in step (kernel start, duration, idle gap before it) from torch.profiler (CUPTI).
+Dev tool: shows where the step's time goes beyond the kernels themselves (launch gaps, host syncs)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from torch.profiler import ProfilerActivity, profile
+
+import bench
+import ucd_b200 as U
+
+fusedmode = len(sys.argv) > 1 and sys.argv[1] == "fused"
+wl = dict(bench.WORKLOAD)
+B, H, W, C_old = wl["B"], wl["H"], wl["W"], wl["C_old"]
+dev = torch.device("cuda", 0)
+inp = {k: v.to(dev) for k, v in bench.make_inputs(0, B, wl).items()}
+conloss = U.PixelConLossV2(temperature=0.07)
+unce = U.UnbiasedCrossEntropy(old_cl=C_old, ignore_index=255, reduction="none")
+unkd = U.UnbiasedKnowledgeDistillationLoss(alpha=1.0)
+fused = U.FusedUnbiasedLosses(old_cl=C_old, ignore_index=255, alpha=1.0)
+
+
+def step():
+    f_n = inp["f_n"].detach().requires_grad_(True)
+    lr = inp["logits_lr"].detach().requires_grad_(True)
+    if fusedmode:
+        tup = U.pre_contrastive_pixel(f_n, inp["labels"], l_po=inp["l_po"], f_o=inp["f_o"])
+        con = conloss(*tup)
+        ce, kd = fused(lr, inp["l_po"], inp["labels"])
+    else:
+        outputs = U.interpolate_bilinear(lr, (H, W))
+        with torch.no_grad():
+            outputs_old = U.interpolate_bilinear(inp["l_po"], (H, W))
+        tup = U.pre_contrastive_pixel(f_n, inp["labels"], l_po=inp["l_po"], f_o=inp["f_o"])
+        ce = unce(outputs, inp["labels"]).mean()
+        con = conloss(*tup)
+        kd = unkd(outputs, outputs_old)
+    (ce + con / 100 + 10 * kd).backward()
+
+
+for _ in range(5):
+    step()
+torch.cuda.synchronize()
+NSTEP = 4
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    for _ in range(NSTEP):
+        step()
+    torch.cuda.synchronize()
+ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+ev.sort(key=lambda e: e.time_range.start)
+per = len(ev) // NSTEP
+# the third step (steady state)
+sel = ev[2 * per:3 * per]
+t0 = sel[0].time_range.start
+prev_end = ev[2 * per - 1].time_range.end
+busy = gaps = 0.0
+print("%8s %8s %8s  %s" % ("start", "dur", "gap", "kernel"))
+for e in sel:
+    s, d = e.time_range.start, e.time_range.end - e.time_range.start
+    gap = s - prev_end
+    print("%8.1f %8.1f %8.1f  %s" % (s - t0, d, gap, e.name[:90]))
+    busy += d
+    gaps += max(gap, 0.0)
+    prev_end = max(prev_end, e.time_range.end)
+print("kernels per step %d | busy %.1f us | idle gaps %.1f us | span %.1f us" % (per, busy, gaps, sel[-1].time_range.end - t0))

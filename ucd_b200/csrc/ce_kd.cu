@@ -45,13 +45,14 @@ struct Vec<1> {
 };
 
 // fixed-order final reduction of per-block partial sums: out[k] = sum_b part[k*nblk + b]
-__global__ void reduce_partials_kernel(const float* __restrict__ part, int nblk, int nk, float* __restrict__ out) {
+__global__ void reduce_partials_kernel(const float* __restrict__ part, int nblk, int nk, float* __restrict__ out,
+                                       float scale) {
   __shared__ float red[32];
   for (int k = 0; k < nk; ++k) {
     float acc = 0.f;
     for (int i = threadIdx.x; i < nblk; i += blockDim.x) acc += part[(size_t)k * nblk + i];
     float r = block_sum(acc, red);
-    if (threadIdx.x == 0) out[k] = r;
+    if (threadIdx.x == 0) out[k] = r * scale;
   }
 }
 
@@ -481,7 +482,7 @@ extern "C" int ucd_unce_fwd(const float* x, int64_t* y, float* loss_px, float* l
                                                         old_cl, HW, ignore_index);
   UCD_CHECK_LAUNCH("unce_fwd_kernel");
   if (stats) {
-    reduce_partials_kernel<<<1, 256, 0, st>>>(part, grid, 2, stats);
+    reduce_partials_kernel<<<1, 256, 0, st>>>(part, grid, 2, stats, 1.f);
     UCD_CHECK_LAUNCH("reduce_partials_kernel");
   }
   return UCD_OK;
@@ -513,7 +514,8 @@ extern "C" int ucd_unce_bwd(const float* x, const int64_t* y, const float* lse_a
 // variant 0: unbiased KD (loss.py:139-184); 1: plain KD on the first C_old channels (loss.py:112-136);
 // 2: unbiased KD with the pixel weight [mask == 0] (MaskKnowledgeDistillationLoss, loss.py:218-256)
 static int kd_fwd_impl(const float* x, const float* t, const float* mask, float alpha, float* out_px, float* stats,
-                       float* lse3, float* scratch, int B, int C, int C_old, int64_t HW, int variant, void* stream) {
+                       float* lse3, float* scratch, int B, int C, int C_old, int64_t HW, int variant, float stats_scale,
+                       void* stream) {
   UCD_CHECK_ARG(x && t && stats && lse3 && scratch, "ucd_kd_fwd: null pointer");
   UCD_CHECK_ARG(B > 0 && HW > 0 && C_old >= 1 && C >= C_old, "ucd_kd_fwd: bad shape C=%d C_old=%d", C, C_old);
   UCD_CHECK_ARG(variant >= 0 && variant <= 2, "ucd_kd_fwd: bad variant %d", variant);
@@ -526,7 +528,7 @@ static int kd_fwd_impl(const float* x, const float* t, const float* mask, float 
   else
     unkd_fwd_kernel<1><<<grid, kStreamThreads, 0, st>>>(x, t, mask, alpha, out_px, lse3, scratch, B, Cu, C, C_old, mz, HW);
   UCD_CHECK_LAUNCH("unkd_fwd_kernel");
-  reduce_partials_kernel<<<1, 256, 0, st>>>(scratch, grid, 1, stats);
+  reduce_partials_kernel<<<1, 256, 0, st>>>(scratch, grid, 1, stats, stats_scale);
   UCD_CHECK_LAUNCH("reduce_partials_kernel");
   return UCD_OK;
 }
@@ -555,7 +557,7 @@ static int kd_bwd_impl(const float* x, const float* t, const float* mask, float 
 extern "C" int ucd_unkd_fwd(const float* x, const float* t, const float* mask, float alpha, float* out_px,
                             float* stats, float* lse3, float* scratch, int B, int C, int C_old, int64_t HW,
                             void* stream) {
-  return kd_fwd_impl(x, t, mask, alpha, out_px, stats, lse3, scratch, B, C, C_old, HW, 0, stream);
+  return kd_fwd_impl(x, t, mask, alpha, out_px, stats, lse3, scratch, B, C, C_old, HW, 0, 1.f, stream);
 }
 
 extern "C" int ucd_unkd_bwd(const float* x, const float* t, const float* mask, float alpha, const float* lse3,
@@ -566,8 +568,8 @@ extern "C" int ucd_unkd_bwd(const float* x, const float* t, const float* mask, f
 
 extern "C" int ucd_kd_fwd(const float* x, const float* t, const float* mask, float alpha, float* out_px,
                           float* stats, float* lse3, float* scratch, int B, int C, int C_old, int64_t HW,
-                          int variant, void* stream) {
-  return kd_fwd_impl(x, t, mask, alpha, out_px, stats, lse3, scratch, B, C, C_old, HW, variant, stream);
+                          int variant, float stats_scale, void* stream) {
+  return kd_fwd_impl(x, t, mask, alpha, out_px, stats, lse3, scratch, B, C, C_old, HW, variant, stats_scale, stream);
 }
 
 extern "C" int ucd_kd_bwd(const float* x, const float* t, const float* mask, float alpha, const float* lse3,

@@ -588,15 +588,17 @@ __global__ void con_combine_kernel(const float* __restrict__ part, int splits, l
   stats[2 * rows_pad + i] = num;
 }
 
-// finalize: per-row loss terms, unit gradient, per-block partial sums.  block = 256 threads (one per feature)
+// finalize: per-row loss terms, unit gradient, per-block partial sums.  block = 4 rows x 64 threads, a thread owns
+// one float4 of its row: splits + splits2 independent 16 B streaming loads in flight per thread.
 __global__ void __launch_bounds__(256)
 con_finalize_kernel(const float* __restrict__ stats, const float* __restrict__ loss_part,
                     const float* __restrict__ v_part, const float* __restrict__ u_part, int splits, int splits2,
                     long long rows_pad, const int* __restrict__ n_rows_p, float inv_tau,
                     int need_grad, float* __restrict__ grad_unit, float* __restrict__ block_part) {
   const int n_rows = *n_rows_p;
+  const int sub = threadIdx.x >> 6, q = threadIdx.x & 63;
   float lsum = 0.f, lcnt = 0.f;
-  for (long long row = blockIdx.x; row < n_rows; row += gridDim.x) {
+  for (long long row = (long long)blockIdx.x * 4 + sub; row < n_rows; row += (long long)gridDim.x * 4) {
     const float num = stats[2 * rows_pad + row];
     float L = 0.f, T = 0.f;
     for (int s = 0; s < splits2; ++s) {
@@ -605,30 +607,50 @@ con_finalize_kernel(const float* __restrict__ stats, const float* __restrict__ l
     }
     const bool valid = num != 0.f;
     if (need_grad) {
-      float V = 0.f, U = 0.f;
-      for (int s = 0; s < splits; ++s) V += v_part[((size_t)s * rows_pad + row) * 256 + threadIdx.x];
-      for (int s = 0; s < splits2; ++s) U += u_part[((size_t)s * rows_pad + row) * 256 + threadIdx.x];
-      grad_unit[(size_t)row * 256 + threadIdx.x] = valid ? (inv_tau / num) * (T * V - U) : 0.f;
+      float4 V = make_float4(0.f, 0.f, 0.f, 0.f), U = V;
+#pragma unroll 4
+      for (int s = 0; s < splits; ++s) {
+        const float4 t = __ldcs(reinterpret_cast<const float4*>(v_part + ((size_t)s * rows_pad + row) * 256) + q);
+        V.x += t.x, V.y += t.y, V.z += t.z, V.w += t.w;
+      }
+#pragma unroll 4
+      for (int s = 0; s < splits2; ++s) {
+        const float4 t = __ldcs(reinterpret_cast<const float4*>(u_part + ((size_t)s * rows_pad + row) * 256) + q);
+        U.x += t.x, U.y += t.y, U.z += t.z, U.w += t.w;
+      }
+      const float k = valid ? inv_tau / num : 0.f;
+      float4 g;
+      g.x = valid ? k * (T * V.x - U.x) : 0.f;
+      g.y = valid ? k * (T * V.y - U.y) : 0.f;
+      g.z = valid ? k * (T * V.z - U.z) : 0.f;
+      g.w = valid ? k * (T * V.w - U.w) : 0.f;
+      reinterpret_cast<float4*>(grad_unit + (size_t)row * 256)[q] = g;
     }
-    if (threadIdx.x == 0 && valid) {
+    if (q == 0 && valid) {
       lsum += -L / num;
       lcnt += 1.f;
     }
   }
-  if (threadIdx.x == 0) {
-    block_part[blockIdx.x] = lsum;
-    block_part[gridDim.x + blockIdx.x] = lcnt;
+  __shared__ float sh[2][4];
+  if (q == 0) sh[0][sub] = lsum, sh[1][sub] = lcnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {  // fixed order
+    block_part[blockIdx.x] = (sh[0][0] + sh[0][1]) + (sh[0][2] + sh[0][3]);
+    block_part[gridDim.x + blockIdx.x] = (sh[1][0] + sh[1][1]) + (sh[1][2] + sh[1][3]);
   }
 }
 
+// out = {sum of row losses, number of valid rows, their ratio (the loss; NaN when no row is valid, like the reference)}
 __global__ void con_reduce_out_kernel(const float* __restrict__ block_part, int nblk, float* __restrict__ out) {
   __shared__ float red[32];
+  __shared__ float res[2];
   for (int k = 0; k < 2; ++k) {
     float acc = 0.f;
     for (int i = threadIdx.x; i < nblk; i += blockDim.x) acc += block_part[(size_t)k * nblk + i];
     const float r = block_sum(acc, red);
-    if (threadIdx.x == 0) out[k] = r;
+    if (threadIdx.x == 0) out[k] = r, res[k] = r;
   }
+  if (threadIdx.x == 0) out[2] = res[0] / res[1];
 }
 
 __global__ void con_bwd_kernel(const float* __restrict__ grad_unit, const float* __restrict__ out,

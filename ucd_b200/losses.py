@@ -171,15 +171,15 @@ class _UnkdFn(torch.autograd.Function):
         stats = torch.empty(1, device=dev, dtype=torch.float32)
         lse3 = torch.empty((3,) + px_shape, device=dev, dtype=torch.float32)
         scratch = torch.empty(_lib.lib().ucd_reduce_scratch_floats(), device=dev, dtype=torch.float32)
+        # the reduce kernel applies the sign and the 1/(B*HW) of the reduction: no scalar torch kernels afterwards
+        scale = -1.0 / float(B * HW) if reduction == "mean" else -1.0
         check(_lib.lib().ucd_kd_fwd(ptr(x), ptr(t), ptr(m), float(alpha), ptr(out_px), ptr(stats), ptr(lse3),
-                                    ptr(scratch), B, C, C_old, HW, variant, cur_stream()), "kd_fwd")
+                                    ptr(scratch), B, C, C_old, HW, variant, scale, cur_stream()), "kd_fwd")
         ctx.save_for_backward(x, t, m, lse3)
         ctx.cfg = (B, C, C_old, HW, float(alpha), reduction, variant)
         if reduction == "none":
             return out_px
-        if reduction == "sum":
-            return -stats[0]
-        return -stats[0] / float(B * HW)
+        return stats[0]
 
     @staticmethod
     def backward(ctx, g):
@@ -521,7 +521,7 @@ class _ConFn(torch.autograd.Function):
         max_row_tiles = rows["max_tiles"]
         ws_bytes = L.ucd_con_workspace_bytes(max_row_tiles, cols["n_chunks"] * cols["chunk_tiles"])
         ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
-        out = torch.empty(2, device=dev, dtype=torch.float32)
+        out = torch.empty(3, device=dev, dtype=torch.float32)
         need_grad = bool(ctx.needs_input_grad[0])
         grad_unit = (torch.empty(max_row_tiles * TILE, FEAT_DIM, device=dev, dtype=torch.float32)
                      if need_grad else None)
@@ -535,12 +535,14 @@ class _ConFn(torch.autograd.Function):
         world = 1
         if group is not None:
             import torch.distributed as dist
-            dist.all_reduce(out, group=group)      # {sum of row losses, #valid rows} over all ranks
+            dist.all_reduce(out[:2], group=group)  # {sum of row losses, #valid rows} over all ranks
             world = dist.get_world_size(group)
         ctx.save_for_backward(grad_unit, out, rows["n_rows"], rows.get("row_ref"))
         ctx.n_a = anchor.shape[0]
         ctx.world = world if ddp_scale else 1
-        return out[0] / out[1]
+        if group is not None:
+            return out[0] / out[1]
+        return out[2]  # the ratio comes from the reduce kernel: no extra launch
 
     @staticmethod
     def backward(ctx, g):
