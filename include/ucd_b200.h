@@ -146,7 +146,8 @@ int ucd_con_prep_labels(const int64_t* labels, const float* l_po, int B, int C_o
  * min/max valid label per tile. */
 int ucd_con_prep_pack(const float* f_n, const float* f_o, const float* l_po, const int32_t* px_meta,
                       int32_t* blk_meta, const int32_t* counts, int B, int C_old, int h, int w, int max_label,
-                      float* anchor_f32, float* contrast_f32, int32_t* la, int32_t* lc,
+                      float* anchor_f32, float* contrast_f32, void* la, void* lc,
+                      int label_bytes /* element size of la / lc: 1 (int8, max_label <= 127) or 4 (int32) */,
                       void* feat_tiles, void* prob_tiles, int32_t* lab_tiles, int32_t* tile_range,
                       int32_t* row_range /*[ceil(n_px/128)][2], anchors only*/, int32_t* row_ref, float* inv_norm,
                       int64_t max_tiles, void* stream);

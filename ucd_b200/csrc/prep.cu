@@ -175,8 +175,9 @@ __device__ __forceinline__ size_t tile_chunk_off(long long tile, int chunks_per_
 __global__ void __launch_bounds__(128)
 prep_pack_kernel(const float* __restrict__ f_n, const float* __restrict__ f_o, const int* __restrict__ px_meta,
                  int* __restrict__ blk_base, int nblk, int nb, const int* __restrict__ counts, int n_px, int hw,
-                 float* __restrict__ anchor_f32, float* __restrict__ contrast_f32, int* __restrict__ la,
-                 int* __restrict__ lc, __nv_bfloat16* __restrict__ feat_tiles, int* __restrict__ lab_tiles,
+                 float* __restrict__ anchor_f32, float* __restrict__ contrast_f32, void* __restrict__ la,
+                 void* __restrict__ lc, int label_bytes, __nv_bfloat16* __restrict__ feat_tiles,
+                 int* __restrict__ lab_tiles,
                  int* __restrict__ row_ref, float* __restrict__ inv_norm) {
   __shared__ float tile[256][33];
   __shared__ float ss[4][32];
@@ -221,10 +222,18 @@ prep_pack_kernel(const float* __restrict__ f_n, const float* __restrict__ f_o, c
     slot_s[lane] = slot;
     if (slot >= 0) {
       const int m = px_meta[(size_t)PX_MIX * n_px + p];
-      lc[src == 0 ? slot : n_a + slot] = m;
+      // the tuple's label vectors in the element type the reference hands out (int8 on VOC / Cityscapes)
+      const int cslot = src == 0 ? slot : n_a + slot;
+      if (label_bytes == 1)
+        static_cast<signed char*>(lc)[cslot] = (signed char)m;
+      else
+        static_cast<int*>(lc)[cslot] = m;
       lab_tiles[src == 0 ? sslot : n_a + sslot] = m;
       if (src == 0) {
-        la[slot] = m;
+        if (label_bytes == 1)
+          static_cast<signed char*>(la)[slot] = (signed char)m;
+        else
+          static_cast<int*>(la)[slot] = m;
         row_ref[sslot] = slot;
         inv_norm[slot] = inv;
       }
@@ -445,14 +454,16 @@ extern "C" int ucd_con_tile_ranges(const int32_t* lab_tiles, int64_t n_tiles, co
 
 extern "C" int ucd_con_prep_pack(const float* f_n, const float* f_o, const float* l_po, const int32_t* px_meta,
                                  int32_t* blk_meta, const int32_t* counts, int B, int C_old, int h, int w,
-                                 int max_label, float* anchor_f32, float* contrast_f32, int32_t* la, int32_t* lc,
-                                 void* feat_tiles, void* prob_tiles, int32_t* lab_tiles, int32_t* tile_range,
+                                 int max_label, float* anchor_f32, float* contrast_f32, void* la, void* lc,
+                                 int label_bytes, void* feat_tiles, void* prob_tiles, int32_t* lab_tiles, int32_t* tile_range,
                                  int32_t* row_range, int32_t* row_ref, float* inv_norm, int64_t max_tiles, void* stream) {
   UCD_CHECK_ARG(f_n && f_o && l_po && px_meta && blk_meta && counts && anchor_f32 && contrast_f32 && la && lc &&
                     feat_tiles && prob_tiles && lab_tiles && tile_range && row_range && row_ref && inv_norm,
                 "ucd_con_prep_pack: null pointer");
   UCD_CHECK_ARG(aligned16(feat_tiles) && aligned16(prob_tiles) && aligned16(lab_tiles),
                 "ucd_con_prep_pack: tiles must be 16 B aligned");
+  UCD_CHECK_ARG(label_bytes == 4 || (label_bytes == 1 && max_label <= 127),
+                "ucd_con_prep_pack: label_bytes must be 4, or 1 when max_label <= 127");
   const int n_px = B * h * w;
   UCD_CHECK_ARG(max_tiles >= ucd_con_max_tiles(n_px), "ucd_con_prep_pack: max_tiles too small");
   cudaStream_t st = (cudaStream_t)stream;
@@ -465,8 +476,8 @@ extern "C" int ucd_con_prep_pack(const float* f_n, const float* f_o, const float
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(tiles)");
   dim3 grid((n_px + 31) / 32, 2);
   prep_pack_kernel<<<grid, 128, 0, st>>>(f_n, f_o, px_meta, blk_meta, nblk, nb, counts, n_px, h * w, anchor_f32,
-                                         contrast_f32, la, lc, (__nv_bfloat16*)feat_tiles, lab_tiles, row_ref,
-                                         inv_norm);
+                                         contrast_f32, la, lc, label_bytes, (__nv_bfloat16*)feat_tiles, lab_tiles,
+                                         row_ref, inv_norm);
   UCD_CHECK_LAUNCH("prep_pack_kernel");
   prep_prob_kernel<<<(n_px + 255) / 256, 256, 0, st>>>(l_po, px_meta, blk_meta, nblk, nb, counts, n_px, h * w, C_old,
                                                        kpad, (__nv_bfloat16*)prob_tiles);

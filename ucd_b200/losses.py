@@ -378,8 +378,9 @@ def _build_pack(f_n, f_o, l_po, labels, max_label):
     copied.record()
     pk.anchor_f32 = torch.empty(n_px, FEAT_DIM, device=dev, dtype=torch.float32)
     pk.contrast_f32 = torch.empty(2 * n_px, FEAT_DIM, device=dev, dtype=torch.float32)
-    pk.la = torch.empty(n_px, **i32)
-    pk.lc = torch.empty(2 * n_px, **i32)
+    ldt = _label_dtype(pk.max_label)   # the tuple's label vectors come out of the pack kernel in their final type
+    pk.la = torch.empty(n_px, device=dev, dtype=ldt)
+    pk.lc = torch.empty(2 * n_px, device=dev, dtype=ldt)
     pk.feat_tiles = torch.empty(pk.max_tiles, FEAT_DIM // 8, TILE, 8, device=dev, dtype=torch.bfloat16)
     pk.prob_tiles = torch.empty(pk.max_tiles, pk.kpad // 8, TILE, 8, device=dev, dtype=torch.bfloat16)
     pk.lab_tiles = torch.empty(pk.max_tiles, TILE, **i32)
@@ -389,7 +390,7 @@ def _build_pack(f_n, f_o, l_po, labels, max_label):
     pk.inv_norm = torch.empty(n_px, device=dev, dtype=torch.float32)
     check(L.ucd_con_prep_pack(ptr(f_n), ptr(f_o), ptr(l_po), ptr(pk.px_meta), ptr(pk.blk_meta), ptr(pk.counts), B,
                               pk.c_old, h, w, pk.max_label, ptr(pk.anchor_f32), ptr(pk.contrast_f32), ptr(pk.la),
-                              ptr(pk.lc), ptr(pk.feat_tiles), ptr(pk.prob_tiles), ptr(pk.lab_tiles),
+                              ptr(pk.lc), pk.la.element_size(), ptr(pk.feat_tiles), ptr(pk.prob_tiles), ptr(pk.lab_tiles),
                               ptr(pk.tile_range), ptr(pk.row_range), ptr(pk.row_ref), ptr(pk.inv_norm),
                               pk.max_tiles, st),
           "con_prep_pack")
@@ -471,9 +472,7 @@ def pre_contrastive_pixel(f_n, l_n, l_po=None, f_o=None, max_label=20):
             "the single/double pixel-to-pixel branches (utils/loss.py:278-289) are outside this hot path")
     pack = _build_pack(f_n.detach(), f_o.detach(), l_po.detach(), l_n, max_label)
     anchor = _AnchorFn.apply(f_n, pack)
-    ldt = _label_dtype(max_label)
-    out = (anchor, pack.contrast_f32[:pack.n_c], pack.la[:pack.n_a].to(ldt), pack.lc[:pack.n_c].to(ldt),
-           JointProb(pack))
+    out = (anchor, pack.contrast_f32[:pack.n_c], pack.la[:pack.n_a], pack.lc[:pack.n_c], JointProb(pack))
     return out
 
 
