@@ -100,6 +100,77 @@ upsample_fwd_kernel(const float* __restrict__ in, float* __restrict__ out, long 
   }
 }
 
+// Forward, interval form (the one the training shapes take).  block = (plane, low-res row interval k, column tile):
+// all output rows whose upper tap is source row k are contiguous in memory and share both source rows, so
+//   out(Y, X) = fma(t0(X), h0(Y), t1(X) * h1(Y))   with  t_r(X) = fma(v_r0, w0, v_r1 * w1)
+// (exactly ATen's generic-kernel operation order) costs one FMUL + one FMA per output after 4 loads per thread.
+// Consecutive blocks write consecutive ~32 KB runs: the whole grid is one sequential write stream.
+constexpr int kUpMaxIvRows = 96;  // rows of one interval the weight table holds (scale factors up to ~60)
+template <int VEC>
+__global__ void __launch_bounds__(kUpThreads)
+upsample_fwd_interval_kernel(const float* __restrict__ in, float* __restrict__ out, int h, int w, int H, int W,
+                             float scale_h, float scale_w, int tw, int n_col_tiles) {
+  __shared__ float s_h0[kUpMaxIvRows], s_h1[kUpMaxIvRows];
+  __shared__ int s_lo[3], s_hi[3];
+  const int wv = (W + VEC - 1) / VEC;
+  const int rp = kUpThreads / tw;  // rows per pass
+  const int per_plane = h * n_col_tiles;
+  const long long plane = blockIdx.x / per_plane;
+  const int rem = (int)(blockIdx.x - plane * per_plane);
+  const int k = rem / n_col_tiles, col_tile = rem - k * n_col_tiles;
+  // rows of this interval: all Y with tap.i0 == k (contiguous); candidates evaluated in parallel by 3 warps
+  const float inv = (float)H / (float)h;
+  int lo = (int)floorf(((float)k - 0.5f) * inv) - 2, hi = (int)ceilf(((float)k + 1.5f) * inv) + 2;
+  lo = max(lo, 0), hi = min(hi, H - 1);
+  if (threadIdx.x < kUpMaxIvRows) {
+    const int Y = lo + (int)threadIdx.x;
+    bool match = false;
+    if (Y <= hi) {
+      const Tap ty = bilinear_tap(Y, scale_h, h, H);
+      match = ty.i0 == k;
+      s_h0[threadIdx.x] = ty.w0, s_h1[threadIdx.x] = ty.w1;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, match);
+    if ((threadIdx.x & 31) == 0) {
+      const int wq = threadIdx.x >> 5;
+      s_lo[wq] = bal ? wq * 32 + __ffs(bal) - 1 : 1 << 30;
+      s_hi[wq] = bal ? wq * 32 + 31 - __clz(bal) : -1;
+    }
+  }
+  __syncthreads();
+  const int ia = min(s_lo[0], min(s_lo[1], s_lo[2])), ib = max(s_hi[0], max(s_hi[1], s_hi[2]));
+  const int nrow = ib - ia + 1;
+  if (nrow <= 0) return;
+  const int Ya = lo + ia;
+  const int xg = col_tile * tw + (int)threadIdx.x % tw, rphase = (int)threadIdx.x / tw;
+  if (xg >= wv || rphase >= rp) return;
+  const int X = xg * VEC;
+  const int k1 = min(k + 1, h - 1);
+  const float* r0 = in + (size_t)plane * h * w + (size_t)k * w;
+  const float* r1 = in + (size_t)plane * h * w + (size_t)k1 * w;
+  float t0[VEC], t1[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const Tap tx = bilinear_tap(min(X + i, W - 1), scale_w, w, W);
+    t0[i] = __fmaf_rn(__ldg(r0 + tx.i0), tx.w0, __fmul_rn(__ldg(r0 + tx.i1), tx.w1));
+    t1[i] = __fmaf_rn(__ldg(r1 + tx.i0), tx.w0, __fmul_rn(__ldg(r1 + tx.i1), tx.w1));
+  }
+  float* dst = out + (size_t)plane * H * W + (size_t)(Ya + rphase) * W + X;
+  const size_t step = (size_t)rp * W;
+#pragma unroll 4
+  for (int r = rphase; r < nrow; r += rp) {
+    const float h0 = s_h0[ia + r], h1 = s_h1[ia + r];
+    float o[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) o[i] = __fmaf_rn(t0[i], h0, __fmul_rn(t1[i], h1));
+    if (VEC == 4)
+      stg_stream4(dst, make_float4(o[0], o[1], o[2], o[3]));
+    else
+      stg_stream1(dst, o[0]);
+    dst += step;
+  }
+}
+
 // Adjoint.  block = (plane, group of RY low-res rows).  Dynamic smem: colsum[RY][W] | wrow[ny_cap][RY].
 //   step 0: per full-res row Y of the group's footprint, its weight towards each of the RY low-res rows
 //   step 1: stream the footprint rows once (VEC=4: 128-bit loads), reduce along y in registers -> colsum
@@ -221,6 +292,18 @@ extern "C" int ucd_upsample_bilinear_fwd(const float* in, float* out, int64_t pl
   const float sh = (float)h / (float)H, sw = (float)w / (float)W;
   const bool v4 = (W % 4 == 0) && aligned16(out);
   const int wv = v4 ? W / 4 : W;
+  // upsampling beyond ATen's small-output regime (every training shape): interval kernel
+  if (H + W > 128 && H >= h && W >= w && (double)H / h <= 60.0 && planes * (long long)h < (1ll << 30) / 64) {
+    const int tw = wv < kUpThreads ? wv : kUpThreads;
+    const int nct = (wv + tw - 1) / tw;
+    const unsigned nblk = (unsigned)(planes * h * nct);
+    if (v4)
+      upsample_fwd_interval_kernel<4><<<nblk, kUpThreads, 0, st>>>(in, out, h, w, H, W, sh, sw, tw, nct);
+    else
+      upsample_fwd_interval_kernel<1><<<nblk, kUpThreads, 0, st>>>(in, out, h, w, H, W, sh, sw, tw, nct);
+    UCD_CHECK_LAUNCH("upsample_fwd_interval_kernel");
+    return UCD_OK;
+  }
   const long long work = (long long)H * wv;
   const int gx = (int)((work + kUpThreads - 1) / kUpThreads);
   // planes per block: enough to amortise the tap computation (>= 16 planes when there are that many), few enough
