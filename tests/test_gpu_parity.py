@@ -52,7 +52,11 @@ def test_umma_selftest(U):
 
 @pytest.mark.parametrize("shape,size", [((2, 5, 9, 13), (144, 208)), ((2, 21, 33, 33), (513, 513)),
                                         ((1, 17, 32, 32), (512, 512)), ((1, 3, 32, 64), (512, 1024)),
-                                        ((1, 2, 7, 5), (7, 5)), ((1, 1, 16, 16), (40, 24))])
+                                        ((1, 2, 7, 5), (7, 5)), ((1, 1, 16, 16), (40, 24)),
+                                        # interval / sweep kernels: scales 8, 32, mixed, rows that do not fill a segment
+                                        ((2, 3, 64, 64), (512, 512)), ((1, 2, 16, 16), (512, 512)),
+                                        ((1, 4, 24, 24), (384, 384)), ((2, 2, 32, 32), (256, 512)),
+                                        ((1, 2, 40, 16), (320, 256)), ((1, 2, 33, 32), (66, 512))])
 def test_upsample_fwd_bwd(U, shape, size):
     g = torch.Generator().manual_seed(11)
     x = torch.randn(*shape, generator=g)
