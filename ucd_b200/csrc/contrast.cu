@@ -163,8 +163,11 @@ __device__ __forceinline__ void sweep1_cols_neg(const uint32_t (&r)[32], float s
 // thousands of negatives with exp(s) up to e^14) x = exp(.)/neg_i <= 2.5e-4 and
 //   log2(den) = log2(neg_i) + x log2(e) - O(x^2),   1/den = (1 - x)/neg_i + O(x^2),   |O(x^2)| <= 3e-8,
 // so the log and the reciprocal leave the MUFU (one ex2 per pair remains).  Small neg_i takes the exact path.
+// In the series path x itself comes out of the ex2: x = 2^(s' ), s' = (s - m) log2(e) - log2(neg_i) = fma(acc, sc, c0),
+// then (s - m) log2(e) - log2(den) = s' - x log2(e), Ucoef = w neg_i/den = w (1 - x), and T_i = (1/neg_i) sum Ucoef
+// (the 1/neg_i is applied once per row at the end): 11 instructions per pair.
 struct RowC {
-  float mraw, negi, inv_neg, lneg2;
+  float mraw, negi, inv_neg, lneg2, c0;
   bool series;
 };
 
@@ -183,18 +186,6 @@ __device__ __forceinline__ void sweep2_cols(const uint32_t (&r)[32], const uint3
     for (int u = 0; u < 4; ++u) {
       const int col = cbase + j4 + u;
       const float acc = __uint_as_float(r[j4 + u]);
-      const float sh2 = (acc - rc.mraw) * sc;  // (s - m) * log2(e)
-      const float e = ex2f(sh2);
-      float l2, rd;
-      if (rc.series) {
-        const float x = e * rc.inv_neg;
-        l2 = fmaf(x, kLog2e, rc.lneg2);
-        rd = fmaf(-x, rc.inv_neg, rc.inv_neg);
-      } else {
-        const float den = e + rc.negi;
-        l2 = lg2f(den);
-        rd = rcpf(den);
-      }
       float mp = (ls[u] == la) ? 1.f : 0.f;
       if (SELF) mp -= (col == rself) ? 1.f : 0.f;
       if (!FULL) mp = (col < nv) ? mp : 0.f;
@@ -202,10 +193,20 @@ __device__ __forceinline__ void sweep2_cols(const uint32_t (&r)[32], const uint3
       if (PMODE == 1) pv = (gt_row && ls[u] >= min_new) ? 1.f : __uint_as_float(pr[j4 + u]);
       if (PMODE == 2) pv = (FULL || col < nv) ? __ldg(dp + col) : 0.f;
       const float w = mp * pv;
-      lacc = fmaf(w, sh2 - l2, lacc);
-      const float wr = w * rd;
-      tacc += wr;
-      uo[u] = wr * rc.negi;
+      if (rc.series) {
+        const float s2 = fmaf(acc, sc, rc.c0);
+        const float x = ex2f(s2);
+        lacc = fmaf(w, fmaf(-x, kLog2e, s2), lacc);
+        uo[u] = fmaf(-w, x, w);
+        tacc += uo[u];  // times 1/neg_i at the end of the sweep
+      } else {
+        const float sh2 = (acc - rc.mraw) * sc;  // (s - m) * log2(e)
+        const float den = ex2f(sh2) + rc.negi;
+        lacc = fmaf(w, sh2 - lg2f(den), lacc);
+        const float wr = w * rcpf(den);
+        tacc += wr;
+        uo[u] = wr * rc.negi;
+      }
     }
     pk[j4 / 2] = bf16x2_bits(uo[0], uo[1]);
     pk[j4 / 2 + 1] = bf16x2_bits(uo[2], uo[3]);
@@ -426,7 +427,7 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
     const float sc = a.inv_tau * kLog2e;
     float mx = -3.0e38f, neg = 0.f, num = 0.f;   // sweep 1
     float lacc = 0.f, tacc = 0.f;                // sweep 2
-    RowC rc = {0.f, 0.f, 0.f, 0.f, false};
+    RowC rc = {0.f, 0.f, 0.f, 0.f, 0.f, false};
     int min_new = 0;
     bool gt_row = false;
     if (PHASE == 2) {
@@ -435,6 +436,7 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
       rc.series = rc.negi >= 4096.f;
       rc.inv_neg = rc.series ? 1.f / rc.negi : 0.f;
       rc.lneg2 = rc.series ? log2f(rc.negi) : 0.f;
+      rc.c0 = -fmaf(rc.mraw, sc, rc.lneg2);
       if (PMODE == 1) {
         min_new = *a.min_new;
         gt_row = la >= min_new;
@@ -526,6 +528,7 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
     }
     // [128][3] scratch in C stage 0: every tile load has landed and every MMA that reads the stages has retired
     // by now.  (NOT the probability region: with no active tile the row-probability copy may still be in flight.)
+    if (PHASE == 2 && rc.series) tacc *= rc.inv_neg;  // the series path accumulated sum_j Ucoef_ij = neg_i T_i
     float* comb = reinterpret_cast<float*>(smem + OFF_C);
     if (half == 1) {
       comb[r * 3 + 0] = PHASE == 1 ? mx : lacc;
