@@ -400,8 +400,8 @@ def main():
                         parallelism="dp%d, all-gathered contrast columns" % world),
             roofline=dict(bound="tensor", kernel="ucd_con_fwd (sweep 1 + combine + sweep 2 + finalize)",
                           achieved=con_tflops, peak=bf16_peak, unit="TFLOP/s", frac=con_tflops / bf16_peak,
-                          traffic=(8.93e7 if (world == 1 and B == WORKLOAD["B"]) else None),
-                          traffic_note="dram read+write of the two sweep kernels per step, ncu --set full, profiles/r01d_ncu_full.md",
+                          traffic=(9.18e7 if (world == 1 and B == WORKLOAD["B"]) else None),
+                          traffic_note="dram read+write of the two sweep kernels per step, ncu --set full, profiles/r01f_ncu_full.md (sweep 1: 21.4 MB read + 45.0 MB written, sweep 2: 22.9 + 2.6)",
                           flop_per_pair=f_pair, ms=con_ms, peak_source=peak_src),
             roofline_hbm=hbm,
             call_ms={k: round(v, 4) for k, v in sorted(call_ms.items())},
