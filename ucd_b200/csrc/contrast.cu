@@ -46,7 +46,9 @@ constexpr int kMaxTilesPerCta = 8192;  // column tiles one CTA walks (bit mask i
 
 // A: row tile loaded | CF/CE: column stage full/empty | SF: S accumulator ready | SE: S buffer free (no-grad runs)
 // EF[2*buf+half]: E/Ucoef half written to TMEM | PF/PE: probability stage full/empty | V: all MMAs retired
-enum { BAR_A = 0, BAR_CF = 1, BAR_CE = 3, BAR_SF = 5, BAR_SE = 7, BAR_EF = 9, BAR_PF = 13, BAR_PE = 14, BAR_V = 15 };
+// SR (sweep 2): every epilogue warp has read the S accumulator into registers
+enum { BAR_A = 0, BAR_CF = 1, BAR_CE = 3, BAR_SF = 5, BAR_SE = 7, BAR_EF = 9, BAR_PF = 13, BAR_PE = 14, BAR_V = 15,
+       BAR_SR = 16 };
 
 struct ConArgs {
   const __nv_bfloat16* feat_tiles;
@@ -171,10 +173,12 @@ struct RowC {
   bool series;
 };
 
-template <bool FULL, bool SELF, int PMODE>
+// SERIES is decided per warp (all 32 rows of the warp have neg_i >= 4096), so the pair loop has no divergent branch;
+// thr = the row's threshold for the GT-new override of P (min_new for a GT-new row, INT_MAX otherwise).
+template <bool FULL, bool SELF, int PMODE, bool SERIES>
 __device__ __forceinline__ void sweep2_cols(const uint32_t (&r)[32], const uint32_t (&pr)[32],
                                             const int* __restrict__ lab, int cbase, int nv, int la, int rself,
-                                            float sc, const RowC rc, bool gt_row, int min_new,
+                                            float sc, const RowC rc, int thr,
                                             const float* __restrict__ dp, float& lacc, float& tacc,
                                             uint32_t (&pk)[16]) {
 #pragma unroll
@@ -186,14 +190,14 @@ __device__ __forceinline__ void sweep2_cols(const uint32_t (&r)[32], const uint3
     for (int u = 0; u < 4; ++u) {
       const int col = cbase + j4 + u;
       const float acc = __uint_as_float(r[j4 + u]);
-      float mp = (ls[u] == la) ? 1.f : 0.f;
-      if (SELF) mp -= (col == rself) ? 1.f : 0.f;
-      if (!FULL) mp = (col < nv) ? mp : 0.f;
+      bool pos = ls[u] == la;
+      if (SELF) pos = pos && col != rself;
+      if (!FULL) pos = pos && col < nv;
       float pv = 1.f;
-      if (PMODE == 1) pv = (gt_row && ls[u] >= min_new) ? 1.f : __uint_as_float(pr[j4 + u]);
+      if (PMODE == 1) pv = (ls[u] >= thr) ? 1.f : __uint_as_float(pr[j4 + u]);
       if (PMODE == 2) pv = (FULL || col < nv) ? __ldg(dp + col) : 0.f;
-      const float w = mp * pv;
-      if (rc.series) {
+      const float w = pos ? pv : 0.f;
+      if (SERIES) {
         const float s2 = fmaf(acc, sc, rc.c0);
         const float x = ex2f(s2);
         lacc = fmaf(w, fmaf(-x, kLog2e, s2), lacc);
@@ -252,6 +256,7 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
     mbar_init(BAR(BAR_PF), 1);
     mbar_init(BAR(BAR_PE), 1);
     mbar_init(BAR(BAR_V), 1);
+    mbar_init(BAR(BAR_SR), kEpiWarps);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(&s_tmem), 512);
@@ -357,13 +362,22 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
       for (int tt = next_active(0); tt < n; tt = next_active(tt + 1)) {
         const int stage = t & 1, sb = t % NS;
         mbar_wait_t(BAR(BAR_CF + stage), (t >> 1) & 1, c_idle);
-        mbar_wait_t(BAR(BAR_SE + sb), ((t / NS) & 1) ^ 1, c_idle);
+        // sweep 1: the S buffer is free when the V MMAs that read E out of it have retired.  Sweep 2 has one S
+        // buffer but parks Ucoef in the P columns: S may be overwritten as soon as the epilogue holds it in registers.
+        if (PHASE == 1)
+          mbar_wait_t(BAR(BAR_SE + sb), ((t / NS) & 1) ^ 1, c_idle);
+        else
+          mbar_wait_t(BAR(BAR_SR), (t & 1) ^ 1, c_idle);
         tc_fence_after();
         const uint32_t sc = sbase + OFF_C + stage * kTileBytes;
 #pragma unroll
         for (int ks = 0; ks < 16; ++ks)
           umma_bf16(tS + sb * 128, umma_desc(sbase + OFF_A + ks * 2 * kChunkB, kChunkB, 128),
                     umma_desc(sc + ks * 2 * kChunkB, kChunkB, 128), idesc_s, ks > 0);
+        if (PHASE == 2) {  // the P columns (Ucoef of the previous tile lives there) are free once its U MMAs retired
+          mbar_wait_t(BAR(BAR_SE), (t & 1) ^ 1, c_idle);
+          tc_fence_after();
+        }
         for (int c = 0; c < n_pc; ++c) {  // P = pA pC^T accumulated over the K chunks of pC
           const int u = t * n_pc + c;
           mbar_wait_t(BAR(BAR_PF), u & 1, c_idle);
@@ -398,7 +412,8 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
         for (int h = 0; h < 2; ++h) {
           mbar_wait_t(BAR(BAR_EF + 2 * sb + h), (t / NS) & 1, c_idle);
           tc_fence_after();
-          const uint32_t te = tS + sb * 128 + h * 64;  // 32 columns of packed bf16 pairs = 64 K values
+          // 32 columns of packed bf16 pairs = 64 K values: E over the S buffer (sweep 1), Ucoef over P (sweep 2)
+          const uint32_t te = (PHASE == 1 ? tS + sb * 128 : tmem + 128) + h * 64;
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
             umma_bf16_ts(tV, te + kk * 8, umma_desc(sc + (uint32_t)(h * 64 + kk * 16) * 16u, 128, kChunkB), idesc_v,
@@ -428,8 +443,8 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
     float mx = -3.0e38f, neg = 0.f, num = 0.f;   // sweep 1
     float lacc = 0.f, tacc = 0.f;                // sweep 2
     RowC rc = {0.f, 0.f, 0.f, 0.f, 0.f, false};
-    int min_new = 0;
-    bool gt_row = false;
+    int thr = 0x7fffffff;
+    bool warp_series = false;
     if (PHASE == 2) {
       rc.mraw = a.stats[grow];
       rc.negi = a.stats[a.rows_pad + grow];
@@ -438,9 +453,11 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
       rc.lneg2 = rc.series ? log2f(rc.negi) : 0.f;
       rc.c0 = -fmaf(rc.mraw, sc, rc.lneg2);
       if (PMODE == 1) {
-        min_new = *a.min_new;
-        gt_row = la >= min_new;
+        const int min_new = *a.min_new;
+        if (la >= min_new) thr = min_new;  // GT-new row: P = 1 against GT-new columns (loss.py:385-393)
       }
+      warp_series = __all_sync(0xffffffffu, rc.series);
+      rc.series = warp_series;  // rows of a mixed warp all take the exact path
     }
     int t = 0;  // number of active tiles processed so far (drives stage / parity bookkeeping)
     long long w_sf = 0, w_ee = 0;  // w_ee: unused since E moved to tensor memory
@@ -460,7 +477,7 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
       // own (already consumed) S range in tensor memory; the V/U MMA reads its A operand from there.
       auto emit = [&](int cc, const uint32_t (&pk)[16]) {  // cc = chunk 0/1 within this thread's column half
         if (!a.need_grad) return;
-        tmem_st16(tmem + lane_addr + sb * 128 + half * 64 + cc * 16, pk);
+        tmem_st16(tmem + lane_addr + (PHASE == 1 ? sb * 128 : 128) + half * 64 + cc * 16, pk);
         if (cc == 1) {
           tmem_st_wait();
           tc_fence_before();
@@ -500,12 +517,24 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
           tmem_ld_wait();
           tmem_ld_fence(rv);
           if (PMODE == 1) tmem_ld_fence(pv);
-          if (full && !self)
-            sweep2_cols<true, false, PMODE>(rv, pv, lab, c0 + cc * 32, 128, la, r, sc, rc, gt_row, min_new,
-                                            dp, lacc, tacc, pk);
-          else
-            sweep2_cols<false, true, PMODE>(rv, pv, lab, c0 + cc * 32, loc.nvalid, la, self ? r : -1, sc, rc,
-                                            gt_row, min_new, dp, lacc, tacc, pk);
+          if (cc == 1) {  // S (and P) of this tile are in registers: the next tile's S MMAs may start
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(BAR_SR));
+          }
+          if (full && !self) {
+            if (warp_series)
+              sweep2_cols<true, false, PMODE, true>(rv, pv, lab, c0 + cc * 32, 128, la, r, sc, rc, thr, dp, lacc, tacc, pk);
+            else
+              sweep2_cols<true, false, PMODE, false>(rv, pv, lab, c0 + cc * 32, 128, la, r, sc, rc, thr, dp, lacc, tacc, pk);
+          } else {
+            if (warp_series)
+              sweep2_cols<false, true, PMODE, true>(rv, pv, lab, c0 + cc * 32, loc.nvalid, la, self ? r : -1, sc, rc,
+                                                    thr, dp, lacc, tacc, pk);
+            else
+              sweep2_cols<false, true, PMODE, false>(rv, pv, lab, c0 + cc * 32, loc.nvalid, la, self ? r : -1, sc, rc,
+                                                     thr, dp, lacc, tacc, pk);
+          }
           emit(cc, pk);
         }
       }
