@@ -34,8 +34,8 @@ CPU_SAMPLE_B = 3   # images in the bounded CPU sample of the same workload (N^2 
 
 # kernels launched by each C-ABI entry point (for gpu_launches; memsets are not kernels)
 KERNELS_PER_CALL = {"ucd_upsample_bilinear_fwd": 1, "ucd_upsample_bilinear_bwd": 1, "ucd_unce_fwd": 1,
-                    "ucd_unce_bwd": 1, "ucd_unkd_fwd": 2, "ucd_unkd_bwd": 1, "ucd_con_prep_labels": 2,
-                    "ucd_con_prep_pack": 2, "ucd_con_prep_bwd": 1, "ucd_con_fwd": 5, "ucd_con_bwd": 1,
+                    "ucd_unce_bwd": 1, "ucd_kd_fwd": 2, "ucd_kd_bwd": 1, "ucd_con_prep_labels": 2,
+                    "ucd_con_prep_pack": 4, "ucd_con_prep_bwd": 1, "ucd_con_fwd": 5, "ucd_con_bwd": 1,
                     "ucd_con_pack_rows": 1}
 
 
@@ -380,7 +380,7 @@ def main():
         C = wl["C"]
         hbm = {}
         for name, nbytes in (("ucd_unce_fwd", npx * (4 * C + 8 + 4 + 8)), ("ucd_unce_bwd", npx * (8 * C + 8 + 8)),
-                             ("ucd_unkd_fwd", npx * (4 * C + 4 * C_old + 12)), ("ucd_unkd_bwd", npx * (8 * C + 4 * C_old + 12)),
+                             ("ucd_kd_fwd", npx * (4 * C + 4 * C_old + 12)), ("ucd_kd_bwd", npx * (8 * C + 4 * C_old + 12)),
                              ("ucd_upsample_bilinear_fwd", npx * 4 * (C + C_old)), ("ucd_upsample_bilinear_bwd", npx * 4 * C)):
             if name in call_ms:
                 gbs = nbytes / (call_ms[name] * 1e-3) / 1e9

@@ -139,6 +139,9 @@ int64_t ucd_con_blk_meta_ints(int64_t n_px, int nb);
  * blk_meta: per-block exclusive offsets for both orders.  counts = {N_a, N_o, min_new, n_px}. */
 int ucd_con_prep_labels(const int64_t* labels, const float* l_po, int B, int C_old, int h, int w,
                         int H, int W, int max_label, int32_t* px_meta, int32_t* blk_meta, int32_t* counts,
+                        int32_t* counts_host /* optional: device-accessible (mapped, pinned) HOST int32[4] that receives
+                        a copy of counts from the kernel itself - a host that needs N_a / N_o for tensor shapes then
+                        waits on an event instead of queueing a D2H copy behind other transfers; NULL to skip */,
                         void* stream);
 /* fp32 rows / labels are written in the reference's row order (pixel order b,y,x); the bf16 tiles are
  * written CLASS-SORTED (stable counting sort by label, anchors first, then pseudo columns) so that most

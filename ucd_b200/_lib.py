@@ -36,7 +36,7 @@ _PROTOS = {
     "ucd_con_num_bins": (c_int, [c_int, c_int]),
     "ucd_con_px_meta_ints": (c_int64, [c_int64]),
     "ucd_con_blk_meta_ints": (c_int64, [c_int64, c_int]),
-    "ucd_con_prep_labels": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P]),
+    "ucd_con_prep_labels": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P]),
     "ucd_con_prep_pack": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, P, c_int, P, P, P, P,
                                   P, P, P, c_int64, P]),
     "ucd_con_prep_bwd": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, P]),

@@ -146,7 +146,8 @@ __device__ int block_excl_scan(int* __restrict__ data, int n, int* sh /*[1024]*/
 
 // counts -> exclusive offsets for the four tables; totals into counts[0..1]
 __global__ void __launch_bounds__(1024)
-prep_scan_kernel(int* __restrict__ blk_base, int nblk, int nb, int* __restrict__ counts, int n_px) {
+prep_scan_kernel(int* __restrict__ blk_base, int nblk, int nb, int* __restrict__ counts, int n_px,
+                 int* __restrict__ counts_host) {
   __shared__ int sh[1024];
   const BlkMeta bm(blk_base, nblk, nb);
   const int ta = block_excl_scan(bm.ref, nblk, sh);
@@ -157,6 +158,11 @@ prep_scan_kernel(int* __restrict__ blk_base, int nblk, int nb, int* __restrict__
     counts[0] = ta;
     counts[1] = to;
     counts[3] = n_px;
+    if (counts_host != nullptr) {  // mapped pinned host memory: the host reads it after an event, no copy engine involved
+      volatile int* hp = counts_host;
+      hp[0] = ta, hp[1] = to, hp[2] = counts[2], hp[3] = n_px;
+      __threadfence_system();
+    }
   }
 }
 
@@ -416,7 +422,7 @@ extern "C" int64_t ucd_con_blk_meta_ints(int64_t n_px, int nb) {
 
 extern "C" int ucd_con_prep_labels(const int64_t* labels, const float* l_po, int B, int C_old, int h, int w, int H,
                                    int W, int max_label, int32_t* px_meta, int32_t* blk_meta, int32_t* counts,
-                                   void* stream) {
+                                   int32_t* counts_host, void* stream) {
   UCD_CHECK_ARG(labels && l_po && px_meta && blk_meta && counts, "ucd_con_prep_labels: null pointer");
   UCD_CHECK_ARG(B > 0 && C_old > 0 && h > 0 && w > 0 && H > 0 && W > 0, "ucd_con_prep_labels: bad shape");
   UCD_CHECK_ARG((long long)B * h * w < (1ll << 30), "ucd_con_prep_labels: too many pixels");
@@ -436,7 +442,7 @@ extern "C" int ucd_con_prep_labels(const int64_t* labels, const float* l_po, int
                                                      (float)H / (float)h, (float)W / (float)w, px_meta, blk_meta, nb,
                                                      counts);
   UCD_CHECK_LAUNCH("prep_labels_kernel");
-  prep_scan_kernel<<<1, 1024, 0, st>>>(blk_meta, nblk, nb, counts, n_px);
+  prep_scan_kernel<<<1, 1024, 0, st>>>(blk_meta, nblk, nb, counts, n_px, counts_host);
   UCD_CHECK_LAUNCH("prep_scan_kernel");
   return UCD_OK;
 }

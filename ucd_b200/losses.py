@@ -368,12 +368,12 @@ def _build_pack(f_n, f_o, l_po, labels, max_label):
     pk.blk_meta = torch.empty(L.ucd_con_blk_meta_ints(n_px, nb), **i32)
     pk.counts = torch.empty(4, **i32)
     st = cur_stream()
-    check(L.ucd_con_prep_labels(ptr(labels), ptr(l_po), B, pk.c_old, h, w, H, W, pk.max_label, ptr(pk.px_meta),
-                                ptr(pk.blk_meta), ptr(pk.counts), st), "con_prep_labels")
-    # The tuple API needs N_a / N_o on the host (tensor shapes).  Start the 16-byte copy now and wait for it only
-    # after the pack kernels are queued, so the GPU has work while the host catches up.
+    # The tuple API needs N_a / N_o on the host (tensor shapes).  The scan kernel stores them straight into mapped
+    # pinned host memory (no D2H copy that could queue behind other transfers on the copy engine); the host waits
+    # for the event only after the pack kernels are queued, so the GPU has work while the host catches up.
     counts_host = _pinned_counts(dev)
-    counts_host.copy_(pk.counts, non_blocking=True)
+    check(L.ucd_con_prep_labels(ptr(labels), ptr(l_po), B, pk.c_old, h, w, H, W, pk.max_label, ptr(pk.px_meta),
+                                ptr(pk.blk_meta), ptr(pk.counts), counts_host.data_ptr(), st), "con_prep_labels")
     copied = torch.cuda.Event()
     copied.record()
     pk.anchor_f32 = torch.empty(n_px, FEAT_DIM, device=dev, dtype=torch.float32)
