@@ -98,8 +98,26 @@ def gen_sibling():
     print("sibling_losses:", {k: float(v) for k, v in fx.items() if k.endswith("_out") and v.ndim == 0})
 
 
+def gen_att_map():
+    """segmentation_module.py:86-94 `att_map` (the module itself needs inplace_abn, which is not installed: the method is
+    lifted out of the reference source with ast and executed unmodified)."""
+    import ast
+    src = open(os.path.join(REF, "segmentation_module.py")).read()
+    fn = next(n for n in ast.walk(ast.parse(src)) if isinstance(n, ast.FunctionDef) and n.name == "att_map")
+    ns = {"torch": torch}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "segmentation_module.py", "exec"), ns)
+    g = torch.Generator().manual_seed(99)
+    x = torch.randn(3, 16, 6, 5, generator=g, dtype=torch.float64)
+    y = ns["att_map"](None, x.clone())
+    np.savez_compressed(os.path.join(OUT, "att_map.npz"), x=x.numpy(), y=y.numpy())
+    print("att_map:", float(y.abs().sum()))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "att_map":
+        return gen_att_map()
+    gen_att_map()
     if len(sys.argv) > 1 and sys.argv[1] == "sibling":
         return gen_sibling()
     gen_sibling()

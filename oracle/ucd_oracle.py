@@ -290,6 +290,19 @@ def unbiased_kd(x: torch.Tensor, t: torch.Tensor, alpha: float = 1.0, reduction:
 
 
 # ----------------------------------------------------------------------------
+# feature hand-off
+# ----------------------------------------------------------------------------
+def att_map(x: torch.Tensor) -> torch.Tensor:
+    """segmentation_module.py:86-94: per-pixel energy sum_c x^2, divided per image by its Frobenius norm, applied as a
+    detached positive per-pixel scale.  pre_contrastive_pixel L2-normalises every pixel's feature vector
+    (utils/loss.py:363-365), so this scale cancels there: feeding the raw head output gives the same anchors and
+    the same gradient with respect to the head output."""
+    a = (x ** 2).sum(dim=1)
+    a = a / a.flatten(1).norm(dim=1).view(-1, 1, 1)
+    return a.unsqueeze(1).detach() * x
+
+
+# ----------------------------------------------------------------------------
 # sibling losses on the same kernels (SURVEY section 8(f), row N3)
 # ----------------------------------------------------------------------------
 def _reduce_neg(per_px: torch.Tensor, reduction: str) -> torch.Tensor:

@@ -531,3 +531,22 @@ def test_sibling_losses_vs_oracle(U, shape, c_old):
         torch.testing.assert_close(out.cpu().double(), ref.detach(), rtol=5e-5, atol=5e-6, msg=lambda m: f"{tag}: {m}")
         assert cos(xc.grad, xr.grad) > 1 - 1e-6, tag
 
+
+def test_raw_head_features_equal_att_map_features(U, golden_dir):
+    """Row N2: the attention map of segmentation_module.py:86-94 cancels under the anchor normalisation, so the prep
+    kernel may read the raw head output: same loss, same gradient with respect to the head output."""
+    fx, case, (B, h, w, H, W, C, C_old) = load_case(golden_dir, "voc15-5s_b2_corr")
+    res = []
+    for use_att in (True, False):
+        x = case["f_n"].cuda().requires_grad_(True)
+        xo = case["f_o"].cuda()
+        f_n = O.att_map(x) if use_att else x
+        f_o = O.att_map(xo) if use_att else xo
+        tup = U.pre_contrastive_pixel(f_n, case["labels"].cuda(), l_po=case["l_po"].cuda(), f_o=f_o)
+        loss = U.PixelConLossV2(temperature=0.07)(*tup)
+        loss.backward()
+        res.append((loss.item(), x.grad.clone()))
+    assert res[0][0] == pytest.approx(res[1][0], rel=1e-4)
+    assert cos(res[0][1], res[1][1]) > 1 - 1e-5
+    torch.testing.assert_close(res[0][1], res[1][1], rtol=5e-3, atol=5e-3 * float(res[1][1].abs().max()))
+
