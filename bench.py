@@ -296,6 +296,47 @@ def main():
     barrier()
     ms_fused = f0.elapsed_time(f1) / args.steps
 
+    # ---- opt-in sync-free step (N1 fused CE/KD + N4 contrastive without the 5-tuple), for information: eager, and
+    #      (single GPU) forward + backward replayed from one CUDA graph ----
+    con_static = U.PixelContrastiveDistillation(temperature=0.07, gather_negatives=world > 1)
+    gs = {k: devin[k].clone() for k in ("f_n", "f_o", "l_po", "logits_lr", "labels")}
+    gs["f_n"].requires_grad_(True), gs["logits_lr"].requires_grad_(True)
+
+    def step_static():
+        gs["f_n"].grad = gs["logits_lr"].grad = None
+        ce, kd = fused(gs["logits_lr"], gs["l_po"], gs["labels"])
+        (ce + con_static(gs["f_n"], gs["labels"], gs["l_po"], gs["f_o"]) / 100 + 10 * kd).backward()
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(args.steps):
+            fn()
+        a1.record()
+        barrier()
+        return a0.elapsed_time(a1) / args.steps
+
+    ms_static = timed(step_static)
+    ms_graph = None
+    if world == 1:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                step_static()
+            torch.cuda.current_stream().wait_stream(side)
+            gs["f_n"].grad = gs["logits_lr"].grad = None
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                ce, kd = fused(gs["logits_lr"], gs["l_po"], gs["labels"])
+                (ce + con_static(gs["f_n"], gs["labels"], gs["l_po"], gs["f_o"]) / 100 + 10 * kd).backward()
+            ms_graph = timed(graph.replay)
+        except Exception as exc:  # informational leg only
+            ms_graph = "capture failed: %s" % (str(exc).splitlines()[0][:120],)
+
     # ---- end-to-end through the public API with host buffers (e2e) ----
     # Every step copies its inputs from pinned host memory and copies losses + both gradients back.  Like a
     # DataLoader with pin_memory / non_blocking prefetch, the copies of step i+1 / i-1 run on a side stream while
@@ -410,6 +451,9 @@ def main():
                      h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
             n1_fused=dict(note="same step with the opt-in FusedUnbiasedLosses (upsample+CE+KD from low-res logits)",
                           ms_per_step=ms_fused_max, value=pairs_total / (ms_fused_max * 1e-3) / 1e6, unit=UNIT),
+            n4_sync_free=dict(note="rank 0: N1 fused CE/KD + PixelContrastiveDistillation (no 5-tuple, no host sync); "
+                                   "graph = forward+backward replayed from one CUDA graph (single GPU only)",
+                              ms_per_step_eager=ms_static, ms_per_step_graph=ms_graph),
             gpu_launches=int(launches), clocks=clocks,
             losses=dict(con=float(state["con"]), ce=float(state["ce"]), kd=float(state["kd"])),
         )

@@ -184,13 +184,17 @@ int ucd_con_pack_rows(const float* rows, const int32_t* labels, int64_t n, void*
  *   out float[3]  = {sum_i loss_i over rows with num_i != 0, number of such rows, their ratio (= the loss)}
  *   grad_unit [max_row_tiles*128, 256] = d(sum_i loss_i)/d a_i   (scaled by g/M in ucd_con_bwd)
  * ---------------------------------------------------------------------------------------- */
-size_t ucd_con_workspace_bytes(int64_t max_row_tiles, int64_t max_col_tiles);
+/* plan_row_tiles (here and in ucd_con_fwd, same value): row tiles expected to hold anchors, 0 = max_row_tiles.  Only a
+ * planning hint (column splits are chosen for that many row blocks); results do not depend on it beyond summation
+ * order.  Used by hosts that size for the worst case because they do not read N_a back (sync-free path). */
+size_t ucd_con_workspace_bytes(int64_t max_row_tiles, int64_t max_col_tiles, int64_t plan_row_tiles);
 int ucd_con_fwd(const void* feat_tiles, const void* prob_tiles, const int32_t* lab_tiles,
                 const int32_t* chunk_counts, int n_chunks, int64_t chunk_tiles, const void* row_feat_tiles,
                 const void* row_prob_tiles, const int32_t* row_lab_tiles, const int32_t* n_rows,
                 const int32_t* tile_range, const int32_t* row_range, int64_t self_tile0, const int32_t* min_new, int p_mode, int kpad, const float* dense_p,
                 int64_t ldp, float inv_temperature, int need_grad, float* out, float* grad_unit,
-                void* workspace, size_t workspace_bytes, int64_t max_row_tiles, void* stream);
+                void* workspace, size_t workspace_bytes, int64_t max_row_tiles, int64_t plan_row_tiles,
+                void* stream);
 /* d_anchor[row_ref[i],:] = (*g_scalar) * g_mul / out[1] * grad_unit[i,:] for i < min(*n_rows, max_rows);
  * row_ref NULL = identity */
 int ucd_con_bwd(const float* grad_unit, const float* out, const float* g_scalar, float g_mul,

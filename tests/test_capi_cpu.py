@@ -40,8 +40,8 @@ def test_version_and_sizes(L):
     assert lib.ucd_reduce_scratch_floats() > 0
     assert lib.ucd_con_max_tiles(3072) == 49
     assert lib.ucd_con_prob_kpad(16) == 16 and lib.ucd_con_prob_kpad(14) == 16 and lib.ucd_con_prob_kpad(17) == 32
-    assert lib.ucd_con_workspace_bytes(24, 49) > 24 * 128 * 256 * 4 * 2
-    assert lib.ucd_con_workspace_bytes(0, 49) == 0
+    assert lib.ucd_con_workspace_bytes(24, 49, 0) > 24 * 128 * 256 * 4 * 2
+    assert lib.ucd_con_workspace_bytes(0, 49, 0) == 0
 
 
 def test_argument_validation_reports_errors(L):

@@ -34,7 +34,15 @@ def _worker(rank, world, port, ret):
         g_ref = f_refs[rank].grad
         a, b = f_n.grad.double().cpu().reshape(-1), g_ref.reshape(-1)
         cos = float(a @ b / (a.norm() * b.norm()))
-        ret[rank] = (abs(loss.item() - ref.item()) / abs(ref.item()), cos, float(a.norm() / b.norm()))
+        # the sync-free module (no 5-tuple) takes the same exchange step
+        f_s = c["f_n"].cuda().requires_grad_(True)
+        loss_s = U.PixelContrastiveDistillation(temperature=0.07, gather_negatives=True, ddp_grad_scale=False)(
+            f_s, c["labels"].cuda(), c["l_po"].cuda(), c["f_o"].cuda())
+        loss_s.backward()
+        s_rel = abs(loss_s.item() - loss.item()) / abs(loss.item())
+        s_cos = float(torch.nn.functional.cosine_similarity(f_s.grad.reshape(1, -1).double(),
+                                                            f_n.grad.reshape(1, -1).double()))
+        ret[rank] = (abs(loss.item() - ref.item()) / abs(ref.item()), cos, float(a.norm() / b.norm()), s_rel, s_cos)
     finally:
         dist.destroy_process_group()
 
@@ -47,7 +55,8 @@ def test_global_negatives_two_gpus():
         ret = m.dict()
         mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
         for r in range(world):
-            rel, cos, ratio = ret[r]
+            rel, cos, ratio, s_rel, s_cos = ret[r]
+            assert s_rel <= 1e-5 and s_cos >= 1 - 1e-6, (r, s_rel, s_cos)
             assert rel <= 1e-3, (r, rel)
             assert cos >= 0.999, (r, cos)
             assert abs(ratio - 1) < 2e-2, (r, ratio)

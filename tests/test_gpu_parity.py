@@ -550,3 +550,65 @@ def test_raw_head_features_equal_att_map_features(U, golden_dir):
     assert cos(res[0][1], res[1][1]) > 1 - 1e-5
     torch.testing.assert_close(res[0][1], res[1][1], rtol=5e-3, atol=5e-3 * float(res[1][1].abs().max()))
 
+
+# ------------------------------------------------------------------------------------------------
+# sync-free contrastive module, CUDA-graph capture of forward + backward
+@pytest.mark.parametrize("name", ["tiny_b2", "voc15-5s_b3_512", "city13-6_b3", "voc15-5s_b2_corr"])
+def test_sync_free_contrastive_matches_tuple_path(U, golden_dir, name):
+    fx, case, (B, h, w, H, W, C, C_old) = load_case(golden_dir, name)
+    dev = {k: v.cuda() for k, v in case.items()}
+    f1 = dev["f_n"].clone().requires_grad_(True)
+    ref = U.PixelConLossV2(temperature=0.07)(*U.pre_contrastive_pixel(f1, dev["labels"], l_po=dev["l_po"], f_o=dev["f_o"]))
+    ref.backward()
+    f2 = dev["f_n"].clone().requires_grad_(True)
+    out = U.PixelContrastiveDistillation(temperature=0.07)(f2, dev["labels"], dev["l_po"], dev["f_o"])
+    out.backward()
+    assert out.item() == pytest.approx(ref.item(), rel=2e-6)          # same kernels, other split -> summation order
+    assert out.item() == pytest.approx(float(fx["con"][1]), rel=REL)  # and the reference fixture
+    assert cos(f2.grad, f1.grad) > 1 - 1e-6
+    torch.testing.assert_close(f2.grad, f1.grad, rtol=1e-3, atol=1e-5 * float(f1.grad.abs().max()))
+
+
+def test_sync_free_step_in_cuda_graph(U, golden_dir):
+    """Capture contrastive + fused CE/KD forward and backward once, replay on new data: equal to the eager modules."""
+    _, case_a, (B, h, w, H, W, C, C_old) = load_case(golden_dir, "voc15-5s_b3_512")
+    case_b = O.synthetic_case(B, h, w, H, W, C, C_old, rank=1)
+    con = U.PixelContrastiveDistillation(temperature=0.07)
+    fused = U.FusedUnbiasedLosses(old_cl=C_old, alpha=1.0)
+    st = {k: v.cuda().clone() for k, v in case_a.items()}
+    st["f_n"].requires_grad_(True), st["logits_lr"].requires_grad_(True)
+
+    def step():
+        ce, kd = fused(st["logits_lr"], st["l_po"], st["labels"])
+        loss = ce + con(st["f_n"], st["labels"], st["l_po"], st["f_o"]) / 100 + 10 * kd
+        loss.backward()
+        return loss
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            st["f_n"].grad = st["logits_lr"].grad = None
+            step()
+    torch.cuda.current_stream().wait_stream(side)
+    st["f_n"].grad = st["logits_lr"].grad = None
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        loss_s = step()
+    for case in (case_b, case_a):
+        with torch.no_grad():
+            for k in ("f_n", "f_o", "l_po", "logits_lr", "labels"):
+                st[k].copy_(case[k].cuda())
+        graph.replay()
+        torch.cuda.synchronize()
+        # eager reference through the drop-in modules on the same data
+        f = case["f_n"].cuda().requires_grad_(True)
+        lr = case["logits_lr"].cuda().requires_grad_(True)
+        lab = case["labels"].cuda()
+        ce, kd = U.FusedUnbiasedLosses(old_cl=C_old, alpha=1.0)(lr, case["l_po"].cuda(), lab.clone())
+        tup = U.pre_contrastive_pixel(f, lab, l_po=case["l_po"].cuda(), f_o=case["f_o"].cuda())
+        ref = ce + U.PixelConLossV2(temperature=0.07)(*tup) / 100 + 10 * kd
+        ref.backward()
+        assert loss_s.item() == pytest.approx(ref.item(), rel=1e-5)
+        assert cos(st["f_n"].grad, f.grad) > 1 - 1e-6 and cos(st["logits_lr"].grad, lr.grad) > 1 - 1e-6
+

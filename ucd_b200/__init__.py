@@ -4,10 +4,10 @@ Drop-in loss modules with the reference's names and signatures; see ucd_b200/los
 include/ucd_b200.h (the C ABI) and INTEGRATION.md.
 """
 from .losses import (ContrastPack, FusedUnbiasedLosses, JointProb, KnowledgeDistillationLoss,  # noqa: F401
-                     MaskCrossEntropy, MaskKnowledgeDistillationLoss, PixelConLossV2, UnbiasedCrossEntropy,
-                     UnbiasedKnowledgeDistillationLoss, interpolate_bilinear, pre_contractive_pixel,
-                     pre_contrastive_pixel)
+                     MaskCrossEntropy, MaskKnowledgeDistillationLoss, PixelConLossV2,
+                     PixelContrastiveDistillation, UnbiasedCrossEntropy, UnbiasedKnowledgeDistillationLoss,
+                     interpolate_bilinear, pre_contractive_pixel, pre_contrastive_pixel)
 
 __all__ = ["PixelConLossV2", "UnbiasedCrossEntropy", "UnbiasedKnowledgeDistillationLoss", "pre_contrastive_pixel",
            "pre_contractive_pixel", "interpolate_bilinear", "JointProb", "ContrastPack", "FusedUnbiasedLosses",
-           "KnowledgeDistillationLoss", "MaskKnowledgeDistillationLoss", "MaskCrossEntropy"]
+           "PixelContrastiveDistillation", "KnowledgeDistillationLoss", "MaskKnowledgeDistillationLoss", "MaskCrossEntropy"]

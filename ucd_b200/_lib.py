@@ -42,9 +42,9 @@ _PROTOS = {
     "ucd_con_prep_bwd": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, P]),
     "ucd_con_tile_ranges": (c_int, [P, c_int64, P, P, P]),
     "ucd_con_pack_rows": (c_int, [P, P, c_int64, P, P, c_int64, P]),
-    "ucd_con_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "ucd_con_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "ucd_con_fwd": (c_int, [P, P, P, P, c_int, c_int64, P, P, P, P, P, P, c_int64, P, c_int, c_int, P, c_int64,
-                            c_float, c_int, P, P, P, c_size_t, c_int64, P]),
+                            c_float, c_int, P, P, P, c_size_t, c_int64, c_int64, P]),
     "ucd_con_bwd": (c_int, [P, P, P, c_float, P, P, P, c_int64, P]),
     "ucd_con_debug_trace": (c_int, [P]),
     "ucd_con_debug_splits": (c_int, [c_int64, c_int64]),

@@ -710,14 +710,18 @@ struct ConPlan {
   size_t off_stats_part, off_stats, off_loss_part, off_v, off_u, off_block, total;
 };
 
-static ConPlan make_plan(long long max_row_tiles, long long max_col_tiles) {
+// plan_row_tiles: row tiles expected to hold anchors (<= max_row_tiles, 0 = all of them).  A caller that sizes its
+// buffers for the worst case without knowing N_a on the host (the sync-free path) passes its estimate here so that
+// the column splits are chosen for the CTAs that will actually run; the rest exit at once.
+static ConPlan make_plan(long long max_row_tiles, long long max_col_tiles, long long plan_row_tiles = 0) {
+  if (plan_row_tiles <= 0 || plan_row_tiles > max_row_tiles) plan_row_tiles = max_row_tiles;
   ConPlan p;
   // choose the number of column splits that best fills 148 SMs without tiny per-CTA ranges
   int best = 1;
   double best_eff = 0.0;
   for (int s = 1; s <= 16; ++s) {
     if (s > 1 && max_col_tiles / s < 4) break;
-    const long long ctas = max_row_tiles * s;
+    const long long ctas = plan_row_tiles * s;
     const long long waves = (ctas + kNumSMs - 1) / kNumSMs;
     const double eff = (double)ctas / (double)(waves * kNumSMs);
     if (eff > best_eff + 0.03) {
@@ -769,9 +773,9 @@ static int launch_sweep(const ConArgs& a, long long max_row_tiles, cudaStream_t 
 
 using namespace ucd;
 
-extern "C" size_t ucd_con_workspace_bytes(int64_t max_row_tiles, int64_t max_col_tiles) {
+extern "C" size_t ucd_con_workspace_bytes(int64_t max_row_tiles, int64_t max_col_tiles, int64_t plan_row_tiles) {
   if (max_row_tiles <= 0 || max_col_tiles <= 0) return 0;
-  return make_plan(max_row_tiles, max_col_tiles).total;
+  return make_plan(max_row_tiles, max_col_tiles, plan_row_tiles).total;
 }
 
 extern "C" int ucd_con_fwd(const void* feat_tiles, const void* prob_tiles, const int32_t* lab_tiles,
@@ -780,7 +784,7 @@ extern "C" int ucd_con_fwd(const void* feat_tiles, const void* prob_tiles, const
                            const int32_t* tile_range, const int32_t* row_range, int64_t self_tile0, const int32_t* min_new, int p_mode, int kpad, const float* dense_p,
                            int64_t ldp,
                            float inv_temperature, int need_grad, float* out, float* grad_unit, void* workspace,
-                           size_t workspace_bytes, int64_t max_row_tiles, void* stream) {
+                           size_t workspace_bytes, int64_t max_row_tiles, int64_t plan_row_tiles, void* stream) {
   UCD_CHECK_ARG(feat_tiles && lab_tiles && chunk_counts && out && workspace, "ucd_con_fwd: null pointer");
   UCD_CHECK_ARG(n_chunks >= 1 && n_chunks <= kMaxChunks, "ucd_con_fwd: n_chunks=%d outside [1,%d]", n_chunks, kMaxChunks);
   UCD_CHECK_ARG(row_feat_tiles && row_lab_tiles && n_rows, "ucd_con_fwd: null row pointer");
@@ -800,7 +804,7 @@ extern "C" int ucd_con_fwd(const void* feat_tiles, const void* prob_tiles, const
     set_error("ucd_con_fwd: joint-probability width kpad=%d not supported (multiple of 16 up to 112, i.e. C_old <= 112)", kpad);
     return UCD_ENOSUP;
   }
-  const ConPlan plan = make_plan(max_row_tiles, (int64_t)n_chunks * chunk_tiles);
+  const ConPlan plan = make_plan(max_row_tiles, (int64_t)n_chunks * chunk_tiles, plan_row_tiles);
   UCD_CHECK_ARG(workspace_bytes >= plan.total, "ucd_con_fwd: workspace too small (%zu < %zu)", workspace_bytes, plan.total);
   UCD_CHECK_ARG(max_row_tiles * (plan.splits > plan.splits2 ? plan.splits : plan.splits2) < (1ll << 31),
                 "ucd_con_fwd: grid too large");

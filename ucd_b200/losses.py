@@ -341,7 +341,7 @@ def _pinned_counts(dev):
     return buf
 
 
-def _build_pack(f_n, f_o, l_po, labels, max_label):
+def _build_pack(f_n, f_o, l_po, labels, max_label, sync=True):
     _need_cuda(f_n, f_o, l_po, labels)
     if f_n.dim() != 4 or f_n.shape[1] != FEAT_DIM or f_o.shape != f_n.shape:
         raise ValueError("pre_contrastive_pixel: f_n / f_o must be [B,%d,h,w]" % FEAT_DIM)
@@ -374,8 +374,10 @@ def _build_pack(f_n, f_o, l_po, labels, max_label):
     counts_host = _pinned_counts(dev)
     check(L.ucd_con_prep_labels(ptr(labels), ptr(l_po), B, pk.c_old, h, w, H, W, pk.max_label, ptr(pk.px_meta),
                                 ptr(pk.blk_meta), ptr(pk.counts), counts_host.data_ptr(), st), "con_prep_labels")
-    copied = torch.cuda.Event()
-    copied.record()
+    copied = None
+    if sync:
+        copied = torch.cuda.Event()
+        copied.record()
     pk.anchor_f32 = torch.empty(n_px, FEAT_DIM, device=dev, dtype=torch.float32)
     pk.contrast_f32 = torch.empty(2 * n_px, FEAT_DIM, device=dev, dtype=torch.float32)
     ldt = _label_dtype(pk.max_label)   # the tuple's label vectors come out of the pack kernel in their final type
@@ -395,6 +397,8 @@ def _build_pack(f_n, f_o, l_po, labels, max_label):
                               pk.max_tiles, st),
           "con_prep_pack")
     pk.l_po = l_po
+    if not sync:  # sync-free path: N_a / N_o stay on the device, buffers keep their worst-case sizes
+        return pk
     # the one host sync of the tuple API: the 5-tuple's tensor shapes depend on N_a / N_o
     copied.synchronize()
     pk.n_a, pk.n_o, pk.min_new, _ = (int(v) for v in counts_host.tolist())
@@ -518,7 +522,8 @@ class _ConFn(torch.autograd.Function):
         L = _lib.lib()
         dev = anchor.device
         max_row_tiles = rows["max_tiles"]
-        ws_bytes = L.ucd_con_workspace_bytes(max_row_tiles, cols["n_chunks"] * cols["chunk_tiles"])
+        plan_tiles = rows.get("plan_tiles", 0)
+        ws_bytes = L.ucd_con_workspace_bytes(max_row_tiles, cols["n_chunks"] * cols["chunk_tiles"], plan_tiles)
         ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
         out = torch.empty(3, device=dev, dtype=torch.float32)
         need_grad = bool(ctx.needs_input_grad[0])
@@ -530,14 +535,16 @@ class _ConFn(torch.autograd.Function):
                             rows["self_tile0"], ptr(cols["min_new"]), p_mode,
                             cols["kpad"], ptr(dense_p), 0 if dense_p is None else dense_p.shape[1], inv_tau,
                             1 if need_grad else 0, ptr(out), ptr(grad_unit), ptr(ws), ws_bytes, max_row_tiles,
-                            cur_stream()), "con_fwd")
+                            plan_tiles, cur_stream()), "con_fwd")
         world = 1
         if group is not None:
             import torch.distributed as dist
             dist.all_reduce(out[:2], group=group)  # {sum of row losses, #valid rows} over all ranks
             world = dist.get_world_size(group)
         ctx.save_for_backward(grad_unit, out, rows["n_rows"], rows.get("row_ref"))
-        ctx.n_a = anchor.shape[0]
+        ctx.static_pack = rows.get("static_pack")   # sync-free path: `anchor` is f_n itself
+        ctx.n_a = anchor.shape[0] if ctx.static_pack is None else ctx.static_pack.n_px
+        ctx.in_dtype = anchor.dtype
         ctx.world = world if ddp_scale else 1
         if group is not None:
             return out[0] / out[1]
@@ -551,6 +558,13 @@ class _ConFn(torch.autograd.Function):
         # each rank's local contribution scaled by world (columns carry no gradient, loss.py:366,395).
         check(_lib.lib().ucd_con_bwd(ptr(grad_unit), ptr(out), ptr(_f32c(g.reshape(1))), float(ctx.world),
                                      ptr(n_rows), ptr(row_ref), ptr(d_anchor), ctx.n_a, cur_stream()), "con_bwd")
+        pk = ctx.static_pack
+        if pk is not None:  # continue through the anchor gather + normalise adjoint to f_n (rows >= N_a are never read)
+            B, h, w = pk.shape
+            df = torch.empty(B, FEAT_DIM, h, w, device=g.device, dtype=torch.float32)
+            check(_lib.lib().ucd_con_prep_bwd(ptr(d_anchor), ptr(pk.anchor_f32), ptr(pk.inv_norm), ptr(pk.px_meta),
+                                              ptr(pk.blk_meta), ptr(df), B, h, w, cur_stream()), "con_prep_bwd")
+            d_anchor = df.to(ctx.in_dtype)
         return d_anchor, None, None, None, None, None, None, None
 
 
@@ -652,6 +666,55 @@ class PixelConLossV2(nn.Module):
                     min_new=None)
         rows = dict(feat=rfeat, prob=None, lab=rlab, range=rrange, n_rows=n_rows, max_tiles=rt, self_tile0=0)
         return _ConFn.apply(anchor_features, cols, rows, inv_tau, p_mode, dense_p, None, False)
+
+
+class PixelContrastiveDistillation(nn.Module):
+    """Opt-in, sync-free form of ``PixelConLossV2()(*pre_contrastive_pixel(f_n, l_n, l_po=..., f_o=...))``
+    (train.py:115-116): the same kernels, but the 5-tuple is never materialised, so N_a / N_o
+    stay on the device, nothing waits for the host, and forward + backward can be captured in a CUDA graph
+    (buffers have their worst-case sizes; row blocks beyond N_a exit at once).
+
+    Differences a caller must know: a batch without any new-class pixel does not raise (the reference does,
+    utils/loss.py:355) - the GT-new override of P simply never fires; a batch without anchors gives NaN (0/0).
+    ``expected_anchor_fraction`` only steers how the column range is split over CTAs."""
+
+    def __init__(self, temperature=0.07, max_label=20, *, gather_negatives=False, process_group=None,
+                 ddp_grad_scale=True, expected_anchor_fraction=0.65):
+        super().__init__()
+        self.temperature = temperature
+        self.max_label = int(max_label)
+        self.gather_negatives = gather_negatives
+        self.process_group = process_group
+        self.ddp_grad_scale = ddp_grad_scale
+        self.expected_anchor_fraction = float(expected_anchor_fraction)
+
+    def _group(self):
+        if not self.gather_negatives:
+            return None
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            return None
+        group = self.process_group if self.process_group is not None else dist.group.WORLD
+        return group if dist.get_world_size(group) > 1 else None
+
+    def forward(self, f_n, l_n, l_po, f_o):
+        pack = _build_pack(f_n.detach(), f_o.detach(), l_po.detach(), l_n, self.max_label, sync=False)
+        cap_tiles = (pack.n_px + TILE - 1) // TILE
+        plan_tiles = max(1, min(cap_tiles, int(cap_tiles * self.expected_anchor_fraction + 0.999)))
+        rows = dict(feat=pack.feat_tiles, prob=pack.prob_tiles, lab=pack.lab_tiles, n_rows=pack.counts[0:1],
+                    range=pack.row_range, row_ref=pack.row_ref, max_tiles=cap_tiles, self_tile0=0,
+                    plan_tiles=plan_tiles, static_pack=pack)
+        group = self._group()
+        if group is None:
+            cols = dict(feat=pack.feat_tiles, prob=pack.prob_tiles, lab=pack.lab_tiles, range=pack.tile_range,
+                        counts=pack.counts[:2].contiguous(), n_chunks=1, chunk_tiles=pack.max_tiles, kpad=pack.kpad,
+                        min_new=pack.counts[2:3])
+        else:
+            cols = gather_contrast_columns(pack.feat_tiles, pack.prob_tiles, pack.lab_tiles, pack.tile_range,
+                                           pack.counts, group)
+            cols["kpad"] = pack.kpad
+            rows["self_tile0"] = cols["self_tile0"]
+        return _ConFn.apply(f_n, cols, rows, 1.0 / float(self.temperature), 1, None, group, self.ddp_grad_scale)
 
 
 # ----------------------------------------------------------------------------------------------
