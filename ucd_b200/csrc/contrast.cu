@@ -18,8 +18,10 @@
 // The gradient needs no third sweep: backward is a scaled copy of (T V - U)/(tau num).
 //
 // CTA = one 128-row block x one contiguous range of column tiles ("split").  Warp roles: warp 0 issues
-// bulk async copies (TMA engine) of pre-tiled bf16 operands, warp 1 owns TMEM and issues tcgen05.mma,
-// warps 2-5 are the epilogue (one thread per row, accumulators read with tcgen05.ld).
+// bulk async copies (TMA engine) of pre-tiled bf16 operands, warp 1 owns TMEM and issues the S (and P) MMAs,
+// warp 2 issues the V / U MMAs (A operand = E / Ucoef read from tensor memory), warps 3-10 are the epilogue
+// (two per SM sub-partition; one thread per row and column half, accumulators read with tcgen05.ld, E / Ucoef
+// written back with tcgen05.st).  Everything is handed over through mbarriers; no __syncthreads in the tile loop.
 #include "umma.cuh"
 
 #include <stdlib.h>
@@ -732,8 +734,10 @@ static ConPlan make_plan(long long max_row_tiles, long long max_col_tiles, long 
   while ((max_col_tiles + best - 1) / best > kMaxTilesPerCta) ++best;
   p.splits = best;
   p.splits2 = best > 1 ? (best + 1) / 2 : 1;
-  if (const char* e = getenv("UCD_SPLITS1")) p.splits = atoi(e) > 0 ? atoi(e) : p.splits;    // tuning knobs
-  if (const char* e = getenv("UCD_SPLITS2")) p.splits2 = atoi(e) > 0 ? atoi(e) : p.splits2;
+  static const int env_s1 = getenv("UCD_SPLITS1") ? atoi(getenv("UCD_SPLITS1")) : 0;  // tuning knobs, read once
+  static const int env_s2 = getenv("UCD_SPLITS2") ? atoi(getenv("UCD_SPLITS2")) : 0;
+  if (env_s1 > 0) p.splits = env_s1;
+  if (env_s2 > 0) p.splits2 = env_s2;
   while ((max_col_tiles + p.splits - 1) / p.splits > kMaxTilesPerCta) ++p.splits;
   while ((max_col_tiles + p.splits2 - 1) / p.splits2 > kMaxTilesPerCta) ++p.splits2;
   p.rows_pad = max_row_tiles * 128;

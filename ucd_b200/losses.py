@@ -679,7 +679,7 @@ class PixelContrastiveDistillation(nn.Module):
     ``expected_anchor_fraction`` only steers how the column range is split over CTAs."""
 
     def __init__(self, temperature=0.07, max_label=20, *, gather_negatives=False, process_group=None,
-                 ddp_grad_scale=True, expected_anchor_fraction=0.65):
+                 ddp_grad_scale=True, expected_anchor_fraction=1.0):
         super().__init__()
         self.temperature = temperature
         self.max_label = int(max_label)
