@@ -57,3 +57,5 @@ for grad in (True, False):
               "mma total %.0f (idle %.0f) | producer total %.0f (wait stage %.0f, wait P %.0f)" % (
                   grad, sw + 1, x.shape[0], nt.mean(), (x[:, 8] / nt).mean(), (x[:, 9] / nt).mean(), (x[:, 10] / nt).mean(),
                   (x[:, 4] / nt).mean(), (x[:, 5] / nt).mean(), (x[:, 0] / nt).mean(), (x[:, 1] / nt).mean(), (x[:, 2] / nt).mean()))
+        print("      per CTA cycles: set-up %.0f | tile loop %.0f | tail (wait last MMAs, write partials) %.0f" % (
+            x[:, 7].mean(), x[:, 8].mean(), x[:, 15].mean()))

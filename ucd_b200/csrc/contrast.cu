@@ -227,6 +227,7 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
   __shared__ uint32_t s_tmem;
   __shared__ uint32_t s_mask[kMaxTilesPerCta / 32];  // bit tt: column tile k0+tt can hold an equal-label pair (or self)
 
+  const long long c_entry = clock64();      // debug trace: CTA set-up and tail cycles
   constexpr int NS = (PHASE == 1) ? 2 : 1;  // S accumulator buffers in TMEM
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rb = blockIdx.x / a.splits, split = blockIdx.x - rb * a.splits;
@@ -551,7 +552,9 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
     if (a.trace && warp == 3 && lane == 0) {  // one representative epilogue thread
       long long* tr = a.trace + (size_t)blockIdx.x * 16;
       tr[8] = clock64() - c_start, tr[9] = w_sf, tr[10] = w_ee, tr[11] = t;
+      tr[7] = c_start - c_entry;
     }
+    const long long c_tail = clock64();
     // ---- per-row outputs: the two column halves of a row combine through shared memory ----
     if (a.need_grad && t > 0) {  // all MMAs retired: accumulator final, E buffers free for reuse below
       mbar_wait(BAR(BAR_V), 0);
@@ -597,6 +600,7 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
       }
     }
     tc_fence_before();
+    if (a.trace && warp == 3 && lane == 0) a.trace[(size_t)blockIdx.x * 16 + 15] = clock64() - c_tail;
   }
   __syncthreads();
   if (warp == 1) {
