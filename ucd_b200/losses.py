@@ -9,6 +9,11 @@ Same class names, constructor and ``forward`` signatures as the reference so tha
 * ``pre_contrastive_pixel(f_n, l_n, l_po=None, f_o=None)`` (alias ``pre_contractive_pixel``)
                                                             utils/loss.py:258-399 / utils/utils.py:256-397
 * ``interpolate_bilinear(x, size)`` for ``F.interpolate(..., mode='bilinear')``   segmentation_module.py:133
+* siblings on the same kernels: ``KnowledgeDistillationLoss`` (loss.py:112-136),
+  ``MaskKnowledgeDistillationLoss`` (:218-256), ``MaskCrossEntropy`` (:186-216)
+
+Opt-in, beyond the drop-in surface: ``FusedUnbiasedLosses`` (N1: upsample + UNCE + UNKD from the low-res logits),
+``PixelContrastiveDistillation`` (N4: prep + contrastive loss without the 5-tuple, no host sync, CUDA-graph capturable).
 
 Everything runs in hand-written sm_100a CUDA kernels behind the C ABI of include/ucd_b200.h
 (ucd_b200/_lib.py).  PyTorch is used for device memory, streams, autograd glue and NCCL only.
