@@ -580,23 +580,35 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
         a.loss_part[(size_t)split * 2 * a.rows_pad + a.rows_pad + grow] = tacc + comb[r * 3 + 1];
       }
     }
-    if (a.need_grad) {  // each half writes 128 of the row's 256 accumulator columns
-      const size_t prow = (size_t)split * a.rows_pad + grow;
-      float4* dst = reinterpret_cast<float4*>(a.acc_part + prow * 256 + half * 128);
-      if (t > 0) {
+    if (a.need_grad) {  // each half writes 128 of the 256 accumulator columns of its rows
+      // tcgen05.ld hands a thread 32 consecutive columns of ITS row; stored directly, one instruction would touch 32
+      // different 128-byte lines with 16 bytes each.  A per-warp [32][36] transposition buffer in the (now idle) C stage
+      // turns that into 4 full lines per instruction.
+      float* xp = reinterpret_cast<float*>(smem + OFF_C + 4096) + (size_t)(warp - 3) * (32 * 36);
+      const size_t prow0 = (size_t)split * a.rows_pad + (size_t)rb * 128 + quarter * 32;  // first row of this warp
+      float* dstw = a.acc_part + prow0 * 256 + half * 128;
+      const int orow = lane >> 3, ocol = (lane & 7) * 4;
 #pragma unroll 1
-        for (int cc = 0; cc < 4; ++cc) {
+      for (int cc = 0; cc < 4; ++cc) {
+        if (t > 0) {
           uint32_t rv[32];
           tmem_ld32(tmem + lane_addr + 256 + half * 128 + cc * 32, rv);
           tmem_ld_wait();
           tmem_ld_fence(rv);
 #pragma unroll
           for (int k = 0; k < 8; ++k)
-            dst[cc * 8 + k] = make_float4(__uint_as_float(rv[4 * k]), __uint_as_float(rv[4 * k + 1]),
-                                          __uint_as_float(rv[4 * k + 2]), __uint_as_float(rv[4 * k + 3]));
+            *reinterpret_cast<float4*>(xp + lane * 36 + 4 * k) =
+                make_float4(__uint_as_float(rv[4 * k]), __uint_as_float(rv[4 * k + 1]), __uint_as_float(rv[4 * k + 2]),
+                            __uint_as_float(rv[4 * k + 3]));
+          __syncwarp();
         }
-      } else {
-        for (int k = 0; k < 32; ++k) dst[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int row = it * 4 + orow;
+          const float4 v = t > 0 ? *reinterpret_cast<const float4*>(xp + row * 36 + ocol) : make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(dstw + (size_t)row * 256 + cc * 32 + ocol) = v;
+        }
+        __syncwarp();
       }
     }
     tc_fence_before();
