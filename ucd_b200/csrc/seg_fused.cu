@@ -186,11 +186,15 @@ __global__ void __launch_bounds__(TX * kRG) seg_fused_kernel(const FusedArgs a, 
         valid_acc += ign ? 0.f : 1.f;
         kd_acc += kdpx;
       }
+      // phase B sees: label -1 = no CE gradient (ignored / out of image), -2 = background-remapped pixel (its CE
+      // gradient subtracts p_c exp(lse - lse_old) over the old classes; s_fold is 0 for every other pixel)
+      const bool off = dead || !colok;
+      const bool isbkg = !off && lab[q] == 0 && a.old_cl > 0;
       s_lse2[j] = lse2;
-      s_fold[j] = ex2f(lse2 - lseo2);       // exp(lse - lse_old)
-      s_fb[j] = q0 * ex2f(lse2 - lseb2);    // q0 exp(lse - lse_bkg)
+      s_fold[j] = isbkg ? ex2f(lse2 - lseo2) : 0.f;  // exp(lse - lse_old)
+      s_fb[j] = q0 * ex2f(lse2 - lseb2);             // q0 exp(lse - lse_bkg)
       s_lt2[j] = lset2;
-      s_lab[j] = (dead || !colok) ? -1 : (int)lab[q];
+      s_lab[j] = off ? -1 : (isbkg ? -2 : (int)lab[q]);
       s_h0[j] = colok ? h0[q] : 0.f;        // out-of-image columns contribute nothing
       s_h1[j] = colok ? h1[q] : 0.f;
     }
@@ -222,6 +226,7 @@ __global__ void __launch_bounds__(TX * kRG) seg_fused_kernel(const FusedArgs a, 
     if (c < Co) v0 = u[((size_t)(C + c) * 2) * TX + xl], v1 = u[((size_t)(C + c) * 2 + 1) * TX + xl];
     const bool in_sb = (c == 0) || (c >= Co);
     const bool old_fg = (c >= 1) && (c < Co);
+    const float oldc = (c < a.old_cl) ? 1.f : 0.f;  // uniform: channel c belongs to the old classes
     float ce0 = 0.f, ce1 = 0.f, kd0 = 0.f, kd1 = 0.f;
 #pragma unroll
     for (int j = 0; j < kRPT; ++j) {
@@ -229,12 +234,9 @@ __global__ void __launch_bounds__(TX * kRG) seg_fused_kernel(const FusedArgs a, 
       const float x = __fmaf_rn(u0, h0, __fmul_rn(u1, h1));
       const int lab = s_lab[j];
       const float p = ex2f(fmaf(x, kLog2e, -s_lse2[j]));
-      float sub;
-      if (lab == 0 && a.old_cl > 0)
-        sub = (c < a.old_cl) ? p * s_fold[j] : 0.f;
-      else
-        sub = (c == lab) ? 1.f : 0.f;
-      const float dce = (lab < 0) ? 0.f : (p - sub);
+      // dCE/dx_c = p_c - [old c] p_c fold - [c == label]   (fold = 0 unless the pixel was remapped to background)
+      const float sub = fmaf(p * oldc, s_fold[j], (c == lab) ? 1.f : 0.f);
+      const float dce = (lab == -1) ? 0.f : (p - sub);
       float dkd = p;
       if (in_sb) dkd -= p * s_fb[j];
       if (old_fg) dkd -= ex2f(fmaf(__fmaf_rn(v0, h0, __fmul_rn(v1, h1)), a2, -s_lt2[j]));
