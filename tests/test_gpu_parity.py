@@ -584,6 +584,8 @@ def test_sync_free_step_in_cuda_graph(U, golden_dir):
         loss.backward()
         return loss
 
+    if hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
+        torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)   # warm-up and capture streams differ
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
