@@ -217,6 +217,7 @@ __global__ void __launch_bounds__(TX * kRG) seg_fused_kernel(const FusedArgs a, 
   const int cx_lo = bilinear_tap(min(X0, a.W - 1), a.scale_w, a.w, a.W).i0;  // first low-res column of this tile
   float* mycell = cell + (size_t)warp * ncell;
   // lanes of a warp hold consecutive X of one row group, so tx.i0 is non-decreasing along the warp
+  const int nj = (nrow + kRG - 1) / kRG;  // rows per thread that exist in this interval
   const int key = colok ? tx.i0 : -1 - lane;
   const int key_prev = __shfl_up_sync(0xffffffffu, key, 1);
   const bool head = (lane == 0) || (key != key_prev);
@@ -230,6 +231,7 @@ __global__ void __launch_bounds__(TX * kRG) seg_fused_kernel(const FusedArgs a, 
     float ce0 = 0.f, ce1 = 0.f, kd0 = 0.f, kd1 = 0.f;
 #pragma unroll
     for (int j = 0; j < kRPT; ++j) {
+      if (j >= nj) break;  // block-uniform: an interior 16x interval has 16 rows = 4 per thread, not kRPT
       const float h0 = s_h0[j], h1 = s_h1[j];  // zero for rows this thread does not own
       const float x = __fmaf_rn(u0, h0, __fmul_rn(u1, h1));
       const int lab = s_lab[j];
