@@ -321,14 +321,14 @@ seg_fused_gather_kernel(const FusedArgs a, int TX, int ntx, int ncx_cap) {
   }
 }
 
-__global__ void seg_fused_sums_kernel(const float* __restrict__ psum, int nblk, float* __restrict__ sums) {
+__global__ void __launch_bounds__(1024)
+seg_fused_sums_kernel(const float* __restrict__ psum, int nblk, float* __restrict__ sums) {
   __shared__ float red[32];
-  for (int k = 0; k < 3; ++k) {
-    float acc = 0.f;
-    for (int i = threadIdx.x; i < nblk; i += blockDim.x) acc += psum[(size_t)k * nblk + i];
-    const float r = block_sum(acc, red);
-    if (threadIdx.x == 0) sums[k] = r;
-  }
+  const int k = blockIdx.x;  // one block per sum, fixed order
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < nblk; i += blockDim.x) acc += psum[(size_t)k * nblk + i];
+  const float r = block_sum(acc, red);
+  if (threadIdx.x == 0) sums[k] = r;
 }
 
 struct FusedPlan {
@@ -413,7 +413,7 @@ extern "C" int ucd_seg_fused_fwd(const float* lr, const float* lr_old, int64_t* 
     UCD_LAUNCH_FUSED(32);
 #undef UCD_LAUNCH_FUSED
   UCD_CHECK_LAUNCH("seg_fused_kernel");
-  seg_fused_sums_kernel<<<1, 256, 0, st>>>(a.psum, (int)p.nblk, sums);
+  seg_fused_sums_kernel<<<3, 1024, 0, st>>>(a.psum, (int)p.nblk, sums);
   UCD_CHECK_LAUNCH("seg_fused_sums_kernel");
   if (need_grad) {
     const long long n = (long long)B * C * h * w;
