@@ -83,6 +83,20 @@ def ptr(t):
     return None if t is None else c_void_p(t.data_ptr())
 
 
+_raw_stream = None
+
+
 def cur_stream():
+    """cudaStream_t of torch's current stream on the current device.  Uses torch's raw-stream accessor when it exists:
+    `torch.cuda.current_stream()` builds a Stream object through several Python layers and was ~20 % of the host time of
+    a step at small batch (scripts/host_profile.py)."""
+    global _raw_stream
     import torch
-    return c_void_p(torch.cuda.current_stream().cuda_stream)
+    if _raw_stream is None:
+        get_raw = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+        get_dev = getattr(torch._C, "_cuda_getDevice", None)
+        if get_raw is not None and get_dev is not None:
+            _raw_stream = lambda: get_raw(get_dev())                      # noqa: E731
+        else:
+            _raw_stream = lambda: torch.cuda.current_stream().cuda_stream  # noqa: E731
+    return c_void_p(_raw_stream())
