@@ -56,7 +56,11 @@ def test_umma_selftest(U):
                                         # interval / sweep kernels: scales 8, 32, mixed, rows that do not fill a segment
                                         ((2, 3, 64, 64), (512, 512)), ((1, 2, 16, 16), (512, 512)),
                                         ((1, 4, 24, 24), (384, 384)), ((2, 2, 32, 32), (256, 512)),
-                                        ((1, 2, 40, 16), (320, 256)), ((1, 2, 33, 32), (66, 512))])
+                                        ((1, 2, 40, 16), (320, 256)), ((1, 2, 33, 32), (66, 512)),
+                                        # largest scale of the interval kernel (40x) and beyond it (generic kernel)
+                                        ((1, 2, 4, 8), (160, 320)), ((1, 1, 3, 8), (144, 384)), ((1, 1, 5, 7), (171, 93)),
+                                        # sweep backward with a shortened segment (37x along y) over several segments
+                                        ((1, 2, 8, 8), (296, 256)), ((1, 1, 24, 8), (888, 256))])
 def test_upsample_fwd_bwd(U, shape, size):
     g = torch.Generator().manual_seed(11)
     x = torch.randn(*shape, generator=g)

@@ -105,7 +105,7 @@ upsample_fwd_kernel(const float* __restrict__ in, float* __restrict__ out, long 
 //   out(Y, X) = fma(t0(X), h0(Y), t1(X) * h1(Y))   with  t_r(X) = fma(v_r0, w0, v_r1 * w1)
 // (exactly ATen's generic-kernel operation order) costs one FMUL + one FMA per output after 4 loads per thread.
 // Consecutive blocks write consecutive ~32 KB runs: the whole grid is one sequential write stream.
-constexpr int kUpMaxIvRows = 96;  // rows of one interval the weight table holds (scale factors up to ~60)
+constexpr int kUpMaxIvRows = 96;  // candidate rows of one interval (2*scale + 5): scale factors up to 40
 template <int VEC>
 __global__ void __launch_bounds__(kUpThreads)
 upsample_fwd_interval_kernel(const float* __restrict__ in, float* __restrict__ out, int h, int w, int H, int W,
@@ -285,7 +285,7 @@ upsample_bwd_kernel(const float* __restrict__ gout, float* __restrict__ gin, int
 // above it, whose lower-tap part belongs to the segment's first row): per 128-bit load 8 FMAs fold the x weights,
 // 4 more the y weights; a low-res row is emitted when the sweep leaves its interval (shared-memory gather over the
 // threads whose taps hit each cell, fixed order).  No atomics, no re-reads beyond 1/seg_rows.
-constexpr int kUpSweepCap = 640;  // tap-table rows: (seg_rows + 1) * scale + 8 must fit
+constexpr int kUpSweepCap = 640;  // tap-table rows: (seg_rows + 2) * scale + 8 must fit (footprint + margins)
 template <int UN>
 __global__ void __launch_bounds__(256)
 upsample_bwd_sweep_kernel(const float* __restrict__ gout, float* __restrict__ gin, int h, int w, int H, int W,
@@ -392,7 +392,7 @@ extern "C" int ucd_upsample_bilinear_fwd(const float* in, float* out, int64_t pl
   const bool v4 = (W % 4 == 0) && aligned16(out);
   const int wv = v4 ? W / 4 : W;
   // upsampling beyond ATen's small-output regime (every training shape): interval kernel
-  if (H + W > 128 && H >= h && W >= w && (double)H / h <= 60.0 && planes * (long long)h < (1ll << 30) / 64) {
+  if (H + W > 128 && H >= h && W >= w && (double)H / h <= 40.0 /* candidate rows per interval: 2*scale + 5 <= kUpMaxIvRows */ && planes * (long long)h < (1ll << 30) / 64) {
     const int tw = wv < kUpThreads ? wv : kUpThreads;
     const int nct = (wv + tw - 1) / tw;
     const unsigned nblk = (unsigned)(planes * h * nct);
@@ -440,9 +440,9 @@ extern "C" int ucd_upsample_bilinear_bwd(const float* gout, float* gin, int64_t 
   // low-res rows per block: 16 measured best (98 us vs 106 / 113 us for 8 / 4 at 24x17x512x512: re-reading the
   // interval above the segment is not free), reduced until the tap table fits; 8 rows of loads in flight per thread
   int seg_rows = 16;
-  while (seg_rows > 1 && (seg_rows + 1) * (H / (h > 0 ? h : 1)) + 8 > kUpSweepCap) seg_rows >>= 1;
+  while (seg_rows > 1 && (seg_rows + 2) * (H / (h > 0 ? h : 1)) + 8 > kUpSweepCap) seg_rows >>= 1;
   if (v4 && H % h == 0 && W % w == 0 && (W / w) % 8 == 0 && W / 4 <= 256 && (W / 4) % 32 == 0 && w <= W / 4 &&
-      (seg_rows + 1) * (H / h) + 8 <= kUpSweepCap) {
+      (seg_rows + 2) * (H / h) + 8 <= kUpSweepCap) {
     const int nseg = (h + seg_rows - 1) / seg_rows;
     UCD_CHECK_ARG(planes * nseg < (1ll << 31), "ucd_upsample_bilinear_bwd: too many blocks");
     const unsigned nb = (unsigned)(planes * nseg);
