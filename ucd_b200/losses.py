@@ -284,9 +284,12 @@ class MaskCrossEntropy(nn.Module):
             raise TypeError("MaskCrossEntropy: old_cl=None cannot be compared with the labels (loss.py:210)")
         old_cl = 0 if self.old_cl is None else int(self.old_cl)  # None: every channel is a plain log-softmax
         ign = int(self.ignore_index)
-        tgt = targets.clone()  # the reference leaves `targets` untouched here
+        # the reference leaves `targets` untouched here; a label in [1, old_cl) must give zero loss and zero gradient
+        # (the zero-filled channel): map it to ignore_index in a private copy (torch.where: no host sync)
         if old_cl > 1:
-            tgt[(targets >= 1) & (targets < old_cl)] = ign  # zero loss and zero gradient, as the zero channel gives
+            tgt = torch.where((targets >= 1) & (targets < old_cl), torch.full_like(targets, ign), targets).contiguous()
+        else:
+            tgt = targets.clone()
         loss = _UnceFn.apply(inputs, tgt, old_cl, ign, "none")
         if outputs_old is not None:
             t = _f32c(outputs_old.detach())
