@@ -69,6 +69,30 @@ def test_product_refuses_cpu_tensors(L):
         ucd_b200.pre_contrastive_pixel(f, torch.zeros(1, 64, 64, dtype=torch.int64), l_po=torch.randn(1, 4, 4, 4), f_o=f)
 
 
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    """No extension -> RuntimeError naming the build command; nothing falls back to PyTorch or the oracle."""
+    from ucd_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "libucd_b200.so"))
+    with pytest.raises(RuntimeError, match="ucd_b200.build"):
+        _lib.lib()
+    import ucd_b200
+    if torch.cuda.is_available():   # on a GPU box the modules themselves must raise, too
+        with pytest.raises(RuntimeError, match="missing"):
+            ucd_b200.interpolate_bilinear(torch.randn(1, 1, 4, 4, device="cuda"), (8, 8))
+
+
+def test_sibling_and_opt_in_modules_exported():
+    import inspect
+    import ucd_b200 as U
+    for name in ("KnowledgeDistillationLoss", "MaskKnowledgeDistillationLoss", "MaskCrossEntropy", "FusedUnbiasedLosses",
+                 "PixelContrastiveDistillation"):
+        assert inspect.isclass(getattr(U, name)), name
+    assert list(inspect.signature(U.KnowledgeDistillationLoss.forward).parameters)[1:] == ["inputs", "targets", "mask"]
+    assert list(inspect.signature(U.MaskCrossEntropy.forward).parameters)[1:] == ["inputs", "targets", "outputs_old"]
+    assert list(inspect.signature(U.MaskCrossEntropy.__init__).parameters)[1:] == ["old_cl", "reduction", "ignore_index"]
+
+
 def test_reference_signatures_preserved():
     """Constructor / forward signatures the trainer relies on (train.py:32,38,50,115-116,133)."""
     import inspect
