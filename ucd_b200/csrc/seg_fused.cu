@@ -97,6 +97,13 @@ __global__ void __launch_bounds__(TX * kRG) seg_fused_kernel(const FusedArgs a, 
   const int k1 = min(k + 1, a.h - 1);  // lower tap row (weight 0 when clamped)
 
   const Tap tx = bilinear_tap(colok ? X : a.W - 1, a.scale_w, a.w, a.W);
+  // the labels of this thread's rows come from HBM: request them now, they arrive while the tap rows are staged
+  long long lab_pre[kRPT];
+#pragma unroll
+  for (int j = 0; j < kRPT; ++j) {
+    const int r = rg + j * kRG;
+    lab_pre[j] = (r < nrow && colok) ? a.labels[((size_t)b * a.H + Ya + r) * a.W + X] : 0;
+  }
   // x-blended tap rows for every channel of this column (channels split over the row groups)
   {
     const float* pn = a.lr + (size_t)b * C * a.h * a.w;
@@ -140,7 +147,7 @@ __global__ void __launch_bounds__(TX * kRG) seg_fused_kernel(const FusedArgs a, 
       lab[q] = 0;
       if (live[q] && colok) {
         long long* lp = a.labels + ((size_t)b * a.H + Y) * a.W + X;
-        lab[q] = *lp;
+        lab[q] = lab_pre[jb + q];
         if (lab[q] < a.old_cl) {  // utils/loss.py:104-105
           if (lab[q] != 0) *lp = 0;
           lab[q] = 0;
