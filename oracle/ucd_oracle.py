@@ -11,7 +11,7 @@ computes on this path:
 
 * ``downsample_labels`` / ``prep_labels``  <- utils/loss.py:259-270, 354-361
 * ``pre_contrastive_pixel``               <- utils/loss.py:273-276, 363-395
-* ``pixel_con_loss`` (+ closed-form grad) <- utils/loss.py:412-466
+* ``pixel_con_loss`` (+ closed-form grad, + row-blocked streaming form for large sizes) <- utils/loss.py:412-466
 * ``unbiased_ce``                         <- utils/loss.py:96-109
 * ``unbiased_kd``                         <- utils/loss.py:148-184
 * ``upsample_bilinear``                   <- segmentation_module.py:133
@@ -246,6 +246,67 @@ def pixel_con_loss_closed_form(A, Cst, la, lc, P=None, temperature=0.07, self_co
     U = (w * neg / den) @ Cst                       # sum_j w_ij neg_i/den_ij c_j
     dA = (kappa / temperature)[:, None] * (T[:, None] * V - U)
     return loss, dA
+
+
+def pixel_con_loss_streaming(A, Cst, la, lc, pa=None, pc=None, min_new=None, temperature=0.07, self_col=None,
+                             block=256, want_grad=True):
+    """Row-blocked fp64 evaluation of utils/loss.py:412-466 (closed form of SURVEY.md Appendix A.2) with the
+    joint-probability weights of utils/loss.py:369-393 formed block by block, so that memory is O(block x N_c)
+    instead of O(N_a x N_c): the oracle for sizes where the dense restatement does not fit (the bench workload:
+    23 419 x 41 102 pairs).  ``pa`` / ``pc`` are the softmax rows of the anchors / contrast columns (None: P == 1),
+    ``min_new`` the GT-new threshold of the override ``P[i,j] = 1 where la_i >= min_new and lc_j >= min_new``.
+
+    Returns (loss, dA or None, n_valid_rows); dA is dL/dA for the unit-norm anchor rows (fp64).  Checked against
+    ``pixel_con_loss`` / ``pixel_con_loss_closed_form`` and the reference fixtures in tests/test_oracle.py.
+    """
+    A = A.detach().double()
+    Cst = Cst.detach().double()
+    n_a = A.shape[0]
+    la, lc = la.reshape(-1).long(), lc.reshape(-1).long()
+    if self_col is None:
+        self_col = torch.arange(n_a)
+    if pa is not None:
+        pa, pc = pa.detach().double(), pc.detach().double()
+        gt_c = lc >= int(min_new)
+    row_sum = torch.zeros(n_a, dtype=torch.float64)
+    num_all = torch.zeros(n_a, dtype=torch.float64)
+    G = torch.zeros(n_a, A.shape[1], dtype=torch.float64) if want_grad else None
+    for r0 in range(0, n_a, block):
+        r1 = min(n_a, r0 + block)
+        a = A[r0:r1]
+        same = (la[r0:r1, None] == lc[None, :])
+        pos = same.double()
+        sc = self_col[r0:r1]
+        ok = sc >= 0
+        pos[torch.arange(r1 - r0)[ok], sc[ok]] -= 1.0
+        s = (a @ Cst.T) / temperature
+        e = torch.exp(s)
+        e[same] = 0.0                                    # masked exp: negatives only
+        neg = e.sum(1, keepdim=True)
+        m = s.max(1, keepdim=True).values
+        sh = s - m
+        den = torch.exp(sh) + neg
+        if pa is not None:
+            w = pa[r0:r1] @ pc.T
+            gt_a = la[r0:r1] >= int(min_new)
+            w[gt_a[:, None] & gt_c[None, :]] = 1.0
+            w *= pos
+        else:
+            w = pos
+        num = pos.sum(1)
+        row_sum[r0:r1] = (w * (sh - torch.log(den))).sum(1)
+        num_all[r0:r1] = num
+        if want_grad:
+            T = (w / den).sum(1, keepdim=True)
+            V = e @ Cst
+            U = (w * (neg / den)) @ Cst
+            k = torch.where(num != 0, 1.0 / (temperature * torch.where(num != 0, num, torch.ones_like(num))),
+                            torch.zeros_like(num))
+            G[r0:r1] = k[:, None] * (T * V - U)
+    keep = num_all != 0
+    M = int(keep.sum())
+    loss = (-(row_sum[keep] / num_all[keep])).sum() / M
+    return loss, (G / M if want_grad else None), M
 
 
 # ----------------------------------------------------------------------------

@@ -46,11 +46,14 @@ constexpr uint32_t kConSmem = OFF_BAR + 256;
 constexpr int kMaxChunks = 16;        // ranks whose columns are gathered (one 8-GPU box: 8)
 constexpr int kMaxTilesPerCta = 8192;  // column tiles one CTA walks (bit mask in shared memory)
 
-// A: row tile loaded | CF/CE: column stage full/empty | SF: S accumulator ready | SE: S buffer free (no-grad runs)
-// EF[2*buf+half]: E/Ucoef half written to TMEM | PF/PE: probability stage full/empty | V: all MMAs retired
+// A: row tile loaded | CF[4*stage+q]: quarter q (8 of the 32 k-chunks = 4 K steps of S) of a column stage has landed |
+// CE: column stage empty | SF: S accumulator ready | SE: S buffer free | EF[((buf*2+half)*2+chunk]: 32 columns of
+// E/Ucoef written to TMEM (2 K steps of V/U) | PF/PE: probability stage full/empty | V: all MMAs retired
 // SR (sweep 2): every epilogue warp has read the S accumulator into registers
-enum { BAR_A = 0, BAR_CF = 1, BAR_CE = 3, BAR_SF = 5, BAR_SE = 7, BAR_EF = 9, BAR_PF = 13, BAR_PE = 14, BAR_V = 15,
-       BAR_SR = 16 };
+// The quarter / chunk granularity shortens the load -> S -> epilogue -> V/U -> stage-free cycle that two stages have to
+// cover twice per two tiles: S starts on the first 16 KB of a tile, V/U on the first 32 columns of E.
+enum { BAR_A = 0, BAR_CF = 1, BAR_CE = 9, BAR_SF = 11, BAR_SE = 13, BAR_EF = 15, BAR_PF = 23, BAR_PE = 24, BAR_V = 25,
+       BAR_SR = 26 };
 
 struct ConArgs {
   const __nv_bfloat16* feat_tiles;
@@ -249,12 +252,11 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
     s_pre[a.n_chunks] = acc;
     mbar_init(BAR(BAR_A), 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(BAR(BAR_CF + i), 1);
+      for (int q = 0; q < 4; ++q) mbar_init(BAR(BAR_CF + 4 * i + q), 1);
       mbar_init(BAR(BAR_CE + i), 1 + kEpiWarps);  // tcgen05.commit + the epilogue warps (they read the stage's labels)
       mbar_init(BAR(BAR_SF + i), 1);
       mbar_init(BAR(BAR_SE + i), a.need_grad ? 1 : kEpiWarps);  // S buffer free: V MMAs retired / epilogue done
-      mbar_init(BAR(BAR_EF + 2 * i), 4);
-      mbar_init(BAR(BAR_EF + 2 * i + 1), 4);
+      for (int q = 0; q < 4; ++q) mbar_init(BAR(BAR_EF + 4 * i + q), 4);
     }
     mbar_init(BAR(BAR_PF), 1);
     mbar_init(BAR(BAR_PE), 1);
@@ -313,18 +315,26 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
     return n;
   };
 
+  // The three issuing roles run WARP-UNIFORM: all 32 lanes walk the tile loop and wait on the barriers, and the
+  // uniform-datapath instructions (bulk copies, tcgen05.mma, tcgen05.commit) sit in elect_one_sync() blocks, so that
+  // ptxas emits them back to back from uniform registers (see umma.cuh; `if (lane == 0)` costs an ELECT/BRA.U.ANY
+  // loop around every one of them).
   if (warp == 0) {
     // ===================== producer: bulk async copies =====================
-    if (lane == 0 && n > 0) {
+    if (n > 0) {
       const uint8_t* ft = reinterpret_cast<const uint8_t*>(a.feat_tiles);
       const uint8_t* pt = reinterpret_cast<const uint8_t*>(a.prob_tiles);
       const uint8_t* rft = reinterpret_cast<const uint8_t*>(a.row_feat);
       const uint8_t* rpt = reinterpret_cast<const uint8_t*>(a.row_prob);
       const uint32_t pbytes = pa_bytes;
-      mbar_arrive_expect_tx(BAR(BAR_A), kTileBytes + ((PHASE == 2 && PMODE == 1) ? pbytes : 0u));
-      for (int q = 0; q < 4; ++q)
-        bulk_g2s(sbase + OFF_A + q * 16384u, rft + (size_t)rb * kTileBytes + q * 16384u, 16384u, BAR(BAR_A));
-      if (PHASE == 2 && PMODE == 1) bulk_g2s(sbase + OFF_PA, rpt + (size_t)rb * pbytes, pbytes, BAR(BAR_A));
+      if (elect_one_sync()) {
+        mbar_arrive_expect_tx(BAR(BAR_A), kTileBytes + ((PHASE == 2 && PMODE == 1) ? pbytes : 0u));
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          bulk_g2s(sbase + OFF_A + q * 16384u, rft + (size_t)rb * kTileBytes + q * 16384u, 16384u, BAR(BAR_A));
+        if (PHASE == 2 && PMODE == 1) bulk_g2s(sbase + OFF_PA, rpt + (size_t)rb * pbytes, pbytes, BAR(BAR_A));
+      }
+      __syncwarp();
       long long w_ce = 0, w_pe = 0;
       const long long c_start = clock64();
       int t = 0;
@@ -332,102 +342,150 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
         const TileLoc loc = locate_tile(k0 + tt, s_pre, s_ncols, a.n_chunks, a.chunk_tiles);
         const int stage = t & 1;
         mbar_wait_t(BAR(BAR_CE + stage), ((t >> 1) & 1) ^ 1, w_ce);
-        mbar_arrive_expect_tx(BAR(BAR_CF + stage), kTileBytes + 512u);
-        const uint32_t dst = sbase + OFF_C + stage * kTileBytes;
-        for (int q = 0; q < 4; ++q)
-          bulk_g2s(dst + q * 16384u, ft + (size_t)loc.gtile * kTileBytes + q * 16384u, 16384u, BAR(BAR_CF + stage));
-        bulk_g2s(sbase + OFF_LAB + stage * 512u, a.lab_tiles + loc.gtile * 128, 512u, BAR(BAR_CF + stage));
+        if (elect_one_sync()) {
+          const uint32_t dst = sbase + OFF_C + stage * kTileBytes;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t bq = BAR(BAR_CF + 4 * stage + q);
+            mbar_arrive_expect_tx(bq, 16384u + (q == 0 ? 512u : 0u));
+            bulk_g2s(dst + q * 16384u, ft + (size_t)loc.gtile * kTileBytes + q * 16384u, 16384u, bq);
+            if (q == 0) bulk_g2s(sbase + OFF_LAB + stage * 512u, a.lab_tiles + loc.gtile * 128, 512u, bq);
+          }
+        }
+        __syncwarp();
         for (int c = 0; c < n_pc; ++c) {  // column probabilities, one K chunk at a time through a single buffer
           const int u = t * n_pc + c;
           const uint32_t kb = (uint32_t)min(pc_k, a.kpad - c * pc_k) * 256u;
           mbar_wait_t(BAR(BAR_PE), (u & 1) ^ 1, w_pe);
-          mbar_arrive_expect_tx(BAR(BAR_PF), kb);
-          bulk_g2s(sbase + off_pc, pt + (size_t)loc.gtile * pbytes + (size_t)c * pc_k * 256u, kb, BAR(BAR_PF));
+          if (elect_one_sync()) {
+            mbar_arrive_expect_tx(BAR(BAR_PF), kb);
+            bulk_g2s(sbase + off_pc, pt + (size_t)loc.gtile * pbytes + (size_t)c * pc_k * 256u, kb, BAR(BAR_PF));
+          }
+          __syncwarp();
         }
         ++t;
       }
-      if (a.trace) {
+      if (a.trace && lane == 0) {
         long long* tr = a.trace + (size_t)blockIdx.x * 16;
         tr[0] = clock64() - c_start, tr[1] = w_ce, tr[2] = w_pe, tr[3] = t;
       }
     }
   } else if (warp == 1) {
-    // ===================== S issuer: S = A C^T (and P = pA pC^T in sweep 2), one thread =====================
-    // A single thread sustains one tcgen05.mma per ~110-120 clk (measured, scripts/mma_rate.py), more than the
-    // 64 clk an N=128 K step occupies the tensor pipe; S and V/U are therefore issued by two different warps.
-    if (lane == 0 && n > 0) {
+    // ===================== S issuer: S = A C^T (and P = pA pC^T in sweep 2) =====================
+    // S and V/U are issued by two different warps so that neither waits behind the other's barriers.
+    if (n > 0) {
       constexpr uint32_t idesc_s = umma_idesc(128, 128, 0, 0);   // A K-major, B K-major
       const uint32_t tS = tmem, tP = tmem + 128;
+      const uint64_t adesc0 = umma_desc(sbase + OFF_A, kChunkB, 128);
+      const uint64_t cdesc0 = umma_desc(sbase + OFF_C, kChunkB, 128);
+      const uint64_t padesc0 = umma_desc(sbase + OFF_PA, kChunkB, 128);
+      const uint64_t pcdesc0 = umma_desc(sbase + off_pc, kChunkB, 128);
       mbar_wait(BAR(BAR_A), 0);
       long long c_idle = 0;
       const long long c_start = clock64();
       int t = 0;
       for (int tt = next_active(0); tt < n; tt = next_active(tt + 1)) {
         const int stage = t & 1, sb = t % NS;
-        mbar_wait_t(BAR(BAR_CF + stage), (t >> 1) & 1, c_idle);
         // sweep 1: the S buffer is free when the V MMAs that read E out of it have retired.  Sweep 2 has one S
         // buffer but parks Ucoef in the P columns: S may be overwritten as soon as the epilogue holds it in registers.
         if (PHASE == 1)
           mbar_wait_t(BAR(BAR_SE + sb), ((t / NS) & 1) ^ 1, c_idle);
         else
           mbar_wait_t(BAR(BAR_SR), (t & 1) ^ 1, c_idle);
-        tc_fence_after();
-        const uint32_t sc = sbase + OFF_C + stage * kTileBytes;
+        for (int q = 0; q < 4; ++q) {  // 4 K steps per landed quarter of the column tile
+          mbar_wait_t(BAR(BAR_CF + 4 * stage + q), (t >> 1) & 1, c_idle);
+          tc_fence_after();
+          if (elect_one_sync()) {
+            const uint64_t cdesc = umma_desc_adv(cdesc0, stage * kTileBytes + (uint32_t)q * 16384u);
+            const uint64_t adesc = umma_desc_adv(adesc0, (uint32_t)q * 16384u);
 #pragma unroll
-        for (int ks = 0; ks < 16; ++ks)
-          umma_bf16(tS + sb * 128, umma_desc(sbase + OFF_A + ks * 2 * kChunkB, kChunkB, 128),
-                    umma_desc(sc + ks * 2 * kChunkB, kChunkB, 128), idesc_s, ks > 0);
-        if (PHASE == 2) {  // the P columns (Ucoef of the previous tile lives there) are free once its U MMAs retired
+            for (int ks = 0; ks < 4; ++ks)
+              umma_bf16(tS + sb * 128, umma_desc_adv(adesc, ks * 2 * kChunkB), umma_desc_adv(cdesc, ks * 2 * kChunkB),
+                        idesc_s, (q > 0 || ks > 0) ? 1u : 0u);
+            if (q == 3 && PHASE == 1) {
+              umma_commit(BAR(BAR_SF + sb));
+              if (!a.need_grad) umma_commit(BAR(BAR_CE + stage));  // no V pass: the stage is free once S is done
+            }
+          }
+          __syncwarp();
+        }
+        if (PHASE == 2) {
+          // the P columns (Ucoef of the previous tile lives there, whatever PMODE is) are free once its U MMAs
+          // retired: the epilogue of this tile must not get SF before that
           mbar_wait_t(BAR(BAR_SE), (t & 1) ^ 1, c_idle);
           tc_fence_after();
+          if (n_pc == 0) {
+            if (elect_one_sync()) {
+              umma_commit(BAR(BAR_SF + sb));
+              if (!a.need_grad) umma_commit(BAR(BAR_CE + stage));
+            }
+            __syncwarp();
+          }
+          for (int c = 0; c < n_pc; ++c) {  // P = pA pC^T accumulated over the K chunks of pC
+            const int u = t * n_pc + c;
+            mbar_wait_t(BAR(BAR_PF), u & 1, c_idle);
+            tc_fence_after();
+            const int ksteps = min(pc_k, a.kpad - c * pc_k) >> 4;
+            if (elect_one_sync()) {
+              for (int ks = 0; ks < ksteps; ++ks)
+                umma_bf16(tP, umma_desc_adv(padesc0, (uint32_t)(c * (pc_k >> 3) + ks * 2) * kChunkB),
+                          umma_desc_adv(pcdesc0, ks * 2 * kChunkB), idesc_s, (c > 0 || ks > 0) ? 1u : 0u);
+              umma_commit(BAR(BAR_PE));
+              if (c == n_pc - 1) {
+                umma_commit(BAR(BAR_SF + sb));
+                if (!a.need_grad) umma_commit(BAR(BAR_CE + stage));
+              }
+            }
+            __syncwarp();
+          }
         }
-        for (int c = 0; c < n_pc; ++c) {  // P = pA pC^T accumulated over the K chunks of pC
-          const int u = t * n_pc + c;
-          mbar_wait_t(BAR(BAR_PF), u & 1, c_idle);
-          tc_fence_after();
-          const int ksteps = min(pc_k, a.kpad - c * pc_k) >> 4;
-          for (int ks = 0; ks < ksteps; ++ks)
-            umma_bf16(tP, umma_desc(sbase + OFF_PA + (uint32_t)(c * (pc_k >> 3) + ks * 2) * kChunkB, kChunkB, 128),
-                      umma_desc(sbase + off_pc + ks * 2 * kChunkB, kChunkB, 128), idesc_s, (c > 0 || ks > 0) ? 1u : 0u);
-          umma_commit(BAR(BAR_PE));
-        }
-        umma_commit(BAR(BAR_SF + sb));
-        if (!a.need_grad) umma_commit(BAR(BAR_CE + stage));  // no V/U pass: the stage is free once S is done
         ++t;
       }
-      if (!a.need_grad) umma_commit(BAR(BAR_V));
-      if (a.trace) {
+      if (!a.need_grad) {
+        if (elect_one_sync()) umma_commit(BAR(BAR_V));
+        __syncwarp();
+      }
+      if (a.trace && lane == 0) {
         long long* tr = a.trace + (size_t)blockIdx.x * 16;
         tr[4] = clock64() - c_start, tr[5] = c_idle, tr[6] = t;
       }
     }
   } else if (warp == 2) {
-    // ===================== V/U issuer: acc += E x C with E (bf16) read from tensor memory, one thread ============
-    if (lane == 0 && n > 0 && a.need_grad) {
+    // ===================== V/U issuer: acc += E x C with E (bf16) read from tensor memory ============
+    if (n > 0 && a.need_grad) {
       constexpr uint32_t idesc_v = umma_idesc(128, 256, 0, 1);   // A from TMEM, B MN-major
       const uint32_t tS = tmem, tV = tmem + 256;
+      const uint64_t vdesc0 = umma_desc(sbase + OFF_C, 128, kChunkB);
       long long c_idle = 0;
       const long long c_start = clock64();
       int t = 0;
       for (int tt = next_active(0); tt < n; tt = next_active(tt + 1)) {
         const int stage = t & 1, sb = t % NS;
-        const uint32_t sc = sbase + OFF_C + stage * kTileBytes;
-        for (int h = 0; h < 2; ++h) {
-          mbar_wait_t(BAR(BAR_EF + 2 * sb + h), (t / NS) & 1, c_idle);
-          tc_fence_after();
-          // 32 columns of packed bf16 pairs = 64 K values: E over the S buffer (sweep 1), Ucoef over P (sweep 2)
-          const uint32_t te = (PHASE == 1 ? tS + sb * 128 : tmem + 128) + h * 64;
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            umma_bf16_ts(tV, te + kk * 8, umma_desc(sc + (uint32_t)(h * 64 + kk * 16) * 16u, 128, kChunkB), idesc_v,
-                         (t > 0 || h > 0 || kk > 0) ? 1u : 0u);
+        for (int u = 0; u < 4; ++u) {  // (chunk 0, half 0), (chunk 0, half 1), (chunk 1, half 0), (chunk 1, half 1)
+          const int cc = u >> 1, h = u & 1;
+          mbar_wait_t(BAR(BAR_EF + (sb * 2 + h) * 2 + cc), (t / NS) & 1, c_idle);
+          tc_fence_after();
+          // 16 columns of packed bf16 pairs = 32 K values: E over the S buffer (sweep 1), Ucoef over P (sweep 2)
+          const uint32_t te = (PHASE == 1 ? tS + sb * 128 : tmem + 128) + h * 64 + cc * 16;
+          if (elect_one_sync()) {
+            const uint64_t vdesc = umma_desc_adv(vdesc0, stage * kTileBytes + (uint32_t)(h * 64 + cc * 32) * 16u);
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk)
+              umma_bf16_ts(tV, te + kk * 8, umma_desc_adv(vdesc, (uint32_t)kk * 256u), idesc_v,
+                           (t > 0 || u > 0 || kk > 0) ? 1u : 0u);
+            if (u == 3) {
+              umma_commit(BAR(BAR_CE + stage));  // tile t no longer needs its C stage ...
+              umma_commit(BAR(BAR_SE + sb));     // ... nor its S buffer (E lived there)
+            }
+          }
+          __syncwarp();
         }
-        umma_commit(BAR(BAR_CE + stage));  // tile t no longer needs its C stage ...
-        umma_commit(BAR(BAR_SE + sb));     // ... nor its S buffer (E lived there)
         ++t;
       }
-      umma_commit(BAR(BAR_V));
-      if (a.trace) {
+      if (elect_one_sync()) umma_commit(BAR(BAR_V));
+      __syncwarp();
+      if (a.trace && lane == 0) {
         long long* tr = a.trace + (size_t)blockIdx.x * 16;
         tr[12] = clock64() - c_start, tr[13] = c_idle, tr[14] = t;
       }
@@ -481,12 +539,10 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
       auto emit = [&](int cc, const uint32_t (&pk)[16]) {  // cc = chunk 0/1 within this thread's column half
         if (!a.need_grad) return;
         tmem_st16(tmem + lane_addr + (PHASE == 1 ? sb * 128 : 128) + half * 64 + cc * 16, pk);
-        if (cc == 1) {
-          tmem_st_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(BAR(BAR_EF + 2 * sb + half));
-        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR(BAR_EF + (sb * 2 + half) * 2 + cc));
       };
       const int c0 = half * 64;  // first column of this thread's half
       if (PHASE == 1) {

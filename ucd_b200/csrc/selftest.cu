@@ -149,26 +149,62 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int mode, int iters, l
     mbar_wait(bar, 0);
     cycles[0] = clock64() - c0;
   }
-  // modes 12..13: ONE warp, warp-uniform loop, MMA issued by the elected lane: 12 SS N=128 | 13 TS N=128
-  if ((mode == 12 || mode == 13) && warp == 0) {
-    const uint32_t idesc = umma_idesc(128, 128, 0, 0);
+  // modes 12..15: ONE warp, warp-uniform loop, 16 K steps per elect_one_sync() block (straight-line UTCHMMA in SASS):
+  //   12 SS N=128 | 13 TS N=128 | 14 SS N=64 | 15 TS N=256 (B MN-major)
+  if (mode >= 12 && mode <= 15 && warp == 0) {
+    const bool ts = mode == 13 || mode == 15;
+    const int N = mode == 14 ? 64 : (mode == 15 ? 256 : 128);
+    const bool mn = mode == 15;
+    const uint32_t idesc = umma_idesc(128, N, 0, mn ? 1 : 0);
+    const uint64_t a0 = umma_desc(sbase + ST_OFF_A, 2048, 128);
+    const uint64_t b0 = mn ? umma_desc(sbase + ST_OFF_C, 128, 2048) : umma_desc(sbase + ST_OFF_C, 2048, 128);
     const long long c0 = clock64();
-    for (int i = 0; i < iters; ++i) {
-      const int ks = i & 15;
-      const uint64_t bdesc = umma_desc(sbase + ST_OFF_C + ks * 4096, 2048, 128);
-      const uint64_t adesc = umma_desc(sbase + ST_OFF_A + ks * 4096, 2048, 128);
-      if (elect_one()) {
-        if (mode == 13)
-          umma_bf16_ts(tmem + 256, tmem + ks * 8, bdesc, idesc, 1u);
-        else
-          umma_bf16(tmem + 256, adesc, bdesc, idesc, 1u);
+    for (int i = 0; i < iters; i += 16) {
+      if (elect_one_sync()) {
+#pragma unroll
+        for (int ks = 0; ks < 16; ++ks) {
+          const uint64_t bdesc = umma_desc_adv(b0, mn ? (ks & 7) * 256 : ks * 4096);
+          if (ts)
+            umma_bf16_ts(tmem + 256, tmem + ks * 8, bdesc, idesc, 1u);
+          else
+            umma_bf16(tmem + 256, umma_desc_adv(a0, ks * 4096), bdesc, idesc, 1u);
+        }
       }
       __syncwarp();
     }
-    if (elect_one()) umma_commit(bar);
+    if (elect_one_sync()) umma_commit(bar);
     __syncwarp();
     mbar_wait(bar, 0);
     if (threadIdx.x == 0) cycles[0] = clock64() - c0;
+  }
+  // mode 16: the sweep-1 mix from TWO warps: warp 0 issues 16 SS N=128 per tile (S), warp 1 issues 8 TS N=256 MN-major
+  // per tile (V), no data dependence between them: cycles per tile-equivalent / 16 is reported (iters = S MMAs).
+  if (mode == 16 && warp < 2) {
+    const uint32_t mybar = bar + (warp == 1 ? 8 : 0);
+    const uint32_t idesc_s = umma_idesc(128, 128, 0, 0), idesc_v = umma_idesc(128, 256, 0, 1);
+    const uint64_t a0 = umma_desc(sbase + ST_OFF_A, 2048, 128);
+    const uint64_t bk = umma_desc(sbase + ST_OFF_C, 2048, 128), bm = umma_desc(sbase + ST_OFF_C, 128, 2048);
+    const long long c0 = clock64();
+    for (int i = 0; i < iters; i += 16) {
+      if (elect_one_sync()) {
+        if (warp == 0) {
+#pragma unroll
+          for (int ks = 0; ks < 16; ++ks)
+            umma_bf16(tmem + (i & 16 ? 128 : 0), umma_desc_adv(a0, ks * 4096), umma_desc_adv(bk, ks * 4096), idesc_s, 1u);
+        } else {
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma_bf16_ts(tmem + 256, tmem + kk * 8, umma_desc_adv(bm, kk * 256), idesc_v, 1u);
+        }
+      }
+      __syncwarp();
+    }
+    if (elect_one_sync()) umma_commit(mybar);
+    __syncwarp();
+    mbar_wait(mybar, 0);
+    __syncwarp();
+    if (threadIdx.x == 0) cycles[0] = clock64() - c0;   // warp 0 finishes last or not: see mode 17 for the V side
+    if (threadIdx.x == 32) cycles[1] = clock64() - c0;
   }
   // modes 9..11: TWO issuing threads (warps 0 and 1), each its own accumulator: 9 SS N=128 | 10 TS N=128 | 11 SS N=64
   if (mode >= 9 && mode <= 11 && (threadIdx.x == 0 || threadIdx.x == 32)) {
@@ -264,10 +300,11 @@ extern "C" int ucd_selftest_umma(int variant, float* max_err_host) {
 }
 
 extern "C" int ucd_selftest_mma_rate(int mode, int iters, float* cycles_per_instr_host) {
-  UCD_CHECK_ARG(mode >= 0 && mode <= 13 && iters > 0 && cycles_per_instr_host, "ucd_selftest_mma_rate: bad argument");
+  UCD_CHECK_ARG(mode >= 0 && mode <= 16 && iters > 0 && cycles_per_instr_host, "ucd_selftest_mma_rate: bad argument");
   long long* d = nullptr;
   cudaError_t e;
-  if ((e = cudaMalloc(&d, 8)) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+  if ((e = cudaMalloc(&d, 16)) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+  cudaMemset(d, 0, 16);
   if ((e = cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM)) != cudaSuccess)
     return cuda_fail(e, "cudaFuncSetAttribute(mma_rate_kernel)");
   long long h = 0;
@@ -278,7 +315,9 @@ extern "C" int ucd_selftest_mma_rate(int mode, int iters, float* cycles_per_inst
       return cuda_fail(e, "mma_rate_kernel");
     }
   }
-  cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
+  long long h2[2] = {0, 0};
+  cudaMemcpy(h2, d, 16, cudaMemcpyDeviceToHost);
+  h = h2[0] > h2[1] ? h2[0] : h2[1];
   cudaFree(d);
   *cycles_per_instr_host = (float)h / (float)iters;
   return UCD_OK;

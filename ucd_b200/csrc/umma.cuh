@@ -121,10 +121,23 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// one lane of a converged warp (warp-uniform control flow around it keeps MMA operands in uniform registers)
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n.reg .pred P1;\nelect.sync _|P1, 0xffffffff;\nselp.b32 %0, 1, 0, P1;\n}" : "=r"(pred));
+// One lane of a converged warp, in the form ptxas recognises (elect.sync whose predicate guards the block directly):
+// inside `if (elect_one_sync()) { ... }` the compiler knows a single thread is active, keeps the operands of the
+// uniform-datapath instructions (UTCHMMA, UBLKCP, UTCBAR) in uniform registers and emits them back to back.  Under a
+// plain `if (lane == 0)` every such instruction is wrapped in an ELECT / BRA.U.ANY loop over the "possibly divergent"
+// active threads, which serialises the descriptor arithmetic with the issue: one tcgen05.mma per ~110-120 clk
+// (profiles/r01f_mma_rate.txt) instead of one per pipe slot.  The leader is the same lane every time (PTX ISA:
+// the election is deterministic for a given membermask), so a tcgen05.commit in a later block tracks the MMAs of
+// an earlier one.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0, laneid = 0;
+  asm volatile(
+      "{\n.reg .b32 %%rx;\n.reg .pred %%px;\n"
+      "elect.sync %%rx|%%px, %2;\n"
+      "@%%px mov.s32 %1, 1;\n"
+      "mov.s32 %0, %%rx;\n}"
+      : "+r"(laneid), "+r"(pred)
+      : "r"(0xFFFFFFFFu));
   return pred != 0;
 }
 
@@ -142,6 +155,9 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_b
   d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
   return d;                // base_offset = 0, lbo_mode = 0, layout_type = SWIZZLE_NONE
 }
+// Same descriptor, start address advanced by `bytes` (multiple of 16; shared-memory addresses stay below 256 KB, so the
+// 14-bit address field cannot carry into the LBO field): one add instead of a mask/shift/or chain per MMA.
+__device__ __forceinline__ uint64_t umma_desc_adv(uint64_t desc, uint32_t bytes) { return desc + (uint64_t)(bytes >> 4); }
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32
 __host__ __device__ constexpr uint32_t umma_idesc(int M, int N, int a_mn_major, int b_mn_major) {
   return (1u << 4)                       // D format F32
