@@ -50,6 +50,7 @@ _PROTOS = {
     "ucd_con_debug_splits": (c_int, [c_int64, c_int64]),
     "ucd_selftest_umma": (c_int, [c_int, ctypes.POINTER(c_float)]),
     "ucd_selftest_mma_rate": (c_int, [c_int, c_int, ctypes.POINTER(c_float)]),
+    "ucd_selftest_mma_mix": (c_int, [c_int] * 8 + [ctypes.POINTER(c_float)]),
     "ucd_selftest_pipe_rate": (c_int, [c_int, c_int, c_int, ctypes.POINTER(c_float)]),
 }
 EXPORTED = tuple(_PROTOS)

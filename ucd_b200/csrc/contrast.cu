@@ -34,26 +34,45 @@ constexpr uint32_t kTileBytes = 65536;  // 128 rows x 256 bf16
 constexpr uint32_t kChunkB = 2048;      // one 8-element k-chunk for 128 rows
 constexpr uint32_t kESub = 16384;       // 128 rows x 64 columns bf16
 
+constexpr uint32_t kSlotBytes = 32768;  // half a column tile: 16 of its 32 k-chunks (128 features) x 128 columns
+
 // shared memory map (bytes)
 constexpr uint32_t OFF_A = 0;
-constexpr uint32_t OFF_C = 65536;     // 2 stages
+constexpr uint32_t OFF_C = 65536;     // ring of half-tile slots: 5 in sweep 1, 4 in sweep 2 (the 5th is OFF_E there)
 constexpr uint32_t OFF_E = 196608;    // 32 KB: sweep 2 probability operands
 constexpr uint32_t OFF_PA = OFF_E;    // sweep 2: row probabilities [kpad/8][128][8] bf16 (kpad*256 B <= 28 KB)
 constexpr uint32_t kProbBytes = 32768;  // OFF_PA .. OFF_LAB: the column probabilities use what pA leaves, in K chunks
-constexpr uint32_t OFF_LAB = 229376;  // 2 x 128 int32
-constexpr uint32_t OFF_BAR = 230400;
+constexpr uint32_t OFF_LAB = 229376;  // 3 x 128 int32 (labels of the up to three column tiles in flight)
+constexpr uint32_t OFF_BAR = 230912;
 constexpr uint32_t kConSmem = OFF_BAR + 256;
 constexpr int kMaxChunks = 16;        // ranks whose columns are gathered (one 8-GPU box: 8)
-constexpr int kMaxTilesPerCta = 8192;  // column tiles one CTA walks (bit mask in shared memory)
+constexpr int kMaxTilesPerCta = 4096;  // column tiles one CTA walks (bit mask in shared memory)
 
-// A: row tile loaded | CF[4*stage+q]: quarter q (8 of the 32 k-chunks = 4 K steps of S) of a column stage has landed |
-// CE: column stage empty | SF: S accumulator ready | SE: S buffer free | EF[((buf*2+half)*2+chunk]: 32 columns of
-// E/Ucoef written to TMEM (2 K steps of V/U) | PF/PE: probability stage full/empty | V: all MMAs retired
-// SR (sweep 2): every epilogue warp has read the S accumulator into registers
-// The quarter / chunk granularity shortens the load -> S -> epilogue -> V/U -> stage-free cycle that two stages have to
-// cover twice per two tiles: S starts on the first 16 KB of a tile, V/U on the first 32 columns of E.
-enum { BAR_A = 0, BAR_CF = 1, BAR_CE = 9, BAR_SF = 11, BAR_SE = 13, BAR_EF = 15, BAR_PF = 23, BAR_PE = 24, BAR_V = 25,
-       BAR_SR = 26 };
+// Column tiles stream through a RING of half-tile slots (feature halves: k-chunks 0-15 / 16-31 of the tile, 32 KB each).
+// A tile's two slots stay occupied from their load until the V/U MMAs of the tile have retired (V reads every feature
+// of 16 columns per K step), i.e. for load + S + epilogue + V; with whole-tile stages only two fit beside the 64 KB
+// anchor tile and every second tile waited ~750 clk for its stage (profiles/r02a_*).  Five half slots keep 2.5 tiles
+// in flight: the first half of tile t+2 is loaded - and its 8 S K-steps issued - while tile t still holds its slots.
+//
+// A: row tile loaded | HF[2*slot+q]: 16 KB quarter q (4 K steps of S) of a slot has landed | HE[slot]: slot empty
+// (tcgen05.commit of the tile's last V/U MMA + the 8 epilogue warps, which read the tile's labels) | SF: S accumulator
+// ready | SE: S buffer free | EF[(buf*2+half)*2+chunk]: 32 columns of E/Ucoef written to TMEM (2 K steps of V/U) |
+// PF/PE: probability stage full/empty | V: all MMAs retired | SR (sweep 2): S accumulator is in the epilogue's registers
+enum { BAR_A = 0, BAR_HF = 1, BAR_HE = 11, BAR_SF = 16, BAR_SE = 18, BAR_EF = 20, BAR_PF = 28, BAR_PE = 29, BAR_V = 30,
+       BAR_SR = 31 };
+
+// position in the slot ring: slot index and the parity of its use count
+template <int NSLOT>
+struct Ring {
+  int slot = 0;
+  uint32_t par = 0;
+  __device__ __forceinline__ void next() {
+    if (++slot == NSLOT) {
+      slot = 0;
+      par ^= 1u;
+    }
+  }
+};
 
 struct ConArgs {
   const __nv_bfloat16* feat_tiles;
@@ -108,6 +127,35 @@ __device__ __forceinline__ TileLoc locate_tile(int k, const int* pre, const int*
   t.dcol0 = (long long)lt * 128;
   return t;
 }
+
+// The tile loops visit their tiles in increasing order: the chunk a tile belongs to is tracked in registers and only
+// advanced (shared-memory reads) when a chunk boundary is crossed.  (locate_tile per tile - a dependent chain of
+// shared-memory loads and branches - cost every epilogue warp ~300 clk per tile, ncu source view r02.)
+struct TileCursor {
+  int c, base, next, ncols;
+  long long chunk_tiles;
+  const int* pre;
+  const int* ncols_arr;
+  int n_chunks;
+  __device__ __forceinline__ void init(const int* pre_, const int* ncols_, int n_chunks_, long long chunk_tiles_) {
+    pre = pre_, ncols_arr = ncols_, n_chunks = n_chunks_, chunk_tiles = chunk_tiles_;
+    c = 0, base = 0, next = pre_[1], ncols = ncols_[0];
+  }
+  __device__ __forceinline__ TileLoc seek(int k) {  // k must not decrease between calls
+    while (c + 1 < n_chunks && k >= next) {
+      ++c;
+      base = next;
+      next = pre[c + 1];
+      ncols = ncols_arr[c];
+    }
+    const int lt = k - base;
+    TileLoc t;
+    t.gtile = (long long)c * chunk_tiles + lt;
+    t.nvalid = min(128, ncols - lt * 128);
+    t.dcol0 = (long long)lt * 128;
+    return t;
+  }
+};
 
 __device__ __forceinline__ uint32_t bf16x2_bits(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
@@ -231,7 +279,13 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
   __shared__ uint32_t s_mask[kMaxTilesPerCta / 32];  // bit tt: column tile k0+tt can hold an equal-label pair (or self)
 
   const long long c_entry = clock64();      // debug trace: CTA set-up and tail cycles
-  constexpr int NS = (PHASE == 1) ? 2 : 1;  // S accumulator buffers in TMEM
+  // Tensor memory: sweep 1: S [0,128) | E (bf16 pairs, two buffers of 64 columns) [128,256) | V [256,512)
+  //                sweep 2: S [0,128) | P, later Ucoef [128,256) | U [256,512)
+  // ONE S accumulator: it is free again as soon as the epilogue holds the tile in registers (SR), so the S MMAs of
+  // tile t+1 run under the epilogue of tile t whatever the V/U MMAs of earlier tiles are doing.  (With E written over
+  // S in place, S(t+2) had to wait for V(t): epilogue -> V tail -> S -> epilogue was a two-tile cycle of ~4.9 k clk.)
+  constexpr int NE = (PHASE == 1) ? 2 : 1;  // E buffers in TMEM (sweep 2 parks Ucoef in the consumed P columns)
+  constexpr int NSLOT = (PHASE == 1) ? 5 : 4;  // half-tile slots (sweep 2 keeps 32 KB for the probability operands)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rb = blockIdx.x / a.splits, split = blockIdx.x - rb * a.splits;
   const int n_rows = *a.n_rows;
@@ -251,9 +305,12 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
     }
     s_pre[a.n_chunks] = acc;
     mbar_init(BAR(BAR_A), 1);
+    for (int i = 0; i < 5; ++i) {
+      mbar_init(BAR(BAR_HF + 2 * i), 1);
+      mbar_init(BAR(BAR_HF + 2 * i + 1), 1);
+      mbar_init(BAR(BAR_HE + i), 1 + kEpiWarps);  // tcgen05.commit + the epilogue warps (they read the tile's labels)
+    }
     for (int i = 0; i < 2; ++i) {
-      for (int q = 0; q < 4; ++q) mbar_init(BAR(BAR_CF + 4 * i + q), 1);
-      mbar_init(BAR(BAR_CE + i), 1 + kEpiWarps);  // tcgen05.commit + the epilogue warps (they read the stage's labels)
       mbar_init(BAR(BAR_SF + i), 1);
       mbar_init(BAR(BAR_SE + i), a.need_grad ? 1 : kEpiWarps);  // S buffer free: V MMAs retired / epilogue done
       for (int q = 0; q < 4; ++q) mbar_init(BAR(BAR_EF + 4 * i + q), 4);
@@ -303,7 +360,6 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
     }
     __syncthreads();
   }
-  auto tile_overlaps = [&](int tt) -> bool { return (s_mask[tt >> 5] >> (tt & 31)) & 1u; };
   // next tile index >= tt that this sweep has to process (sweep 1: every tile; sweep 2: next set mask bit)
   auto next_active = [&](int tt) -> int {
     if (PHASE == 1) return tt;
@@ -338,21 +394,30 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
       long long w_ce = 0, w_pe = 0;
       const long long c_start = clock64();
       int t = 0;
+      Ring<NSLOT> ring;
+      TileCursor cur;
+      cur.init(s_pre, s_ncols, a.n_chunks, a.chunk_tiles);
       for (int tt = next_active(0); tt < n; tt = next_active(tt + 1)) {
-        const TileLoc loc = locate_tile(k0 + tt, s_pre, s_ncols, a.n_chunks, a.chunk_tiles);
-        const int stage = t & 1;
-        mbar_wait_t(BAR(BAR_CE + stage), ((t >> 1) & 1) ^ 1, w_ce);
-        if (elect_one_sync()) {
-          const uint32_t dst = sbase + OFF_C + stage * kTileBytes;
+        const TileLoc loc = cur.seek(k0 + tt);
+        const int lb = t % 3;  // label buffer: reloaded for tile t+3, whose first slot is freed after tile t (or t+1)
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint32_t bq = BAR(BAR_CF + 4 * stage + q);
-            mbar_arrive_expect_tx(bq, 16384u + (q == 0 ? 512u : 0u));
-            bulk_g2s(dst + q * 16384u, ft + (size_t)loc.gtile * kTileBytes + q * 16384u, 16384u, bq);
-            if (q == 0) bulk_g2s(sbase + OFF_LAB + stage * 512u, a.lab_tiles + loc.gtile * 128, 512u, bq);
+        for (int fh = 0; fh < 2; ++fh) {
+          mbar_wait_t(BAR(BAR_HE + ring.slot), ring.par ^ 1u, w_ce);
+          if (elect_one_sync()) {
+            const uint32_t dst = sbase + OFF_C + (uint32_t)ring.slot * kSlotBytes;
+            const uint8_t* src = ft + (size_t)loc.gtile * kTileBytes + (size_t)fh * kSlotBytes;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              const uint32_t bq = BAR(BAR_HF + 2 * ring.slot + q);
+              const bool with_labels = fh == 0 && q == 0;
+              mbar_arrive_expect_tx(bq, 16384u + (with_labels ? 512u : 0u));
+              bulk_g2s(dst + q * 16384u, src + q * 16384u, 16384u, bq);
+              if (with_labels) bulk_g2s(sbase + OFF_LAB + lb * 512u, a.lab_tiles + loc.gtile * 128, 512u, bq);
+            }
           }
+          __syncwarp();
+          ring.next();
         }
-        __syncwarp();
         for (int c = 0; c < n_pc; ++c) {  // column probabilities, one K chunk at a time through a single buffer
           const int u = t * n_pc + c;
           const uint32_t kb = (uint32_t)min(pc_k, a.kpad - c * pc_k) * 256u;
@@ -384,19 +449,19 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
       long long c_idle = 0;
       const long long c_start = clock64();
       int t = 0;
+      Ring<NSLOT> ring;
       for (int tt = next_active(0); tt < n; tt = next_active(tt + 1)) {
-        const int stage = t & 1, sb = t % NS;
-        // sweep 1: the S buffer is free when the V MMAs that read E out of it have retired.  Sweep 2 has one S
-        // buffer but parks Ucoef in the P columns: S may be overwritten as soon as the epilogue holds it in registers.
-        if (PHASE == 1)
-          mbar_wait_t(BAR(BAR_SE + sb), ((t / NS) & 1) ^ 1, c_idle);
-        else
-          mbar_wait_t(BAR(BAR_SR), (t & 1) ^ 1, c_idle);
-        for (int q = 0; q < 4; ++q) {  // 4 K steps per landed quarter of the column tile
-          mbar_wait_t(BAR(BAR_CF + 4 * stage + q), (t >> 1) & 1, c_idle);
+        constexpr int sb = 0;
+        const int slot_a = ring.slot;  // the tile's first slot (features 0-127); the second one follows in the ring
+        // S may be overwritten as soon as the epilogue holds the previous tile in registers
+        mbar_wait_t(BAR(BAR_SR), (t & 1) ^ 1, c_idle);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {  // 4 K steps per landed 16 KB quarter of the column tile (two per slot)
+          const int hq = q & 1;
+          mbar_wait_t(BAR(BAR_HF + 2 * ring.slot + hq), ring.par, c_idle);
           tc_fence_after();
           if (elect_one_sync()) {
-            const uint64_t cdesc = umma_desc_adv(cdesc0, stage * kTileBytes + (uint32_t)q * 16384u);
+            const uint64_t cdesc = umma_desc_adv(cdesc0, (uint32_t)ring.slot * kSlotBytes + (uint32_t)hq * 16384u);
             const uint64_t adesc = umma_desc_adv(adesc0, (uint32_t)q * 16384u);
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
@@ -404,11 +469,16 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
                         idesc_s, (q > 0 || ks > 0) ? 1u : 0u);
             if (q == 3 && PHASE == 1) {
               umma_commit(BAR(BAR_SF + sb));
-              if (!a.need_grad) umma_commit(BAR(BAR_CE + stage));  // no V pass: the stage is free once S is done
+              if (!a.need_grad) {  // no V pass: the slots are free once S is done
+                umma_commit(BAR(BAR_HE + slot_a));
+                umma_commit(BAR(BAR_HE + ring.slot));
+              }
             }
           }
           __syncwarp();
+          if (hq == 1) ring.next();
         }
+        const int slot_b = (slot_a + 1 == NSLOT) ? 0 : slot_a + 1;
         if (PHASE == 2) {
           // the P columns (Ucoef of the previous tile lives there, whatever PMODE is) are free once its U MMAs
           // retired: the epilogue of this tile must not get SF before that
@@ -417,7 +487,10 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
           if (n_pc == 0) {
             if (elect_one_sync()) {
               umma_commit(BAR(BAR_SF + sb));
-              if (!a.need_grad) umma_commit(BAR(BAR_CE + stage));
+              if (!a.need_grad) {
+                umma_commit(BAR(BAR_HE + slot_a));
+                umma_commit(BAR(BAR_HE + slot_b));
+              }
             }
             __syncwarp();
           }
@@ -433,7 +506,10 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
               umma_commit(BAR(BAR_PE));
               if (c == n_pc - 1) {
                 umma_commit(BAR(BAR_SF + sb));
-                if (!a.need_grad) umma_commit(BAR(BAR_CE + stage));
+                if (!a.need_grad) {
+                  umma_commit(BAR(BAR_HE + slot_a));
+                  umma_commit(BAR(BAR_HE + slot_b));
+                }
               }
             }
             __syncwarp();
@@ -453,34 +529,42 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
   } else if (warp == 2) {
     // ===================== V/U issuer: acc += E x C with E (bf16) read from tensor memory ============
     if (n > 0 && a.need_grad) {
-      constexpr uint32_t idesc_v = umma_idesc(128, 256, 0, 1);   // A from TMEM, B MN-major
-      const uint32_t tS = tmem, tV = tmem + 256;
+      constexpr uint32_t idesc_v = umma_idesc(128, 128, 0, 1);   // A from TMEM, B MN-major: one feature half (slot)
+      const uint32_t tV = tmem + 256;
       const uint64_t vdesc0 = umma_desc(sbase + OFF_C, 128, kChunkB);
       long long c_idle = 0;
       const long long c_start = clock64();
       int t = 0;
+      int slot_a = 0;
       for (int tt = next_active(0); tt < n; tt = next_active(tt + 1)) {
-        const int stage = t & 1, sb = t % NS;
+        const int eb = t % NE;
+        const int slot_b = (slot_a + 1 == NSLOT) ? 0 : slot_a + 1;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {  // (chunk 0, half 0), (chunk 0, half 1), (chunk 1, half 0), (chunk 1, half 1)
           const int cc = u >> 1, h = u & 1;
-          mbar_wait_t(BAR(BAR_EF + (sb * 2 + h) * 2 + cc), (t / NS) & 1, c_idle);
+          mbar_wait_t(BAR(BAR_EF + (eb * 2 + h) * 2 + cc), (t / NE) & 1, c_idle);
           tc_fence_after();
-          // 16 columns of packed bf16 pairs = 32 K values: E over the S buffer (sweep 1), Ucoef over P (sweep 2)
-          const uint32_t te = (PHASE == 1 ? tS + sb * 128 : tmem + 128) + h * 64 + cc * 16;
+          // 16 columns of packed bf16 pairs = 32 K values: E buffer eb (sweep 1), Ucoef over P (sweep 2)
+          const uint32_t te = tmem + 128 + (PHASE == 1 ? eb * 64 + h * 32 : h * 64) + cc * 16;
           if (elect_one_sync()) {
-            const uint64_t vdesc = umma_desc_adv(vdesc0, stage * kTileBytes + (uint32_t)(h * 64 + cc * 32) * 16u);
+            const uint32_t rowoff = (uint32_t)(h * 64 + cc * 32) * 16u;
+            const uint64_t vda = umma_desc_adv(vdesc0, (uint32_t)slot_a * kSlotBytes + rowoff);
+            const uint64_t vdb = umma_desc_adv(vdesc0, (uint32_t)slot_b * kSlotBytes + rowoff);
 #pragma unroll
-            for (int kk = 0; kk < 2; ++kk)
-              umma_bf16_ts(tV, te + kk * 8, umma_desc_adv(vdesc, (uint32_t)kk * 256u), idesc_v,
-                           (t > 0 || u > 0 || kk > 0) ? 1u : 0u);
+            for (int kk = 0; kk < 2; ++kk) {
+              const uint32_t acc = (t > 0 || u > 0 || kk > 0) ? 1u : 0u;
+              umma_bf16_ts(tV, te + kk * 8, umma_desc_adv(vda, (uint32_t)kk * 256u), idesc_v, acc);         // features 0-127
+              umma_bf16_ts(tV + 128, te + kk * 8, umma_desc_adv(vdb, (uint32_t)kk * 256u), idesc_v, acc);   // 128-255
+            }
             if (u == 3) {
-              umma_commit(BAR(BAR_CE + stage));  // tile t no longer needs its C stage ...
-              umma_commit(BAR(BAR_SE + sb));     // ... nor its S buffer (E lived there)
+              umma_commit(BAR(BAR_HE + slot_a));  // tile t no longer needs its two slots ...
+              umma_commit(BAR(BAR_HE + slot_b));
+              umma_commit(BAR(BAR_SE + eb));      // ... nor its E buffer (sweep 2: the P columns)
             }
           }
           __syncwarp();
         }
+        slot_a = (slot_b + 1 == NSLOT) ? 0 : slot_b + 1;
         ++t;
       }
       if (elect_one_sync()) umma_commit(BAR(BAR_V));
@@ -520,29 +604,36 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
       warp_series = __all_sync(0xffffffffu, rc.series);
       rc.series = warp_series;  // rows of a mixed warp all take the exact path
     }
-    int t = 0;  // number of active tiles processed so far (drives stage / parity bookkeeping)
-    long long w_sf = 0, w_ee = 0;  // w_ee: unused since E moved to tensor memory
+    int t = 0;  // number of active tiles processed so far (drives buffer / parity bookkeeping)
+    int slot_a = 0;  // first ring slot of the current tile
+    long long w_sf = 0, w_ee = 0;  // w_ee: wait for a free E buffer (sweep 1)
     const long long c_start = clock64();
+    TileCursor cur;
+    cur.init(s_pre, s_ncols, a.n_chunks, a.chunk_tiles);
+    uint32_t mword = (PHASE == 1 && n > 0) ? s_mask[0] : 0u;  // sweep 1: overlap bits of tiles [32w, 32w+32) in a register
     for (int tt = next_active(0); tt < n; tt = next_active(tt + 1)) {
-      const TileLoc loc = locate_tile(k0 + tt, s_pre, s_ncols, a.n_chunks, a.chunk_tiles);
-      const int stage = t & 1, sb = t % NS;
+      const TileLoc loc = cur.seek(k0 + tt);
+      if (PHASE == 1 && (tt & 31) == 0 && tt > 0) mword = s_mask[tt >> 5];
+      constexpr int sb = 0;
+      const int eb = t % NE;
+      const int slot_b = (slot_a + 1 == NSLOT) ? 0 : slot_a + 1;
       const bool full = loc.nvalid == 128;
       const bool self = loc.gtile == self_tile;
-      const int* lab = reinterpret_cast<const int*>(smem + OFF_LAB + stage * 512);
+      const int* lab = reinterpret_cast<const int*>(smem + OFF_LAB + (t % 3) * 512);
       const float* dp = (PMODE == 2) ? a.dense_p + (size_t)min(grow, (long long)n_rows - 1) * a.ldp + loc.dcol0 : nullptr;
-      const bool all_neg = PHASE == 1 && full && !tile_overlaps(tt);
-      mbar_wait_t(BAR(BAR_SF + sb), (t / NS) & 1, w_sf);
+      const bool all_neg = PHASE == 1 && full && !((mword >> (tt & 31)) & 1u);
+      mbar_wait_t(BAR(BAR_SF + sb), t & 1, w_sf);
       tc_fence_after();
       // E / Ucoef sub-tile hand-off to the MMA warp: 32 packed bf16 of this row go to k-chunks (cc&1)*4..+3
       // E / Ucoef hand-off to the MMA warp: the 32 bf16 of this chunk overwrite the first columns of the thread's
       // own (already consumed) S range in tensor memory; the V/U MMA reads its A operand from there.
       auto emit = [&](int cc, const uint32_t (&pk)[16]) {  // cc = chunk 0/1 within this thread's column half
         if (!a.need_grad) return;
-        tmem_st16(tmem + lane_addr + (PHASE == 1 ? sb * 128 : 128) + half * 64 + cc * 16, pk);
+        tmem_st16(tmem + lane_addr + 128 + (PHASE == 1 ? eb * 64 + half * 32 : half * 64) + cc * 16, pk);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(BAR(BAR_EF + (sb * 2 + half) * 2 + cc));
+        if (lane == 0) mbar_arrive(BAR(BAR_EF + (eb * 2 + half) * 2 + cc));
       };
       const int c0 = half * 64;  // first column of this thread's half
       if (PHASE == 1) {
@@ -558,14 +649,20 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
             sweep1_cols<false, true>(rv, lab, c0 + cc * 32, loc.nvalid, la, self ? r : -1, sc, mx, neg, num, pk);
           emit(cc, pk);
         };
-        const uint32_t tb = tmem + lane_addr + sb * 128 + c0;
+        const uint32_t tb = tmem + lane_addr + c0;
         tmem_ld32(tb, r0);
+        tmem_ld32(tb + 32, r1);
+        if (a.need_grad) {  // E buffer eb is free once the V MMAs of tile t-2 have retired (rarely a real wait; the
+          mbar_wait_t(BAR(BAR_SE + eb), ((t >> 1) & 1) ^ 1, w_ee);  // barrier round trip hides under the loads)
+        }
         tmem_ld_wait();
         tmem_ld_fence(r0);
-        tmem_ld32(tb + 32, r1);
-        proc(0, r0);
-        tmem_ld_wait();
         tmem_ld_fence(r1);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR(BAR_SR));  // S of this tile is in registers: the next tile's S MMAs may start
+        tc_fence_after();
+        proc(0, r0);
         proc(1, r1);
       } else {
 #pragma unroll 1
@@ -600,9 +697,11 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (!a.need_grad) mbar_arrive(BAR(BAR_SE + sb));
-        mbar_arrive(BAR(BAR_CE + stage));
+        if (PHASE == 2 && !a.need_grad) mbar_arrive(BAR(BAR_SE));
+        mbar_arrive(BAR(BAR_HE + slot_a));  // this warp no longer reads the tile's labels
+        mbar_arrive(BAR(BAR_HE + slot_b));
       }
+      slot_a = (slot_b + 1 == NSLOT) ? 0 : slot_b + 1;
       ++t;
     }
     if (a.trace && warp == 3 && lane == 0) {  // one representative epilogue thread

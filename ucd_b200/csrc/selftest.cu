@@ -177,11 +177,14 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int mode, int iters, l
     mbar_wait(bar, 0);
     if (threadIdx.x == 0) cycles[0] = clock64() - c0;
   }
-  // mode 16: the sweep-1 mix from TWO warps: warp 0 issues 16 SS N=128 per tile (S), warp 1 issues 8 TS N=256 MN-major
-  // per tile (V), no data dependence between them: cycles per tile-equivalent / 16 is reported (iters = S MMAs).
-  if (mode == 16 && warp < 2) {
+  // modes 16..19: the sweep-1 mix from TWO warps, no data dependence between them; cycles per tile / 16 is reported
+  // (iters = S MMAs).  warp 0 issues the 16 S K-steps of a tile (N=128), warp 1 the V K-steps:
+  //   16: S = SS, V = 8 x TS N=256           17: S = SS, V = 16 x TS N=128 (feature halves, as the ring kernel does)
+  //   18: S = TS (anchor tile in TMEM), V = 16 x TS N=128      19: S = 8 TS + 8 SS (half the anchor tile in TMEM), V as 17
+  if (mode >= 16 && mode <= 19 && warp < 2) {
     const uint32_t mybar = bar + (warp == 1 ? 8 : 0);
-    const uint32_t idesc_s = umma_idesc(128, 128, 0, 0), idesc_v = umma_idesc(128, 256, 0, 1);
+    const uint32_t idesc_s = umma_idesc(128, 128, 0, 0), idesc_v = umma_idesc(128, 256, 0, 1),
+                   idesc_h = umma_idesc(128, 128, 0, 1);
     const uint64_t a0 = umma_desc(sbase + ST_OFF_A, 2048, 128);
     const uint64_t bk = umma_desc(sbase + ST_OFF_C, 2048, 128), bm = umma_desc(sbase + ST_OFF_C, 128, 2048);
     const long long c0 = clock64();
@@ -189,12 +192,23 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int mode, int iters, l
       if (elect_one_sync()) {
         if (warp == 0) {
 #pragma unroll
-          for (int ks = 0; ks < 16; ++ks)
-            umma_bf16(tmem + (i & 16 ? 128 : 0), umma_desc_adv(a0, ks * 4096), umma_desc_adv(bk, ks * 4096), idesc_s, 1u);
-        } else {
+          for (int ks = 0; ks < 16; ++ks) {
+            const bool ts = mode == 18 || (mode == 19 && ks < 8);
+            if (ts)
+              umma_bf16_ts(tmem + 128, tmem + ks * 8, umma_desc_adv(bk, ks * 4096), idesc_s, 1u);
+            else
+              umma_bf16(tmem + 128, umma_desc_adv(a0, ks * 4096), umma_desc_adv(bk, ks * 4096), idesc_s, 1u);
+          }
+        } else if (mode == 16) {
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
-            umma_bf16_ts(tmem + 256, tmem + kk * 8, umma_desc_adv(bm, kk * 256), idesc_v, 1u);
+            umma_bf16_ts(tmem + 256, tmem + 192 + kk * 8, umma_desc_adv(bm, kk * 256), idesc_v, 1u);
+        } else {
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            umma_bf16_ts(tmem + 256, tmem + 192 + kk * 8, umma_desc_adv(bm, kk * 256), idesc_h, 1u);
+            umma_bf16_ts(tmem + 384, tmem + 192 + kk * 8, umma_desc_adv(bm, 32768 + kk * 256), idesc_h, 1u);
+          }
         }
       }
       __syncwarp();
@@ -203,7 +217,7 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int mode, int iters, l
     __syncwarp();
     mbar_wait(mybar, 0);
     __syncwarp();
-    if (threadIdx.x == 0) cycles[0] = clock64() - c0;   // warp 0 finishes last or not: see mode 17 for the V side
+    if (threadIdx.x == 0) cycles[0] = clock64() - c0;
     if (threadIdx.x == 32) cycles[1] = clock64() - c0;
   }
   // modes 9..11: TWO issuing threads (warps 0 and 1), each its own accumulator: 9 SS N=128 | 10 TS N=128 | 11 SS N=64
@@ -225,6 +239,73 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int mode, int iters, l
     umma_commit(mybar);
     mbar_wait(mybar, 0);
     if (threadIdx.x == 0) cycles[0] = clock64() - c0;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// Two-warp mix probe with explicit tensor-memory placement: warp 0 issues the 16 S K-steps of a tile (N=128; SS, or TS
+// with the A operand at column s_a), accumulating alternately at columns s_acc0 / s_acc1 per tile; warp 1 issues the V
+// K-steps (TS, A operand at column v_a: 16 x N=128 into v_acc and v_acc+128, or 8 x N=256 into v_acc).
+__global__ void __launch_bounds__(128, 1) mma_mix_kernel(int s_ts, int s_a, int s_acc0, int s_acc1, int v_n256, int v_a,
+                                                         int v_acc, int tiles, long long* __restrict__ cycles) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint32_t s_tmem;
+  const int warp = threadIdx.x >> 5;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar = sbase + ST_OFF_BAR;
+  for (int i = threadIdx.x; i < (int)(ST_OFF_E / 4); i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    mbar_init(bar + 8, 1);
+    fence_mbar_init();
+  }
+  fence_proxy_async();
+  if (warp == 0) tmem_alloc(smem_u32(&s_tmem), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+  if (warp < 2) {
+    const uint32_t mybar = bar + (warp == 1 ? 8 : 0);
+    const uint32_t idesc_s = umma_idesc(128, 128, 0, 0), idesc_v = umma_idesc(128, 256, 0, 1),
+                   idesc_h = umma_idesc(128, 128, 0, 1);
+    const uint64_t a0 = umma_desc(sbase + ST_OFF_A, 2048, 128);
+    const uint64_t bk = umma_desc(sbase + ST_OFF_C, 2048, 128), bm = umma_desc(sbase + ST_OFF_C, 128, 2048);
+    const long long c0 = clock64();
+    for (int t = 0; t < tiles; ++t) {
+      if (elect_one_sync()) {
+        if (warp == 0) {
+          const uint32_t d = tmem + ((t & 1) ? s_acc1 : s_acc0);
+#pragma unroll
+          for (int ks = 0; ks < 16; ++ks) {
+            if (s_ts)
+              umma_bf16_ts(d, tmem + s_a + ks * 8, umma_desc_adv(bk, ks * 4096), idesc_s, ks > 0);
+            else
+              umma_bf16(d, umma_desc_adv(a0, ks * 4096), umma_desc_adv(bk, ks * 4096), idesc_s, ks > 0);
+          }
+        } else if (v_n256) {
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma_bf16_ts(tmem + v_acc, tmem + v_a + kk * 8, umma_desc_adv(bm, kk * 256), idesc_v, 1u);
+        } else {
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            umma_bf16_ts(tmem + v_acc, tmem + v_a + kk * 8, umma_desc_adv(bm, kk * 256), idesc_h, 1u);
+            umma_bf16_ts(tmem + v_acc + 128, tmem + v_a + kk * 8, umma_desc_adv(bm, 32768 + kk * 256), idesc_h, 1u);
+          }
+        }
+      }
+      __syncwarp();
+    }
+    if (elect_one_sync()) umma_commit(mybar);
+    __syncwarp();
+    mbar_wait(mybar, 0);
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) cycles[warp] = clock64() - c0;
   }
   __syncthreads();
   if (warp == 0) {
@@ -300,7 +381,7 @@ extern "C" int ucd_selftest_umma(int variant, float* max_err_host) {
 }
 
 extern "C" int ucd_selftest_mma_rate(int mode, int iters, float* cycles_per_instr_host) {
-  UCD_CHECK_ARG(mode >= 0 && mode <= 16 && iters > 0 && cycles_per_instr_host, "ucd_selftest_mma_rate: bad argument");
+  UCD_CHECK_ARG(mode >= 0 && mode <= 19 && iters > 0 && cycles_per_instr_host, "ucd_selftest_mma_rate: bad argument");
   long long* d = nullptr;
   cudaError_t e;
   if ((e = cudaMalloc(&d, 16)) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
@@ -388,3 +469,26 @@ extern "C" int ucd_selftest_pipe_rate(int mode, int warps, int iters, float* cyc
   return UCD_OK;
 }
 
+
+extern "C" int ucd_selftest_mma_mix(int s_ts, int s_a, int s_acc0, int s_acc1, int v_n256, int v_a, int v_acc, int tiles,
+                                    float* cycles_per_tile_host) {
+  UCD_CHECK_ARG(tiles > 0 && cycles_per_tile_host, "ucd_selftest_mma_mix: bad argument");
+  long long* d = nullptr;
+  cudaError_t e;
+  if ((e = cudaMalloc(&d, 16)) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+  cudaMemset(d, 0, 16);
+  if ((e = cudaFuncSetAttribute(mma_mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM)) != cudaSuccess)
+    return cuda_fail(e, "cudaFuncSetAttribute(mma_mix_kernel)");
+  for (int rep = 0; rep < 2; ++rep) {
+    mma_mix_kernel<<<1, 128, ST_SMEM>>>(s_ts, s_a, s_acc0, s_acc1, v_n256, v_a, v_acc, tiles, d);
+    if ((e = cudaDeviceSynchronize()) != cudaSuccess) {
+      cudaFree(d);
+      return cuda_fail(e, "mma_mix_kernel");
+    }
+  }
+  long long h2[2] = {0, 0};
+  cudaMemcpy(h2, d, 16, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  *cycles_per_tile_host = (float)(h2[0] > h2[1] ? h2[0] : h2[1]) / (float)tiles;
+  return UCD_OK;
+}
