@@ -4,7 +4,7 @@
  * One shared library (ucd_b200/libucd_b200.so), extern "C", plain pointers and sizes, no torch
  * types.  Every pointer is a DEVICE pointer unless its name ends in _host.  Every entry point is
  * asynchronous on `stream` (a cudaStream_t passed as void*), allocates nothing, keeps no global
- * mutable state and returns 0 on success or a negative UCD_E* code; the message of the last
+ * mutable state, reads no environment variable and returns 0 on success or a negative UCD_E* code; the message of the last
  * failure on the calling thread is available from ucd_last_error().
  *
  * Each function names the reference interface (file:line under the UCD tree) it replaces.  The
@@ -165,6 +165,13 @@ int ucd_con_tile_ranges(const int32_t* lab_tiles, int64_t n_tiles, const int32_t
 int ucd_con_pack_rows(const float* rows, const int32_t* labels, int64_t n, void* feat_tiles,
                       int32_t* lab_tiles, int64_t max_tiles, void* stream);
 
+/* Pixel-to-pixel branches of pre_contrastive_pixel (utils/loss.py:273-289, f_o and/or l_po absent): every pixel of
+ * f [B,256,h,w] becomes a unit-norm row (F.normalize, eps 1e-12) of rows [B*h*w, 256] in (b,y,x) order;
+ * inv_norm [B*h*w] is saved for the adjoint df = (g - (g.a) a) * inv_norm scattered back to [B,256,h,w]. */
+int ucd_rows_normalize_fwd(const float* f, float* rows, float* inv_norm, int B, int h, int w, void* stream);
+int ucd_rows_normalize_bwd(const float* g_rows, const float* rows, const float* inv_norm, float* df, int B, int h,
+                           int w, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * PixelConLossV2   (utils/loss.py:412-466), fused: the N_a x N_c matrices are never materialised.
  *
@@ -187,9 +194,21 @@ int ucd_con_pack_rows(const float* rows, const int32_t* labels, int64_t n, void*
 /* plan_row_tiles (here and in ucd_con_fwd, same value): row tiles expected to hold anchors, 0 = max_row_tiles.  Only a
  * planning hint (column splits are chosen for that many row blocks); results do not depend on it beyond summation
  * order.  Used by hosts that size for the worst case because they do not read N_a back (sync-free path). */
-size_t ucd_con_workspace_bytes(int64_t max_row_tiles, int64_t max_col_tiles, int64_t plan_row_tiles);
+size_t ucd_con_workspace_bytes(int64_t max_row_tiles, int64_t max_col_tiles, int64_t plan_row_tiles,
+                               int64_t local_col_tiles /* chunk_tiles for a two-part run (part 1 + part 2), else 0 */);
+/* Column arrays and the exchange payload.  chunk_stride_bytes == 0: feat_tiles / prob_tiles / lab_tiles / tile_range are
+ * [n_chunks][chunk_tiles][...] arrays of their own and chunk_counts is [n_chunks][2].  chunk_stride_bytes > 0: every
+ * rank ships ONE contiguous payload (header {N_a, N_o, min_new, n_px}, tile ranges, label tiles, probability tiles,
+ * feature tiles; ucd_b200/losses.py::payload_layout) and the all-gathered buffer is [n_chunks][chunk_stride_bytes];
+ * the five pointers address the sub-arrays of chunk 0 (part 1: of chunk `local_chunk`), chunk c lies c * stride bytes
+ * further, and min_new points at chunk 0's header entry (the kernel takes the minimum over all chunks: no MIN
+ * all-reduce).  part: 0 = everything in one call; 1 = only sweep 1 over the LOCAL chunk (pointers address that chunk
+ * alone, e.g. the rank's own payload while the all-gather is still in flight); 2 = sweep 1 over the other chunks, the
+ * combine, sweep 2 over all chunks and the finalize (pointers address the gathered buffer).  Parts 1 and 2 must be
+ * called with the same n_chunks / chunk_tiles / max_row_tiles / plan_row_tiles / workspace. */
 int ucd_con_fwd(const void* feat_tiles, const void* prob_tiles, const int32_t* lab_tiles,
-                const int32_t* chunk_counts, int n_chunks, int64_t chunk_tiles, const void* row_feat_tiles,
+                const int32_t* chunk_counts, int n_chunks, int64_t chunk_tiles, int64_t chunk_stride_bytes,
+                int local_chunk, int part, const void* row_feat_tiles,
                 const void* row_prob_tiles, const int32_t* row_lab_tiles, const int32_t* n_rows,
                 const int32_t* tile_range, const int32_t* row_range, int64_t self_tile0, const int32_t* min_new, int p_mode, int kpad, const float* dense_p,
                 int64_t ldp, float inv_temperature, int need_grad, float* out, float* grad_unit,
@@ -199,19 +218,6 @@ int ucd_con_fwd(const void* feat_tiles, const void* prob_tiles, const int32_t* l
  * row_ref NULL = identity */
 int ucd_con_bwd(const float* grad_unit, const float* out, const float* g_scalar, float g_mul,
                 const int32_t* n_rows, const int32_t* row_ref, float* d_anchor, int64_t max_rows, void* stream);
-
-/* Debug aids (never on the product path): per-role cycle counters of the sweep CTAs, see contrast.cu */
-int ucd_con_debug_trace(void* device_buffer_or_null);
-int ucd_con_debug_splits(int64_t max_row_tiles, int64_t max_col_tiles);
-
-/* Self-test of the tcgen05/TMEM/bulk-copy building blocks: C[M=128,N] = A[128,K] * B[N,K]^T in bf16
- * with the production tile layout, and D[128,256] = E[128,128] * Bt (MN-major B). Returns max abs
- * error through *max_err_host (synchronises). */
-int ucd_selftest_umma(int variant, float* max_err_host);
-/* tcgen05.mma issue-rate probe (cycles per instruction for a chain of `iters` MMAs; modes in selftest.cu) */
-int ucd_selftest_mma_rate(int mode, int iters, float* cycles_per_instr_host);
-/* CUDA-core pipe probe behind the sweep epilogue's design (ex2 / bf16 pack rates; modes in selftest.cu) */
-int ucd_selftest_pipe_rate(int mode, int warps, int iters, float* cycles_per_iter_host);
 
 #ifdef __cplusplus
 }

@@ -113,8 +113,27 @@ def gen_att_map():
     print("att_map:", float(y.abs().sum()))
 
 
+def gen_p2p():
+    """The pixel-to-pixel branches of pre_contrastive_pixel (utils/loss.py:278-289: no old-model logits) on a small
+    seeded case: outputs, labels and the gradient of a fixed linear functional, single (f_o None) and double."""
+    case = synthetic_case(2, 5, 7, 80, 112, 21, 16)
+    fx = dict(shape=np.array([2, 5, 7, 80, 112, 21, 16]))
+    w = torch.randn(2 * 2 * 5 * 7, 1, 256, generator=torch.Generator().manual_seed(77), dtype=torch.float64)
+    fx["w"] = w.numpy()
+    for tag, f_o in (("single", None), ("double", case["f_o"].double())):
+        f_n = case["f_n"].double().requires_grad_(True)
+        out, lab = pre_contrastive_pixel(f_n, case["labels"], l_po=None, f_o=f_o)
+        (out * w[:out.shape[0]]).sum().backward()
+        fx[tag + "_out"], fx[tag + "_lab"], fx[tag + "_grad"] = out.detach().numpy(), lab.numpy(), f_n.grad.numpy()
+    np.savez_compressed(os.path.join(OUT, "pixel_to_pixel.npz"), **fx)
+    print("pixel_to_pixel", fx["single_out"].shape, fx["double_out"].shape, np.unique(fx["single_lab"]))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "p2p":
+        return gen_p2p()
+    gen_p2p()
     if len(sys.argv) > 1 and sys.argv[1] == "att_map":
         return gen_att_map()
     gen_att_map()

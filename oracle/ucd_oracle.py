@@ -10,7 +10,7 @@ floating point so that autograd yields reference gradients), what the reference
 computes on this path:
 
 * ``downsample_labels`` / ``prep_labels``  <- utils/loss.py:259-270, 354-361
-* ``pre_contrastive_pixel``               <- utils/loss.py:273-276, 363-395
+* ``pre_contrastive_pixel``               <- utils/loss.py:273-276, 363-395 (``pixel_to_pixel``: :278-289)
 * ``pixel_con_loss`` (+ closed-form grad, + row-blocked streaming form for large sizes) <- utils/loss.py:412-466
 * ``unbiased_ce``                         <- utils/loss.py:96-109
 * ``unbiased_kd``                         <- utils/loss.py:148-184
@@ -189,6 +189,37 @@ def pre_contrastive_pixel(f_n: torch.Tensor, labels: torch.Tensor, l_po: torch.T
     gt_c = lc >= prep.min_new
     P = torch.where(gt_a[:, None] & gt_c[None, :], torch.ones((), dtype=P.dtype), P)
     return A, Cst, la, lc, P.detach(), prep
+
+
+def pixel_to_pixel(f_n: torch.Tensor, labels: torch.Tensor, f_o: Optional[torch.Tensor] = None, max_label: int = 20):
+    """The branches of utils/loss.py:278-289 (no old-model logits): every pixel is a unit-norm row, labels are the
+    clamped low-res label map; with ``f_o`` the detached old-model rows (and the labels again) are appended.
+    Returns (Output [n, 1, 256], Lable [n] int64) like loss.py:399."""
+    h, w = f_n.shape[-2:]
+    lab = torch.from_numpy(downsample_labels(labels.cpu().numpy(), h, w, max_label).reshape(-1))
+    out = _unit(_rows(f_n))
+    if f_o is not None:
+        out = torch.cat([out, _unit(_rows(f_o.detach()))])
+        lab = torch.cat([lab, lab])
+    return out.unsqueeze(1), lab
+
+
+def contrast_operands(f_n: torch.Tensor, labels: torch.Tensor, l_po: torch.Tensor, f_o: torch.Tensor,
+                      max_label: int = 20):
+    """``pre_contrastive_pixel`` without the dense joint-probability matrix: returns
+    (A, Cst, la, lc, pa, pc, prep) with pa / pc the old-model softmax rows of the anchors / contrast columns,
+    so that ``pixel_con_loss_streaming`` can form P = pa pc^T (+ GT-new override, utils/loss.py:369-393) block
+    by block.  Same row order as the reference (utils/loss.py:360-366)."""
+    prep = prep_labels(labels.detach().cpu().numpy(), l_po.detach().cpu().numpy(), max_label)
+    anchor = torch.from_numpy(prep.anchor)
+    pseudo = torch.from_numpy(prep.pseudo_mask)
+    mix = torch.from_numpy(prep.mix.reshape(-1))
+    A = _unit(_rows(f_n)[anchor])
+    Cst = torch.cat([A, _unit(_rows(f_o.detach())[pseudo])], dim=0).detach()
+    la = mix[anchor]
+    lc = torch.cat([la, mix[pseudo]])
+    p = torch.softmax(_rows(l_po.detach()), dim=1)
+    return A, Cst, la, lc, p[anchor], torch.cat([p[anchor], p[pseudo]]), prep
 
 
 # ----------------------------------------------------------------------------

@@ -4,6 +4,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from torch.profiler import profile, ProfilerActivity
 import ucd_b200 as U
+from ucd_b200 import _lib
+_lib.debug_lib(as_product=True)   # the traced build (per-role cycle counters) serves the modules of this process
 from bench import make_inputs, WORKLOAD
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 24
@@ -32,8 +34,7 @@ for grad in (True, False):
         print("%10.1f us  x%-3d %s" % (t, c, k[:90]))
 
 # ---- per-role cycle counters (ucd_con_debug_trace) ----
-from ucd_b200 import _lib
-L = _lib.lib()
+L = _lib.debug_lib()
 n_px = B * 32 * 32
 rt, ct = (n_px + 127) // 128, L.ucd_con_max_tiles(n_px)
 splits = L.ucd_con_debug_splits(rt, ct)

@@ -3,7 +3,7 @@ import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from ucd_b200 import _lib
-L = _lib.lib()
+L = _lib.debug_lib()
 torch.zeros(1, device="cuda")
 # (label, s_ts, s_a, s_acc0, s_acc1, v_n256, v_a, v_acc)
 cfgs = [

@@ -2,7 +2,7 @@ import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from ucd_b200 import _lib
-L = _lib.lib()
+L = _lib.debug_lib()
 names = ["SS N=64", "SS N=128", "SS N=256 (B MN-major)", "TS N=64", "TS N=128", "TS N=256 (B MN-major)", "SS N=256 (B K-major)",
          "TS N=128 alternating 2 accumulators", "SS N=128 alternating 2 accumulators", "2 threads: SS N=128", "2 threads: TS N=128", "2 threads: SS N=64", "elect_one_sync: SS N=128", "elect_one_sync: TS N=128", "elect_one_sync: SS N=64", "elect_one_sync: TS N=256 (B MN-major)",
          "2 warps, per tile 16 S (SS N=128) + 8 V (TS N=256): cycles per tile / 16",

@@ -2,7 +2,7 @@ import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from ucd_b200 import _lib
-L = _lib.lib()
+L = _lib.debug_lib()
 names = ["8 ex2", "4 cvt.bf16x2 + 8 fadd", "8 ex2 + 4 cvt.bf16x2", "8 ex2 + int round pack (8 iadd, 4 prmt)", "8 fadd"]
 torch.zeros(1, device="cuda")
 for warps in (4, 8, 16):

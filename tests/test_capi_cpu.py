@@ -15,11 +15,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def L():
     from ucd_b200 import _lib, build
     build.build()
+    build.build(debug=True)
     return _lib
 
 
-def declared_functions():
-    src = open(os.path.join(ROOT, "include", "ucd_b200.h")).read()
+def declared_functions(header="ucd_b200.h"):
+    src = open(os.path.join(ROOT, "include", header)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(ucd_[a-z0-9_]+)\s*\(", src)))
 
@@ -34,14 +35,33 @@ def test_header_symbols_exported_and_bound(L):
     assert sorted(L.EXPORTED) == names, "ctypes prototypes and header disagree"
 
 
+def test_debug_entry_points_only_in_the_debug_library(L):
+    """Tracing, tuning knobs and the tcgen05 probes (include/ucd_b200_debug.h) are compiled into
+    libucd_b200_debug.so only: the product library exports none of them, reads no environment variable and keeps
+    no global debug state."""
+    dbg = declared_functions("ucd_b200_debug.h")
+    assert sorted(L.DEBUG_EXPORTED) == dbg and len(dbg) >= 5
+    prod, debug = ctypes.CDLL(L.LIB_PATH), ctypes.CDLL(L.DEBUG_LIB_PATH)
+    for n in dbg:
+        assert not hasattr(prod, n), "product library exports the debug entry point %s" % n
+        assert hasattr(debug, n), n
+    for n in declared_functions():
+        assert hasattr(debug, n), n
+    blob = open(L.LIB_PATH, "rb").read()
+    assert b"UCD_SPLITS" not in blob and b"UCD_UP_GY" not in blob   # (the static CUDA runtime has its own getenv)
+    assert b"UCD_SPLITS1" in open(L.DEBUG_LIB_PATH, "rb").read()
+
+
 def test_version_and_sizes(L):
     lib = L.lib()
     assert lib.ucd_version() >= 100
     assert lib.ucd_reduce_scratch_floats() > 0
     assert lib.ucd_con_max_tiles(3072) == 49
     assert lib.ucd_con_prob_kpad(16) == 16 and lib.ucd_con_prob_kpad(14) == 16 and lib.ucd_con_prob_kpad(17) == 32
-    assert lib.ucd_con_workspace_bytes(24, 49, 0) > 24 * 128 * 256 * 4 * 2
-    assert lib.ucd_con_workspace_bytes(0, 49, 0) == 0
+    assert lib.ucd_con_workspace_bytes(24, 49, 0, 0) > 24 * 128 * 256 * 4 * 2
+    assert lib.ucd_con_workspace_bytes(0, 49, 0, 0) == 0
+    # a two-part run (local chunk + 7 remote chunks) needs partial slots for both launches
+    assert lib.ucd_con_workspace_bytes(24, 8 * 49, 0, 49) > lib.ucd_con_workspace_bytes(24, 8 * 49, 0, 0)
 
 
 def test_argument_validation_reports_errors(L):
@@ -51,7 +71,7 @@ def test_argument_validation_reports_errors(L):
     with pytest.raises(RuntimeError, match="null pointer"):
         L.check(rc, "unce_fwd")
     err = ctypes.c_float()
-    assert lib.ucd_selftest_umma(7, ctypes.byref(err)) == -1
+    assert L.debug_lib().ucd_selftest_umma(7, ctypes.byref(err)) == -1
 
 
 def test_product_refuses_cpu_tensors(L):
@@ -80,6 +100,24 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     if torch.cuda.is_available():   # on a GPU box the modules themselves must raise, too
         with pytest.raises(RuntimeError, match="missing"):
             ucd_b200.interpolate_bilinear(torch.randn(1, 1, 4, 4, device="cuda"), (8, 8))
+
+
+def test_payload_layout_and_views():
+    """Host logic of the exchange payload: sections are aligned, disjoint and typed views alias the buffer."""
+    from ucd_b200.losses import payload_layout, payload_views
+    lay = payload_layout(49, 16)
+    secs = sorted((lay[k], k) for k in ("counts", "range", "lab", "prob", "feat"))
+    assert all(off % 256 == 0 for off, _ in secs) and secs[0] == (0, "counts")
+    assert lay["nbytes"] >= 49 * (8 + 512 + 16 * 256 + 65536) and lay["nbytes"] % 256 == 0
+    buf = torch.zeros(2, lay["nbytes"], dtype=torch.uint8)
+    v = payload_views(buf, 49, 16)
+    assert v["counts"].shape == (2, 4) and v["feat"].shape == (2, 49, 32, 128, 8) and v["prob"].shape == (2, 49, 2, 128, 8)
+    assert v["lab"].shape == (2, 49, 128) and v["range"].shape == (2, 49, 2)
+    v["counts"][1, 2] = 7
+    v["feat"][1, 48, 31, 127, 7] = 1.0
+    one = payload_views(buf[1], 49, 16)
+    assert int(one["counts"][2]) == 7 and float(one["feat"][48, 31, 127, 7]) == 1.0
+    assert int(buf[0].sum()) == 0
 
 
 def test_sibling_and_opt_in_modules_exported():

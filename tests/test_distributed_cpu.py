@@ -1,7 +1,8 @@
-"""world_size-2 gloo test (CPU) of the one exchange step of the data-parallel path: the all-gather
-of packed contrast columns (ucd_b200.losses.gather_contrast_columns).  Tiles are packed here on the CPU
-from oracle outputs with the documented layout; the gathered chunks must reproduce the column set of
-the rank-sharded oracle (oracle.pre_contrastive_pixel_global)."""
+"""world_size-2 gloo test (CPU) of the one exchange step of the data-parallel path: the single all-gather
+of every rank's payload (ucd_b200.losses.gather_contrast_columns / payload_layout).  Payloads are filled here on the
+CPU from oracle outputs with the documented layout; the gathered chunks must reproduce the column set of
+the rank-sharded oracle (oracle.pre_contrastive_pixel_global), synchronously and with the asynchronous
+(overlappable) form of the collective."""
 import os
 
 import numpy as np
@@ -30,7 +31,7 @@ def _worker(rank, world, port, ret):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        from ucd_b200.losses import gather_contrast_columns
+        from ucd_b200.losses import gather_contrast_columns, payload_layout, payload_views
         cases = [O.synthetic_case(2, 8, 8, 128, 128, 6, 4, rank=r) for r in range(world)]
         c = cases[rank]
         A, Cst, la, lc, P, prep = O.pre_contrastive_pixel(c["f_n"], c["labels"], c["l_po"], c["f_o"])
@@ -44,16 +45,23 @@ def _worker(rank, world, port, ret):
         lab[:lc.numel()] = lc.to(torch.int32)
         counts = torch.tensor([A.shape[0], Cst.shape[0] - A.shape[0], prep.min_new, n_px], dtype=torch.int32)
         rng = torch.stack([lab.view(T, TILE).clamp_min(0).amin(1), lab.view(T, TILE).amax(1)], 1).to(torch.int32)
-        g = gather_contrast_columns(feat, prob, lab.view(T, TILE), rng, counts, dist.group.WORLD)
+        payload = torch.zeros(payload_layout(T, 16)["nbytes"], dtype=torch.uint8)
+        pv = payload_views(payload, T, 16)
+        pv["feat"].copy_(feat), pv["prob"].copy_(prob), pv["lab"].copy_(lab.view(T, TILE))
+        pv["range"].copy_(rng), pv["counts"].copy_(counts)
+        g = gather_contrast_columns(payload, T, 16, dist.group.WORLD)
+        g2 = gather_contrast_columns(payload, T, 16, dist.group.WORLD, async_op=True)   # the overlappable form
+        g2["work"].wait()
+        assert torch.equal(g2["buf"], g["buf"]) and g["chunk_stride"] == payload.numel() and g["rank"] == rank
         assert g["range"].shape == (world, T, 2) and torch.equal(g["range"][rank], rng)
         # reference: the rank-sharded oracle on all ranks' inputs
         per_rank, Cg, lcg, min_new = O.pre_contrastive_pixel_global(
             [x["f_n"] for x in cases], [x["labels"] for x in cases], [x["l_po"] for x in cases], [x["f_o"] for x in cases])
         assert g["n_chunks"] == world and g["chunk_tiles"] == T and g["self_tile0"] == rank * T
-        assert int(g["min_new"]) == min_new
+        assert int(g["counts"][:, 2].min()) == min_new   # the sweeps take the global threshold from the headers
         cols, labs, off = [], [], 0
         for r in range(world):
-            n_c = int(g["counts"][r].sum())
+            n_c = int(g["counts"][r, :2].sum())
             cols.append(unpack_tiles(g["feat"][r])[:n_c])
             labs.append(g["lab"][r].reshape(-1)[:n_c])
             assert bool((g["lab"][r].reshape(-1)[n_c:] == -1).all())

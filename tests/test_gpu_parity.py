@@ -46,7 +46,7 @@ def test_umma_selftest(U):
     from ucd_b200 import _lib
     for variant in (0, 1, 2):
         err = ctypes.c_float(-1.0)
-        _lib.check(_lib.lib().ucd_selftest_umma(variant, ctypes.byref(err)), "selftest")
+        _lib.check(_lib.debug_lib().ucd_selftest_umma(variant, ctypes.byref(err)), "selftest")
         assert 0 <= err.value < 2e-3, (variant, err.value)
 
 
@@ -324,6 +324,137 @@ def test_full_size_properties(U):
     prep = O.prep_labels(case["labels"].numpy(), case["l_po"].numpy())
     gz = g1.permute(0, 2, 3, 1).reshape(-1, 256)[torch.from_numpy(~prep.anchor).cuda()]
     assert gz.numel() == 0 or float(gz.abs().max()) == 0.0
+
+
+def _streaming_reference(case, max_label=20, block=256):
+    """fp64 reference loss and d loss / d f_n at sizes where the dense N_a x N_c restatement does not fit: the
+    row-blocked oracle (pinned against the reference fixtures in tests/test_oracle.py) + autograd through the
+    anchor gather / normalisation."""
+    f_ref = case["f_n"].double().requires_grad_(True)
+    A, Cst, la, lc, pa, pc, prep = O.contrast_operands(f_ref, case["labels"], case["l_po"].double(),
+                                                       case["f_o"].double(), max_label=max_label)
+    loss, dA, _ = O.pixel_con_loss_streaming(A, Cst, la, lc, pa, pc, prep.min_new, block=block)
+    A.backward(dA)
+    return loss, f_ref.grad, prep, (la, lc)
+
+
+def test_bench_workload_against_streaming_oracle(U):
+    """The benchmarked size itself (BASELINE configs[1] per GPU: B=24 @512x512, 23 419 anchors x 41 102 contrast
+    columns, 4 column splits): loss within 1e-3 and gradient cosine >= 0.999 against the fp64 oracle, for the whole
+    gradient, and per anchor row on a seeded sample of 512 rows plus the rows either side of every 128-row tile
+    boundary next to a column-split boundary (the rows whose column ranges start / end a CTA)."""
+    case = O.synthetic_case(24, 32, 32, 512, 512, 17, 16, correlated=True)
+    ref_loss, ref_grad, prep, (la, lc) = _streaming_reference(case)
+    f_n = case["f_n"].cuda().requires_grad_(True)
+    tup = U.pre_contrastive_pixel(f_n, case["labels"].cuda(), l_po=case["l_po"].cuda(), f_o=case["f_o"].cuda())
+    assert tup[0].shape[0] == la.numel() == 23419 and tup[1].shape[0] == lc.numel() == 41102
+    assert np.array_equal(tup[2].cpu().numpy(), la.numpy()) and np.array_equal(tup[3].cpu().numpy(), lc.numpy())
+    loss = U.PixelConLossV2(temperature=0.07)(*tup)
+    loss.backward()
+    assert loss.item() == pytest.approx(ref_loss.item(), rel=REL)
+    assert cos(f_n.grad, ref_grad) >= COS
+    # per-row check (pixel = one anchor row of the gradient)
+    g = f_n.grad.permute(0, 2, 3, 1).reshape(-1, 256).double().cpu()
+    r = ref_grad.permute(0, 2, 3, 1).reshape(-1, 256)
+    anchor_px = np.nonzero(prep.anchor)[0]
+    n_a = anchor_px.size
+    rs = np.random.RandomState(7)
+    rows = set(rs.choice(n_a, 512, replace=False).tolist())
+    for b in range(128, n_a, 128):
+        rows.update((b - 1, b))
+    rows.update((0, n_a - 1))
+    rows = np.array(sorted(rows))
+    px = torch.from_numpy(anchor_px[rows])
+    gs, rs_ = g[px], r[px]
+    norms = rs_.norm(dim=1)
+    row_cos = (gs * rs_).sum(1) / (gs.norm(dim=1) * norms).clamp_min(1e-300)
+    big = norms > 1e-3 * norms.max()          # rows whose gradient is not pure cancellation noise
+    assert int(big.sum()) >= 256
+    assert float(row_cos[big].min()) >= COS, float(row_cos[big].min())
+    # pixels that are not anchors get exactly zero
+    assert float(g[torch.from_numpy(~prep.anchor)].abs().max()) == 0.0
+
+
+def test_ade_real_size_unbiased_losses(U):
+    """BASELINE configs[2] at its real size: ADE 100-50 step 1, 3 x 151 / 101 classes at 512x512 (475 MB of logits):
+    upsample + UNCE(.mean) + UNKD through the drop-in modules and through the fused N1 module, against the fp64
+    oracle chain evaluated image by image (losses 1e-3 - in fact 1e-5 - and logit-gradient cosine >= 0.999)."""
+    B, h, w, H, W, C, C_old = 3, 32, 32, 512, 512, 151, 101
+    case = O.synthetic_case(B, h, w, H, W, C, C_old)
+    n_px = float(B * H * W)
+    ce_ref = kd_ref = 0.0
+    g_ref = torch.zeros(B, C, h, w, dtype=torch.float64)
+    for b in range(B):                         # per image: bounds the fp64 temporaries (317 MB per logit tensor)
+        lr = case["logits_lr"][b:b + 1].double().requires_grad_(True)
+        x = O.upsample_bilinear(lr, H, W)
+        t = O.upsample_bilinear(case["l_po"][b:b + 1].double(), H, W)
+        ce = O.unbiased_ce(x, case["labels"][b:b + 1].clone(), C_old, 255, "none").sum() / n_px
+        kd = O.unbiased_kd(x, t, 1.0, "sum") / n_px      # 'mean' = sum over pixels / (B H W), sign included
+        (ce + 10 * kd).backward()
+        ce_ref, kd_ref = ce_ref + ce.item(), kd_ref + kd.item()
+        g_ref[b] = lr.grad[0]
+    lr = case["logits_lr"].cuda().requires_grad_(True)
+    labels = case["labels"].cuda()
+    out = U.interpolate_bilinear(lr, (H, W))
+    with torch.no_grad():
+        old = U.interpolate_bilinear(case["l_po"].cuda(), (H, W))
+    ce = U.UnbiasedCrossEntropy(old_cl=C_old, ignore_index=255, reduction="none")(out, labels).mean()
+    kd = U.UnbiasedKnowledgeDistillationLoss(alpha=1.0)(out, old)
+    (ce + 10 * kd).backward()
+    assert ce.item() == pytest.approx(ce_ref, rel=1e-5) and kd.item() == pytest.approx(kd_ref, rel=1e-5)
+    assert cos(lr.grad, g_ref) >= COS
+    torch.testing.assert_close(lr.grad.cpu().double(), g_ref, rtol=2e-3, atol=1e-5 * float(g_ref.abs().max()))
+    del out, old
+    lr2 = case["logits_lr"].cuda().requires_grad_(True)
+    ce2, kd2 = U.FusedUnbiasedLosses(old_cl=C_old, ignore_index=255, alpha=1.0)(lr2, case["l_po"].cuda(),
+                                                                              case["labels"].cuda())
+    (ce2 + 10 * kd2).backward()
+    assert ce2.item() == pytest.approx(ce_ref, rel=1e-5) and kd2.item() == pytest.approx(kd_ref, rel=1e-5)
+    assert cos(lr2.grad, g_ref) >= COS
+
+
+def test_ade_real_size_wide_joint_probability(U):
+    """ADE 100-50 step 1 contrastive term at its real per-GPU size (3 x 32 x 32 pixels, 101 old classes -> K = 112
+    joint-probability width streamed in K chunks, labels up to 150): the reference itself crashes here (SURVEY A.1);
+    the oracle is the patched reference (max_label = C - 1)."""
+    case = O.synthetic_case(3, 32, 32, 512, 512, 151, 101, correlated=True)
+    _compare_contrastive(U, case, max_label=150)
+
+
+@pytest.mark.parametrize("tag", ["single", "double"])
+def test_pixel_to_pixel_branches(U, golden_dir, tag):
+    """pre_contrastive_pixel without old-model logits (utils/loss.py:278-289) against the reference's own outputs:
+    labels bit-exact, rows and gradient to fp32 accuracy."""
+    fx = np.load(os.path.join(golden_dir, "pixel_to_pixel.npz"))
+    B, h, w, H, W, C, C_old = (int(v) for v in fx["shape"])
+    case = O.synthetic_case(B, h, w, H, W, C, C_old)
+    f_n = case["f_n"].cuda().requires_grad_(True)
+    out, lab = U.pre_contrastive_pixel(f_n, case["labels"].cuda(), f_o=case["f_o"].cuda() if tag == "double" else None)
+    assert out.shape == fx[tag + "_out"].shape and lab.dtype == torch.int8
+    assert np.array_equal(lab.cpu().numpy(), fx[tag + "_lab"])
+    torch.testing.assert_close(out.cpu().double(), torch.from_numpy(fx[tag + "_out"]), rtol=1e-5, atol=1e-6)
+    (out * torch.from_numpy(fx["w"])[:out.shape[0]].float().cuda()).sum().backward()
+    torch.testing.assert_close(f_n.grad.cpu().double(), torch.from_numpy(fx[tag + "_grad"]), rtol=1e-4, atol=1e-5)
+    with pytest.raises(UnboundLocalError):   # l_po without f_o: `Output` is unassigned in the reference (loss.py:399)
+        U.pre_contrastive_pixel(f_n, case["labels"].cuda(), l_po=case["l_po"].cuda())
+
+
+def test_foreign_anchor_tensor_is_loud(U):
+    """A cast / clone of the anchors cannot use the packed operands: the dense fallback warns, and refuses above
+    max_dense_bytes; contrast features that require grad are refused (only d/d anchor is formed)."""
+    case = O.synthetic_case(2, 8, 8, 128, 128, 6, 4)
+    f_n = case["f_n"].cuda().requires_grad_(True)
+    tup = U.pre_contrastive_pixel(f_n, case["labels"].cuda(), l_po=case["l_po"].cuda(), f_o=case["f_o"].cuda())
+    con = U.PixelConLossV2(temperature=0.07)
+    ref = con(*tup)
+    with pytest.warns(RuntimeWarning, match="dense"):
+        out = con(tup[0].clone(), *tup[1:])
+    assert out.item() == pytest.approx(ref.item(), rel=1e-4)
+    con.max_dense_bytes = 16
+    with pytest.raises(RuntimeError, match="max_dense_bytes"):
+        con(tup[0].clone(), *tup[1:])
+    with pytest.raises(RuntimeError, match="requires grad"):
+        U.PixelConLossV2(temperature=0.07)(tup[0].detach(), tup[1].clone().requires_grad_(True), tup[2], tup[3], None)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -40,12 +40,18 @@ _PROTOS = {
     "ucd_con_prep_pack": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, P, c_int, P, P, P, P,
                                   P, P, P, c_int64, P]),
     "ucd_con_prep_bwd": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, P]),
+    "ucd_rows_normalize_fwd": (c_int, [P, P, P, c_int, c_int, c_int, P]),
+    "ucd_rows_normalize_bwd": (c_int, [P, P, P, P, c_int, c_int, c_int, P]),
     "ucd_con_tile_ranges": (c_int, [P, c_int64, P, P, P]),
     "ucd_con_pack_rows": (c_int, [P, P, c_int64, P, P, c_int64, P]),
-    "ucd_con_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
-    "ucd_con_fwd": (c_int, [P, P, P, P, c_int, c_int64, P, P, P, P, P, P, c_int64, P, c_int, c_int, P, c_int64,
-                            c_float, c_int, P, P, P, c_size_t, c_int64, c_int64, P]),
+    "ucd_con_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64]),
+    "ucd_con_fwd": (c_int, [P, P, P, P, c_int, c_int64, c_int64, c_int, c_int, P, P, P, P, P, P, c_int64, P, c_int, c_int,
+                            P, c_int64, c_float, c_int, P, P, P, c_size_t, c_int64, c_int64, P]),
     "ucd_con_bwd": (c_int, [P, P, P, c_float, P, P, P, c_int64, P]),
+}
+EXPORTED = tuple(_PROTOS)
+# include/ucd_b200_debug.h: exported by libucd_b200_debug.so only (python -m ucd_b200.build --debug)
+_DEBUG_PROTOS = {
     "ucd_con_debug_trace": (c_int, [P]),
     "ucd_con_debug_splits": (c_int, [c_int64, c_int64]),
     "ucd_selftest_umma": (c_int, [c_int, ctypes.POINTER(c_float)]),
@@ -53,7 +59,9 @@ _PROTOS = {
     "ucd_selftest_mma_mix": (c_int, [c_int] * 8 + [ctypes.POINTER(c_float)]),
     "ucd_selftest_pipe_rate": (c_int, [c_int, c_int, c_int, ctypes.POINTER(c_float)]),
 }
-EXPORTED = tuple(_PROTOS)
+DEBUG_EXPORTED = tuple(_DEBUG_PROTOS)
+DEBUG_LIB_PATH = os.path.join(_HERE, "libucd_b200_debug.so")
+_debug = None
 
 
 def lib():
@@ -71,6 +79,24 @@ def lib():
             fn.argtypes = args
         _lib = h
     return _lib
+
+
+def debug_lib(as_product=False):
+    """The debug build (tracing, tuning knobs, tcgen05 probes); never used by the product modules.  With
+    ``as_product=True`` the modules of this process run on it too (scripts that trace the product kernels)."""
+    global _debug, _lib
+    if _debug is None:
+        if not os.path.exists(DEBUG_LIB_PATH):
+            raise RuntimeError("ucd_b200: %s is missing - build it with `python -m ucd_b200.build --debug`" % DEBUG_LIB_PATH)
+        h = ctypes.CDLL(DEBUG_LIB_PATH)
+        for name, (res, args) in list(_PROTOS.items()) + list(_DEBUG_PROTOS.items()):
+            fn = getattr(h, name)
+            fn.restype = res
+            fn.argtypes = args
+        _debug = h
+    if as_product:
+        _lib = _debug
+    return _debug
 
 
 def check(rc, what=""):

@@ -23,6 +23,9 @@
 // (two per SM sub-partition; one thread per row and column half, accumulators read with tcgen05.ld, E / Ucoef
 // written back with tcgen05.st).  Everything is handed over through mbarriers; no __syncthreads in the tile loop.
 #include "umma.cuh"
+#ifdef UCD_DEBUG_KNOBS
+#include "../../include/ucd_b200_debug.h"
+#endif
 
 #include <stdlib.h>
 
@@ -78,9 +81,15 @@ struct ConArgs {
   const __nv_bfloat16* feat_tiles;
   const __nv_bfloat16* prob_tiles;
   const int* lab_tiles;
-  const int* chunk_counts;  // [n_chunks][2] = {N_a, N_o}
+  const int* chunk_counts;  // chunk c: {N_a, N_o} at chunk_counts + c * (chunk_stride ? chunk_stride / 4 : 2)
   int n_chunks;
   long long chunk_tiles;
+  // chunk_stride > 0: the five column arrays of chunk c (one rank's exchange payload) start chunk_stride bytes after
+  // those of chunk c-1 (pointers address chunk `chunk_origin`); 0: every array is [n_chunks][chunk_tiles][...] on its own
+  long long chunk_stride;
+  int chunk_origin;
+  int chunk_lo, chunk_hi, chunk_skip;  // this launch walks the columns of chunks [lo, hi) except `skip`
+  int split_base;                      // first partial slot of this launch (sweep 1 may run as two launches)
   const __nv_bfloat16* row_feat;  // row (anchor) tiles: [row_block][32][128][8]
   const __nv_bfloat16* row_prob;  // [row_block][kpad/8][128][8]
   const int* row_lab;             // [row_block][128]
@@ -111,10 +120,18 @@ __device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, long 
 }
 
 struct TileLoc {
-  long long gtile;  // tile index in the gathered buffers
+  long long gtile;  // tile index in global numbering: chunk * chunk_tiles + tile within the chunk
   int nvalid;       // valid columns in this tile (1..128)
   long long dcol0;  // first column in "dense" numbering (single-chunk compat path)
+  int c, lt;        // chunk and tile within the chunk
 };
+
+// byte offset of tile (c, lt) of a column array with `tile_bytes` per tile
+__device__ __forceinline__ size_t tile_off(const TileLoc& t, size_t tile_bytes, long long chunk_tiles, long long chunk_stride,
+                                           int chunk_origin) {
+  return chunk_stride ? (size_t)((long long)(t.c - chunk_origin) * chunk_stride) + (size_t)t.lt * tile_bytes
+                      : (size_t)((long long)(t.c - chunk_origin) * chunk_tiles + t.lt) * tile_bytes;
+}
 
 __device__ __forceinline__ TileLoc locate_tile(int k, const int* pre, const int* ncols, int n_chunks,
                                                long long chunk_tiles) {
@@ -125,6 +142,7 @@ __device__ __forceinline__ TileLoc locate_tile(int k, const int* pre, const int*
   t.gtile = (long long)c * chunk_tiles + lt;
   t.nvalid = min(128, ncols[c] - lt * 128);
   t.dcol0 = (long long)lt * 128;
+  t.c = c, t.lt = lt;
   return t;
 }
 
@@ -153,6 +171,7 @@ struct TileCursor {
     t.gtile = (long long)c * chunk_tiles + lt;
     t.nvalid = min(128, ncols - lt * 128);
     t.dcol0 = (long long)lt * 128;
+    t.c = c, t.lt = lt;
     return t;
   }
 };
@@ -298,7 +317,11 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
   if (threadIdx.x == 0) {
     int acc = 0;
     for (int c = 0; c < a.n_chunks; ++c) {
-      const int nc = a.chunk_counts[2 * c] + a.chunk_counts[2 * c + 1];
+      int nc = 0;
+      if (c >= a.chunk_lo && c < a.chunk_hi && c != a.chunk_skip) {
+        const int* cc = a.chunk_counts + (long long)(c - a.chunk_origin) * (a.chunk_stride ? a.chunk_stride / 4 : 2);
+        nc = cc[0] + cc[1];
+      }
       s_ncols[c] = nc;
       s_pre[c] = acc;
       acc += (nc + 127) >> 7;
@@ -352,7 +375,9 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
       bool ov = false;
       if (tt < n) {
         const TileLoc loc = locate_tile(k0 + tt, s_pre, s_ncols, a.n_chunks, a.chunk_tiles);
-        const int lo = __ldg(a.tile_range + 2 * loc.gtile), hi = __ldg(a.tile_range + 2 * loc.gtile + 1);
+        const int* tr = reinterpret_cast<const int*>(reinterpret_cast<const uint8_t*>(a.tile_range) +
+                                                     tile_off(loc, 8, a.chunk_tiles, a.chunk_stride, a.chunk_origin));
+        const int lo = __ldg(tr), hi = __ldg(tr + 1);
         ov = loc.gtile == self_tile || !(hi < row_lo || lo > row_hi);
       }
       const unsigned bits = __ballot_sync(0xffffffffu, ov);
@@ -405,14 +430,18 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
           mbar_wait_t(BAR(BAR_HE + ring.slot), ring.par ^ 1u, w_ce);
           if (elect_one_sync()) {
             const uint32_t dst = sbase + OFF_C + (uint32_t)ring.slot * kSlotBytes;
-            const uint8_t* src = ft + (size_t)loc.gtile * kTileBytes + (size_t)fh * kSlotBytes;
+            const uint8_t* src = ft + tile_off(loc, kTileBytes, a.chunk_tiles, a.chunk_stride, a.chunk_origin) +
+                                 (size_t)fh * kSlotBytes;
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
               const uint32_t bq = BAR(BAR_HF + 2 * ring.slot + q);
               const bool with_labels = fh == 0 && q == 0;
               mbar_arrive_expect_tx(bq, 16384u + (with_labels ? 512u : 0u));
               bulk_g2s(dst + q * 16384u, src + q * 16384u, 16384u, bq);
-              if (with_labels) bulk_g2s(sbase + OFF_LAB + lb * 512u, a.lab_tiles + loc.gtile * 128, 512u, bq);
+              if (with_labels)
+                bulk_g2s(sbase + OFF_LAB + lb * 512u, reinterpret_cast<const uint8_t*>(a.lab_tiles) +
+                                                          tile_off(loc, 512, a.chunk_tiles, a.chunk_stride, a.chunk_origin),
+                         512u, bq);
             }
           }
           __syncwarp();
@@ -424,7 +453,8 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
           mbar_wait_t(BAR(BAR_PE), (u & 1) ^ 1, w_pe);
           if (elect_one_sync()) {
             mbar_arrive_expect_tx(BAR(BAR_PF), kb);
-            bulk_g2s(sbase + off_pc, pt + (size_t)loc.gtile * pbytes + (size_t)c * pc_k * 256u, kb, BAR(BAR_PF));
+            bulk_g2s(sbase + off_pc, pt + tile_off(loc, pbytes, a.chunk_tiles, a.chunk_stride, a.chunk_origin) +
+                                         (size_t)c * pc_k * 256u, kb, BAR(BAR_PF));
           }
           __syncwarp();
         }
@@ -598,7 +628,9 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
       rc.lneg2 = rc.series ? log2f(rc.negi) : 0.f;
       rc.c0 = -fmaf(rc.mraw, sc, rc.lneg2);
       if (PMODE == 1) {
-        const int min_new = *a.min_new;
+        int min_new = 0x7fffffff;  // global GT-new threshold = minimum over every rank's chunk header
+        for (int c = 0; c < (a.chunk_stride ? a.n_chunks : 1); ++c)
+          min_new = min(min_new, __ldg(a.min_new + (long long)(c - a.chunk_origin) * (a.chunk_stride / 4)));
         if (la >= min_new) thr = min_new;  // GT-new row: P = 1 against GT-new columns (loss.py:385-393)
       }
       warp_series = __all_sync(0xffffffffu, rc.series);
@@ -727,9 +759,10 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
     asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
     if (half == 0) {
       if (PHASE == 1) {
-        a.stats_part[(size_t)split * 3 * a.rows_pad + grow] = fmaxf(mx, comb[r * 3 + 0]);
-        a.stats_part[(size_t)split * 3 * a.rows_pad + a.rows_pad + grow] = neg + comb[r * 3 + 1];
-        a.stats_part[(size_t)split * 3 * a.rows_pad + 2 * a.rows_pad + grow] = num + comb[r * 3 + 2];
+        const size_t slot = (size_t)(split + a.split_base);
+        a.stats_part[slot * 3 * a.rows_pad + grow] = fmaxf(mx, comb[r * 3 + 0]);
+        a.stats_part[slot * 3 * a.rows_pad + a.rows_pad + grow] = neg + comb[r * 3 + 1];
+        a.stats_part[slot * 3 * a.rows_pad + 2 * a.rows_pad + grow] = num + comb[r * 3 + 2];
       } else {
         a.loss_part[(size_t)split * 2 * a.rows_pad + grow] = (lacc + comb[r * 3 + 0]) * kLn2;
         a.loss_part[(size_t)split * 2 * a.rows_pad + a.rows_pad + grow] = tacc + comb[r * 3 + 1];
@@ -740,7 +773,8 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
       // different 128-byte lines with 16 bytes each.  A per-warp [32][36] transposition buffer in the (now idle) C stage
       // turns that into 4 full lines per instruction.
       float* xp = reinterpret_cast<float*>(smem + OFF_C + 4096) + (size_t)(warp - 3) * (32 * 36);
-      const size_t prow0 = (size_t)split * a.rows_pad + (size_t)rb * 128 + quarter * 32;  // first row of this warp
+      const size_t prow0 = (size_t)(split + (PHASE == 1 ? a.split_base : 0)) * a.rows_pad + (size_t)rb * 128 +
+                           quarter * 32;  // first row of this warp
       float* dstw = a.acc_part + prow0 * 256 + half * 128;
       const int orow = lane >> 3, ocol = (lane & 7) * 4;
 #pragma unroll 1
@@ -874,27 +908,26 @@ __global__ void con_bwd_kernel(const float* __restrict__ grad_unit, const float*
 }
 
 constexpr int kFinalizeBlocks = kNumSMs * 4;
-static long long* g_trace = nullptr;  // debug only (ucd_con_debug_trace)
+#ifdef UCD_DEBUG_KNOBS
+static long long* g_trace = nullptr;  // debug builds only (ucd_con_debug_trace)
+#endif
 
 struct ConPlan {
-  int splits;   // column splits of sweep 1
-  int splits2;  // column splits of sweep 2 (few active tiles per CTA: fewer, longer CTAs amortise the fixed cost)
+  int splits;        // column splits of sweep 1 (one launch over all chunks), or of its REMOTE part (two-part run)
+  int splits_local;  // two-part run: column splits of the launch over the local chunk (0 = single launch)
+  int splits2;       // column splits of sweep 2 (few active tiles per CTA: fewer, longer CTAs amortise the fixed cost)
   long long rows_pad;
   size_t off_stats_part, off_stats, off_loss_part, off_v, off_u, off_block, total;
+  int splits1_total() const { return splits + splits_local; }
 };
 
-// plan_row_tiles: row tiles expected to hold anchors (<= max_row_tiles, 0 = all of them).  A caller that sizes its
-// buffers for the worst case without knowing N_a on the host (the sync-free path) passes its estimate here so that
-// the column splits are chosen for the CTAs that will actually run; the rest exit at once.
-static ConPlan make_plan(long long max_row_tiles, long long max_col_tiles, long long plan_row_tiles = 0) {
-  if (plan_row_tiles <= 0 || plan_row_tiles > max_row_tiles) plan_row_tiles = max_row_tiles;
-  ConPlan p;
-  // choose the number of column splits that best fills 148 SMs without tiny per-CTA ranges
+// number of column splits that best fills the SMs with `row_tiles` row blocks without tiny per-CTA column ranges
+static int choose_splits(long long row_tiles, long long col_tiles) {
   int best = 1;
   double best_eff = 0.0;
   for (int s = 1; s <= 16; ++s) {
-    if (s > 1 && max_col_tiles / s < 4) break;
-    const long long ctas = plan_row_tiles * s;
+    if (s > 1 && col_tiles / s < 4) break;
+    const long long ctas = row_tiles * s;
     const long long waves = (ctas + kNumSMs - 1) / kNumSMs;
     const double eff = (double)ctas / (double)(waves * kNumSMs);
     if (eff > best_eff + 0.03) {
@@ -902,13 +935,33 @@ static ConPlan make_plan(long long max_row_tiles, long long max_col_tiles, long 
       best = s;
     }
   }
-  while ((max_col_tiles + best - 1) / best > kMaxTilesPerCta) ++best;
-  p.splits = best;
+  while ((col_tiles + best - 1) / best > kMaxTilesPerCta) ++best;
+  return best;
+}
+
+// plan_row_tiles: row tiles expected to hold anchors (<= max_row_tiles, 0 = all of them).  A caller that sizes its
+// buffers for the worst case without knowing N_a on the host (the sync-free path) passes its estimate here so that
+// the column splits are chosen for the CTAs that will actually run; the rest exit at once.
+// local_col_tiles > 0: sweep 1 runs as two launches (local chunk, then the other chunks) with separate partial slots.
+static ConPlan make_plan(long long max_row_tiles, long long max_col_tiles, long long plan_row_tiles = 0,
+                         long long local_col_tiles = 0) {
+  if (plan_row_tiles <= 0 || plan_row_tiles > max_row_tiles) plan_row_tiles = max_row_tiles;
+  ConPlan p;
+  if (local_col_tiles > 0 && local_col_tiles < max_col_tiles) {
+    p.splits_local = choose_splits(plan_row_tiles, local_col_tiles);
+    p.splits = choose_splits(plan_row_tiles, max_col_tiles - local_col_tiles);
+  } else {
+    p.splits_local = 0;
+    p.splits = choose_splits(plan_row_tiles, max_col_tiles);
+  }
+  const int best = choose_splits(plan_row_tiles, max_col_tiles);
   p.splits2 = best > 1 ? (best + 1) / 2 : 1;
+#ifdef UCD_DEBUG_KNOBS
   static const int env_s1 = getenv("UCD_SPLITS1") ? atoi(getenv("UCD_SPLITS1")) : 0;  // tuning knobs, read once
   static const int env_s2 = getenv("UCD_SPLITS2") ? atoi(getenv("UCD_SPLITS2")) : 0;
   if (env_s1 > 0) p.splits = env_s1;
   if (env_s2 > 0) p.splits2 = env_s2;
+#endif
   while ((max_col_tiles + p.splits - 1) / p.splits > kMaxTilesPerCta) ++p.splits;
   while ((max_col_tiles + p.splits2 - 1) / p.splits2 > kMaxTilesPerCta) ++p.splits2;
   p.rows_pad = max_row_tiles * 128;
@@ -918,10 +971,10 @@ static ConPlan make_plan(long long max_row_tiles, long long max_col_tiles, long 
     o += (bytes + 255) & ~(size_t)255;
     return r;
   };
-  p.off_stats_part = take((size_t)p.splits * 3 * p.rows_pad * 4);
+  p.off_stats_part = take((size_t)p.splits1_total() * 3 * p.rows_pad * 4);
   p.off_stats = take((size_t)3 * p.rows_pad * 4);
   p.off_loss_part = take((size_t)p.splits2 * 2 * p.rows_pad * 4);
-  p.off_v = take((size_t)p.splits * p.rows_pad * 256 * 4);
+  p.off_v = take((size_t)p.splits1_total() * p.rows_pad * 256 * 4);
   p.off_u = take((size_t)p.splits2 * p.rows_pad * 256 * 4);
   p.off_block = take((size_t)2 * kFinalizeBlocks * 4);
   p.total = o;
@@ -930,16 +983,13 @@ static ConPlan make_plan(long long max_row_tiles, long long max_col_tiles, long 
 
 template <int PHASE, int PMODE>
 static int launch_sweep(const ConArgs& a, long long max_row_tiles, cudaStream_t st) {
-  static bool configured = false;  // benign race: attribute set is idempotent
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(con_sweep_kernel<PHASE, PMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)kConSmem);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(con_sweep_kernel)");
-    configured = true;
-  }
+  // the attribute is per device: set it on every call (a process may drive several GPUs), it costs ~1 us
+  cudaError_t e = cudaFuncSetAttribute(con_sweep_kernel<PHASE, PMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)kConSmem);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(con_sweep_kernel)");
   const unsigned grid = (unsigned)(max_row_tiles * a.splits);
   con_sweep_kernel<PHASE, PMODE><<<grid, kConThreads, kConSmem, st>>>(a);
-  cudaError_t e = cudaGetLastError();
+  e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "con_sweep_kernel launch");
   return UCD_OK;
 }
@@ -948,20 +998,27 @@ static int launch_sweep(const ConArgs& a, long long max_row_tiles, cudaStream_t 
 
 using namespace ucd;
 
-extern "C" size_t ucd_con_workspace_bytes(int64_t max_row_tiles, int64_t max_col_tiles, int64_t plan_row_tiles) {
+extern "C" size_t ucd_con_workspace_bytes(int64_t max_row_tiles, int64_t max_col_tiles, int64_t plan_row_tiles,
+                                          int64_t local_col_tiles) {
   if (max_row_tiles <= 0 || max_col_tiles <= 0) return 0;
-  return make_plan(max_row_tiles, max_col_tiles, plan_row_tiles).total;
+  return make_plan(max_row_tiles, max_col_tiles, plan_row_tiles, local_col_tiles).total;
 }
 
 extern "C" int ucd_con_fwd(const void* feat_tiles, const void* prob_tiles, const int32_t* lab_tiles,
-                           const int32_t* chunk_counts, int n_chunks, int64_t chunk_tiles, const void* row_feat_tiles,
+                           const int32_t* chunk_counts, int n_chunks, int64_t chunk_tiles, int64_t chunk_stride_bytes,
+                           int local_chunk, int part, const void* row_feat_tiles,
                            const void* row_prob_tiles, const int32_t* row_lab_tiles, const int32_t* n_rows,
                            const int32_t* tile_range, const int32_t* row_range, int64_t self_tile0, const int32_t* min_new, int p_mode, int kpad, const float* dense_p,
                            int64_t ldp,
                            float inv_temperature, int need_grad, float* out, float* grad_unit, void* workspace,
                            size_t workspace_bytes, int64_t max_row_tiles, int64_t plan_row_tiles, void* stream) {
-  UCD_CHECK_ARG(feat_tiles && lab_tiles && chunk_counts && out && workspace, "ucd_con_fwd: null pointer");
+  UCD_CHECK_ARG(feat_tiles && lab_tiles && chunk_counts && workspace, "ucd_con_fwd: null pointer");
+  UCD_CHECK_ARG(part == 1 || out, "ucd_con_fwd: null out");
   UCD_CHECK_ARG(n_chunks >= 1 && n_chunks <= kMaxChunks, "ucd_con_fwd: n_chunks=%d outside [1,%d]", n_chunks, kMaxChunks);
+  UCD_CHECK_ARG(part >= 0 && part <= 2, "ucd_con_fwd: part must be 0 (all), 1 (sweep 1 over the local chunk) or 2 (the rest)");
+  UCD_CHECK_ARG(part == 0 || (local_chunk >= 0 && local_chunk < n_chunks && n_chunks > 1),
+                "ucd_con_fwd: a two-part run needs n_chunks > 1 and a valid local_chunk");
+  UCD_CHECK_ARG(chunk_stride_bytes >= 0 && chunk_stride_bytes % 16 == 0, "ucd_con_fwd: chunk_stride_bytes must be a multiple of 16");
   UCD_CHECK_ARG(row_feat_tiles && row_lab_tiles && n_rows, "ucd_con_fwd: null row pointer");
   UCD_CHECK_ARG(tile_range && row_range, "ucd_con_fwd: null tile range pointer");
   UCD_CHECK_ARG(aligned16(row_feat_tiles) && (!row_prob_tiles || aligned16(row_prob_tiles)),
@@ -971,7 +1028,7 @@ extern "C" int ucd_con_fwd(const void* feat_tiles, const void* prob_tiles, const
   UCD_CHECK_ARG(p_mode >= 0 && p_mode <= 2, "ucd_con_fwd: bad p_mode");
   UCD_CHECK_ARG(p_mode != 1 || (prob_tiles && row_prob_tiles && min_new), "ucd_con_fwd: p_mode 1 needs prob tiles and min_new");
   UCD_CHECK_ARG(p_mode != 2 || (dense_p && n_chunks == 1), "ucd_con_fwd: dense P needs a single chunk");
-  UCD_CHECK_ARG(!need_grad || grad_unit, "ucd_con_fwd: need_grad without grad_unit");
+  UCD_CHECK_ARG(!need_grad || grad_unit || part == 1, "ucd_con_fwd: need_grad without grad_unit");
   UCD_CHECK_ARG(aligned16(feat_tiles) && aligned16(lab_tiles) && (!prob_tiles || aligned16(prob_tiles)),
                 "ucd_con_fwd: tile buffers must be 16 B aligned");
   UCD_CHECK_ARG(inv_temperature > 0.f, "ucd_con_fwd: bad temperature");
@@ -979,7 +1036,7 @@ extern "C" int ucd_con_fwd(const void* feat_tiles, const void* prob_tiles, const
     set_error("ucd_con_fwd: joint-probability width kpad=%d not supported (multiple of 16 up to 112, i.e. C_old <= 112)", kpad);
     return UCD_ENOSUP;
   }
-  const ConPlan plan = make_plan(max_row_tiles, (int64_t)n_chunks * chunk_tiles, plan_row_tiles);
+  const ConPlan plan = make_plan(max_row_tiles, (int64_t)n_chunks * chunk_tiles, plan_row_tiles, part ? chunk_tiles : 0);
   UCD_CHECK_ARG(workspace_bytes >= plan.total, "ucd_con_fwd: workspace too small (%zu < %zu)", workspace_bytes, plan.total);
   UCD_CHECK_ARG(max_row_tiles * (plan.splits > plan.splits2 ? plan.splits : plan.splits2) < (1ll << 31),
                 "ucd_con_fwd: grid too large");
@@ -992,6 +1049,8 @@ extern "C" int ucd_con_fwd(const void* feat_tiles, const void* prob_tiles, const
   a.chunk_counts = chunk_counts;
   a.n_chunks = n_chunks;
   a.chunk_tiles = chunk_tiles;
+  a.chunk_stride = chunk_stride_bytes;
+  a.chunk_origin = part == 1 ? local_chunk : 0;
   a.row_feat = (const __nv_bfloat16*)row_feat_tiles;
   a.row_prob = (const __nv_bfloat16*)row_prob_tiles;
   a.row_lab = row_lab_tiles;
@@ -1003,25 +1062,41 @@ extern "C" int ucd_con_fwd(const void* feat_tiles, const void* prob_tiles, const
   a.dense_p = dense_p;
   a.ldp = ldp;
   a.inv_tau = inv_temperature;
-  a.splits = plan.splits;
   a.need_grad = need_grad;
   a.kpad = kpad;
   a.rows_pad = plan.rows_pad;
   a.stats_part = (float*)(ws + plan.off_stats_part);
   a.stats = (const float*)(ws + plan.off_stats);
   a.loss_part = (float*)(ws + plan.off_loss_part);
+#ifdef UCD_DEBUG_KNOBS
   a.trace = g_trace;
-  // sweep 1
+#else
+  a.trace = nullptr;
+#endif
+  int rc;
+  // sweep 1: one launch over every chunk, or (two-part run) the local chunk first - while the exchange of the other
+  // ranks' columns is still in flight - and the remaining chunks in the second call
   a.acc_part = (float*)(ws + plan.off_v);
-  int rc = launch_sweep<1, 0>(a, max_row_tiles, st);
+  if (part == 1) {
+    a.chunk_lo = local_chunk, a.chunk_hi = local_chunk + 1, a.chunk_skip = -1;
+    a.split_base = 0, a.splits = plan.splits_local;
+    return launch_sweep<1, 0>(a, max_row_tiles, st);
+  }
+  a.chunk_lo = 0, a.chunk_hi = n_chunks, a.chunk_skip = part == 2 ? local_chunk : -1;
+  a.split_base = part == 2 ? plan.splits_local : 0, a.splits = plan.splits;
+  if (part == 2) a.self_tile0 = -1;  // the anchors' own columns sit in the skipped (local) chunk
+  rc = launch_sweep<1, 0>(a, max_row_tiles, st);
   if (rc != UCD_OK) return rc;
+  const int splits1 = part == 2 ? plan.splits1_total() : plan.splits;
   if (a.trace) a.trace += (size_t)max_row_tiles * plan.splits * 16;  // sweep 2 counters follow sweep 1's
-  con_combine_kernel<<<(unsigned)((plan.rows_pad + 255) / 256), 256, 0, st>>>(a.stats_part, plan.splits, plan.rows_pad,
+  con_combine_kernel<<<(unsigned)((plan.rows_pad + 255) / 256), 256, 0, st>>>(a.stats_part, splits1, plan.rows_pad,
                                                                                (float*)(ws + plan.off_stats));
   UCD_CHECK_LAUNCH("con_combine_kernel");
-  // sweep 2
+  // sweep 2: all chunks
   a.acc_part = (float*)(ws + plan.off_u);
   a.splits = plan.splits2;
+  a.split_base = 0, a.chunk_skip = -1;
+  a.self_tile0 = self_tile0;
   if (p_mode == 0)
     rc = launch_sweep<2, 0>(a, max_row_tiles, st);
   else if (p_mode == 1)
@@ -1031,7 +1106,7 @@ extern "C" int ucd_con_fwd(const void* feat_tiles, const void* prob_tiles, const
   if (rc != UCD_OK) return rc;
   float* block_part = (float*)(ws + plan.off_block);
   con_finalize_kernel<<<kFinalizeBlocks, 256, 0, st>>>(a.stats, a.loss_part, (const float*)(ws + plan.off_v),
-                                                       (const float*)(ws + plan.off_u), plan.splits, plan.splits2,
+                                                       (const float*)(ws + plan.off_u), splits1, plan.splits2,
                                                        plan.rows_pad,
                                                        n_rows, inv_temperature, need_grad, grad_unit, block_part);
   UCD_CHECK_LAUNCH("con_finalize_kernel");
@@ -1054,6 +1129,7 @@ extern "C" int ucd_con_bwd(const float* grad_unit, const float* out, const float
   return UCD_OK;
 }
 
+#ifdef UCD_DEBUG_KNOBS
 // Debug aid (not part of the product path): when set to a device buffer of
 // 2 * max_row_tiles * splits * 16 int64, every CTA of the two sweeps records per-role cycle counters:
 //   [0] producer total, [1] wait for a free C stage, [2] wait for the P stage, [3] tiles loaded
@@ -1066,3 +1142,4 @@ extern "C" int ucd_con_debug_trace(void* device_buffer) {
 extern "C" int ucd_con_debug_splits(int64_t max_row_tiles, int64_t max_col_tiles) {
   return make_plan(max_row_tiles, max_col_tiles).splits;
 }
+#endif  // UCD_DEBUG_KNOBS

@@ -389,6 +389,69 @@ prep_bwd_kernel(const float* __restrict__ g_anchor, const float* __restrict__ an
   }
 }
 
+// Pixel-to-pixel branches of pre_contrastive_pixel (utils/loss.py:273-289): EVERY pixel becomes a unit-norm row
+// [n_px, 256] in (b, y, x) order.  block = 32 consecutive pixels, coalesced NCHW reads -> shared tile -> row writes.
+__global__ void __launch_bounds__(128)
+rows_normalize_kernel(const float* __restrict__ f, float* __restrict__ rows, float* __restrict__ inv_norm, int n_px,
+                      int hw) {
+  __shared__ float tile[256][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int p = blockIdx.x * 32 + lane;
+  if (p < n_px) {
+    const int b = p / hw, q = p - b * hw;
+    const float* src = f + ((size_t)b * 256 + warp * 64) * hw + q;
+#pragma unroll 8
+    for (int c = 0; c < 64; ++c) tile[warp * 64 + c][lane] = src[(size_t)c * hw];
+  }
+  __syncthreads();
+  for (int pi = warp; pi < 32; pi += 4) {
+    const int pp = blockIdx.x * 32 + pi;
+    if (pp >= n_px) break;
+    float v[8], ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      v[k] = tile[lane + 32 * k][pi];
+      ss = fmaf(v[k], v[k], ss);
+    }
+    ss = warp_sum(ss);
+    const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);  // F.normalize: x / max(||x||, eps)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) rows[(size_t)pp * 256 + lane + 32 * k] = v[k] * inv;
+    if (lane == 0) inv_norm[pp] = inv;
+  }
+}
+
+// adjoint: df[b,:,y,x] = (g - (g.a) a) * inv_norm for every pixel
+__global__ void __launch_bounds__(128)
+rows_normalize_bwd_kernel(const float* __restrict__ g_rows, const float* __restrict__ rows,
+                          const float* __restrict__ inv_norm, float* __restrict__ df, int n_px, int hw) {
+  __shared__ float tile[256][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int pi = warp; pi < 32; pi += 4) {
+    const int pp = blockIdx.x * 32 + pi;
+    if (pp >= n_px) break;
+    float g[8], a[8], dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      g[k] = g_rows[(size_t)pp * 256 + lane + 32 * k];
+      a[k] = rows[(size_t)pp * 256 + lane + 32 * k];
+      dot = fmaf(g[k], a[k], dot);
+    }
+    dot = warp_sum(dot);
+    const float inv = inv_norm[pp];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) tile[lane + 32 * k][pi] = (g[k] - dot * a[k]) * inv;
+  }
+  __syncthreads();
+  const int p = blockIdx.x * 32 + lane;
+  if (p < n_px) {
+    const int b = p / hw, q = p - b * hw;
+    float* dp = df + ((size_t)b * 256 + warp * 64) * hw + q;
+#pragma unroll 8
+    for (int c = 0; c < 64; ++c) dp[(size_t)c * hw] = tile[warp * 64 + c][lane];
+  }
+}
+
 // compat path: caller-supplied fp32 rows [n,256] (+labels) -> bf16 tiles.  warp per row.
 __global__ void __launch_bounds__(256)
 pack_rows_kernel(const float* __restrict__ rows, const int* __restrict__ labels, long long n,
@@ -468,8 +531,9 @@ extern "C" int ucd_con_prep_pack(const float* f_n, const float* f_o, const float
                 "ucd_con_prep_pack: null pointer");
   UCD_CHECK_ARG(aligned16(feat_tiles) && aligned16(prob_tiles) && aligned16(lab_tiles),
                 "ucd_con_prep_pack: tiles must be 16 B aligned");
-  UCD_CHECK_ARG(label_bytes == 4 || (label_bytes == 1 && max_label <= 127),
-                "ucd_con_prep_pack: label_bytes must be 4, or 1 when max_label <= 127");
+  // la / lc hold GT labels (<= max_label) AND pseudo labels (old-model argmax, <= C_old - 1): both must fit
+  UCD_CHECK_ARG(label_bytes == 4 || (label_bytes == 1 && max_label <= 127 && C_old - 1 <= 127),
+                "ucd_con_prep_pack: label_bytes must be 4, or 1 when max_label <= 127 and C_old <= 128");
   const int n_px = B * h * w;
   UCD_CHECK_ARG(max_tiles >= ucd_con_max_tiles(n_px), "ucd_con_prep_pack: max_tiles too small");
   cudaStream_t st = (cudaStream_t)stream;
@@ -520,5 +584,24 @@ extern "C" int ucd_con_pack_rows(const float* rows, const int32_t* labels, int64
     pack_rows_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(rows, labels, n, (__nv_bfloat16*)feat_tiles, lab_tiles);
     UCD_CHECK_LAUNCH("pack_rows_kernel");
   }
+  return UCD_OK;
+}
+
+extern "C" int ucd_rows_normalize_fwd(const float* f, float* rows, float* inv_norm, int B, int h, int w, void* stream) {
+  UCD_CHECK_ARG(f && rows && inv_norm, "ucd_rows_normalize_fwd: null pointer");
+  UCD_CHECK_ARG(B > 0 && h > 0 && w > 0 && (long long)B * h * w < (1ll << 30), "ucd_rows_normalize_fwd: bad shape");
+  const int n_px = B * h * w;
+  rows_normalize_kernel<<<(n_px + 31) / 32, 128, 0, (cudaStream_t)stream>>>(f, rows, inv_norm, n_px, h * w);
+  UCD_CHECK_LAUNCH("rows_normalize_kernel");
+  return UCD_OK;
+}
+
+extern "C" int ucd_rows_normalize_bwd(const float* g_rows, const float* rows, const float* inv_norm, float* df, int B,
+                                      int h, int w, void* stream) {
+  UCD_CHECK_ARG(g_rows && rows && inv_norm && df, "ucd_rows_normalize_bwd: null pointer");
+  UCD_CHECK_ARG(B > 0 && h > 0 && w > 0 && (long long)B * h * w < (1ll << 30), "ucd_rows_normalize_bwd: bad shape");
+  const int n_px = B * h * w;
+  rows_normalize_bwd_kernel<<<(n_px + 31) / 32, 128, 0, (cudaStream_t)stream>>>(g_rows, rows, inv_norm, df, n_px, h * w);
+  UCD_CHECK_LAUNCH("rows_normalize_bwd_kernel");
   return UCD_OK;
 }

@@ -6,6 +6,7 @@
 //               operand from there (the production path of the sweeps)
 // Used by tests/test_gpu_umma.py; not on the product path.
 #include "umma.cuh"
+#include "../../include/ucd_b200_debug.h"
 
 #include <stdlib.h>
 #include <vector>

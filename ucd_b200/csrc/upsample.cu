@@ -410,7 +410,9 @@ extern "C" int ucd_upsample_bilinear_fwd(const float* in, float* out, int64_t pl
   long long want_y = (32ll * kNumSMs + gx - 1) / gx;
   if (want_y < 1) want_y = 1;
   if (want_y > (planes + 15) / 16) want_y = (planes + 15) / 16;
+#ifdef UCD_DEBUG_KNOBS
   if (const char* e = getenv("UCD_UP_GY")) want_y = atoi(e) > 0 ? atoi(e) : want_y;  // tuning knob
+#endif
   if (want_y > planes) want_y = planes;
   const int ppb = (int)((planes + want_y - 1) / want_y);
   const int gy = (int)((planes + ppb - 1) / ppb);

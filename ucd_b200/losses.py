@@ -32,9 +32,19 @@ TILE = 128
 
 
 def _need_cuda(*tensors):
+    cur = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError("ucd_b200: expected CUDA tensors (there is no CPU fallback for this path)")
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            # kernels are launched on the current device / its current stream: a tensor living elsewhere would be
+            # dereferenced in the wrong context
+            raise RuntimeError("ucd_b200: tensor on cuda:%d but the current device is cuda:%d - wrap the call in "
+                               "`with torch.cuda.device(tensor.device):`" % (t.device.index, cur))
 
 
 def _f32c(t):
@@ -309,6 +319,37 @@ class MaskCrossEntropy(nn.Module):
 # ----------------------------------------------------------------------------------------------
 # contrastive prep
 # ----------------------------------------------------------------------------------------------
+def payload_layout(max_tiles, kpad):
+    """Byte layout of one rank's exchange payload: the ONE contiguous buffer that holds everything another rank needs
+    of this rank's contrast columns, so that the exchange step is a single all-gather.  Sections are
+    256-byte aligned: header int32[4] = {N_a, N_o, min_new, n_px} | tile ranges int32[T,2] | label tiles int32[T,128] |
+    probability tiles bf16[T,kpad/8,128,8] | feature tiles bf16[T,32,128,8]."""
+    al = lambda n: (n + 255) & ~255  # noqa: E731
+    off = {"counts": 0}
+    o = 256
+    for name, nbytes in (("range", max_tiles * 8), ("lab", max_tiles * TILE * 4), ("prob", max_tiles * kpad * TILE * 2),
+                         ("feat", max_tiles * FEAT_DIM * TILE * 2)):
+        off[name] = o
+        o += al(nbytes)
+    off["nbytes"] = o
+    return off
+
+
+def payload_views(buf, max_tiles, kpad):
+    """Typed views into a payload buffer ``buf`` uint8 [..., nbytes] (one rank's, or the gathered [W, nbytes])."""
+    lay = payload_layout(max_tiles, kpad)
+    assert buf.dtype == torch.uint8 and buf.shape[-1] == lay["nbytes"]
+
+    def sec(name, nbytes, dtype, shape):
+        v = buf[..., lay[name]:lay[name] + nbytes].view(dtype)
+        return v.unflatten(-1, shape)
+    T = max_tiles
+    return dict(counts=sec("counts", 16, torch.int32, (4,)), range=sec("range", T * 8, torch.int32, (T, 2)),
+                lab=sec("lab", T * TILE * 4, torch.int32, (T, TILE)),
+                prob=sec("prob", T * kpad * TILE * 2, torch.bfloat16, (T, kpad // 8, TILE, 8)),
+                feat=sec("feat", T * FEAT_DIM * TILE * 2, torch.bfloat16, (T, FEAT_DIM // 8, TILE, 8)))
+
+
 class ContrastPack:
     """Device-side product of the prep kernels for one batch: bf16 operand tiles for the tensor-core
     sweeps plus the metadata the backward needs.  Shared by the 5 tuple slots."""
@@ -319,7 +360,8 @@ class ContrastPack:
         self.c_old = 0
         self.kpad = 0
         self.max_tiles = 0
-        self.counts = None         # int32[4] device: N_a, N_o, min_new, n_px
+        self.payload = None        # uint8 [payload_layout(...)["nbytes"]]: counts + range + lab + prob + feat tiles
+        self.counts = None         # int32[4] device: N_a, N_o, min_new, n_px (view into payload, like the tile arrays)
         self.n_a = self.n_o = self.min_new = None   # host copies (one sync)
         self.px_meta = self.blk_meta = None         # see include/ucd_b200.h (ucd_con_prep_labels)
         self.label_n = self.mix = self.flags = None  # views of px_meta planes 0..2
@@ -349,7 +391,12 @@ def _pinned_counts(dev):
     return buf
 
 
-def _build_pack(f_n, f_o, l_po, labels, max_label, sync=True):
+def _multi_rank():
+    import torch.distributed as dist
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def _build_pack(f_n, f_o, l_po, labels, max_label, sync=True, require_new_class=True):
     _need_cuda(f_n, f_o, l_po, labels)
     if f_n.dim() != 4 or f_n.shape[1] != FEAT_DIM or f_o.shape != f_n.shape:
         raise ValueError("pre_contrastive_pixel: f_n / f_o must be [B,%d,h,w]" % FEAT_DIM)
@@ -374,7 +421,11 @@ def _build_pack(f_n, f_o, l_po, labels, max_label, sync=True):
     pk.px_meta = torch.empty(7, n_px, **i32)
     pk.label_n, pk.mix, pk.flags = pk.px_meta[0], pk.px_meta[1], pk.px_meta[2]
     pk.blk_meta = torch.empty(L.ucd_con_blk_meta_ints(n_px, nb), **i32)
-    pk.counts = torch.empty(4, **i32)
+    # everything another rank needs of this rank's columns lives in ONE buffer (the exchange payload); the kernels
+    # write their outputs straight into its sections
+    pk.payload = torch.empty(payload_layout(pk.max_tiles, pk.kpad)["nbytes"], device=dev, dtype=torch.uint8)
+    pv = payload_views(pk.payload, pk.max_tiles, pk.kpad)
+    pk.counts = pv["counts"]
     st = cur_stream()
     # The tuple API needs N_a / N_o on the host (tensor shapes).  The scan kernel stores them straight into mapped
     # pinned host memory (no D2H copy that could queue behind other transfers on the copy engine); the host waits
@@ -388,13 +439,12 @@ def _build_pack(f_n, f_o, l_po, labels, max_label, sync=True):
         copied.record()
     pk.anchor_f32 = torch.empty(n_px, FEAT_DIM, device=dev, dtype=torch.float32)
     pk.contrast_f32 = torch.empty(2 * n_px, FEAT_DIM, device=dev, dtype=torch.float32)
-    ldt = _label_dtype(pk.max_label)   # the tuple's label vectors come out of the pack kernel in their final type
+    # the tuple's label vectors come out of the pack kernel in their final type; they hold GT labels (<= max_label)
+    # and pseudo labels (old-model argmax, <= C_old - 1)
+    ldt = _label_dtype(max(pk.max_label, pk.c_old - 1))
     pk.la = torch.empty(n_px, device=dev, dtype=ldt)
     pk.lc = torch.empty(2 * n_px, device=dev, dtype=ldt)
-    pk.feat_tiles = torch.empty(pk.max_tiles, FEAT_DIM // 8, TILE, 8, device=dev, dtype=torch.bfloat16)
-    pk.prob_tiles = torch.empty(pk.max_tiles, pk.kpad // 8, TILE, 8, device=dev, dtype=torch.bfloat16)
-    pk.lab_tiles = torch.empty(pk.max_tiles, TILE, **i32)
-    pk.tile_range = torch.empty(pk.max_tiles, 2, **i32)
+    pk.feat_tiles, pk.prob_tiles, pk.lab_tiles, pk.tile_range = pv["feat"], pv["prob"], pv["lab"], pv["range"]
     pk.row_range = torch.empty((n_px + TILE - 1) // TILE, 2, **i32)
     pk.row_ref = torch.empty(n_px, **i32)
     pk.inv_norm = torch.empty(n_px, device=dev, dtype=torch.float32)
@@ -410,7 +460,7 @@ def _build_pack(f_n, f_o, l_po, labels, max_label, sync=True):
     # the one host sync of the tuple API: the 5-tuple's tensor shapes depend on N_a / N_o
     copied.synchronize()
     pk.n_a, pk.n_o, pk.min_new, _ = (int(v) for v in counts_host.tolist())
-    if pk.n_a > 0 and pk.min_new > max(int(max_label), 0):
+    if require_new_class and pk.n_a > 0 and pk.min_new > max(int(max_label), 0):
         # no GT new-class pixel in the batch: the reference raises at utils/loss.py:355 (min() of empty)
         raise RuntimeError("pre_contrastive_pixel: no new-class pixel in the batch "
                            "(the reference raises here too, utils/loss.py:355)")
@@ -459,7 +509,7 @@ class JointProb:
         pa = p[anchor]
         pc = torch.cat([pa, p[pseudo]])
         P = pa @ pc.T
-        la, lc = pk.la[:pk.n_a], pk.lc[:pk.n_c]
+        la, lc = pk.la[:pk.n_a].to(torch.int32), pk.lc[:pk.n_c].to(torch.int32)
         P[(la >= pk.min_new)[:, None] & (lc >= pk.min_new)[None, :]] = 1.0
         return P
 
@@ -471,18 +521,84 @@ def _label_dtype(max_label):
     return torch.int8 if max_label <= 127 else torch.int32
 
 
-def pre_contrastive_pixel(f_n, l_n, l_po=None, f_o=None, max_label=20):
-    """Drop-in for utils/loss.py:258 ``pre_contrastive_pixel`` (v2 branch, the one ``train.py`` reaches).
+class _RowsFn(torch.autograd.Function):
+    """Every pixel of f [B,256,h,w] as a unit-norm row [B*h*w, 256] (utils/loss.py:273-276 + F.normalize)."""
 
-    Returns the 5-tuple ``(Output_anchor, Output_contrast, Lable_anchor, Lable_contrast, JM_p)`` in the
-    reference's row order; ``JM_p`` is a :class:`JointProb` handle (call ``.dense()`` for the matrix).
+    @staticmethod
+    def forward(ctx, f):
+        x = _f32c(f)
+        B, D, h, w = x.shape
+        rows = torch.empty(B * h * w, D, device=x.device, dtype=torch.float32)
+        inv = torch.empty(B * h * w, device=x.device, dtype=torch.float32)
+        check(_lib.lib().ucd_rows_normalize_fwd(ptr(x), ptr(rows), ptr(inv), B, h, w, cur_stream()), "rows_normalize_fwd")
+        ctx.save_for_backward(rows, inv)
+        ctx.shape, ctx.in_dtype = (B, D, h, w), f.dtype
+        return rows
+
+    @staticmethod
+    def backward(ctx, g):
+        rows, inv = ctx.saved_tensors
+        B, D, h, w = ctx.shape
+        df = torch.empty(B, D, h, w, device=g.device, dtype=torch.float32)
+        check(_lib.lib().ucd_rows_normalize_bwd(ptr(_f32c(g)), ptr(rows), ptr(inv), ptr(df), B, h, w, cur_stream()),
+              "rows_normalize_bwd")
+        return df.to(ctx.in_dtype)
+
+
+def _pixel_to_pixel(f_n, l_n, f_o, max_label):
+    """The branches of utils/loss.py:278-289 (no old-model logits): all pixels, labels = the clamped low-res label map."""
+    _need_cuda(f_n, l_n, f_o)
+    if f_n.dim() != 4 or f_n.shape[1] != FEAT_DIM or (f_o is not None and f_o.shape != f_n.shape):
+        raise ValueError("pre_contrastive_pixel: f_n / f_o must be [B,%d,h,w]" % FEAT_DIM)
+    B, _, h, w = f_n.shape
+    if l_n.dim() != 3 or l_n.shape[0] != B:
+        raise ValueError("pre_contrastive_pixel: l_n must be [B,H,W]")
+    L = _lib.lib()
+    dev = f_n.device
+    labels = l_n.to(torch.int64).contiguous()
+    H, W = labels.shape[-2:]
+    n_px = B * h * w
+    i32 = dict(device=dev, dtype=torch.int32)
+    # the label kernel of the v2 path with a one-channel dummy old-model map (its argmax is 0 everywhere): plane 0 of
+    # px_meta is the reference's label_n (bilinear downsample, truncation, clamp to [0, max_label]; loss.py:261-270)
+    px_meta = torch.empty(7, n_px, **i32)
+    blk_meta = torch.empty(L.ucd_con_blk_meta_ints(n_px, L.ucd_con_num_bins(int(max_label), 1)), **i32)
+    counts = torch.empty(4, **i32)
+    dummy = torch.zeros(B, 1, h, w, device=dev, dtype=torch.float32)
+    check(L.ucd_con_prep_labels(ptr(labels), ptr(dummy), B, 1, h, w, H, W, int(max_label), ptr(px_meta), ptr(blk_meta),
+                                ptr(counts), None, cur_stream()), "con_prep_labels")
+    lab = px_meta[0].to(_label_dtype(int(max_label)))
+    out = _RowsFn.apply(f_n)
+    if f_o is not None:   # "pixel to pixel double": new-model rows, then the (detached) old-model rows
+        out = torch.cat((out, _RowsFn.apply(f_o.detach())), dim=0)
+        lab = torch.cat((lab, lab))
+    return out.unsqueeze(1), lab
+
+
+def pre_contrastive_pixel(f_n, l_n, l_po=None, f_o=None, max_label=20, require_new_class=None):
+    """Drop-in for utils/loss.py:258 ``pre_contrastive_pixel``.
+
+    With ``l_po`` and ``f_o`` (the v2 branch ``train.py`` reaches) it returns the 5-tuple ``(Output_anchor,
+    Output_contrast, Lable_anchor, Lable_contrast, JM_p)`` in the reference's row order; ``JM_p`` is a
+    :class:`JointProb` handle (call ``.dense()`` for the matrix).  Without ``l_po`` it returns ``(Output.unsqueeze(1),
+    Lable)`` of the pixel-to-pixel branches (loss.py:278-289: all pixels; with ``f_o`` the old-model rows are appended).
+    ``l_po`` without ``f_o`` raises like the reference does (its ``Output`` is undefined there, loss.py:399).
     ``max_label`` generalises the reference's hard-coded VOC clamp ``label_n > 20 -> 0`` (loss.py:270).
+
+    ``require_new_class``: the reference raises when the batch holds no new-class pixel (``min()`` of an empty tensor,
+    loss.py:355).  True keeps that; False never raises (the GT-new override of P then simply never fires).  The default
+    None means True in a single process and False when a multi-rank process group is initialised: there one rank
+    raising alone would leave the other ranks blocked in the exchange collectives of ``PixelConLossV2(gather_negatives
+    =True)``, and the threshold that matters is the global minimum anyway.
     """
-    if l_po is None or f_o is None:
-        raise NotImplementedError(
-            "ucd_b200.pre_contrastive_pixel implements the l_po+f_o (v2) branch used by the UCD trainer; "
-            "the single/double pixel-to-pixel branches (utils/loss.py:278-289) are outside this hot path")
-    pack = _build_pack(f_n.detach(), f_o.detach(), l_po.detach(), l_n, max_label)
+    if l_po is None:
+        return _pixel_to_pixel(f_n, l_n, f_o, max_label)
+    if f_o is None:
+        raise UnboundLocalError("pre_contrastive_pixel: l_po without f_o is undefined in the reference too "
+                                "(utils/loss.py:399 returns an unassigned `Output`)")
+    if require_new_class is None:
+        require_new_class = not _multi_rank()
+    pack = _build_pack(f_n.detach(), f_o.detach(), l_po.detach(), l_n, max_label, require_new_class=require_new_class)
     anchor = _AnchorFn.apply(f_n, pack)
     out = (anchor, pack.contrast_f32[:pack.n_c], pack.la[:pack.n_a], pack.lc[:pack.n_c], JointProb(pack))
     return out
@@ -494,56 +610,75 @@ pre_contractive_pixel = pre_contrastive_pixel  # spelling used by utils/utils.py
 # ----------------------------------------------------------------------------------------------
 # PixelConLossV2
 # ----------------------------------------------------------------------------------------------
-def _all_gather(t, group):
-    import torch.distributed as dist
-    world = dist.get_world_size(group)
-    t = t.contiguous()
-    out = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), device=t.device, dtype=t.dtype)
-    dist.all_gather_into_tensor(out, t, group=group)      # concatenation along dim 0 (gloo and nccl agree)
-    return out.view((world,) + tuple(t.shape))
+def _local_cols(pack):
+    """Column-side arguments of the sweeps for this rank's own pack (single chunk)."""
+    return dict(feat=pack.feat_tiles, prob=pack.prob_tiles, lab=pack.lab_tiles, range=pack.tile_range,
+                counts=pack.counts, n_chunks=1, chunk_tiles=pack.max_tiles, kpad=pack.kpad, min_new=pack.counts[2:3],
+                payload=pack.payload)
 
 
-def gather_contrast_columns(feat_tiles, prob_tiles, lab_tiles, tile_range, counts, group):
-    """The one exchange step of the data-parallel path: every rank contributes its packed
-    contrast columns; rank r's tiles become chunk r of the gathered buffers.
+def gather_contrast_columns(payload, max_tiles, kpad, group, async_op=False):
+    """The one exchange step of the data-parallel path: a SINGLE all-gather of every rank's payload
+    (:func:`payload_layout`); rank r's columns become chunk r of the gathered buffer.  ``max_tiles`` / ``kpad`` must be
+    equal on all ranks (same per-rank pixel count and old-class count).
 
-    feat_tiles [T,32,128,8] bf16, prob_tiles [T,Kp/8,128,8] bf16, lab_tiles [T,128] int32, tile_range [T,2]
-    int32 and counts int32[>=3] = {N_a, N_o, min_new} of this rank (T must be equal on all ranks).
-    Returns dict(feat, prob, lab, range, counts [W,2], min_new [1] (global MIN), n_chunks, chunk_tiles, self_tile0).
-    No gradient flows through the gathered columns (they are detached in the reference, loss.py:366,395),
-    so backward needs no collective.
-    """
+    Returns dict(buf [W, nbytes] uint8, feat / prob / lab / range / counts = typed views [W, ...], n_chunks,
+    chunk_tiles, chunk_stride (bytes), self_tile0, work).  The global GT-new threshold is the minimum of
+    ``counts[:, 2]`` - the sweeps take it from the headers, no MIN all-reduce.  With ``async_op=True`` the collective is
+    only enqueued (NCCL stream) and ``work.wait()`` must be called before the gathered buffer is consumed: sweep 1 over
+    the LOCAL columns runs in between.  No gradient flows through the gathered columns (they are detached in the
+    reference, loss.py:366,395), so backward needs no collective."""
     import torch.distributed as dist
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    min_new = counts[2:3].clone()
-    dist.all_reduce(min_new, op=dist.ReduceOp.MIN, group=group)
-    return dict(feat=_all_gather(feat_tiles, group), prob=_all_gather(prob_tiles, group),
-                lab=_all_gather(lab_tiles, group), range=_all_gather(tile_range, group),
-                counts=_all_gather(counts[:2], group), min_new=min_new,
-                n_chunks=world, chunk_tiles=feat_tiles.shape[0], self_tile0=rank * feat_tiles.shape[0])
+    payload = payload.contiguous()
+    buf = torch.empty(world, payload.numel(), device=payload.device, dtype=torch.uint8)
+    work = dist.all_gather_into_tensor(buf.view(-1), payload, group=group, async_op=async_op)
+    out = payload_views(buf, max_tiles, kpad)
+    out.update(buf=buf, n_chunks=world, chunk_tiles=max_tiles, chunk_stride=payload.numel(),
+               self_tile0=rank * max_tiles, rank=rank, work=work if async_op else None)
+    return out
 
 
 class _ConFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, anchor, cols, rows, inv_tau, p_mode, dense_p, group, ddp_scale):
-        """cols / rows: dicts of device buffers (see PixelConLossV2._run)."""
+        """cols / rows: dicts of device buffers (see PixelConLossV2.forward).  With a process group, ``cols`` holds the
+        LOCAL payload; the all-gather of all ranks' payloads is enqueued first and sweep 1 over the local columns runs
+        while it is in flight."""
         L = _lib.lib()
         dev = anchor.device
         max_row_tiles = rows["max_tiles"]
         plan_tiles = rows.get("plan_tiles", 0)
-        ws_bytes = L.ucd_con_workspace_bytes(max_row_tiles, cols["n_chunks"] * cols["chunk_tiles"], plan_tiles)
-        ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
         out = torch.empty(3, device=dev, dtype=torch.float32)
         need_grad = bool(ctx.needs_input_grad[0])
         grad_unit = (torch.empty(max_row_tiles * TILE, FEAT_DIM, device=dev, dtype=torch.float32)
                      if need_grad else None)
-        check(L.ucd_con_fwd(ptr(cols["feat"]), ptr(cols["prob"]), ptr(cols["lab"]), ptr(cols["counts"]),
-                            cols["n_chunks"], cols["chunk_tiles"], ptr(rows["feat"]), ptr(rows["prob"]),
-                            ptr(rows["lab"]), ptr(rows["n_rows"]), ptr(cols["range"]), ptr(rows["range"]),
-                            rows["self_tile0"], ptr(cols["min_new"]), p_mode,
-                            cols["kpad"], ptr(dense_p), 0 if dense_p is None else dense_p.shape[1], inv_tau,
-                            1 if need_grad else 0, ptr(out), ptr(grad_unit), ptr(ws), ws_bytes, max_row_tiles,
-                            plan_tiles, cur_stream()), "con_fwd")
+
+        def run(c, part, n_chunks, stride, local_chunk, self_tile0, ws, ws_bytes):
+            check(L.ucd_con_fwd(ptr(c["feat"]), ptr(c["prob"]), ptr(c["lab"]), ptr(c["counts"]), n_chunks,
+                                c["chunk_tiles"], stride, local_chunk, part, ptr(rows["feat"]), ptr(rows["prob"]),
+                                ptr(rows["lab"]), ptr(rows["n_rows"]), ptr(c["range"]), ptr(rows["range"]),
+                                self_tile0, ptr(c["min_new"]), p_mode, c["kpad"], ptr(dense_p),
+                                0 if dense_p is None else dense_p.shape[1], inv_tau, 1 if need_grad else 0, ptr(out),
+                                ptr(grad_unit), ptr(ws), ws_bytes, max_row_tiles, plan_tiles, cur_stream()),
+                  "con_fwd")
+
+        if group is None:
+            ws_bytes = L.ucd_con_workspace_bytes(max_row_tiles, cols["n_chunks"] * cols["chunk_tiles"], plan_tiles, 0)
+            ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+            run(cols, 0, cols["n_chunks"], 0, -1, rows["self_tile0"], ws, ws_bytes)
+        else:
+            # one all-gather of the payloads, overlapped with sweep 1 over the local columns
+            g = gather_contrast_columns(cols["payload"], cols["chunk_tiles"], cols["kpad"], group, async_op=True)
+            world, rank, T = g["n_chunks"], g["rank"], cols["chunk_tiles"]
+            ws_bytes = L.ucd_con_workspace_bytes(max_row_tiles, world * T, plan_tiles, T)
+            ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+            run(cols, 1, world, g["chunk_stride"], rank, g["self_tile0"], ws, ws_bytes)
+            g["work"].wait()   # the current stream waits for the gathered buffer; the host does not
+            gc = dict(feat=g["feat"][0], prob=g["prob"][0], lab=g["lab"][0], range=g["range"][0],
+                      counts=g["counts"][0], min_new=g["counts"][0, 2:3], chunk_tiles=T, kpad=cols["kpad"])
+            run(gc, 2, world, g["chunk_stride"], rank, g["self_tile0"], ws, ws_bytes)
+            ctx.gathered = g["buf"]   # keep the buffer alive until the kernels that read it have run
         world = 1
         if group is not None:
             import torch.distributed as dist
@@ -598,6 +733,7 @@ class PixelConLossV2(nn.Module):
         self.process_group = process_group
         # under DDP's gradient averaging the exact global-batch gradient needs the local part scaled by world
         self.ddp_grad_scale = ddp_grad_scale
+        self.max_dense_bytes = 2 << 30   # largest dense P the compat fallback may materialise (see forward)
         print(temperature)  # the reference prints it on construction (utils/loss.py:410)
 
     # -- helpers ---------------------------------------------------------------------------------
@@ -617,26 +753,31 @@ class PixelConLossV2(nn.Module):
         dev = anchor_features.device
         pack = P.pack if isinstance(P, JointProb) else None
         if pack is not None and not (anchor_features.data_ptr() == pack.anchor_f32.data_ptr()
-                                     and anchor_features.shape[0] == pack.n_a):
-            P, pack = P.dense(), None  # handle used with foreign features: fall back to its dense matrix
+                                     and anchor_features.shape[0] == pack.n_a
+                                     and anchor_features.dtype == torch.float32):
+            # the handle came with other features than the ones it was packed from (a cast, clone or slice of the
+            # anchors): the sweeps must run on the caller's values, so the operands are re-packed (compat path) and P
+            # is materialised - N_a x N_c fp32.  Never silently: this is ~1000x the memory of the fused path.
+            import warnings
+            n_bytes = 4.0 * pack.n_a * pack.n_c
+            msg = ("PixelConLossV2: anchor_features is not the tensor pre_contrastive_pixel returned (cast / clone / "
+                   "slice?): falling back to a dense %d x %d joint-probability matrix (%.2f GB).  Pass the tuple "
+                   "through unchanged, or use PixelContrastiveDistillation." % (pack.n_a, pack.n_c, n_bytes / 1e9))
+            if n_bytes > self.max_dense_bytes:
+                raise RuntimeError(msg + "  Refusing: above max_dense_bytes=%d." % self.max_dense_bytes)
+            warnings.warn(msg, RuntimeWarning, stacklevel=2)
+            P, pack = P.dense(), None
         if pack is not None:
             # ---- fast path: operands packed by pre_contrastive_pixel ----
             group = self._group()
-            counts2 = pack.counts[:2]
             rows = dict(feat=pack.feat_tiles, prob=pack.prob_tiles, lab=pack.lab_tiles, n_rows=pack.counts[0:1],
-                        range=pack.row_range, row_ref=pack.row_ref, max_tiles=(pack.n_a + TILE - 1) // TILE,
+                        range=pack.row_range, row_ref=pack.row_ref, max_tiles=max(1, (pack.n_a + TILE - 1) // TILE),
                         self_tile0=0)
-            if group is None:
-                cols = dict(feat=pack.feat_tiles, prob=pack.prob_tiles, lab=pack.lab_tiles, range=pack.tile_range,
-                            counts=counts2.contiguous(), n_chunks=1, chunk_tiles=pack.max_tiles, kpad=pack.kpad,
-                            min_new=pack.counts[2:3])
-            else:
-                cols = gather_contrast_columns(pack.feat_tiles, pack.prob_tiles, pack.lab_tiles, pack.tile_range,
-                                               pack.counts, group)
-                cols["kpad"] = pack.kpad
-                rows["self_tile0"] = cols["self_tile0"]
-            if pack.n_a == 0:
+            cols = _local_cols(pack)
+            if pack.n_a == 0 and group is None:
                 return anchor_features.sum() * 0.0
+            # with a process group every rank must take part in the collectives, anchors or not: the kernels exit for
+            # row blocks beyond N_a and this rank then contributes {0, 0} to the global sums
             return _ConFn.apply(anchor_features, cols, rows, inv_tau, 1, None, group, self.ddp_grad_scale)
 
         # ---- compat path: dense caller-supplied tensors ----
@@ -645,6 +786,12 @@ class PixelConLossV2(nn.Module):
         n_a, n_c = anchor_features.shape[0], contrast_feature.shape[0]
         if n_a == 0 or n_c == 0:
             return anchor_features.sum() * 0.0
+        if contrast_feature.requires_grad and torch.is_grad_enabled():
+            # the reference back-propagates through contrast_feature when it carries a graph (utils/loss.py:445-466);
+            # the sweeps only form d loss / d anchor_features (the v2 prep detaches the contrast side, loss.py:366)
+            raise RuntimeError("PixelConLossV2: contrast_feature requires grad, but this implementation only "
+                               "differentiates w.r.t. anchor_features (the UCD prep detaches the contrast side, "
+                               "utils/loss.py:366); pass contrast_feature.detach() if that is what you mean")
         a32, c32 = _f32c(anchor_features.detach()), _f32c(contrast_feature.detach())
         la = anchor_labels.reshape(-1).to(device=dev, dtype=torch.int32).contiguous()
         lc = contrast_labels.reshape(-1).to(device=dev, dtype=torch.int32).contiguous()
@@ -713,15 +860,7 @@ class PixelContrastiveDistillation(nn.Module):
                     range=pack.row_range, row_ref=pack.row_ref, max_tiles=cap_tiles, self_tile0=0,
                     plan_tiles=plan_tiles, static_pack=pack)
         group = self._group()
-        if group is None:
-            cols = dict(feat=pack.feat_tiles, prob=pack.prob_tiles, lab=pack.lab_tiles, range=pack.tile_range,
-                        counts=pack.counts[:2].contiguous(), n_chunks=1, chunk_tiles=pack.max_tiles, kpad=pack.kpad,
-                        min_new=pack.counts[2:3])
-        else:
-            cols = gather_contrast_columns(pack.feat_tiles, pack.prob_tiles, pack.lab_tiles, pack.tile_range,
-                                           pack.counts, group)
-            cols["kpad"] = pack.kpad
-            rows["self_tile0"] = cols["self_tile0"]
+        cols = _local_cols(pack)
         return _ConFn.apply(f_n, cols, rows, 1.0 / float(self.temperature), 1, None, group, self.ddp_grad_scale)
 
 
