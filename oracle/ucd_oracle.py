@@ -140,15 +140,19 @@ class LabelPrep:
     min_new: int            # min over GT-new labels
 
 
-def prep_labels(labels, l_po, max_label: int = 20) -> LabelPrep:
-    """utils/loss.py:354-361 (v2 branch)."""
+NO_NEW = 0x7f7f7f7f   # min_new of a batch without any new-class pixel (only with require_new=False)
+
+
+def prep_labels(labels, l_po, max_label: int = 20, require_new: bool = True) -> LabelPrep:
+    """utils/loss.py:354-361 (v2 branch).  ``require_new=False`` (rank-sharded oracle: the threshold is the minimum
+    over all ranks) returns min_new = NO_NEW instead of raising when this batch has no new-class pixel."""
     l_po = np.asarray(l_po, F32)
     B, _, h, w = l_po.shape
     g = downsample_labels(labels, h, w, max_label)
     is_new = g.reshape(-1) > 0
-    if not is_new.any():
+    if not is_new.any() and require_new:
         raise ValueError("no new-class pixel in the batch (reference raises at utils/loss.py:355)")
-    min_new = int(g.reshape(-1)[is_new].min())
+    min_new = int(g.reshape(-1)[is_new].min()) if is_new.any() else NO_NEW
     pseudo = np.argmax(l_po, axis=1).astype(np.int64)   # first maximal index, like torch.max
     mix = np.where(g > 0, g, pseudo)
     anchor = mix.reshape(-1) > 0
@@ -500,9 +504,11 @@ def pre_contrastive_pixel_global(f_n_list: Sequence[torch.Tensor], labels_list, 
     """Rank-sharded extension: rows stay per rank, columns are the concatenation over ranks of
     every rank's [anchors ; pseudo] block, min_new is the global minimum.  Returns per-rank
     (A_r, la_r, P_r, self_col_r) plus the shared (Cst, lc)."""
-    preps = [prep_labels(l.cpu().numpy(), lp.detach().cpu().numpy(), max_label)
+    preps = [prep_labels(l.cpu().numpy(), lp.detach().cpu().numpy(), max_label, require_new=False)
              for l, lp in zip(labels_list, l_po_list)]
     min_new = min(p.min_new for p in preps)
+    if min_new == NO_NEW:
+        raise ValueError("no new-class pixel in the global batch (reference raises at utils/loss.py:355)")
     A_l, C_l, la_l, lc_l, pa_l, pc_l, off = [], [], [], [], [], [], []
     col = 0
     for prep, f_n, f_o, l_po in zip(preps, f_n_list, f_o_list, l_po_list):

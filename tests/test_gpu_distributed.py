@@ -4,6 +4,7 @@ shape: 3 images, 32x32 embeddings), the payloads are all-gathered while sweep 1 
 loss / gradients must match the rank-sharded oracle (== the reference on the rank-concatenated batch).  A rank whose
 batch holds no new-class pixel (and one without any anchor) must neither raise nor leave the others blocked in a
 collective."""
+import datetime
 import os
 
 import pytest
@@ -19,7 +20,9 @@ pytestmark = pytest.mark.gpu
 def _worker(rank, world, port, ret):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    # short collective timeout: a mismatch between the ranks must fail this test in a minute, not hold the box
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank),
+                            timeout=datetime.timedelta(seconds=90))
     try:
         import ucd_b200 as U
         cases = [O.synthetic_case(3, 32, 32, 512, 512, 17, 16, rank=r, correlated=True) for r in range(world)]

@@ -449,7 +449,7 @@ def test_foreign_anchor_tensor_is_loud(U):
     ref = con(*tup)
     with pytest.warns(RuntimeWarning, match="dense"):
         out = con(tup[0].clone(), *tup[1:])
-    assert out.item() == pytest.approx(ref.item(), rel=1e-4)
+    assert out.item() == pytest.approx(ref.item(), rel=REL)   # fp32 dense P vs the bf16 probability tiles
     con.max_dense_bytes = 16
     with pytest.raises(RuntimeError, match="max_dense_bytes"):
         con(tup[0].clone(), *tup[1:])

@@ -481,6 +481,8 @@ class _AnchorFn(torch.autograd.Function):
         pk = ctx.pack
         B, h, w = pk.shape
         g = _f32c(g)
+        if pk.n_a == 0:   # no anchor in this batch: nothing flows back
+            return torch.zeros(B, FEAT_DIM, h, w, device=g.device, dtype=ctx.in_dtype), None
         df = torch.empty(B, FEAT_DIM, h, w, device=g.device, dtype=torch.float32)
         check(_lib.lib().ucd_con_prep_bwd(ptr(g), ptr(pk.anchor_f32), ptr(pk.inv_norm), ptr(pk.px_meta),
                                           ptr(pk.blk_meta), ptr(df), B, h, w, cur_stream()), "con_prep_bwd")
@@ -600,6 +602,7 @@ def pre_contrastive_pixel(f_n, l_n, l_po=None, f_o=None, max_label=20, require_n
         require_new_class = not _multi_rank()
     pack = _build_pack(f_n.detach(), f_o.detach(), l_po.detach(), l_n, max_label, require_new_class=require_new_class)
     anchor = _AnchorFn.apply(f_n, pack)
+    anchor._ucd_pack = pack   # lets PixelConLossV2 recognise the tensor it may run the packed operands for
     out = (anchor, pack.contrast_f32[:pack.n_c], pack.la[:pack.n_a], pack.lc[:pack.n_c], JointProb(pack))
     return out
 
@@ -697,6 +700,8 @@ class _ConFn(torch.autograd.Function):
     def backward(ctx, g):
         grad_unit, out, n_rows, row_ref = ctx.saved_tensors
         d_anchor = torch.empty(ctx.n_a, FEAT_DIM, device=g.device, dtype=torch.float32)
+        if ctx.n_a == 0:   # a rank without anchors (it only took part in the collectives)
+            return d_anchor.to(ctx.in_dtype), None, None, None, None, None, None, None
         # With DDP averaging parameter gradients over ranks, the exact gradient of the global-batch loss needs
         # each rank's local contribution scaled by world (columns carry no gradient, loss.py:366,395).
         check(_lib.lib().ucd_con_bwd(ptr(grad_unit), ptr(out), ptr(_f32c(g.reshape(1))), float(ctx.world),
@@ -752,9 +757,12 @@ class PixelConLossV2(nn.Module):
         L = _lib.lib()
         dev = anchor_features.device
         pack = P.pack if isinstance(P, JointProb) else None
-        if pack is not None and not (anchor_features.data_ptr() == pack.anchor_f32.data_ptr()
-                                     and anchor_features.shape[0] == pack.n_a
-                                     and anchor_features.dtype == torch.float32):
+        # the tuple's first slot carries its pack; a view of the packed rows is accepted too (an empty tensor has no
+        # data pointer, so N_a == 0 is decided by the tag or the shape alone)
+        own = pack is not None and (getattr(anchor_features, "_ucd_pack", None) is pack or (
+            anchor_features.dtype == torch.float32 and tuple(anchor_features.shape) == (pack.n_a, FEAT_DIM)
+            and (pack.n_a == 0 or anchor_features.data_ptr() == pack.anchor_f32.data_ptr())))
+        if pack is not None and not own:
             # the handle came with other features than the ones it was packed from (a cast, clone or slice of the
             # anchors): the sweeps must run on the caller's values, so the operands are re-packed (compat path) and P
             # is materialised - N_a x N_c fp32.  Never silently: this is ~1000x the memory of the fused path.
