@@ -2,15 +2,22 @@
 """Benchmark of the UCD distillation-loss hot path (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+                    [--workload voc|ade|city|sweep:<pixels>] [--batch B]
 
 One "step" = one pass of the hot path over one synthetic batch, forward + backward:
   bilinear logit upsample (new: grad, old: no grad) -> pre_contrastive_pixel -> PixelConLossV2
   -> UnbiasedCrossEntropy(...).mean() + con/100 + 10 * UnbiasedKnowledgeDistillationLoss -> backward
 through the reference-shaped modules of ucd_b200 (train.py:115-116,133 wiring).
 
-Workload at every N: BASELINE configs[1] per GPU - VOC 15-5s step 1 (17 classes, 16 old), batch 24 at
-512x512 (32x32 embeddings, D=256).  Weak scaling: each rank holds its own 24 images; with N>1 the
-contrast columns are all-gathered over NCCL so negatives span the global batch.
+Workloads (BASELINE.json configs; default = configs[1] held on one GPU, which is what the metric is quoted on):
+  voc    VOC 15-5s step 1, 17/16 classes, batch 24 @512x512 per GPU (32x32 embeddings); --batch 3 = the real per-GPU
+         batch of configs[1] on 8 GPUs
+  ade    ADE 100-50 step 1, 151/101 classes, batch 3 @512x512 (wide log-softmax, K = 112 joint probability)
+  city   Cityscapes 13-6 step 1, 20/14 classes, batch 3 @512x1024 (32x64 embeddings)
+  sweep:<px>  contrastive term only (prep + loss, fwd + bwd), VOC-like 21/16 classes, <px> pixels per GPU as images of
+         32x32 (configs[4]: 8k .. 256k pixels per GPU)
+Weak scaling: each rank holds its own images; with N>1 the contrast columns of all ranks are exchanged (one
+all-gather over NCCL, overlapped with the sweep over the local columns) so negatives span the global batch.
 metric = pixel pairs (N_a local x N_c global, summed over ranks) per second, in Mpairs/s.
 """
 import argparse
@@ -29,14 +36,45 @@ if ROOT not in sys.path:
 
 METRIC = "ucd_loss_fwd_bwd_pixel_pairs_per_s"
 UNIT = "Mpixel-pairs/s"
-WORKLOAD = dict(name="VOC 15-5s step 1, batch 24 @512x512 per GPU", B=24, h=32, w=32, H=512, W=512, C=17, C_old=16)
-CPU_SAMPLE_B = 3   # images in the bounded CPU sample of the same workload (N^2 fp32 temporaries limit the CPU)
+WORKLOADS = {
+    "voc": dict(name="VOC 15-5s step 1, batch 24 @512x512 per GPU", B=24, h=32, w=32, H=512, W=512, C=17, C_old=16,
+                max_label=20, cpu_sample_B=3),
+    "ade": dict(name="ADE20K 100-50 step 1, batch 3 @512x512 per GPU", B=3, h=32, w=32, H=512, W=512, C=151, C_old=101,
+                max_label=150, cpu_sample_B=1),
+    "city": dict(name="Cityscapes 13-6 step 1, batch 3 @512x1024 per GPU", B=3, h=32, w=64, H=512, W=1024, C=20,
+                 C_old=14, max_label=20, cpu_sample_B=1),
+}
+WORKLOAD = WORKLOADS["voc"]   # default; scripts/ import it
 
-# kernels launched by each C-ABI entry point (for gpu_launches; memsets are not kernels)
+
+def get_workload(spec, batch):
+    if spec.startswith("sweep:"):
+        px = int(spec.split(":", 1)[1])
+        if px % 1024:
+            raise SystemExit("--workload sweep:<pixels>: pixels must be a multiple of 1024 (images of 32x32)")
+        wl = dict(name="contrastive sweep, %d pixels per GPU (VOC-like 21/16 classes, 32x32 embeddings)" % px,
+                  B=px // 1024, h=32, w=32, H=512, W=512, C=21, C_old=16, max_label=20, cpu_sample_B=3, con_only=True)
+    else:
+        if spec not in WORKLOADS:
+            raise SystemExit("--workload must be one of %s or sweep:<pixels>" % ", ".join(WORKLOADS))
+        wl = dict(WORKLOADS[spec], con_only=False)
+    if batch:
+        wl["name"] = wl["name"].replace("batch %d " % wl["B"], "batch %d " % batch)
+        wl["B"] = batch
+    wl["cpu_sample_B"] = min(wl["cpu_sample_B"], wl["B"])
+    return wl
+
+
+# kernels launched by each C-ABI entry point (for gpu_launches; memsets are not kernels).  ucd_con_fwd: sweep 1,
+# combine, sweep 2, finalize, reduce = 5 (a part-1 call launches sweep 1 only: counted from its `part` argument).
 KERNELS_PER_CALL = {"ucd_upsample_bilinear_fwd": 1, "ucd_upsample_bilinear_bwd": 1, "ucd_unce_fwd": 1,
                     "ucd_unce_bwd": 1, "ucd_kd_fwd": 2, "ucd_kd_bwd": 1, "ucd_con_prep_labels": 2,
                     "ucd_con_prep_pack": 4, "ucd_con_prep_bwd": 1, "ucd_con_fwd": 5, "ucd_con_bwd": 1,
-                    "ucd_con_pack_rows": 1}
+                    "ucd_con_pack_rows": 1, "ucd_seg_fused_fwd": 2, "ucd_rows_normalize_fwd": 1,
+                    "ucd_rows_normalize_bwd": 1, "ucd_con_tile_ranges": 1}
+HOST_ONLY_CALLS = ("ucd_last_error", "ucd_version", "ucd_device_ok", "ucd_con_max_tiles", "ucd_con_prob_kpad",
+                   "ucd_con_num_bins", "ucd_con_px_meta_ints", "ucd_con_blk_meta_ints", "ucd_con_workspace_bytes",
+                   "ucd_reduce_scratch_floats", "ucd_seg_fused_workspace_floats")
 
 
 def gen(seed, *shape, scale=1.0):
@@ -125,15 +163,15 @@ class ClockSampler:
 
 
 class CallTimer:
-    """Proxy around the ctypes library: records a CUDA-event pair on the current stream around every C-ABI call,
-    so per-kernel-group device times come from the same timed region as the headline number."""
+    """Proxy around the ctypes library: records a CUDA-event pair on the current stream around every C-ABI call that
+    launches kernels, so per-kernel-group device times come from the same timed region as the headline number."""
 
     def __init__(self, handle):
-        self._h, self.events, self.counts, self.enabled = handle, {}, {}, False
+        self._h, self.events, self.counts, self.launches, self.enabled = handle, {}, {}, 0, False
 
     def __getattr__(self, name):
         fn = getattr(self._h, name)
-        if not name.startswith("ucd_") or name in ("ucd_last_error", "ucd_version", "ucd_device_ok"):
+        if not name.startswith("ucd_") or name in HOST_ONLY_CALLS:
             return fn
 
         def wrapped(*args):
@@ -143,8 +181,14 @@ class CallTimer:
             e0.record()
             rc = fn(*args)
             e1.record()
-            self.events.setdefault(name, []).append((e0, e1))
-            self.counts[name] = self.counts.get(name, 0) + 1
+            key = name
+            k = KERNELS_PER_CALL.get(name, 1)
+            if name == "ucd_con_fwd":      # args[8] = part: 1 = sweep 1 over the local columns only
+                part = int(args[8])
+                key, k = name + (":local" if part == 1 else (":rest" if part == 2 else "")), (1 if part == 1 else 5)
+            self.events.setdefault(key, []).append((e0, e1))
+            self.counts[key] = self.counts.get(key, 0) + 1
+            self.launches += k
             return rc
         return wrapped
 
@@ -154,33 +198,43 @@ class CallTimer:
 
 def cpu_reference_sample(steps, warmup, wl):
     """The reference's CPU implementation of the path (oracle port, torch CPU, all host threads) on a bounded
-    sample of the workload: CPU_SAMPLE_B images of the same shapes."""
+    sample of the workload: cpu_sample_B images of the same shapes (the N^2 fp32 temporaries of the reference
+    formulation bound what the host can hold and finish in seconds)."""
     from oracle import ucd_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
-    case = make_inputs(0, CPU_SAMPLE_B, wl)
+    nb = wl["cpu_sample_B"]
+    case = make_inputs(0, nb, wl)
     times, pairs = [], 0
     for i in range(warmup + steps):
         t0 = time.perf_counter()
         f_n = case["f_n"].clone().requires_grad_(True)
-        lr = case["logits_lr"].clone().requires_grad_(True)
-        res = O.hot_path(f_n, case["f_o"], case["l_po"], lr, case["labels"].clone(), old_cl=wl["C_old"])
-        res.total.backward()
+        if wl["con_only"]:
+            A, Cst, la, lc, P, _ = O.pre_contrastive_pixel(f_n, case["labels"], case["l_po"], case["f_o"],
+                                                           max_label=wl["max_label"])
+            O.pixel_con_loss(A, Cst, la, lc, P).backward()
+            n_a, n_c = A.shape[0], Cst.shape[0]
+        else:
+            lr = case["logits_lr"].clone().requires_grad_(True)
+            res = O.hot_path(f_n, case["f_o"], case["l_po"], lr, case["labels"].clone(), old_cl=wl["C_old"],
+                             max_label=wl["max_label"])
+            res.total.backward()
+            n_a, n_c = res.n_anchor, res.n_contrast
         dt = time.perf_counter() - t0
-        pairs = res.n_anchor * res.n_contrast
+        pairs = n_a * n_c
         if i >= warmup:
             times.append(dt)
     ms = 1e3 * sum(times) / len(times)
+    what = "contrastive term" if wl["con_only"] else "whole path"
     return dict(value=pairs / (ms * 1e-3) / 1e6, unit=UNIT, cores=torch.get_num_threads(), kind="port",
-                sample="%d of the %d images of one step (N_a x N_c = %d pairs), fwd+bwd of the whole path, mean of %d steps"
-                       % (CPU_SAMPLE_B, wl["B"], pairs, len(times))), ms
+                sample="%d of the %d images of one step (N_a x N_c = %d pairs), fwd+bwd of the %s, mean of %d steps"
+                       % (nb, wl["B"], pairs, what, len(times)), ms_per_step=ms, pairs=pairs), ms
 
 
-def run_reference(args):
+def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    wl = WORKLOAD
-    steps, warmup = max(1, min(args.steps, 10)), max(1, min(args.warmup, 2))
+    steps, warmup = max(1, args.steps), max(0, args.warmup)   # as asked; each step is a bounded sample (seconds)
     cb, ms = cpu_reference_sample(steps, warmup, wl)
     line = dict(metric=METRIC, value=cb["value"], unit=UNIT, n_gpus=args.gpus, steps=steps, warmup=warmup,
                 ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
@@ -198,11 +252,15 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ucd_b200")
-    ap.add_argument("--batch", type=int, default=WORKLOAD["B"], help="images per GPU (default: the BASELINE config)")
+    ap.add_argument("--workload", default="voc", help="voc | ade | city | sweep:<pixels per GPU>")
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU (default: the workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the informational N1 / N4 legs")
+    ap.add_argument("--no-parity", action="store_true", help="N>1: skip the concatenated-batch parity check on rank 0")
     args = ap.parse_args()
+    wl = get_workload(args.workload, args.batch)
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, wl)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -220,9 +278,10 @@ def main():
     timer = CallTimer(_lib.lib())
     _lib._lib = timer
 
-    wl = dict(WORKLOAD, B=args.batch)
-    B, H, W, C_old = wl["B"], wl["H"], wl["W"], wl["C_old"]
+    B, H, W, C, C_old, max_label, con_only = wl["B"], wl["H"], wl["W"], wl["C"], wl["C_old"], wl["max_label"], wl["con_only"]
     host = make_inputs(rank, B, wl)
+    if con_only:
+        host.pop("logits_lr")
     # the dataloader hands labels over as uint8 and the trainer casts them on the device (train.py:97-98,
     # dataset/transform.py:350): the end-to-end leg copies uint8 labels and casts after the copy, like the reference
     pinned = {k: (v.to(torch.uint8) if k == "labels" else v).pin_memory() for k, v in host.items()}
@@ -234,12 +293,18 @@ def main():
 
     def step(inp):
         f_n = inp["f_n"].detach().requires_grad_(True)
+        if con_only:
+            tup = U.pre_contrastive_pixel(f_n, inp["labels"], l_po=inp["l_po"], f_o=inp["f_o"], max_label=max_label)
+            con = conloss(*tup)
+            (con / 100).backward()
+            state.update(n_a=tup[0].shape[0], n_c=tup[1].shape[0], con=con.detach(), g_fn=f_n.grad)
+            return con
         lr = inp["logits_lr"].detach().requires_grad_(True)
         outputs = U.interpolate_bilinear(lr, (H, W))
         with torch.no_grad():
             outputs_old = U.interpolate_bilinear(inp["l_po"], (H, W))
         # evaluation order of train.py:115-116,133: prep, criterion, contrastive loss, distillation
-        tup = U.pre_contrastive_pixel(f_n, inp["labels"], l_po=inp["l_po"], f_o=inp["f_o"])
+        tup = U.pre_contrastive_pixel(f_n, inp["labels"], l_po=inp["l_po"], f_o=inp["f_o"], max_label=max_label)
         ce = unce(outputs, inp["labels"]).mean()
         con = conloss(*tup)
         kd = unkd(outputs, outputs_old)
@@ -254,6 +319,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed(fn, n):
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(n):
+            fn()
+        a1.record()
+        barrier()
+        return a0.elapsed_time(a1) / n
+
     # ---- device-resident timing (value) ----
     for _ in range(args.warmup):
         step(devin)
@@ -262,123 +336,127 @@ def main():
     if rank == 0:
         sampler.start()
     timer.enabled = True
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step(devin)
-    e1.record()
-    barrier()
+    t_wall0 = time.perf_counter()
+    ms_dev = timed(lambda: step(devin), args.steps)
+    timed_region_s = time.perf_counter() - t_wall0
     timer.enabled = False
     clocks = sampler.stop() if rank == 0 else None
-    ms_dev = e0.elapsed_time(e1) / args.steps
     call_ms = {k: v / args.steps for k, v in timer.totals_ms().items()}
-    launches = sum(KERNELS_PER_CALL.get(k, 1) * v for k, v in timer.counts.items())
+    launches = timer.launches
+    g_rank0 = state["g_fn"].clone()
+    con_multi = float(state["con"])
 
-    # ---- the same step with the opt-in N1 fusion (FusedUnbiasedLosses: no full-res logits), for information ----
-    fused = U.FusedUnbiasedLosses(old_cl=C_old, ignore_index=255, alpha=1.0)
-
-    def step_fused(inp):
-        f_n = inp["f_n"].detach().requires_grad_(True)
-        lr = inp["logits_lr"].detach().requires_grad_(True)
-        tup = U.pre_contrastive_pixel(f_n, inp["labels"], l_po=inp["l_po"], f_o=inp["f_o"])
-        con = conloss(*tup)
-        ce, kd = fused(lr, inp["l_po"], inp["labels"])
-        (ce + con / 100 + 10 * kd).backward()
-
-    for _ in range(3):
-        step_fused(devin)
-    barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    for _ in range(args.steps):
-        step_fused(devin)
-    f1.record()
-    barrier()
-    ms_fused = f0.elapsed_time(f1) / args.steps
-
-    # ---- opt-in sync-free step (N1 fused CE/KD + N4 contrastive without the 5-tuple), for information: eager, and
-    #      (single GPU) forward + backward replayed from one CUDA graph ----
-    con_static = U.PixelContrastiveDistillation(temperature=0.07, gather_negatives=world > 1)
-    gs = {k: devin[k].clone() for k in ("f_n", "f_o", "l_po", "logits_lr", "labels")}
-    gs["f_n"].requires_grad_(True), gs["logits_lr"].requires_grad_(True)
-
-    def step_static():
-        gs["f_n"].grad = gs["logits_lr"].grad = None
-        ce, kd = fused(gs["logits_lr"], gs["l_po"], gs["labels"])
-        (ce + con_static(gs["f_n"], gs["labels"], gs["l_po"], gs["f_o"]) / 100 + 10 * kd).backward()
-
-    def timed(fn):
+    # ---- the GPU arm at the CPU arm's sample size: a like-for-like ratio for the reference arm ----
+    ms_sample, pairs_sample = None, None
+    if world == 1 and wl["cpu_sample_B"] != B:
+        small = {k: v[:wl["cpu_sample_B"]].contiguous() for k, v in devin.items()}
         for _ in range(3):
-            fn()
+            step(small)
         barrier()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        for _ in range(args.steps):
-            fn()
-        a1.record()
+        ms_sample = timed(lambda: step(small), args.steps)
+        pairs_sample = state["n_a"] * state["n_c"]
+        step(devin)   # restore `state` for the legs below
         barrier()
-        return a0.elapsed_time(a1) / args.steps
 
-    ms_static = timed(step_static)
-    ms_graph = None
-    if world == 1:
-        try:
-            if hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
-                torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                step_static()
-            torch.cuda.current_stream().wait_stream(side)
+    ms_fused = ms_static = ms_graph = None
+    if not con_only and not args.no_extras:
+        # ---- the same step with the opt-in N1 fusion (FusedUnbiasedLosses: no full-res logits), for information ----
+        fused = U.FusedUnbiasedLosses(old_cl=C_old, ignore_index=255, alpha=1.0)
+
+        def step_fused():
+            f_n = devin["f_n"].detach().requires_grad_(True)
+            lr = devin["logits_lr"].detach().requires_grad_(True)
+            tup = U.pre_contrastive_pixel(f_n, devin["labels"], l_po=devin["l_po"], f_o=devin["f_o"], max_label=max_label)
+            con = conloss(*tup)
+            ce, kd = fused(lr, devin["l_po"], devin["labels"])
+            (ce + con / 100 + 10 * kd).backward()
+
+        for _ in range(3):
+            step_fused()
+        barrier()
+        ms_fused = timed(step_fused, args.steps)
+
+        # ---- opt-in sync-free step (N1 fused CE/KD + N4 contrastive without the 5-tuple), for information: eager,
+        #      and (single GPU) forward + backward replayed from one CUDA graph ----
+        con_static = U.PixelContrastiveDistillation(temperature=0.07, max_label=max_label, gather_negatives=world > 1)
+        gs = {k: devin[k].clone() for k in ("f_n", "f_o", "l_po", "logits_lr", "labels")}
+        gs["f_n"].requires_grad_(True), gs["logits_lr"].requires_grad_(True)
+
+        def step_static():
             gs["f_n"].grad = gs["logits_lr"].grad = None
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                ce, kd = fused(gs["logits_lr"], gs["l_po"], gs["labels"])
-                (ce + con_static(gs["f_n"], gs["labels"], gs["l_po"], gs["f_o"]) / 100 + 10 * kd).backward()
-            ms_graph = timed(graph.replay)
-        except Exception as exc:  # informational leg only
-            ms_graph = "capture failed: %s" % (str(exc).splitlines()[0][:120],)
+            ce, kd = fused(gs["logits_lr"], gs["l_po"], gs["labels"])
+            (ce + con_static(gs["f_n"], gs["labels"], gs["l_po"], gs["f_o"]) / 100 + 10 * kd).backward()
+
+        for _ in range(3):
+            step_static()
+        barrier()
+        ms_static = timed(step_static, args.steps)
+        if world == 1:
+            try:
+                if hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
+                    torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    step_static()
+                torch.cuda.current_stream().wait_stream(side)
+                gs["f_n"].grad = gs["logits_lr"].grad = None
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    ce, kd = fused(gs["logits_lr"], gs["l_po"], gs["labels"])
+                    (ce + con_static(gs["f_n"], gs["labels"], gs["l_po"], gs["f_o"]) / 100 + 10 * kd).backward()
+                for _ in range(3):
+                    graph.replay()
+                barrier()
+                ms_graph = timed(graph.replay, args.steps)
+            except Exception as exc:  # informational leg only
+                ms_graph = "capture failed: %s" % (str(exc).splitlines()[0][:120],)
 
     # ---- end-to-end through the public API with host buffers (e2e) ----
-    # Every step copies its inputs from pinned host memory and copies losses + both gradients back.  Like a
-    # DataLoader with pin_memory / non_blocking prefetch, the copies of step i+1 / i-1 run on a side stream while
-    # step i computes; all of them are inside the timed region.
-    out_host = dict(losses=torch.empty(3).pin_memory(), g_fn=torch.empty_like(host["f_n"]).pin_memory(),
-                    g_lr=torch.empty_like(host["logits_lr"]).pin_memory())
-    copy_stream = torch.cuda.Stream()
-    main = torch.cuda.current_stream()
+    # Every step copies its inputs from pinned host memory and copies losses + gradients back.  Like a DataLoader
+    # with pin_memory / non_blocking prefetch, the copies of step i+1 / i-1 run on side streams (one per direction:
+    # two copy engines) while step i computes; all of them are inside the timed region.
+    out_host = dict(losses=torch.empty(3).pin_memory(), g_fn=torch.empty_like(host["f_n"]).pin_memory())
+    if not con_only:
+        out_host["g_lr"] = torch.empty_like(host["logits_lr"]).pin_memory()
+    h2d_stream, d2h_stream = torch.cuda.Stream(), torch.cuda.Stream()
+    main_s = torch.cuda.current_stream()
     slots = [dict() for _ in range(2)]
 
     def prefetch(slot):
-        with torch.cuda.stream(copy_stream):
+        with torch.cuda.stream(h2d_stream):
             for k, v in pinned.items():
                 slot[k] = v.to(dev, non_blocking=True)
             slot["ready"] = torch.cuda.Event()
-            slot["ready"].record(copy_stream)
+            slot["ready"].record(h2d_stream)
 
     def e2e_run(n_steps):
         prefetch(slots[0])
         for i in range(n_steps):
             cur = slots[i % 2]
-            main.wait_event(cur["ready"])
+            main_s.wait_event(cur["ready"])
             if i + 1 < n_steps:
                 prefetch(slots[(i + 1) % 2])
             inp = {k: cur[k] for k in pinned}
             inp["labels"] = inp["labels"].to(torch.long)          # train.py:98
             for v in inp.values():
-                v.record_stream(main)
+                v.record_stream(main_s)
             step(inp)
-            losses = torch.stack([state["con"], state["ce"], state["kd"]])
+            losses = (torch.stack([state["con"], state["ce"], state["kd"]]) if not con_only
+                      else torch.stack([state["con"]] * 3))
             done = torch.cuda.Event()
-            done.record(main)
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(done)
+            done.record(main_s)
+            with torch.cuda.stream(d2h_stream):
+                d2h_stream.wait_event(done)
                 out_host["losses"].copy_(losses, non_blocking=True)
                 out_host["g_fn"].copy_(state["g_fn"], non_blocking=True)
-                out_host["g_lr"].copy_(state["g_lr"], non_blocking=True)
-                for t_ in (losses, state["g_fn"], state["g_lr"]):
-                    t_.record_stream(copy_stream)
-        main.wait_stream(copy_stream)
+                outs = [losses, state["g_fn"]]
+                if not con_only:
+                    out_host["g_lr"].copy_(state["g_lr"], non_blocking=True)
+                    outs.append(state["g_lr"])
+                for t_ in outs:
+                    t_.record_stream(d2h_stream)
+        main_s.wait_stream(d2h_stream)
 
     e2e_run(max(3, args.warmup // 2))
     barrier()
@@ -389,13 +467,48 @@ def main():
     e2b.record()
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t0) / args.steps
-    ms_e2e = max(e2a.elapsed_time(e2b) / args.steps, wall_ms)
+    ev_ms = e2a.elapsed_time(e2b) / args.steps
+    ms_e2e = max(ev_ms, wall_ms)
     h2d = sum(v.numel() * v.element_size() for v in pinned.values())
     d2h = sum(v.numel() * v.element_size() for v in out_host.values())
 
+    # ---- N>1: parity of the data-parallel path, evaluated on rank 0 (the oracle of SURVEY 8e: the single-chunk path
+    #      on the rank-concatenated batch; the CPU oracle itself checks that path at this size in tests/) ----
+    parity = None
+    if world > 1 and not args.no_parity:
+        keys = ("f_n", "f_o", "l_po", "labels")
+        cat = {}
+        for k in keys:
+            parts = [torch.empty_like(devin[k]) for _ in range(world)] if rank == 0 else None
+            dist.gather(devin[k], parts, dst=0)
+            if rank == 0:
+                cat[k] = torch.cat(parts)
+        if rank == 0:
+            f_all = cat["f_n"].detach().requires_grad_(True)
+            single = U.PixelConLossV2(temperature=0.07)
+            tup = U.pre_contrastive_pixel(f_all, cat["labels"], l_po=cat["l_po"], f_o=cat["f_o"], max_label=max_label,
+                                          require_new_class=True)
+            con_single = single(*tup)
+            con_single.backward()
+            g_single = f_all.grad[:B].double()          # rank 0's images come first
+            g_multi = g_rank0.double() * (100.0 / world)  # step() back-propagates con/100; ddp_grad_scale = world
+            g_single = g_single / 1.0
+            cosv = float((g_single * g_multi).sum() / (g_single.norm() * g_multi.norm()).clamp_min(1e-300))
+            rel = abs(con_multi - float(con_single)) / abs(float(con_single))
+            ratio = float(g_multi.norm() / g_single.norm().clamp_min(1e-300))
+            parity = dict(parity_checked=True, loss_data_parallel=con_multi, loss_concatenated_batch=float(con_single),
+                          loss_rel_err=rel, grad_cosine_rank0=cosv, grad_norm_ratio_rank0=ratio,
+                          ok=bool(rel <= 1e-3 and cosv >= 0.999 and abs(ratio - 1) < 2e-2),
+                          n_anchor_global=int(tup[0].shape[0]), n_contrast_global=int(tup[1].shape[0]),
+                          note="rank 0: PixelConLossV2 on the rank-concatenated batch (one chunk) vs the exchanged path; "
+                               "bars: loss 1e-3 rel, gradient cosine 0.999 (BASELINE.json)")
+            del cat, f_all, tup
+        barrier()
+
     # ---- aggregate over ranks: max time, sum of pairs ----
     n_a = state["n_a"]
-    stats = torch.tensor([ms_dev, ms_e2e, float(n_a), float(state["n_c"]), ms_fused], device=dev, dtype=torch.float64)
+    stats = torch.tensor([ms_dev, ms_e2e, float(n_a), float(state["n_c"]), ms_fused or 0.0, ev_ms, wall_ms], device=dev,
+                         dtype=torch.float64)
     if world > 1:
         allst = [torch.zeros_like(stats) for _ in range(world)]
         dist.all_gather(allst, stats)
@@ -413,51 +526,79 @@ def main():
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        bf16_peak = peaks.get("bf16_tflops_sustained", 1400.0)      # kernels are timed inside a long step
+        # a timed region of well under a second runs at full clocks (see `clocks`): the burst figure applies; a long
+        # region under the power cap is compared with the sustained one
+        burst = timed_region_s < 1.0
+        bf16_peak = peaks.get("bf16_tflops" if burst else "bf16_tflops_sustained", 1590.0 if burst else 1400.0)
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        peak_src = "measured (MEASURED_PEAKS.json, sustained bf16 / copy)" if peaks else "fallback"
+        peak_src = ("measured (MEASURED_PEAKS.json: %s bf16, copy bandwidth); timed region %.2f s"
+                    % ("burst" if burst else "sustained", timed_region_s)) if peaks else "fallback (B200_PROFILING.md)"
         f_pair = 4 * 256 + 2 * C_old                                 # algorithmic flop per pixel pair
-        con_ms = call_ms.get("ucd_con_fwd", float("nan"))
+        con_ms = sum(v for k, v in call_ms.items() if k.startswith("ucd_con_fwd"))
         con_tflops = pairs_local * f_pair / (con_ms * 1e-3) / 1e12
         npx = B * H * W
-        C = wl["C"]
         hbm = {}
-        for name, nbytes in (("ucd_unce_fwd", npx * (4 * C + 8 + 4 + 8)), ("ucd_unce_bwd", npx * (8 * C + 8 + 8)),
-                             ("ucd_kd_fwd", npx * (4 * C + 4 * C_old + 12)), ("ucd_kd_bwd", npx * (8 * C + 4 * C_old + 12)),
-                             ("ucd_upsample_bilinear_fwd", npx * 4 * (C + C_old)), ("ucd_upsample_bilinear_bwd", npx * 4 * C)):
-            if name in call_ms:
-                gbs = nbytes / (call_ms[name] * 1e-3) / 1e9
-                hbm[name] = dict(ms=round(call_ms[name], 4), achieved_gbs=round(gbs, 1), frac=round(gbs / hbm_peak, 4))
+        if not con_only:
+            # SURVEY 8(d) algorithmic bytes per full-res pixel (fp32 logits, int64 labels); the per-pixel statistics a
+            # kernel saves for its backward are extra traffic, listed as saved_stat_bytes, NOT counted as achieved
+            for name, nbytes, extra in (
+                    ("ucd_unce_fwd", npx * (4 * C + 8 + 4), npx * 8), ("ucd_unce_bwd", npx * (8 * C + 8 + 4 + 4), npx * 4),
+                    ("ucd_kd_fwd", npx * (4 * C + 4 * C_old), npx * 12), ("ucd_kd_bwd", npx * (8 * C + 4 * C_old), npx * 12),
+                    ("ucd_upsample_bilinear_fwd", npx * 4 * (C + C_old), 0), ("ucd_upsample_bilinear_bwd", npx * 4 * C, 0)):
+                if name in call_ms:
+                    gbs = nbytes / (call_ms[name] * 1e-3) / 1e9
+                    hbm[name] = dict(ms=round(call_ms[name], 4), algorithmic_bytes=nbytes, saved_stat_bytes=extra,
+                                     achieved_gbs=round(gbs, 1), frac=round(gbs / hbm_peak, 4))
+            stream_ms = sum(v["ms"] for v in hbm.values())
+            hbm["chain"] = dict(bytes_per_px=32 * C + 12 * C_old + 28, ms=round(stream_ms, 4),
+                                achieved_gbs=round(npx * (32 * C + 12 * C_old + 28) / (stream_ms * 1e-3) / 1e9, 1),
+                                frac=round(npx * (32 * C + 12 * C_old + 28) / (stream_ms * 1e-3) / 1e9 / hbm_peak, 4))
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
             cpu_baseline, _ = cpu_reference_sample(3, 1, wl)
+        traffic = None
+        traffic_note = "not captured for this workload (ncu --set full is run on the default workload only)"
+        if world == 1 and args.workload == "voc" and B == WORKLOADS["voc"]["B"]:
+            traffic = 8.05e7
+            traffic_note = ("RECORDED, not measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of the two "
+                            "sweep kernels per step from ncu --set full, profiles/r02_ncu_full.md")
         line = dict(
             metric=METRIC, value=pairs_total / (ms_dev_max * 1e-3) / 1e6, unit=UNIT, n_gpus=world, steps=args.steps,
             warmup=args.warmup, ms_per_step=ms_dev_max, higher_is_better=True, scaling="weak", vs_baseline=None,
             dtype="bf16 operands / f32 accumulate (contrastive); f32 (CE, KD, upsample)", data="synthetic",
-            config=dict(workload=wl["name"] if B == WORKLOAD["B"] else wl["name"].replace("batch 24", "batch %d" % B),
+            config=dict(workload=wl["name"], step="contrastive term only" if con_only else "whole hot path",
                         classes=[C, C_old], pixels_per_gpu=B * wl["h"] * wl["w"], n_anchor_rank0=n_a,
                         n_contrast_global=int(n_c_global), pairs_per_step=int(pairs_total), temperature=0.07,
-                        l2="no flush: full-res logits (%.0f MB) exceed the 126 MB L2; the %.0f MB of bf16 column tiles are "
-                           "meant to be L2-resident" % (npx * C * 4 / 1e6, n_c_global * 512 / 1e6),
-                        parallelism="dp%d, all-gathered contrast columns" % world),
+                        l2=("no flush: the inputs of a step exceed the 126 MB L2 (full-res logits %.0f MB; bf16 column "
+                            "tiles %.0f MB are meant to be L2-resident)" % (npx * C * 4 / 1e6, n_c_global * 512 / 1e6))
+                        if not con_only else "no flush: column tiles (%.0f MB) are meant to be L2-resident; V partials "
+                        "stream through" % (n_c_global * 512 / 1e6),
+                        parallelism="dp%d, contrast columns exchanged in one all-gather overlapped with the local sweep" % world),
             roofline=dict(bound="tensor", kernel="ucd_con_fwd (sweep 1 + combine + sweep 2 + finalize)",
                           achieved=con_tflops, peak=bf16_peak, unit="TFLOP/s", frac=con_tflops / bf16_peak,
-                          traffic=(9.18e7 if (world == 1 and B == WORKLOAD["B"]) else None),
-                          traffic_note="dram read+write of the two sweep kernels per step, ncu --set full, profiles/r01f_ncu_full.md (sweep 1: 21.4 MB read + 45.0 MB written, sweep 2: 22.9 + 2.6)",
-                          flop_per_pair=f_pair, ms=con_ms, peak_source=peak_src),
+                          traffic=traffic, traffic_note=traffic_note, flop_per_pair=f_pair, ms=con_ms,
+                          peak_source=peak_src,
+                          frac_of_sustained=con_tflops / peaks.get("bf16_tflops_sustained", 1400.0)),
             roofline_hbm=hbm,
             call_ms={k: round(v, 4) for k, v in sorted(call_ms.items())},
             cpu_baseline=cpu_baseline,
+            value_at_cpu_sample=(dict(value=pairs_sample / (ms_sample * 1e-3) / 1e6, unit=UNIT, ms_per_step=ms_sample,
+                                      pairs=pairs_sample, note="this GPU arm on the CPU arm's bounded sample (%d images): "
+                                      "the like-for-like figure for the reference arm" % wl["cpu_sample_B"])
+                                 if ms_sample else None),
             e2e=dict(value=pairs_total / (ms_e2e_max * 1e-3) / 1e6, unit=UNIT, ms_per_step=ms_e2e_max,
-                     h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
-            n1_fused=dict(note="same step with the opt-in FusedUnbiasedLosses (upsample+CE+KD from low-res logits)",
-                          ms_per_step=ms_fused_max, value=pairs_total / (ms_fused_max * 1e-3) / 1e6, unit=UNIT),
-            n4_sync_free=dict(note="rank 0: N1 fused CE/KD + PixelContrastiveDistillation (no 5-tuple, no host sync); "
-                                   "graph = forward+backward replayed from one CUDA graph (single GPU only)",
-                              ms_per_step_eager=ms_static, ms_per_step_graph=ms_graph),
+                     h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                     rank0_device_event_ms=ev_ms, rank0_wall_ms=wall_ms,
+                     per_rank_ms=[round(float(v), 4) for v in allst[:, 1]]),
+            n1_fused=(dict(note="same step with the opt-in FusedUnbiasedLosses (upsample+CE+KD from low-res logits)",
+                           ms_per_step=ms_fused_max, value=pairs_total / (ms_fused_max * 1e-3) / 1e6, unit=UNIT)
+                      if ms_fused else None),
+            n4_sync_free=(dict(note="rank 0: N1 fused CE/KD + PixelContrastiveDistillation (no 5-tuple, no host sync); "
+                                    "graph = forward+backward replayed from one CUDA graph (single GPU only)",
+                               ms_per_step_eager=ms_static, ms_per_step_graph=ms_graph) if ms_static else None),
+            parity=parity,
             gpu_launches=int(launches), clocks=clocks,
-            losses=dict(con=float(state["con"]), ce=float(state["ce"]), kd=float(state["kd"])),
+            losses={k: float(state[k]) for k in ("con", "ce", "kd") if k in state},
         )
         print(json.dumps(line))
     if world > 1:
