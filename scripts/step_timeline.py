@@ -1,5 +1,6 @@
 """GPU timeline of one drop-in step (kernel start, duration, idle gap before it) from torch.profiler (CUPTI).
-Dev tool: shows where the step's time goes beyond the kernels themselves (launch gaps, host syncs)."""
+Dev tool: shows where the step's time goes beyond the kernels themselves (launch gaps, host syncs).  Under torchrun
+(N ranks) every rank runs the exchanged step and rank 0 prints its timeline (kernels of all its streams, NCCL included)."""
 import os
 import sys
 
@@ -13,9 +14,14 @@ import ucd_b200 as U
 fusedmode = len(sys.argv) > 1 and sys.argv[1] == "fused"
 wl = dict(bench.WORKLOAD)
 B, H, W, C_old = wl["B"], wl["H"], wl["W"], wl["C_old"]
-dev = torch.device("cuda", 0)
-inp = {k: v.to(dev) for k, v in bench.make_inputs(0, B, wl).items()}
-conloss = U.PixelConLossV2(temperature=0.07)
+rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+if world > 1:
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=dev)
+inp = {k: v.to(dev) for k, v in bench.make_inputs(rank, B, wl).items()}
+conloss = U.PixelConLossV2(temperature=0.07, gather_negatives=world > 1)
 unce = U.UnbiasedCrossEntropy(old_cl=C_old, ignore_index=255, reduction="none")
 unkd = U.UnbiasedKnowledgeDistillationLoss(alpha=1.0)
 fused = U.FusedUnbiasedLosses(old_cl=C_old, ignore_index=255, alpha=1.0)
@@ -47,6 +53,10 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     for _ in range(NSTEP):
         step()
     torch.cuda.synchronize()
+if rank != 0:
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0)
 ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
 ev.sort(key=lambda e: e.time_range.start)
 per = len(ev) // NSTEP
@@ -64,3 +74,6 @@ for e in sel:
     gaps += max(gap, 0.0)
     prev_end = max(prev_end, e.time_range.end)
 print("kernels per step %d | busy %.1f us | idle gaps %.1f us | span %.1f us" % (per, busy, gaps, sel[-1].time_range.end - t0))
+if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
