@@ -7,7 +7,8 @@ from .losses import (ContrastPack, FusedUnbiasedLosses, JointProb, KnowledgeDist
                      MaskCrossEntropy, MaskKnowledgeDistillationLoss, PixelConLossV2,
                      PixelContrastiveDistillation, UnbiasedCrossEntropy, UnbiasedKnowledgeDistillationLoss,
                      interpolate_bilinear, pre_contractive_pixel, pre_contrastive_pixel)
+from ._lib import enable_nvtx  # noqa: F401
 
 __all__ = ["PixelConLossV2", "UnbiasedCrossEntropy", "UnbiasedKnowledgeDistillationLoss", "pre_contrastive_pixel",
            "pre_contractive_pixel", "interpolate_bilinear", "JointProb", "ContrastPack", "FusedUnbiasedLosses",
-           "PixelContrastiveDistillation", "KnowledgeDistillationLoss", "MaskKnowledgeDistillationLoss", "MaskCrossEntropy"]
+           "PixelContrastiveDistillation", "enable_nvtx", "KnowledgeDistillationLoss", "MaskKnowledgeDistillationLoss", "MaskCrossEntropy"]
