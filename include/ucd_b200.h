@@ -52,10 +52,13 @@ int ucd_unce_fwd(const float* x, int64_t* y, float* loss_px, float* lse_all, flo
                  int B, int C, int old_cl, int64_t HW, int ignore_index, void* stream);
 /* dx = g * dloss/dx.  g_px [B,HW] per-pixel upstream gradient or NULL; then the upstream gradient is
  * the scalar *g_scalar (device) times g_mul (host), and with mean_over_valid != 0 it is additionally
- * divided by stats[1] (nll_loss 'mean' semantics). */
+ * divided by stats[1] (nll_loss 'mean' semantics).
+ * accumulate != 0 (here and in ucd_unkd_bwd / ucd_kd_bwd): dx += ... instead of dx = ...: the second of two losses
+ * on the same logits (train.py:116 and :133 both consume `outputs`) adds into the first one's gradient buffer, which
+ * replaces autograd's own full-size add kernel (8 % of the drop-in step) by one extra read of dx. */
 int ucd_unce_bwd(const float* x, const int64_t* y, const float* lse_all, const float* lse_old,
                  const float* g_px, const float* g_scalar, float g_mul, const float* stats,
-                 int mean_over_valid, float* dx, int B, int C, int old_cl, int64_t HW,
+                 int mean_over_valid, float* dx, int accumulate, int B, int C, int old_cl, int64_t HW,
                  int ignore_index, void* stream);
 
 /* ------------------------------------------------------------------------------------------
@@ -71,7 +74,7 @@ int ucd_unkd_fwd(const float* x, const float* t, const float* mask, float alpha,
                  void* stream);
 /* dx = upstream * d(-loss_px)/dx; upstream is g_px[B,HW] if non-NULL else *g_scalar * g_mul. */
 int ucd_unkd_bwd(const float* x, const float* t, const float* mask, float alpha, const float* lse3,
-                 const float* g_px, const float* g_scalar, float g_mul, float* dx, int B, int C,
+                 const float* g_px, const float* g_scalar, float g_mul, float* dx, int accumulate, int B, int C,
                  int C_old, int64_t HW, void* stream);
 size_t ucd_reduce_scratch_floats(void);
 
@@ -84,8 +87,8 @@ int ucd_kd_fwd(const float* x, const float* t, const float* mask, float alpha, f
                float* lse3, float* scratch, int B, int C, int C_old, int64_t HW, int variant, float stats_scale,
                void* stream);   /* stats[0] = stats_scale * sum_px(weight * l_px): -1/(B*HW) gives the 'mean' loss */
 int ucd_kd_bwd(const float* x, const float* t, const float* mask, float alpha, const float* lse3,
-               const float* g_px, const float* g_scalar, float g_mul, float* dx, int B, int C, int C_old,
-               int64_t HW, int variant, void* stream);
+               const float* g_px, const float* g_scalar, float g_mul, float* dx, int accumulate, int B, int C,
+               int C_old, int64_t HW, int variant, void* stream);
 /* MaskCrossEntropy's pixel weight (utils/loss.py:207-211): mask[b,p] = 1 if argmax_c t_old[b,c,p] == 0 or
  * labels[b,p] > old_cl, else 0.  t_old [B,C_old,HW] fp32, labels [B,HW] int64, mask [B,HW] fp32. */
 int ucd_bkg_mask(const float* t_old, const int64_t* labels, float* mask, int B, int C_old, int64_t HW,

@@ -457,6 +457,73 @@ def test_foreign_anchor_tensor_is_loud(U):
         U.PixelConLossV2(temperature=0.07)(tup[0].detach(), tup[1].clone().requires_grad_(True), tup[2], tup[3], None)
 
 
+def test_shared_logit_gradient_chain(U):
+    """UNCE and UNKD on the same `outputs` tensor (train.py:116,133) write ONE gradient buffer (the second backward
+    accumulates in its kernel): same gradients as the oracle's autograd in every usage pattern - both losses, either
+    one alone, reversed call order, a third consumer of `outputs`, two backward passes with retain_graph - and no
+    full-size elementwise add kernel on the way."""
+    from torch.profiler import ProfilerActivity, profile
+    B, C, C_old, H, W = 2, 9, 6, 64, 96
+    g = torch.Generator().manual_seed(21)
+    x0 = torch.randn(B, C, H, W, generator=g) * 2
+    t0 = torch.randn(B, C_old, H, W, generator=g) * 2
+    y0 = torch.randint(0, C, (B, H, W), generator=g)
+    y0[0, :3] = 255
+
+    def ref(use_ce, use_kd, extra):
+        x = x0.double().requires_grad_(True)
+        out = x * 1.0
+        loss = 0
+        if use_ce:
+            loss = loss + O.unbiased_ce(out, y0.clone(), C_old, 255, "none").mean()
+        if use_kd:
+            loss = loss + 10 * O.unbiased_kd(out, t0.double(), 1.0)
+        if extra:
+            loss = loss + (out * 0.01).sum()
+        loss.backward()
+        return x.grad
+
+    def ours(use_ce, use_kd, extra, order="ce_first", passes=1):
+        x = x0.cuda().requires_grad_(True)
+        out = x * 1.0                       # a non-leaf `outputs`, like the upsampled logits
+        ce_m = U.UnbiasedCrossEntropy(old_cl=C_old, ignore_index=255, reduction="none")
+        kd_m = U.UnbiasedKnowledgeDistillationLoss(alpha=1.0)
+        calls = [("ce", lambda: ce_m(out, y0.cuda()).mean()), ("kd", lambda: 10 * kd_m(out, t0.cuda()))]
+        if order != "ce_first":
+            calls.reverse()
+        vals = {k: f() for k, f in calls}       # both forwards always run; only the selected ones enter the loss
+        loss = (out * 0.01).sum() if extra else 0
+        if use_ce:
+            loss = loss + vals["ce"]
+        if use_kd:
+            loss = loss + vals["kd"]
+        for i in range(passes):
+            loss.backward(retain_graph=i + 1 < passes)
+        return x.grad / passes
+
+    for use_ce, use_kd, extra, order, passes in [(True, True, False, "ce_first", 1), (True, True, False, "kd_first", 1),
+                                                 (True, False, False, "ce_first", 1), (False, True, False, "ce_first", 1),
+                                                 (False, True, True, "kd_first", 1), (True, True, True, "ce_first", 2)]:
+        want = ref(use_ce, use_kd, extra)
+        got = ours(use_ce, use_kd, extra, order, passes)
+        assert cos(got, want) > 1 - 1e-6, (use_ce, use_kd, extra, order, passes)
+        torch.testing.assert_close(got.cpu().double(), want, rtol=1e-3, atol=1e-5 * float(want.abs().max()))
+    # no elementwise add over the full-size gradients
+    x = x0.cuda().requires_grad_(True)
+    out = U.interpolate_bilinear(x, (2 * H, 2 * W))
+    yy = torch.zeros(B, 2 * H, 2 * W, dtype=torch.int64, device="cuda")
+    tt = U.interpolate_bilinear(t0.cuda(), (2 * H, 2 * W))
+    loss = (U.UnbiasedCrossEntropy(old_cl=C_old, reduction="none")(out, yy).mean()
+            + 10 * U.UnbiasedKnowledgeDistillationLoss()(out, tt))
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        loss.backward()
+        torch.cuda.synchronize()
+    names = [e.key for e in prof.key_averages()]
+    assert any("unkd_bwd_kernel" in n for n in names) and any("unce_bwd_kernel" in n for n in names)
+    big_adds = [e for e in prof.key_averages() if "CUDAFunctor_add" in e.key and e.device_time_total / max(e.count, 1) > 20]
+    assert not big_adds, [e.key for e in big_adds]
+
+
 # ------------------------------------------------------------------------------------------------
 # edge cases and randomised shapes
 # ------------------------------------------------------------------------------------------------

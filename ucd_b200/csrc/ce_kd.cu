@@ -44,6 +44,20 @@ struct Vec<1> {
   static __device__ __forceinline__ void store_stream(float* p, const float (&v)[1]) { stg_stream1(p, v[0]); }
 };
 
+// dx store of the backward kernels.  ACC: add to what is already there - the second of two losses on the same logits
+// accumulates into the first one's gradient buffer, so autograd never runs its own add kernel over two full-size
+// gradients (ucd_b200/losses.py::_GradSlot; it was 8 % of the drop-in step).
+template <int VEC, bool ACC>
+__device__ __forceinline__ void store_dx(float* p, float (&o)[VEC]) {
+  if (ACC) {
+    float old[VEC];
+    Vec<VEC>::load(p, old);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) o[i] += old[i];
+  }
+  Vec<VEC>::store_stream(p, o);
+}
+
 // fixed-order final reduction of per-block partial sums: out[k] = sum_b part[k*nblk + b]
 __global__ void reduce_partials_kernel(const float* __restrict__ part, int nblk, int nk, float* __restrict__ out,
                                        float scale) {
@@ -159,7 +173,7 @@ unce_fwd_kernel(const float* __restrict__ x, long long* __restrict__ y, float* _
 }
 
 // UNCE backward:  dx_c = g * [y != ignore] * ( softmax(x)_c - (y==0 ? [c<old] exp(x_c - lse_old) : [c==y]) )
-template <int VEC>
+template <int VEC, bool ACC>
 __global__ void __launch_bounds__(kStreamThreads)
 unce_bwd_kernel(const float* __restrict__ x, const long long* __restrict__ y, const float* __restrict__ lse_all,
                 const float* __restrict__ lse_old, const float* __restrict__ g_px,
@@ -212,7 +226,7 @@ unce_bwd_kernel(const float* __restrict__ x, const long long* __restrict__ y, co
           sub = (c == lab[i]) ? 1.f : 0.f;
         o[i] = up[i] * (pr - sub);
       }
-      Vec<VEC>::store_stream(dp + (long long)c * HW, o);
+      store_dx<VEC, ACC>(dp + (long long)c * HW, o);
     }
   }
 }
@@ -342,7 +356,7 @@ unkd_fwd_kernel(const float* __restrict__ x, const float* __restrict__ t, const 
 }
 
 // UNKD backward: d(-loss_px)/dx_c = ( p_c - [c in S_b] q0 exp(x_c - lse_b) - [1<=c<C_old] q_c ) / C_old
-template <int VEC>
+template <int VEC, bool ACC>
 __global__ void __launch_bounds__(kStreamThreads)
 unkd_bwd_kernel(const float* __restrict__ x, const float* __restrict__ t, const float* __restrict__ mask,
                 float alpha, const float* __restrict__ lse3, const float* __restrict__ g_px,
@@ -388,7 +402,7 @@ unkd_bwd_kernel(const float* __restrict__ x, const float* __restrict__ t, const 
         const float pr = ex2f(fmaf(v[i], kLog2e, -la2[i]));
         o[i] = up[i] * (pr - pr * fb[i]);
       }
-      Vec<VEC>::store_stream(dp, o);
+      store_dx<VEC, ACC>(dp, o);
     }
 #pragma unroll 4
     for (int c = 1; c < C_old; ++c) {
@@ -401,7 +415,7 @@ unkd_bwd_kernel(const float* __restrict__ x, const float* __restrict__ t, const 
         const float q = ex2f(fmaf(u[i], a2, -lt2[i]));
         o[i] = up[i] * (pr - q);
       }
-      Vec<VEC>::store_stream(dp + (long long)c * HW, o);
+      store_dx<VEC, ACC>(dp + (long long)c * HW, o);
     }
 #pragma unroll 4
     for (int c = C_old; c < C; ++c) {
@@ -412,14 +426,15 @@ unkd_bwd_kernel(const float* __restrict__ x, const float* __restrict__ t, const 
         const float pr = ex2f(fmaf(v[i], kLog2e, -la2[i]));
         o[i] = up[i] * (pr - pr * fb[i]);
       }
-      Vec<VEC>::store_stream(dp + (long long)c * HW, o);
+      store_dx<VEC, ACC>(dp + (long long)c * HW, o);
     }
-    for (int c = C; c < Cs; ++c) {  // channels outside the narrowed view get no gradient
-      float o[VEC];
+    if (!ACC)
+      for (int c = C; c < Cs; ++c) {  // channels outside the narrowed view get no gradient
+        float o[VEC];
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) o[i] = 0.f;
-      Vec<VEC>::store_stream(dp + (long long)c * HW, o);
-    }
+        for (int i = 0; i < VEC; ++i) o[i] = 0.f;
+        Vec<VEC>::store_stream(dp + (long long)c * HW, o);
+      }
   }
 }
 
@@ -490,7 +505,7 @@ extern "C" int ucd_unce_fwd(const float* x, int64_t* y, float* loss_px, float* l
 
 extern "C" int ucd_unce_bwd(const float* x, const int64_t* y, const float* lse_all, const float* lse_old,
                             const float* g_px, const float* g_scalar, float g_mul, const float* stats,
-                            int mean_over_valid, float* dx, int B, int C, int old_cl, int64_t HW,
+                            int mean_over_valid, float* dx, int accumulate, int B, int C, int old_cl, int64_t HW,
                             int ignore_index, void* stream) {
   UCD_CHECK_ARG(x && y && lse_all && lse_old && dx, "ucd_unce_bwd: null pointer");
   UCD_CHECK_ARG(g_px || g_scalar, "ucd_unce_bwd: need g_px or g_scalar");
@@ -499,14 +514,10 @@ extern "C" int ucd_unce_bwd(const float* x, const int64_t* y, const float* lse_a
   cudaStream_t st = (cudaStream_t)stream;
   const bool v4 = can_vec4(HW, {x, lse_all, lse_old, g_px, dx}) && aligned16(y);
   const int grid = stream_grid((long long)B * HW / (v4 ? 4 : 1));
-  if (v4)
-    unce_bwd_kernel<4><<<grid, kStreamThreads, 0, st>>>(x, (const long long*)y, lse_all, lse_old, g_px, g_scalar,
-                                                        g_mul, stats, mean_over_valid, dx, B, C, old_cl, HW,
-                                                        ignore_index);
-  else
-    unce_bwd_kernel<1><<<grid, kStreamThreads, 0, st>>>(x, (const long long*)y, lse_all, lse_old, g_px, g_scalar,
-                                                        g_mul, stats, mean_over_valid, dx, B, C, old_cl, HW,
-                                                        ignore_index);
+  auto kern = v4 ? (accumulate ? unce_bwd_kernel<4, true> : unce_bwd_kernel<4, false>)
+                 : (accumulate ? unce_bwd_kernel<1, true> : unce_bwd_kernel<1, false>);
+  kern<<<grid, kStreamThreads, 0, st>>>(x, (const long long*)y, lse_all, lse_old, g_px, g_scalar, g_mul, stats,
+                                        mean_over_valid, dx, B, C, old_cl, HW, ignore_index);
   UCD_CHECK_LAUNCH("unce_bwd_kernel");
   return UCD_OK;
 }
@@ -534,8 +545,8 @@ static int kd_fwd_impl(const float* x, const float* t, const float* mask, float 
 }
 
 static int kd_bwd_impl(const float* x, const float* t, const float* mask, float alpha, const float* lse3,
-                       const float* g_px, const float* g_scalar, float g_mul, float* dx, int B, int C, int C_old,
-                       int64_t HW, int variant, void* stream) {
+                       const float* g_px, const float* g_scalar, float g_mul, float* dx, int accumulate, int B, int C,
+                       int C_old, int64_t HW, int variant, void* stream) {
   UCD_CHECK_ARG(x && t && lse3 && dx, "ucd_kd_bwd: null pointer");
   UCD_CHECK_ARG(g_px || g_scalar, "ucd_kd_bwd: need g_px or g_scalar");
   UCD_CHECK_ARG(B > 0 && HW > 0 && C_old >= 1 && C >= C_old, "ucd_kd_bwd: bad shape");
@@ -544,12 +555,9 @@ static int kd_bwd_impl(const float* x, const float* t, const float* mask, float 
   const int Cu = variant == 1 ? C_old : C, mz = variant == 2 ? 1 : 0;
   const bool v4 = can_vec4(HW, {x, t, mask, g_px, lse3, dx}) && ((long long)B * HW) % 4 == 0;
   const int grid = stream_grid((long long)B * HW / (v4 ? 4 : 1));
-  if (v4)
-    unkd_bwd_kernel<4><<<grid, kStreamThreads, 0, st>>>(x, t, mask, alpha, lse3, g_px, g_scalar, g_mul, dx, B, Cu, C,
-                                                        C_old, mz, HW);
-  else
-    unkd_bwd_kernel<1><<<grid, kStreamThreads, 0, st>>>(x, t, mask, alpha, lse3, g_px, g_scalar, g_mul, dx, B, Cu, C,
-                                                        C_old, mz, HW);
+  auto kern = v4 ? (accumulate ? unkd_bwd_kernel<4, true> : unkd_bwd_kernel<4, false>)
+                 : (accumulate ? unkd_bwd_kernel<1, true> : unkd_bwd_kernel<1, false>);
+  kern<<<grid, kStreamThreads, 0, st>>>(x, t, mask, alpha, lse3, g_px, g_scalar, g_mul, dx, B, Cu, C, C_old, mz, HW);
   UCD_CHECK_LAUNCH("unkd_bwd_kernel");
   return UCD_OK;
 }
@@ -561,9 +569,9 @@ extern "C" int ucd_unkd_fwd(const float* x, const float* t, const float* mask, f
 }
 
 extern "C" int ucd_unkd_bwd(const float* x, const float* t, const float* mask, float alpha, const float* lse3,
-                            const float* g_px, const float* g_scalar, float g_mul, float* dx, int B, int C,
-                            int C_old, int64_t HW, void* stream) {
-  return kd_bwd_impl(x, t, mask, alpha, lse3, g_px, g_scalar, g_mul, dx, B, C, C_old, HW, 0, stream);
+                            const float* g_px, const float* g_scalar, float g_mul, float* dx, int accumulate, int B,
+                            int C, int C_old, int64_t HW, void* stream) {
+  return kd_bwd_impl(x, t, mask, alpha, lse3, g_px, g_scalar, g_mul, dx, accumulate, B, C, C_old, HW, 0, stream);
 }
 
 extern "C" int ucd_kd_fwd(const float* x, const float* t, const float* mask, float alpha, float* out_px,
@@ -573,9 +581,9 @@ extern "C" int ucd_kd_fwd(const float* x, const float* t, const float* mask, flo
 }
 
 extern "C" int ucd_kd_bwd(const float* x, const float* t, const float* mask, float alpha, const float* lse3,
-                          const float* g_px, const float* g_scalar, float g_mul, float* dx, int B, int C,
-                          int C_old, int64_t HW, int variant, void* stream) {
-  return kd_bwd_impl(x, t, mask, alpha, lse3, g_px, g_scalar, g_mul, dx, B, C, C_old, HW, variant, stream);
+                          const float* g_px, const float* g_scalar, float g_mul, float* dx, int accumulate, int B,
+                          int C, int C_old, int64_t HW, int variant, void* stream) {
+  return kd_bwd_impl(x, t, mask, alpha, lse3, g_px, g_scalar, g_mul, dx, accumulate, B, C, C_old, HW, variant, stream);
 }
 
 extern "C" int ucd_bkg_mask(const float* t_old, const int64_t* labels, float* mask, int B, int C_old, int64_t HW,

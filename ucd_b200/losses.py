@@ -99,11 +99,61 @@ def interpolate_bilinear(x, size):
 
 
 # ----------------------------------------------------------------------------------------------
+# one logit gradient for the losses that consume the same logits
+# ----------------------------------------------------------------------------------------------
+class _GradChain:
+    """`outputs` feeds both the cross-entropy (train.py:116) and the distillation loss (train.py:133).  Autograd would
+    sum their two full-size logit gradients with a kernel of its own (read 2, write 1: 1.3 GB and 8 % of the drop-in
+    step at the BASELINE workload).  Instead the loss modules of this file that are called on the SAME tensor object
+    form a chain: every call after the first takes the previous call's `token` (a 0-d auxiliary output) as an extra
+    autograd input, which makes the engine run their backward passes in reverse call order.  Each backward writes /
+    adds its part into one shared buffer inside its own kernel (``accumulate`` of the C ABI); only the head of the
+    chain - the first call - returns that buffer as the gradient of `outputs`, the others return none.  The engine
+    therefore sees exactly one, complete gradient from this family of losses, and any other consumer of `outputs`
+    is accumulated with it the usual way."""
+
+    __slots__ = ("buf", "token", "calls")
+
+    def __init__(self):
+        self.buf, self.token, self.calls = None, None, 0
+
+    @staticmethod
+    def of(t):
+        """The chain of tensor `t` (created on first use); None when no gradient is needed or the kernels would run
+        on a private copy of `t` (not fp32 / not contiguous)."""
+        if not (torch.is_grad_enabled() and t.requires_grad and t.dtype == torch.float32 and t.is_contiguous()):
+            return None
+        chain = getattr(t, "_ucd_grad_chain", None)
+        if chain is None:
+            chain = t._ucd_grad_chain = _GradChain()
+        return chain
+
+    def take(self, like, seq):
+        """(dx, accumulate): the buffer this backward writes, and whether it must add to it.  `seq` = position of the
+        caller in the chain: the last call runs first in backward and never accumulates (a buffer left behind by a
+        backward pass that died half way is dropped there)."""
+        if seq == self.calls:
+            self.buf = None
+        if self.buf is not None:
+            return self.buf, True
+        self.buf = torch.empty_like(like)
+        return self.buf, False
+
+    def finish(self, is_head, g_ref):
+        """What this backward returns for (inputs, link)."""
+        if is_head:
+            out, self.buf = self.buf, None
+            return out, None
+        return None, torch.zeros((), device=g_ref.device, dtype=torch.float32)
+
+
+# ----------------------------------------------------------------------------------------------
 # MiB unbiased cross-entropy
 # ----------------------------------------------------------------------------------------------
 class _UnceFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, inputs, targets, old_cl, ignore_index, reduction):
+    def forward(ctx, inputs, targets, old_cl, ignore_index, reduction, chain=None, link=None):
+        ctx.chain, ctx.is_head, ctx.seq = chain, link is None, (chain.calls if chain is not None else 0)
         B, C = inputs.shape[0], inputs.shape[1]
         HW = inputs[0, 0].numel()
         x = _f32c(inputs)
@@ -118,17 +168,16 @@ class _UnceFn(torch.autograd.Function):
                                       ptr(scratch), B, C, old_cl, HW, ignore_index, cur_stream()), "unce_fwd")
         ctx.save_for_backward(x, targets, lse, stats)
         ctx.cfg = (B, C, HW, old_cl, ignore_index, reduction)
-        if reduction == "none":
-            return loss_px
-        if reduction == "sum":
-            return stats[0].clone()
-        return stats[0] / stats[1]
+        out = loss_px if reduction == "none" else (stats[0].clone() if reduction == "sum" else stats[0] / stats[1])
+        if chain is None:
+            return out
+        return out, torch.zeros((), device=dev, dtype=torch.float32)   # token: orders the chain's backward passes
 
     @staticmethod
-    def backward(ctx, g):
+    def backward(ctx, g, g_token=None):
         x, targets, lse, stats = ctx.saved_tensors
         B, C, HW, old_cl, ignore_index, reduction = ctx.cfg
-        dx = torch.empty_like(x)
+        dx, acc = ctx.chain.take(x, ctx.seq) if ctx.chain is not None else (torch.empty_like(x), False)
         g_px, g_sc = None, None
         if reduction == "none":
             g_sc = _scalar_grad(g)
@@ -139,9 +188,23 @@ class _UnceFn(torch.autograd.Function):
         if g_sc is not None:
             g_sc = _f32c(g_sc)
         check(_lib.lib().ucd_unce_bwd(ptr(x), ptr(targets), ptr(lse[0]), ptr(lse[1]), ptr(g_px), ptr(g_sc), 1.0,
-                                      ptr(stats), 1 if reduction == "mean" else 0, ptr(dx), B, C, old_cl, HW,
-                                      ignore_index, cur_stream()), "unce_bwd")
-        return dx, None, None, None, None
+                                      ptr(stats), 1 if reduction == "mean" else 0, ptr(dx), 1 if acc else 0, B, C,
+                                      old_cl, HW, ignore_index, cur_stream()), "unce_bwd")
+        if ctx.chain is None:
+            return dx, None, None, None, None, None, None
+        d_in, d_link = ctx.chain.finish(ctx.is_head, g)
+        return d_in, None, None, None, None, None, d_link
+
+
+def _chained(fn, inputs, args):
+    """Apply the autograd Function `fn` to `inputs`, linked into the gradient chain of that tensor (see _GradChain)."""
+    chain = _GradChain.of(inputs)
+    if chain is None:
+        return fn.apply(inputs, *args)
+    chain.calls += 1
+    out, token = fn.apply(inputs, *args, chain, chain.token)
+    chain.token = token
+    return out
 
 
 class UnbiasedCrossEntropy(nn.Module):
@@ -164,7 +227,7 @@ class UnbiasedCrossEntropy(nn.Module):
             raise ValueError("UnbiasedCrossEntropy: inputs [B,C,...] and targets [B,...] shapes disagree")
         old_cl = inputs.shape[1] if self.old_cl is None else int(self.old_cl)  # x[:, 0:None] == all channels
         tgt = targets if targets.is_contiguous() else targets.contiguous()
-        out = _UnceFn.apply(inputs, tgt, old_cl, int(self.ignore_index), self.reduction)
+        out = _chained(_UnceFn, inputs, (tgt, old_cl, int(self.ignore_index), self.reduction))
         if tgt is not targets:
             targets.copy_(tgt)  # keep the in-place remap visible to the caller
         return out
@@ -175,7 +238,8 @@ class UnbiasedCrossEntropy(nn.Module):
 # ----------------------------------------------------------------------------------------------
 class _UnkdFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, inputs, targets, mask, alpha, reduction, variant=0):
+    def forward(ctx, inputs, targets, mask, alpha, reduction, variant=0, chain=None, link=None):
+        ctx.chain, ctx.is_head, ctx.seq = chain, link is None, (chain.calls if chain is not None else 0)
         B, C, C_old = inputs.shape[0], inputs.shape[1], targets.shape[1]
         HW = inputs[0, 0].numel()
         x, t = _f32c(inputs), _f32c(targets)
@@ -192,15 +256,16 @@ class _UnkdFn(torch.autograd.Function):
                                     ptr(scratch), B, C, C_old, HW, variant, scale, cur_stream()), "kd_fwd")
         ctx.save_for_backward(x, t, m, lse3)
         ctx.cfg = (B, C, C_old, HW, float(alpha), reduction, variant)
-        if reduction == "none":
-            return out_px
-        return stats[0]
+        out = out_px if reduction == "none" else stats[0]
+        if chain is None:
+            return out
+        return out, torch.zeros((), device=dev, dtype=torch.float32)   # token: orders the chain's backward passes
 
     @staticmethod
-    def backward(ctx, g):
+    def backward(ctx, g, g_token=None):
         x, t, m, lse3 = ctx.saved_tensors
         B, C, C_old, HW, alpha, reduction, variant = ctx.cfg
-        dx = torch.empty_like(x)
+        dx, acc = ctx.chain.take(x, ctx.seq) if ctx.chain is not None else (torch.empty_like(x), False)
         g_px, g_sc, g_mul = None, None, 1.0
         if reduction == "none":
             g_sc = _scalar_grad(g)
@@ -213,8 +278,11 @@ class _UnkdFn(torch.autograd.Function):
         if g_sc is not None:
             g_sc = _f32c(g_sc)
         check(_lib.lib().ucd_kd_bwd(ptr(x), ptr(t), ptr(m), alpha, ptr(lse3), ptr(g_px), ptr(g_sc), g_mul, ptr(dx),
-                                    B, C, C_old, HW, variant, cur_stream()), "kd_bwd")
-        return dx, None, None, None, None, None
+                                    1 if acc else 0, B, C, C_old, HW, variant, cur_stream()), "kd_bwd")
+        if ctx.chain is None:
+            return dx, None, None, None, None, None, None, None
+        d_in, d_link = ctx.chain.finish(ctx.is_head, g)
+        return d_in, None, None, None, None, None, None, d_link
 
 
 class UnbiasedKnowledgeDistillationLoss(nn.Module):
@@ -233,7 +301,7 @@ class UnbiasedKnowledgeDistillationLoss(nn.Module):
         if mask is not None and tuple(mask.shape) != (inputs.shape[0],) + tuple(inputs.shape[2:]):
             raise ValueError("UnbiasedKnowledgeDistillationLoss: mask must be [B,...]")
         red = self.reduction if self.reduction in ("mean", "sum") else "none"
-        return _UnkdFn.apply(inputs, targets.detach(), mask, self.alpha, red)
+        return _chained(_UnkdFn, inputs, (targets.detach(), mask, self.alpha, red, 0))
 
 
 def _kd_forward(name, variant, self, inputs, targets, mask):
@@ -243,7 +311,7 @@ def _kd_forward(name, variant, self, inputs, targets, mask):
     if mask is not None and tuple(mask.shape) != (inputs.shape[0],) + tuple(inputs.shape[2:]):
         raise ValueError("%s: mask must be [B,...]" % name)
     red = self.reduction if self.reduction in ("mean", "sum") else "none"
-    return _UnkdFn.apply(inputs, targets.detach(), mask, self.alpha, red, variant)
+    return _chained(_UnkdFn, inputs, (targets.detach(), mask, self.alpha, red, variant))
 
 
 class KnowledgeDistillationLoss(nn.Module):
