@@ -71,7 +71,7 @@ KERNELS_PER_CALL = {"ucd_upsample_bilinear_fwd": 1, "ucd_upsample_bilinear_bwd":
                     "ucd_unce_bwd": 1, "ucd_kd_fwd": 2, "ucd_kd_bwd": 1, "ucd_con_prep_labels": 2,
                     "ucd_con_prep_pack": 4, "ucd_con_prep_bwd": 1, "ucd_con_fwd": 5, "ucd_con_bwd": 1,
                     "ucd_con_pack_rows": 1, "ucd_seg_fused_fwd": 2, "ucd_rows_normalize_fwd": 1,
-                    "ucd_rows_normalize_bwd": 1, "ucd_con_tile_ranges": 1}
+                    "ucd_rows_normalize_bwd": 1, "ucd_con_tile_ranges": 1, "ucd_unce_unkd_bwd": 1}
 HOST_ONLY_CALLS = ("ucd_last_error", "ucd_version", "ucd_device_ok", "ucd_con_max_tiles", "ucd_con_prob_kpad",
                    "ucd_con_num_bins", "ucd_con_px_meta_ints", "ucd_con_blk_meta_ints", "ucd_con_workspace_bytes",
                    "ucd_reduce_scratch_floats", "ucd_seg_fused_workspace_floats")
@@ -427,12 +427,17 @@ def main():
     main_s = torch.cuda.current_stream()
     slots = [dict() for _ in range(2)]
 
+    copy_ev = {"h2d": [], "d2h": []}   # (start, end) event pairs on the copy streams: time the copies themselves take
+
     def prefetch(slot):
         with torch.cuda.stream(h2d_stream):
+            a = torch.cuda.Event(enable_timing=True)
+            a.record(h2d_stream)
             for k, v in pinned.items():
                 slot[k] = v.to(dev, non_blocking=True)
-            slot["ready"] = torch.cuda.Event()
+            slot["ready"] = torch.cuda.Event(enable_timing=True)
             slot["ready"].record(h2d_stream)
+            copy_ev["h2d"].append((a, slot["ready"]))
 
     def e2e_run(n_steps):
         prefetch(slots[0])
@@ -452,6 +457,8 @@ def main():
             done.record(main_s)
             with torch.cuda.stream(d2h_stream):
                 d2h_stream.wait_event(done)
+                a = torch.cuda.Event(enable_timing=True)
+                a.record(d2h_stream)
                 out_host["losses"].copy_(losses, non_blocking=True)
                 out_host["g_fn"].copy_(state["g_fn"], non_blocking=True)
                 outs = [losses, state["g_fn"]]
@@ -460,10 +467,14 @@ def main():
                     outs.append(state["g_lr"])
                 for t_ in outs:
                     t_.record_stream(d2h_stream)
+                b = torch.cuda.Event(enable_timing=True)
+                b.record(d2h_stream)
+                copy_ev["d2h"].append((a, b))
         main_s.wait_stream(d2h_stream)
 
     e2e_run(max(3, args.warmup // 2))
     barrier()
+    copy_ev["h2d"].clear(), copy_ev["d2h"].clear()
     t0 = time.perf_counter()
     e2a, e2b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2a.record()
@@ -473,6 +484,7 @@ def main():
     wall_ms = 1e3 * (time.perf_counter() - t0) / args.steps
     ev_ms = e2a.elapsed_time(e2b) / args.steps
     ms_e2e = max(ev_ms, wall_ms)
+    copy_ms = {k: sum(a.elapsed_time(b) for a, b in v) / max(len(v), 1) for k, v in copy_ev.items()}
     h2d = sum(v.numel() * v.element_size() for v in pinned.values())
     d2h = sum(v.numel() * v.element_size() for v in out_host.values())
 
@@ -548,15 +560,21 @@ def main():
             for name, nbytes, extra in (
                     ("ucd_unce_fwd", npx * (4 * C + 8 + 4), npx * 8), ("ucd_unce_bwd", npx * (8 * C + 8 + 4 + 4), npx * 4),
                     ("ucd_kd_fwd", npx * (4 * C + 4 * C_old), npx * 12), ("ucd_kd_bwd", npx * (8 * C + 4 * C_old), npx * 12),
+                    # the two backward passes run as ONE kernel when both losses consume the same logits: judged
+                    # against the fused lower bound of SURVEY 8(d) (read x, t and the labels once, write dx once)
+                    ("ucd_unce_unkd_bwd", npx * (8 * C + 4 * C_old + 8), npx * 16),
                     ("ucd_upsample_bilinear_fwd", npx * 4 * (C + C_old), 0), ("ucd_upsample_bilinear_bwd", npx * 4 * C, 0)):
                 if name in call_ms:
                     gbs = nbytes / (call_ms[name] * 1e-3) / 1e9
                     hbm[name] = dict(ms=round(call_ms[name], 4), algorithmic_bytes=nbytes, saved_stat_bytes=extra,
                                      achieved_gbs=round(gbs, 1), frac=round(gbs / hbm_peak, 4))
             stream_ms = sum(v["ms"] for v in hbm.values())
-            hbm["chain"] = dict(bytes_per_px=32 * C + 12 * C_old + 28, ms=round(stream_ms, 4),
-                                achieved_gbs=round(npx * (32 * C + 12 * C_old + 28) / (stream_ms * 1e-3) / 1e9, 1),
-                                frac=round(npx * (32 * C + 12 * C_old + 28) / (stream_ms * 1e-3) / 1e9 / hbm_peak, 4))
+            # whole streaming chain: the separate-module bytes of SURVEY 8(d), minus what the fused backward no longer
+            # has to move (one read of x, the labels and one lse plane: 4C + 12), so that fusion does not inflate it
+            chain_bpp = 32 * C + 12 * C_old + 28 - ((4 * C + 12) if "ucd_unce_unkd_bwd" in call_ms else 0)
+            hbm["chain"] = dict(bytes_per_px=chain_bpp, ms=round(stream_ms, 4),
+                                achieved_gbs=round(npx * chain_bpp / (stream_ms * 1e-3) / 1e9, 1),
+                                frac=round(npx * chain_bpp / (stream_ms * 1e-3) / 1e9 / hbm_peak, 4))
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
             cpu_baseline, _ = cpu_reference_sample(3, 1, wl)
@@ -595,6 +613,10 @@ def main():
             e2e=dict(value=pairs_total / (ms_e2e_max * 1e-3) / 1e6, unit=UNIT, ms_per_step=ms_e2e_max,
                      h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                      rank0_device_event_ms=ev_ms, rank0_wall_ms=wall_ms,
+                     rank0_h2d_copy_ms_per_step=round(copy_ms["h2d"], 4), rank0_d2h_copy_ms_per_step=round(copy_ms["d2h"], 4),
+                     copy_note="copy times = CUDA events on the two copy streams around the step's transfers (they "
+                               "overlap the compute of the neighbouring steps; at N ranks they share the host's PCIe / "
+                               "memory bandwidth, which is what the e2e figure runs into at N=8)",
                      per_rank_ms=[round(float(v), 4) for v in allst[:, 1]]),
             n1_fused=(dict(note="same step with the opt-in FusedUnbiasedLosses (upsample+CE+KD from low-res logits)",
                            ms_per_step=ms_fused_max, value=pairs_total / (ms_fused_max * 1e-3) / 1e6, unit=UNIT)

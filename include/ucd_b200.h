@@ -89,6 +89,14 @@ int ucd_kd_fwd(const float* x, const float* t, const float* mask, float alpha, f
 int ucd_kd_bwd(const float* x, const float* t, const float* mask, float alpha, const float* lse3,
                const float* g_px, const float* g_scalar, float g_mul, float* dx, int accumulate, int B, int C,
                int C_old, int64_t HW, int variant, void* stream);
+/* UNCE + UNKD backward in one pass (both losses consume the same `outputs`, train.py:116 and :133): the sum of what
+ * ucd_unce_bwd and ucd_kd_bwd (variant 0 or 2) would write, with x read and dx written once.  lse_all is the statistic
+ * both forwards saved (log-sum-exp over all C channels); lse3 as saved by ucd_kd_fwd. */
+int ucd_unce_unkd_bwd(const float* x, const int64_t* y, const float* lse_all, const float* lse_old,
+                      const float* ce_g_px, const float* ce_g_scalar, float ce_g_mul, const float* ce_stats,
+                      int mean_over_valid, int old_cl, int ignore_index, const float* t, const float* mask,
+                      float alpha, const float* lse3, const float* kd_g_px, const float* kd_g_scalar, float kd_g_mul,
+                      int kd_variant, float* dx, int accumulate, int B, int C, int C_old, int64_t HW, void* stream);
 /* MaskCrossEntropy's pixel weight (utils/loss.py:207-211): mask[b,p] = 1 if argmax_c t_old[b,c,p] == 0 or
  * labels[b,p] > old_cl, else 0.  t_old [B,C_old,HW] fp32, labels [B,HW] int64, mask [B,HW] fp32. */
 int ucd_bkg_mask(const float* t_old, const int64_t* labels, float* mask, int B, int C_old, int64_t HW,

@@ -32,6 +32,7 @@ def step(inp):
 out_host = dict(losses=torch.empty(3).pin_memory(), g_fn=torch.empty_like(host["f_n"]).pin_memory(),
                 g_lr=torch.empty_like(host["logits_lr"]).pin_memory())
 copy_stream = torch.cuda.Stream()
+d2h_stream = torch.cuda.Stream()     # one stream per direction, like bench.py
 main = torch.cuda.current_stream()
 slots = [dict() for _ in range(2)]
 
@@ -60,16 +61,17 @@ def e2e_run(n_steps, mode):
             continue
         losses = torch.stack([state["con"], state["ce"], state["kd"]])
         done = torch.cuda.Event(); done.record(main)
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(done)
+        with torch.cuda.stream(d2h_stream):
+            d2h_stream.wait_event(done)
             out_host["losses"].copy_(losses, non_blocking=True)
-            out_host["g_fn"].copy_(state["g_fn"], non_blocking=True)
-            out_host["g_lr"].copy_(state["g_lr"], non_blocking=True)
+            if mode != "lossonly":
+                out_host["g_fn"].copy_(state["g_fn"], non_blocking=True)
+                out_host["g_lr"].copy_(state["g_lr"], non_blocking=True)
             for t_ in (losses, state["g_fn"], state["g_lr"]):
-                t_.record_stream(copy_stream)
-    main.wait_stream(copy_stream)
+                t_.record_stream(d2h_stream)
+    main.wait_stream(d2h_stream)
 
-for mode in ("full", "nocopy"):
+for mode in ("full", "lossonly", "nocopy"):
     e2e_run(5, mode); torch.cuda.synchronize()
     t0 = time.perf_counter(); e2e_run(20, mode); torch.cuda.synchronize()
     print("%s: %.3f ms per step (wall)" % (mode, 1e3 * (time.perf_counter() - t0) / 20))

@@ -519,7 +519,7 @@ def test_shared_logit_gradient_chain(U):
         loss.backward()
         torch.cuda.synchronize()
     names = [e.key for e in prof.key_averages()]
-    assert any("unkd_bwd_kernel" in n for n in names) and any("unce_bwd_kernel" in n for n in names)
+    assert any("unce_unkd_bwd_kernel" in n for n in names), names   # one pass over the logits for both losses
     big_adds = [e for e in prof.key_averages() if "CUDAFunctor_add" in e.key and e.device_time_total / max(e.count, 1) > 20]
     assert not big_adds, [e.key for e in big_adds]
 

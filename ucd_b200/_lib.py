@@ -25,6 +25,8 @@ _PROTOS = {
     "ucd_unkd_bwd": (c_int, [P, P, P, c_float, P, P, P, c_float, P, c_int, c_int, c_int, c_int, c_int64, P]),
     "ucd_kd_fwd": (c_int, [P, P, P, c_float, P, P, P, P, c_int, c_int, c_int, c_int64, c_int, c_float, P]),
     "ucd_kd_bwd": (c_int, [P, P, P, c_float, P, P, P, c_float, P, c_int, c_int, c_int, c_int, c_int64, c_int, P]),
+    "ucd_unce_unkd_bwd": (c_int, [P, P, P, P, P, P, c_float, P, c_int, c_int, c_int, P, P, c_float, P, P, P, c_float, c_int,
+                                  P, c_int, c_int, c_int, c_int, c_int64, P]),
     "ucd_bkg_mask": (c_int, [P, P, P, c_int, c_int, c_int64, c_int, P]),
     "ucd_upsample_bilinear_fwd": (c_int, [P, P, c_int64, c_int, c_int, c_int, c_int, P]),
     "ucd_upsample_bilinear_bwd": (c_int, [P, P, c_int64, c_int, c_int, c_int, c_int, P]),

@@ -438,6 +438,91 @@ unkd_bwd_kernel(const float* __restrict__ x, const float* __restrict__ t, const 
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// UNCE + UNKD backward in ONE pass over the logits: both losses consume the same `outputs` (train.py:116,133) and both
+// gradients are (upstream) x (softmax(x)_c - something): x is read once, softmax once, dx written once.  Two separate
+// kernels (the second accumulating) move 2 x + t + 3 dx = 2.5 GB at the BASELINE workload, this one x + t + dx = 1.26 GB.
+//   dx_c = u_ce ( p_c - [y'==0 ? [c<old_cl] p_c e^{lse - lse_old} : [c==y'] ] )           (UNCE)
+//        + u_kd ( p_c - [c in S_b] p_c q_0 e^{lse - lse_b} - [1<=c<C_old] q_c )           (UNKD; S_b = {0} U new)
+// ------------------------------------------------------------------------------------------
+template <int VEC, bool ACC>
+__global__ void __launch_bounds__(kStreamThreads)
+unce_unkd_bwd_kernel(const float* __restrict__ x, const long long* __restrict__ y, const float* __restrict__ lse_all,
+                     const float* __restrict__ lse_old, const float* __restrict__ ce_g_px,
+                     const float* __restrict__ ce_g_scalar, float ce_g_mul, const float* __restrict__ ce_stats,
+                     int mean_over_valid, int old_cl, int ignore_index, const float* __restrict__ t,
+                     const float* __restrict__ mask, float alpha, const float* __restrict__ lse3,
+                     const float* __restrict__ kd_g_px, const float* __restrict__ kd_g_scalar, float kd_g_mul,
+                     int mask_zero, float* __restrict__ dx, int B, int C, int C_old, long long HW) {
+  const long long gpi = HW / VEC;
+  const long long n_groups = gpi * B;
+  const long long plane = (long long)B * HW;
+  const float a2 = alpha * kLog2e;
+  const float inv_cold = 1.f / (float)C_old;
+  float gs_ce = 0.f;
+  if (ce_g_px == nullptr) {
+    gs_ce = ce_g_scalar[0] * ce_g_mul;
+    if (mean_over_valid) gs_ce = gs_ce / ce_stats[1];
+  }
+  const float gs_kd = (kd_g_px == nullptr) ? kd_g_scalar[0] * kd_g_mul : 0.f;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n_groups;
+       g += (long long)gridDim.x * blockDim.x) {
+    const long long b = g / gpi, p = (g - b * gpi) * VEC;
+    const float* xp = x + (b * C) * HW + p;
+    const float* tp = t + (b * C_old) * HW + p;
+    float* dp = dx + (b * C) * HW + p;
+    const long long* yp = y + b * HW + p;
+    float la2[VEC], lt2[VEC], uce[VEC], ukd[VEC], fold[VEC], fb[VEC];
+    int lab[VEC];
+    {
+      float la[VEC], lo[VEC], lb[VEC], lt[VEC], gp[VEC], gk[VEC], mk[VEC], u0[VEC];
+      Vec<VEC>::load_cached(lse_all + b * HW + p, la);
+      Vec<VEC>::load_cached(lse_old + b * HW + p, lo);
+      Vec<VEC>::load_cached(lse3 + plane + b * HW + p, lb);
+      Vec<VEC>::load_cached(lse3 + 2 * plane + b * HW + p, lt);
+      Vec<VEC>::load_cached(tp, u0);
+      if (ce_g_px != nullptr) Vec<VEC>::load_cached(ce_g_px + b * HW + p, gp);
+      if (kd_g_px != nullptr) Vec<VEC>::load_cached(kd_g_px + b * HW + p, gk);
+      if (mask != nullptr) Vec<VEC>::load_cached(mask + b * HW + p, mk);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        long long tt = yp[i];
+        if (tt < old_cl) tt = 0;
+        const bool dead = (tt == ignore_index) || tt < 0 || tt >= C;
+        lab[i] = dead ? -1 : (int)tt;
+        uce[i] = dead ? 0.f : (ce_g_px != nullptr ? gp[i] : gs_ce);
+        la2[i] = la[i] * kLog2e;
+        lt2[i] = lt[i] * kLog2e;
+        fold[i] = ex2f((la[i] - lo[i]) * kLog2e);
+        float u = (kd_g_px != nullptr ? gk[i] : gs_kd) * inv_cold;
+        if (mask != nullptr) u *= mask_zero ? (mk[i] == 0.f ? 1.f : 0.f) : mk[i];
+        ukd[i] = u;
+        const float q0 = ex2f(fmaf(u0[i], a2, -lt2[i]));
+        fb[i] = q0 * ex2f((la[i] - lb[i]) * kLog2e);
+      }
+    }
+#pragma unroll 4
+    for (int c = 0; c < C; ++c) {
+      float v[VEC], u[VEC], o[VEC];
+      Vec<VEC>::load(xp + (long long)c * HW, v);
+      const bool old_fg = c >= 1 && c < C_old;  // an old foreground class: KD subtracts q_c (uniform over the block)
+      if (old_fg) Vec<VEC>::load(tp + (long long)c * HW, u);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const float pr = ex2f(fmaf(v[i], kLog2e, -la2[i]));
+        float sub_ce;
+        if (lab[i] == 0 && old_cl > 0)
+          sub_ce = (c < old_cl) ? pr * fold[i] : 0.f;
+        else
+          sub_ce = (c == lab[i]) ? 1.f : 0.f;
+        const float sub_kd = old_fg ? ex2f(fmaf(u[i], a2, -lt2[i])) : pr * fb[i];
+        o[i] = fmaf(uce[i], pr - sub_ce, ukd[i] * (pr - sub_kd));
+      }
+      store_dx<VEC, ACC>(dp + (long long)c * HW, o);
+    }
+  }
+}
+
 // MaskCrossEntropy's pixel weight (utils/loss.py:207-211): 1 where the old model predicts background
 // (argmax over channels == 0; ties resolve to the first index like torch.argmax) or the label is > old_cl.
 __global__ void __launch_bounds__(kStreamThreads)
@@ -593,5 +678,29 @@ extern "C" int ucd_bkg_mask(const float* t_old, const int64_t* labels, float* ma
   bkg_mask_kernel<<<stream_grid((long long)B * HW), kStreamThreads, 0, (cudaStream_t)stream>>>(
       t_old, (const long long*)labels, mask, B, C_old, HW, old_cl);
   UCD_CHECK_LAUNCH("bkg_mask_kernel");
+  return UCD_OK;
+}
+
+extern "C" int ucd_unce_unkd_bwd(const float* x, const int64_t* y, const float* lse_all, const float* lse_old,
+                                 const float* ce_g_px, const float* ce_g_scalar, float ce_g_mul, const float* ce_stats,
+                                 int mean_over_valid, int old_cl, int ignore_index, const float* t, const float* mask,
+                                 float alpha, const float* lse3, const float* kd_g_px, const float* kd_g_scalar,
+                                 float kd_g_mul, int kd_variant, float* dx, int accumulate, int B, int C, int C_old,
+                                 int64_t HW, void* stream) {
+  UCD_CHECK_ARG(x && y && lse_all && lse_old && t && lse3 && dx, "ucd_unce_unkd_bwd: null pointer");
+  UCD_CHECK_ARG((ce_g_px || ce_g_scalar) && (kd_g_px || kd_g_scalar), "ucd_unce_unkd_bwd: need g_px or g_scalar for both terms");
+  UCD_CHECK_ARG(!mean_over_valid || ce_stats, "ucd_unce_unkd_bwd: mean_over_valid needs stats");
+  UCD_CHECK_ARG(B > 0 && HW > 0 && C_old >= 1 && C >= C_old, "ucd_unce_unkd_bwd: bad shape");
+  UCD_CHECK_ARG(kd_variant == 0 || kd_variant == 2, "ucd_unce_unkd_bwd: KD variant must be 0 (unbiased) or 2 (masked)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool v4 = can_vec4(HW, {x, lse_all, lse_old, ce_g_px, t, mask, lse3, kd_g_px, dx}) && aligned16(y) &&
+                  ((long long)B * HW) % 4 == 0;
+  const int grid = stream_grid((long long)B * HW / (v4 ? 4 : 1));
+  auto kern = v4 ? (accumulate ? unce_unkd_bwd_kernel<4, true> : unce_unkd_bwd_kernel<4, false>)
+                 : (accumulate ? unce_unkd_bwd_kernel<1, true> : unce_unkd_bwd_kernel<1, false>);
+  kern<<<grid, kStreamThreads, 0, st>>>(x, (const long long*)y, lse_all, lse_old, ce_g_px, ce_g_scalar, ce_g_mul,
+                                        ce_stats, mean_over_valid, old_cl, ignore_index, t, mask, alpha, lse3, kd_g_px,
+                                        kd_g_scalar, kd_g_mul, kd_variant == 2 ? 1 : 0, dx, B, C, C_old, HW);
+  UCD_CHECK_LAUNCH("unce_unkd_bwd_kernel");
   return UCD_OK;
 }

@@ -103,19 +103,21 @@ def interpolate_bilinear(x, size):
 # ----------------------------------------------------------------------------------------------
 class _GradChain:
     """`outputs` feeds both the cross-entropy (train.py:116) and the distillation loss (train.py:133).  Autograd would
-    sum their two full-size logit gradients with a kernel of its own (read 2, write 1: 1.3 GB and 8 % of the drop-in
-    step at the BASELINE workload).  Instead the loss modules of this file that are called on the SAME tensor object
-    form a chain: every call after the first takes the previous call's `token` (a 0-d auxiliary output) as an extra
-    autograd input, which makes the engine run their backward passes in reverse call order.  Each backward writes /
-    adds its part into one shared buffer inside its own kernel (``accumulate`` of the C ABI); only the head of the
-    chain - the first call - returns that buffer as the gradient of `outputs`, the others return none.  The engine
-    therefore sees exactly one, complete gradient from this family of losses, and any other consumer of `outputs`
-    is accumulated with it the usual way."""
+    run the two backward kernels and then sum their full-size logit gradients with a kernel of its own: x read twice,
+    dx written twice and read twice more (2.5 GB + 1.3 GB at the BASELINE workload, a fifth of the drop-in step).
+    Instead the loss modules of this file that are called on the SAME tensor object form a chain: every call after the
+    first takes the previous call's `token` (a 0-d auxiliary output) as an extra autograd input, which makes the engine
+    run their backward passes in reverse call order.  A backward that is not the head of the chain only records its
+    term; the head - the first call - then launches ONE kernel for a cross-entropy + distillation pair
+    (``ucd_unce_unkd_bwd``: x and softmax read once, dx written once) and, for any other combination, the individual
+    kernels with ``accumulate`` into one shared buffer.  Only the head returns a gradient for `outputs`, so the engine
+    sees exactly one, complete gradient from this family of losses; other consumers of `outputs` are accumulated with
+    it the usual way."""
 
-    __slots__ = ("buf", "token", "calls")
+    __slots__ = ("token", "calls", "pending")
 
     def __init__(self):
-        self.buf, self.token, self.calls = None, None, 0
+        self.token, self.calls, self.pending = None, 0, []
 
     @staticmethod
     def of(t):
@@ -128,23 +130,48 @@ class _GradChain:
             chain = t._ucd_grad_chain = _GradChain()
         return chain
 
-    def take(self, like, seq):
-        """(dx, accumulate): the buffer this backward writes, and whether it must add to it.  `seq` = position of the
-        caller in the chain: the last call runs first in backward and never accumulates (a buffer left behind by a
-        backward pass that died half way is dropped there)."""
-        if seq == self.calls:
-            self.buf = None
-        if self.buf is not None:
-            return self.buf, True
-        self.buf = torch.empty_like(like)
-        return self.buf, False
+    def submit(self, term, seq, is_head):
+        """Called from a member's backward: returns (gradient for `inputs`, gradient for the link token)."""
+        if seq == self.calls:      # the last call runs first in a backward pass: drop what a pass that died left behind
+            self.pending = []
+        if not is_head:
+            self.pending.append(term)
+            return None, torch.zeros((), device=term["x"].device, dtype=torch.float32)
+        terms, self.pending = self.pending + [term], []
+        return _launch_terms(terms), None
 
-    def finish(self, is_head, g_ref):
-        """What this backward returns for (inputs, link)."""
-        if is_head:
-            out, self.buf = self.buf, None
-            return out, None
-        return None, torch.zeros((), device=g_ref.device, dtype=torch.float32)
+
+def _launch_terms(terms):
+    """dx = sum of the terms' logit gradients, written by as few passes over the logits as possible."""
+    dx = torch.empty_like(terms[0]["x"])
+    ce = [t for t in terms if t["kind"] == "ce"]
+    kd = [t for t in terms if t["kind"] == "kd" and t["variant"] in (0, 2)]
+    acc = False
+    if ce and kd and ce[0]["C"] == kd[0]["C"] and ce[0]["HW"] == kd[0]["HW"]:
+        c, k = ce[0], kd[0]
+        check(_lib.lib().ucd_unce_unkd_bwd(
+            ptr(c["x"]), ptr(c["targets"]), ptr(c["lse"][0]), ptr(c["lse"][1]), ptr(c["g_px"]), ptr(c["g_sc"]), 1.0,
+            ptr(c["stats"]), c["mean_over_valid"], c["old_cl"], c["ignore_index"], ptr(k["t"]), ptr(k["m"]), k["alpha"],
+            ptr(k["lse3"]), ptr(k["g_px"]), ptr(k["g_sc"]), k["g_mul"], k["variant"], ptr(dx), 0, c["B"], c["C"],
+            k["C_old"], c["HW"], cur_stream()), "unce_unkd_bwd")
+        terms = [t for t in terms if t is not c and t is not k]
+        acc = True
+    for t in terms:
+        _launch_term(t, dx, acc)
+        acc = True
+    return dx
+
+
+def _launch_term(t, dx, acc):
+    if t["kind"] == "ce":
+        check(_lib.lib().ucd_unce_bwd(ptr(t["x"]), ptr(t["targets"]), ptr(t["lse"][0]), ptr(t["lse"][1]), ptr(t["g_px"]),
+                                      ptr(t["g_sc"]), 1.0, ptr(t["stats"]), t["mean_over_valid"], ptr(dx),
+                                      1 if acc else 0, t["B"], t["C"], t["old_cl"], t["HW"], t["ignore_index"],
+                                      cur_stream()), "unce_bwd")
+    else:
+        check(_lib.lib().ucd_kd_bwd(ptr(t["x"]), ptr(t["t"]), ptr(t["m"]), t["alpha"], ptr(t["lse3"]), ptr(t["g_px"]),
+                                    ptr(t["g_sc"]), t["g_mul"], ptr(dx), 1 if acc else 0, t["B"], t["C"], t["C_old"],
+                                    t["HW"], t["variant"], cur_stream()), "kd_bwd")
 
 
 # ----------------------------------------------------------------------------------------------
@@ -177,7 +204,6 @@ class _UnceFn(torch.autograd.Function):
     def backward(ctx, g, g_token=None):
         x, targets, lse, stats = ctx.saved_tensors
         B, C, HW, old_cl, ignore_index, reduction = ctx.cfg
-        dx, acc = ctx.chain.take(x, ctx.seq) if ctx.chain is not None else (torch.empty_like(x), False)
         g_px, g_sc = None, None
         if reduction == "none":
             g_sc = _scalar_grad(g)
@@ -187,12 +213,14 @@ class _UnceFn(torch.autograd.Function):
             g_sc = g.reshape(1)
         if g_sc is not None:
             g_sc = _f32c(g_sc)
-        check(_lib.lib().ucd_unce_bwd(ptr(x), ptr(targets), ptr(lse[0]), ptr(lse[1]), ptr(g_px), ptr(g_sc), 1.0,
-                                      ptr(stats), 1 if reduction == "mean" else 0, ptr(dx), 1 if acc else 0, B, C,
-                                      old_cl, HW, ignore_index, cur_stream()), "unce_bwd")
+        term = dict(kind="ce", x=x, targets=targets, lse=lse, stats=stats, g_px=g_px, g_sc=g_sc,
+                    mean_over_valid=1 if reduction == "mean" else 0, B=B, C=C, HW=HW, old_cl=old_cl,
+                    ignore_index=ignore_index)
         if ctx.chain is None:
+            dx = torch.empty_like(x)
+            _launch_term(term, dx, False)
             return dx, None, None, None, None, None, None
-        d_in, d_link = ctx.chain.finish(ctx.is_head, g)
+        d_in, d_link = ctx.chain.submit(term, ctx.seq, ctx.is_head)
         return d_in, None, None, None, None, None, d_link
 
 
@@ -265,7 +293,6 @@ class _UnkdFn(torch.autograd.Function):
     def backward(ctx, g, g_token=None):
         x, t, m, lse3 = ctx.saved_tensors
         B, C, C_old, HW, alpha, reduction, variant = ctx.cfg
-        dx, acc = ctx.chain.take(x, ctx.seq) if ctx.chain is not None else (torch.empty_like(x), False)
         g_px, g_sc, g_mul = None, None, 1.0
         if reduction == "none":
             g_sc = _scalar_grad(g)
@@ -277,11 +304,13 @@ class _UnkdFn(torch.autograd.Function):
                 g_mul = 1.0 / float(B * HW)
         if g_sc is not None:
             g_sc = _f32c(g_sc)
-        check(_lib.lib().ucd_kd_bwd(ptr(x), ptr(t), ptr(m), alpha, ptr(lse3), ptr(g_px), ptr(g_sc), g_mul, ptr(dx),
-                                    1 if acc else 0, B, C, C_old, HW, variant, cur_stream()), "kd_bwd")
+        term = dict(kind="kd", x=x, t=t, m=m, lse3=lse3, g_px=g_px, g_sc=g_sc, g_mul=g_mul, alpha=alpha, B=B, C=C,
+                    C_old=C_old, HW=HW, variant=variant)
         if ctx.chain is None:
+            dx = torch.empty_like(x)
+            _launch_term(term, dx, False)
             return dx, None, None, None, None, None, None, None
-        d_in, d_link = ctx.chain.finish(ctx.is_head, g)
+        d_in, d_link = ctx.chain.submit(term, ctx.seq, ctx.is_head)
         return d_in, None, None, None, None, None, None, d_link
 
 
