@@ -23,9 +23,14 @@ res = {}
 res["up_fwd"] = (timeit(lambda: U.interpolate_bilinear(lr, (H, W))), npx * 4 * C)
 res["up_bwd"] = (timeit(lambda: torch.autograd.grad(U.interpolate_bilinear(lr, (H, W)), lr, g)) - res["up_fwd"][0], npx * 4 * C)
 x = out.detach().requires_grad_(True)
-res["unce_fwd"] = (timeit(lambda: unce(x, lab)), npx * (4 * C + 20))
+def nograd(fn):
+    def run():
+        with torch.no_grad():   # forward only: no autograd graph (and no gradient chain on the persistent input)
+            return fn()
+    return run
+res["unce_fwd"] = (timeit(nograd(lambda: unce(x, lab))), npx * (4 * C + 12))
 res["unce_fwd+bwd"] = (timeit(lambda: torch.autograd.grad(unce(x, lab).mean(), x)), npx * (12 * C + 36))
-res["unkd_fwd"] = (timeit(lambda: unkd(x, old)), npx * (4 * C + 4 * C_old + 12))
+res["unkd_fwd"] = (timeit(nograd(lambda: unkd(x, old))), npx * (4 * C + 4 * C_old))
 res["unkd_fwd+bwd"] = (timeit(lambda: torch.autograd.grad(unkd(x, old), x)), npx * (12 * C + 8 * C_old + 24))
 print("shape B=%d C=%d C_old=%d %dx%d" % (B, C, C_old, H, W))
 for k, (ms, by) in res.items():

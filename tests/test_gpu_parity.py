@@ -508,6 +508,20 @@ def test_shared_logit_gradient_chain(U):
         got = ours(use_ce, use_kd, extra, order, passes)
         assert cos(got, want) > 1 - 1e-6, (use_ce, use_kd, extra, order, passes)
         torch.testing.assert_close(got.cpu().double(), want, rtol=1e-3, atol=1e-5 * float(want.abs().max()))
+    # a persistent input tensor used step after step (forward + backward each time, and forward-only evaluations in
+    # between) must not link one step's graph to the previous one's
+    xp = x0.cuda().requires_grad_(True)
+    ce_m = U.UnbiasedCrossEntropy(old_cl=C_old, ignore_index=255, reduction="none")
+    kd_m = U.UnbiasedKnowledgeDistillationLoss(alpha=1.0)
+    want = ref(True, True, False)
+    for it in range(3):
+        for _ in range(it * 3):                       # evaluations whose graph is dropped
+            ce_m(xp, y0.cuda()).mean()
+        xp.grad = None
+        (ce_m(xp, y0.cuda()).mean() + 10 * kd_m(xp, t0.cuda())).backward()
+        assert cos(xp.grad, want) > 1 - 1e-6, it
+    (gx,) = torch.autograd.grad(kd_m(xp, t0.cuda()), xp)
+    assert cos(gx, ref(False, True, False) / 10) > 1 - 1e-6
     # no elementwise add over the full-size gradients
     x = x0.cuda().requires_grad_(True)
     out = U.interpolate_bilinear(x, (2 * H, 2 * W))

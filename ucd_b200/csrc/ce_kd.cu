@@ -111,20 +111,30 @@ __device__ __forceinline__ void lse_chunks(const float* __restrict__ xp, long lo
 // ------------------------------------------------------------------------------------------
 // UNCE forward
 // ------------------------------------------------------------------------------------------
+// Channels are walked in chunks of CH (old classes first, then the rest; the running log-sum-exp is snapshotted where
+// the groups meet: lse over the old classes).  The loads of chunk n+1 are issued before chunk n is reduced (two
+// register buffers), so a thread always has CH*VEC*4 bytes in flight while it computes; with CH = 4 the kernel fits
+// three blocks per SM.  (The single-buffered CH = 8 version ran at 124 registers, two blocks per SM and 0.61 of the copy
+// bandwidth: every thread alternated between waiting for its loads and computing.)
+constexpr int kUnceChunk = 4;
+
 template <int VEC>
-__global__ void __launch_bounds__(kStreamThreads)
+__global__ void __launch_bounds__(kStreamThreads, 3)
 unce_fwd_kernel(const float* __restrict__ x, long long* __restrict__ y, float* __restrict__ loss_px,
                 float* __restrict__ lse_all_out, float* __restrict__ lse_old_out, float* __restrict__ part,
                 int B, int C, int old_cl, long long HW, int ignore_index) {
+  constexpr int CH = kUnceChunk;
   const long long gpi = HW / VEC;  // groups per image
   const long long n_groups = gpi * B;
+  const int oc = old_cl < C ? (old_cl > 0 ? old_cl : 0) : C;
+  const int n_old = (oc + CH - 1) / CH, n_chunks = n_old + (C - oc + CH - 1) / CH;
   float loss_acc = 0.f, valid_acc = 0.f;
   for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n_groups;
        g += (long long)gridDim.x * blockDim.x) {
     const long long b = g / gpi, p = (g - b * gpi) * VEC;
     const float* xp = x + (b * C) * HW + p;
     long long* yp = y + b * HW + p;
-    long long lab[VEC];
+    int lab[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
       long long t = yp[i];
@@ -132,17 +142,71 @@ unce_fwd_kernel(const float* __restrict__ x, long long* __restrict__ y, float* _
         if (t != 0) yp[i] = 0;
         t = 0;
       }
-      lab[i] = t;
+      lab[i] = (t < 0 || t > 0x7fffffffLL) ? -1 : (int)t;  // out-of-range labels can never match a channel
     }
-    // log-sum-exp over channel chunks: CH*VEC independent loads in flight, the chunk maximum rescales the
-    // running sum once per chunk (no per-element dependency chain), CH+1 exps per CH elements.
+    auto range = [&](int n, int& c0, int& c1) {  // channels [c0, c1) of chunk n
+      if (n < n_old) {
+        c0 = n * CH;
+        c1 = min(c0 + CH, oc);
+      } else {
+        c0 = oc + (n - n_old) * CH;
+        c1 = min(c0 + CH, C);
+      }
+    };
+    auto load = [&](int n, float (&v)[CH][VEC]) {
+      int c0, c1;
+      range(n, c0, c1);
+#pragma unroll
+      for (int k = 0; k < CH; ++k) {
+        if (c0 + k < c1) {
+          Vec<VEC>::load(xp + (long long)(c0 + k) * HW, v[k]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) v[k][i] = kNegBig;
+        }
+      }
+    };
     float m[VEC], s[VEC], picked[VEC], lse_old2[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) m[i] = kNegBig, s[i] = 0.f, picked[i] = 0.f, lse_old2[i] = kNegBig;
-    lse_chunks<VEC, true>(xp, HW, 0, (old_cl < C ? old_cl : C), lab, m, s, picked);
+    // one chunk into the running (max, sum) pairs: the chunk maximum rescales the sum once, CH + 1 exps per CH elements
+    auto reduce = [&](int n, const float (&v)[CH][VEC]) {
+      int c0, c1;
+      range(n, c0, c1);
+      if (n == n_old) {  // first chunk of the second group: what has been summed so far is lse over the old classes
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) lse_old2[i] = m[i] + lg2f(s[i]);
-    lse_chunks<VEC, true>(xp, HW, (old_cl < C ? old_cl : C), C, lab, m, s, picked);
+        for (int i = 0; i < VEC; ++i) lse_old2[i] = m[i] + lg2f(s[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        float cm = v[0][i];
+#pragma unroll
+        for (int k = 1; k < CH; ++k) cm = fmaxf(cm, v[k][i]);
+        const float nm = fmaxf(m[i], cm * kLog2e);
+        float acc = s[i] * ex2f(m[i] - nm);
+#pragma unroll
+        for (int k = 0; k < CH; ++k) {
+          acc += ex2f(fmaf(v[k][i], kLog2e, -nm));
+          picked[i] = (lab[i] == c0 + k) ? v[k][i] : picked[i];
+        }
+        m[i] = nm;
+        s[i] = acc;
+      }
+    };
+    float va[CH][VEC], vb[CH][VEC];
+    load(0, va);
+    for (int n = 0; n < n_chunks; n += 2) {
+      if (n + 1 < n_chunks) load(n + 1, vb);
+      reduce(n, va);
+      if (n + 1 < n_chunks) {
+        if (n + 2 < n_chunks) load(n + 2, va);
+        reduce(n + 1, vb);
+      }
+    }
+    if (n_old == n_chunks) {  // no channel beyond the old classes
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) lse_old2[i] = m[i] + lg2f(s[i]);
+    }
     float out[VEC], la[VEC], lo[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {

@@ -114,10 +114,11 @@ class _GradChain:
     sees exactly one, complete gradient from this family of losses; other consumers of `outputs` are accumulated with
     it the usual way."""
 
-    __slots__ = ("token", "calls", "pending")
+    __slots__ = ("token", "calls", "pending", "closed")
+    MAX_MEMBERS = 4   # bounds what a chain keeps alive when losses are evaluated over and over without a backward
 
     def __init__(self):
-        self.token, self.calls, self.pending = None, 0, []
+        self.token, self.calls, self.pending, self.closed = None, 0, [], False
 
     @staticmethod
     def of(t):
@@ -126,12 +127,16 @@ class _GradChain:
         if not (torch.is_grad_enabled() and t.requires_grad and t.dtype == torch.float32 and t.is_contiguous()):
             return None
         chain = getattr(t, "_ucd_grad_chain", None)
-        if chain is None:
+        # a chain only links calls of ONE forward pass: once a backward pass has touched it (or it is full) the next
+        # call on the same tensor object - a persistent input used step after step - starts a new chain.  Two chains
+        # on one tensor simply hand autograd two gradients.
+        if chain is None or chain.closed or chain.calls >= _GradChain.MAX_MEMBERS:
             chain = t._ucd_grad_chain = _GradChain()
         return chain
 
     def submit(self, term, seq, is_head):
         """Called from a member's backward: returns (gradient for `inputs`, gradient for the link token)."""
+        self.closed = True
         if seq == self.calls:      # the last call runs first in a backward pass: drop what a pass that died left behind
             self.pending = []
         if not is_head:
