@@ -425,16 +425,18 @@ def main():
         out_host["g_lr"] = torch.empty_like(host["logits_lr"]).pin_memory()
     h2d_stream, d2h_stream = torch.cuda.Stream(), torch.cuda.Stream()
     main_s = torch.cuda.current_stream()
-    slots = [dict() for _ in range(2)]
-
+    # two preallocated device slots for the inputs (no allocator traffic inside the loop), filled alternately
+    slots = [dict(buf={k: torch.empty_like(v, device=dev) for k, v in pinned.items()}, free=None) for _ in range(2)]
     copy_ev = {"h2d": [], "d2h": []}   # (start, end) event pairs on the copy streams: time the copies themselves take
 
     def prefetch(slot):
         with torch.cuda.stream(h2d_stream):
+            if slot["free"] is not None:
+                h2d_stream.wait_event(slot["free"])          # the step that last read this slot has finished
             a = torch.cuda.Event(enable_timing=True)
             a.record(h2d_stream)
             for k, v in pinned.items():
-                slot[k] = v.to(dev, non_blocking=True)
+                slot["buf"][k].copy_(v, non_blocking=True)
             slot["ready"] = torch.cuda.Event(enable_timing=True)
             slot["ready"].record(h2d_stream)
             copy_ev["h2d"].append((a, slot["ready"]))
@@ -446,15 +448,14 @@ def main():
             main_s.wait_event(cur["ready"])
             if i + 1 < n_steps:
                 prefetch(slots[(i + 1) % 2])
-            inp = {k: cur[k] for k in pinned}
+            inp = dict(cur["buf"])
             inp["labels"] = inp["labels"].to(torch.long)          # train.py:98
-            for v in inp.values():
-                v.record_stream(main_s)
             step(inp)
             losses = (torch.stack([state["con"], state["ce"], state["kd"]]) if not con_only
                       else torch.stack([state["con"]] * 3))
             done = torch.cuda.Event()
             done.record(main_s)
+            cur["free"] = done
             with torch.cuda.stream(d2h_stream):
                 d2h_stream.wait_event(done)
                 a = torch.cuda.Event(enable_timing=True)
