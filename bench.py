@@ -255,7 +255,8 @@ def main():
     ap.add_argument("--workload", default="voc", help="voc | ade | city | sweep:<pixels per GPU>")
     ap.add_argument("--batch", type=int, default=0, help="images per GPU (default: the workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip the informational N1 / N4 legs")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the informational legs (N1 / N4 variants, GPU arm at the CPU sample size)")
     ap.add_argument("--no-parity", action="store_true", help="N>1: skip the concatenated-batch parity check on rank 0")
     args = ap.parse_args()
     wl = get_workload(args.workload, args.batch)
@@ -352,7 +353,7 @@ def main():
 
     # ---- the GPU arm at the CPU arm's sample size: a like-for-like ratio for the reference arm ----
     ms_sample, pairs_sample = None, None
-    if world == 1 and wl["cpu_sample_B"] != B:
+    if world == 1 and wl["cpu_sample_B"] != B and not args.no_extras:
         small = {k: v[:wl["cpu_sample_B"]].contiguous() for k, v in devin.items()}
         for _ in range(3):
             step(small)
@@ -582,7 +583,7 @@ def main():
         traffic = None
         traffic_note = "not captured for this workload (ncu --set full is run on the default workload only)"
         if world == 1 and args.workload == "voc" and B == WORKLOADS["voc"]["B"]:
-            traffic = 8.05e7
+            traffic = 8.75e7
             traffic_note = ("RECORDED, not measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of the two "
                             "sweep kernels per step from ncu --set full, profiles/r02_ncu_full.md")
         line = dict(

@@ -23,7 +23,7 @@ def step():
     (ce + con / 100 + 10 * kd).backward()
 for _ in range(5): step()
 torch.cuda.synchronize()
-for n in (20, 20):
+for n in (20, 20, 50, 50, 100):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter(); e0.record()
     for _ in range(n): step()

@@ -12,16 +12,30 @@
 //
 // Two tensor-core sweeps over the column tiles, same kernel template:
 //   sweep 1: S = A C^T (tcgen05, K=256) -> epilogue: exp, masks, row max/neg/num; E = masked exp(S)
-//            in bf16 -> smem -> V += E C (tcgen05 with the SAME C tile read MN-major).
+//            in bf16 -> a separate E region of tensor memory -> V += E C (tcgen05 TS with the SAME C tile read MN-major).
 //   sweep 2: S again and P = pA pC^T (K = padded C_old) -> epilogue: den, log, weights, L_i, T_i;
-//            Ucoef in bf16 -> smem -> U += Ucoef C.
+//            Ucoef in bf16 -> the consumed P columns -> U += Ucoef C.
 // The gradient needs no third sweep: backward is a scaled copy of (T V - U)/(tau num).
 //
 // CTA = one 128-row block x one contiguous range of column tiles ("split").  Warp roles: warp 0 issues
 // bulk async copies (TMA engine) of pre-tiled bf16 operands, warp 1 owns TMEM and issues the S (and P) MMAs,
 // warp 2 issues the V / U MMAs (A operand = E / Ucoef read from tensor memory), warps 3-10 are the epilogue
 // (two per SM sub-partition; one thread per row and column half, accumulators read with tcgen05.ld, E / Ucoef
-// written back with tcgen05.st).  Everything is handed over through mbarriers; no __syncthreads in the tile loop.
+// written back with tcgen05.st).  The issuing warps run warp-uniform with the instructions in elect_one_sync() blocks
+// (umma.cuh).  Everything is handed over through mbarriers; no __syncthreads in the tile loop.
+// Column tiles stream through a ring of half-tile slots (below); S is a single accumulator that is released as soon
+// as the epilogue holds it in registers.
+//
+// Why not cta_group::2 (M = 256 over a CTA pair sharing the column tile)?  One tcgen05.mma.cta_group::2 carries ONE
+// B descriptor that both CTAs apply to their own shared memory, each supplying HALF of B's N extent.  For S = A C^T the
+// N extent is the tile's 128 COLUMNS (CTA r would hold columns 64r..64r+63, all 256 features); for V = E C the N extent
+// is the 256 FEATURES (CTA r would hold features 128r..128r+127 of all 128 columns).  Per CTA that is three of the four
+// 16 KB (column half x feature half) quadrants, and because both CTAs must find their S half and their V half at the
+// same offsets, the quadrant they have in common (own columns x own features) cannot serve both views in both CTAs at
+// once: four 16 KB regions with one duplicate = the same 64 KB per tile as now.  Rotating the rows of CTA 1's copy
+// fixes the S view but then position p of V's K axis means column p in CTA 0 and column p+64 in CTA 1.  And all
+// tcgen05 instructions of a kernel must use the same cta_group, so S cannot be paired while V stays per CTA.  With
+// the same 24 MMAs per 2048 clk of pipe work the pair would not relieve the issue side either.
 #include "umma.cuh"
 #ifdef UCD_DEBUG_KNOBS
 #include "../../include/ucd_b200_debug.h"
