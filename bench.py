@@ -21,6 +21,7 @@ all-gather over NCCL, overlapped with the sweep over the local columns) so negat
 metric = pixel pairs (N_a local x N_c global, summed over ranks) per second, in Mpairs/s.
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -333,13 +334,19 @@ def main():
     for _ in range(args.warmup):
         step(devin)
     barrier()
+    # A full collection of the interpreter's heap (about a million objects once torch is imported) takes 15-150 ms:
+    # one of them inside a 20-40 ms timed region doubled a B=3 bench line (round 2: ADE 2.7 instead of 1.3 ms, one
+    # e2e leg 16.9 instead of 1.3 ms).  Freeze what exists so that collections during the loops only see the
+    # objects the steps create (the collector itself stays on).
+    gc.collect()
+    gc.freeze()
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("UCD_BENCH_NO_SAMPLER"):
         sampler.start()
     t_wall0 = time.perf_counter()
     ms_dev = timed(lambda: step(devin), args.steps)
     timed_region_s = time.perf_counter() - t_wall0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if (rank == 0 and sampler.thr is not None) else None
     # ---- the same loop once more with a CUDA-event pair around every C-ABI call: per-kernel-group device times for
     #      the rooflines and the launch count.  (The ~35 extra event records per step cost host time and stream slots:
     #      this pass runs up to 15 % slower than the plain loop, which is why it is not the headline.) ----

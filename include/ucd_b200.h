@@ -169,6 +169,17 @@ int ucd_con_prep_pack(const float* f_n, const float* f_o, const float* l_po, con
 int ucd_con_prep_bwd(const float* g_anchor, const float* anchor_f32, const float* inv_norm,
                      const int32_t* px_meta, const int32_t* blk_meta, float* df_n, int B, int h, int w,
                      void* stream);
+/* Feature hand-off in bf16 (replaces the fp32 features that segmentation_module.py:86-107 hands to
+ * utils/loss.py:363-366): f_n / f_o are the head's NCHW features as bf16 (e.g. a head under autocast), read as they
+ * are - no fp32 copy of the two feature maps; everything else as ucd_con_prep_pack.  The adjoint writes df_n in bf16. */
+int ucd_con_prep_pack_bf16(const void* f_n, const void* f_o, const float* l_po, const int32_t* px_meta,
+                           int32_t* blk_meta, const int32_t* counts, int B, int C_old, int h, int w, int max_label,
+                           float* anchor_f32, float* contrast_f32, void* la, void* lc, int label_bytes,
+                           void* feat_tiles, void* prob_tiles, int32_t* lab_tiles, int32_t* tile_range,
+                           int32_t* row_range, int32_t* row_ref, float* inv_norm, int64_t max_tiles, void* stream);
+int ucd_con_prep_bwd_bf16(const float* g_anchor, const float* anchor_f32, const float* inv_norm,
+                          const int32_t* px_meta, const int32_t* blk_meta, void* df_n, int B, int h, int w,
+                          void* stream);
 /* min/max valid (>= 0) label of every 128-entry tile; with n_limit != NULL only entries [0, *n_limit) count */
 int ucd_con_tile_ranges(const int32_t* lab_tiles, int64_t n_tiles, const int32_t* n_limit, int32_t* tile_range,
                         void* stream);

@@ -28,6 +28,11 @@ int ucd_selftest_pipe_rate(int mode, int warps, int iters, float* cycles_per_ite
 int ucd_selftest_mma_mix(int s_ts, int s_a, int s_acc0, int s_acc1, int v_n256, int v_a, int v_acc, int tiles,
                          float* cycles_per_tile_host);
 
+/* HBM read-only probe (selftest.cu): microseconds per pass over `bytes` of `buf`; mode 0 register loads, 1 cp.async
+ * ring, 2 strided NCHW walk like the loss kernels; `un` loads in flight per thread, `blocks_per_sm` blocks of 256 */
+int ucd_selftest_read_probe(const void* buf, long long bytes, int mode, int un, int blocks_per_sm, int reps,
+                            float* us_host);
+
 #ifdef __cplusplus
 }
 #endif

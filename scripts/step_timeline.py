@@ -12,7 +12,9 @@ import bench
 import ucd_b200 as U
 
 fusedmode = len(sys.argv) > 1 and sys.argv[1] == "fused"
-wl = dict(bench.WORKLOAD)
+# UCD_WL=voc|ade|city[:batch] picks the workload (default: the bench default)
+_wl = os.environ.get("UCD_WL", "voc").split(":")
+wl = bench.get_workload(_wl[0], int(_wl[1]) if len(_wl) > 1 else 0)
 B, H, W, C_old = wl["B"], wl["H"], wl["W"], wl["C_old"]
 rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
 torch.cuda.set_device(local)
@@ -31,14 +33,14 @@ def step():
     f_n = inp["f_n"].detach().requires_grad_(True)
     lr = inp["logits_lr"].detach().requires_grad_(True)
     if fusedmode:
-        tup = U.pre_contrastive_pixel(f_n, inp["labels"], l_po=inp["l_po"], f_o=inp["f_o"])
+        tup = U.pre_contrastive_pixel(f_n, inp["labels"], l_po=inp["l_po"], f_o=inp["f_o"], max_label=wl["max_label"])
         con = conloss(*tup)
         ce, kd = fused(lr, inp["l_po"], inp["labels"])
     else:
         outputs = U.interpolate_bilinear(lr, (H, W))
         with torch.no_grad():
             outputs_old = U.interpolate_bilinear(inp["l_po"], (H, W))
-        tup = U.pre_contrastive_pixel(f_n, inp["labels"], l_po=inp["l_po"], f_o=inp["f_o"])
+        tup = U.pre_contrastive_pixel(f_n, inp["labels"], l_po=inp["l_po"], f_o=inp["f_o"], max_label=wl["max_label"])
         ce = unce(outputs, inp["labels"]).mean()
         con = conloss(*tup)
         kd = unkd(outputs, outputs_old)
@@ -74,6 +76,8 @@ for e in sel:
     gaps += max(gap, 0.0)
     prev_end = max(prev_end, e.time_range.end)
 print("kernels per step %d | busy %.1f us | idle gaps %.1f us | span %.1f us" % (per, busy, gaps, sel[-1].time_range.end - t0))
+if os.environ.get("UCD_HOST_OPS"):
+    print(prof.key_averages().table(sort_by="self_cpu_time_total", row_limit=14, max_name_column_width=60))
 if world > 1:
     dist.barrier()
     dist.destroy_process_group()

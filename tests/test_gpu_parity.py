@@ -774,6 +774,45 @@ def test_raw_head_features_equal_att_map_features(U, golden_dir):
     assert loss2.item() == pytest.approx(loss.item(), rel=1e-4) and cos(x2.grad, x.grad) > 1 - 1e-5
 
 
+@pytest.mark.parametrize("name", ["voc15-5s_b2_corr", "city13-6_b3"])
+def test_bf16_feature_handoff(U, golden_dir, name):
+    """Row N2, second half: a head that runs in bf16 hands its features over as bf16 NCHW; the prep kernel reads them
+    as they are and the adjoint writes the bf16 gradient.  Checker = the CPU oracle (fp64) on the bf16-rounded
+    features; the integer artefacts must not depend on the feature dtype at all; and the fp32 entry point fed with
+    the same rounded values must produce the same operand tiles bit for bit."""
+    fx, case, (B, h, w, H, W, C, C_old) = load_case(golden_dir, name)
+    fn16, fo16 = case["f_n"].to(torch.bfloat16), case["f_o"].to(torch.bfloat16)
+    x_ref = fn16.double().requires_grad_(True)
+    A, Cst, la, lc, P, _ = O.pre_contrastive_pixel(x_ref, case["labels"], case["l_po"].double(), fo16.double())
+    ref = O.pixel_con_loss(A, Cst, la, lc, P)
+    ref.backward()
+    x = fn16.cuda().requires_grad_(True)
+    tup = U.pre_contrastive_pixel(x, case["labels"].cuda(), l_po=case["l_po"].cuda(), f_o=fo16.cuda())
+    assert tup[4].pack.bf16_feats
+    loss = U.PixelConLossV2(temperature=0.07)(*tup)
+    loss.backward()
+    assert x.grad.dtype == torch.bfloat16 and x.grad.shape == x.shape
+    assert loss.item() == pytest.approx(ref.item(), rel=REL)
+    assert cos(x.grad.float(), x_ref.grad) >= COS
+    assert torch.equal(tup[2].cpu().long(), la.long()) and torch.equal(tup[3].cpu().long(), lc.long())
+    # same values through the fp32 entry point: identical rows and tiles, gradient equal up to the final bf16 rounding
+    x32 = fn16.float().cuda().requires_grad_(True)
+    tup32 = U.pre_contrastive_pixel(x32, case["labels"].cuda(), l_po=case["l_po"].cuda(), f_o=fo16.float().cuda())
+    assert not tup32[4].pack.bf16_feats
+    assert torch.equal(tup32[0], tup[0]) and torch.equal(tup32[1], tup[1])
+    assert torch.equal(tup32[4].pack.feat_tiles, tup[4].pack.feat_tiles)
+    loss32 = U.PixelConLossV2(temperature=0.07)(*tup32)
+    loss32.backward()
+    assert loss32.item() == loss.item()
+    assert torch.equal(x32.grad.to(torch.bfloat16), x.grad)
+    # the sync-free module takes the same route
+    x3 = fn16.cuda().requires_grad_(True)
+    out = U.PixelContrastiveDistillation(temperature=0.07)(x3, case["labels"].cuda(), case["l_po"].cuda(), fo16.cuda())
+    out.backward()
+    assert x3.grad.dtype == torch.bfloat16
+    assert out.item() == pytest.approx(loss.item(), rel=2e-6) and cos(x3.grad.float(), x.grad.float()) > 1 - 1e-5
+
+
 # ------------------------------------------------------------------------------------------------
 # SURVEY section 8(f) row N4: sync-free contrastive module, CUDA-graph capture of forward + backward
 @pytest.mark.parametrize("name", ["tiny_b2", "voc15-5s_b3_512", "city13-6_b3", "voc15-5s_b2_corr"])

@@ -42,6 +42,9 @@ _PROTOS = {
     "ucd_con_prep_pack": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, P, c_int, P, P, P, P,
                                   P, P, P, c_int64, P]),
     "ucd_con_prep_bwd": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, P]),
+    "ucd_con_prep_pack_bf16": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, P, c_int, P, P, P,
+                                       P, P, P, P, c_int64, P]),
+    "ucd_con_prep_bwd_bf16": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, P]),
     "ucd_rows_normalize_fwd": (c_int, [P, P, P, c_int, c_int, c_int, P]),
     "ucd_rows_normalize_bwd": (c_int, [P, P, P, P, c_int, c_int, c_int, P]),
     "ucd_con_tile_ranges": (c_int, [P, c_int64, P, P, P]),
@@ -60,6 +63,7 @@ _DEBUG_PROTOS = {
     "ucd_selftest_mma_rate": (c_int, [c_int, c_int, ctypes.POINTER(c_float)]),
     "ucd_selftest_mma_mix": (c_int, [c_int] * 8 + [ctypes.POINTER(c_float)]),
     "ucd_selftest_pipe_rate": (c_int, [c_int, c_int, c_int, ctypes.POINTER(c_float)]),
+    "ucd_selftest_read_probe": (c_int, [P, ctypes.c_longlong, c_int, c_int, c_int, c_int, ctypes.POINTER(c_float)]),
 }
 DEBUG_EXPORTED = tuple(_DEBUG_PROTOS)
 DEBUG_LIB_PATH = os.path.join(_HERE, "libucd_b200_debug.so")

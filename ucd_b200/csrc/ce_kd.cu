@@ -111,102 +111,114 @@ __device__ __forceinline__ void lse_chunks(const float* __restrict__ xp, long lo
 // ------------------------------------------------------------------------------------------
 // UNCE forward
 // ------------------------------------------------------------------------------------------
-// Channels are walked in chunks of CH (old classes first, then the rest; the running log-sum-exp is snapshotted where
-// the groups meet: lse over the old classes).  The loads of chunk n+1 are issued before chunk n is reduced (two
-// register buffers), so a thread always has CH*VEC*4 bytes in flight while it computes; with CH = 4 the kernel fits
-// three blocks per SM.  (The single-buffered CH = 8 version ran at 124 registers, two blocks per SM and 0.61 of the copy
-// bandwidth: every thread alternated between waiting for its loads and computing.)
-constexpr int kUnceChunk = 4;
+// A thread owns VEC adjacent pixels and walks the channels in chunks of 4 with ONE pointer that advances by 4 planes:
+// 4 independent 128-bit loads, then per pixel the chunk maximum rescales the running sum once (5 exps per 4 elements).
+// Old classes first, then the rest; the running log-sum-exp is snapshotted where the groups meet (lse over the old
+// classes).  x[label] is fetched by its own 4-byte load up front instead of a compare + select per element.
+// Round 2: the first version of this loop executed 37 thread instructions per logit (64-bit index arithmetic, range
+// predicates and label compares per element; ncu: 62 % issue-active at 5.1 TB/s) - it was issue-bound, not memory-
+// bound.  This form needs ~6 per element and 64 registers (4 blocks per SM: a pure read of the same planes reaches
+// 6.3 TB/s with 1024 threads per SM and 4 loads in flight per thread, scripts/read_probe.py).
+template <int VEC>
+__device__ __forceinline__ void lse_chunk4(const float (&v)[4][VEC], float (&m)[VEC], float (&s)[VEC]) {
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const float cm = fmaxf(fmaxf(v[0][i], v[1][i]), fmaxf(v[2][i], v[3][i]));
+    const float nm = fmaxf(m[i], cm * kLog2e);
+    float acc = s[i] * ex2f(m[i] - nm);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc += ex2f(fmaf(v[k][i], kLog2e, -nm));
+    m[i] = nm;
+    s[i] = acc;
+  }
+}
+
+// online log-sum-exp (log2 domain) of the next n planes at xc (plane stride HW); xc advances past them
+template <int VEC>
+__device__ __forceinline__ void lse_planes(const float*& xc, long long HW, int n, float (&m)[VEC], float (&s)[VEC]) {
+  int c = 0;
+  for (; c + 4 <= n; c += 4) {
+    float v[4][VEC];
+    Vec<VEC>::load(xc, v[0]);
+    Vec<VEC>::load(xc + HW, v[1]);
+    Vec<VEC>::load(xc + 2 * HW, v[2]);
+    Vec<VEC>::load(xc + 3 * HW, v[3]);
+    xc += 4 * HW;
+    lse_chunk4<VEC>(v, m, s);
+  }
+  if (c < n) {  // 1-3 planes left: the missing ones count as -inf
+    float v[4][VEC];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (c + k < n) {
+        Vec<VEC>::load(xc + k * HW, v[k]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) v[k][i] = kNegBig;
+      }
+    }
+    xc += (long long)(n - c) * HW;
+    lse_chunk4<VEC>(v, m, s);
+  }
+}
+
+// (image, first pixel) of pixel group g; 32-bit arithmetic whenever the group count allows it
+__device__ __forceinline__ void group_to_bp(long long g, long long gpi, bool small, int vec, long long& b, long long& p) {
+  if (small) {
+    const unsigned bb = (unsigned)g / (unsigned)gpi;
+    b = bb;
+    p = (long long)((unsigned)g - bb * (unsigned)gpi) * vec;
+  } else {
+    b = g / gpi;
+    p = (g - b * gpi) * vec;
+  }
+}
 
 template <int VEC>
-__global__ void __launch_bounds__(kStreamThreads, 3)
+__global__ void __launch_bounds__(kStreamThreads, VEC == 4 ? 4 : 2)
 unce_fwd_kernel(const float* __restrict__ x, long long* __restrict__ y, float* __restrict__ loss_px,
                 float* __restrict__ lse_all_out, float* __restrict__ lse_old_out, float* __restrict__ part,
                 int B, int C, int old_cl, long long HW, int ignore_index) {
-  constexpr int CH = kUnceChunk;
   const long long gpi = HW / VEC;  // groups per image
   const long long n_groups = gpi * B;
+  const bool small = n_groups < (1ll << 31) && gpi < (1ll << 31);
   const int oc = old_cl < C ? (old_cl > 0 ? old_cl : 0) : C;
-  const int n_old = (oc + CH - 1) / CH, n_chunks = n_old + (C - oc + CH - 1) / CH;
   float loss_acc = 0.f, valid_acc = 0.f;
   for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n_groups;
        g += (long long)gridDim.x * blockDim.x) {
-    const long long b = g / gpi, p = (g - b * gpi) * VEC;
+    long long b, p;
+    group_to_bp(g, gpi, small, VEC, b, p);
     const float* xp = x + (b * C) * HW + p;
     long long* yp = y + b * HW + p;
+    long long yl[VEC];
+    if (VEC == 4) {
+      const longlong2 t0 = *reinterpret_cast<const longlong2*>(yp), t1 = *reinterpret_cast<const longlong2*>(yp + 2);
+      yl[0] = t0.x, yl[1] = t0.y, yl[2 % VEC] = t1.x, yl[3 % VEC] = t1.y;
+    } else {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) yl[i] = yp[i];
+    }
     int lab[VEC];
+    float picked[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
-      long long t = yp[i];
+      long long t = yl[i];
       if (t < old_cl) {  // loss.py:104-105: labels[targets < old_cl] = 0 (in place)
         if (t != 0) yp[i] = 0;
         t = 0;
       }
       lab[i] = (t < 0 || t > 0x7fffffffLL) ? -1 : (int)t;  // out-of-range labels can never match a channel
+      // x[label]: its own load, issued before the planes are streamed (the sector is read again by the stream: L2 hit)
+      picked[i] = (lab[i] >= 0 && lab[i] < C) ? __ldg(xp + (long long)lab[i] * HW + i) : 0.f;
     }
-    auto range = [&](int n, int& c0, int& c1) {  // channels [c0, c1) of chunk n
-      if (n < n_old) {
-        c0 = n * CH;
-        c1 = min(c0 + CH, oc);
-      } else {
-        c0 = oc + (n - n_old) * CH;
-        c1 = min(c0 + CH, C);
-      }
-    };
-    auto load = [&](int n, float (&v)[CH][VEC]) {
-      int c0, c1;
-      range(n, c0, c1);
+    float m[VEC], s[VEC], lse_old2[VEC];
 #pragma unroll
-      for (int k = 0; k < CH; ++k) {
-        if (c0 + k < c1) {
-          Vec<VEC>::load(xp + (long long)(c0 + k) * HW, v[k]);
-        } else {
+    for (int i = 0; i < VEC; ++i) m[i] = kNegBig, s[i] = 0.f;
+    const float* xc = xp;
+    lse_planes<VEC>(xc, HW, oc, m, s);
 #pragma unroll
-          for (int i = 0; i < VEC; ++i) v[k][i] = kNegBig;
-        }
-      }
-    };
-    float m[VEC], s[VEC], picked[VEC], lse_old2[VEC];
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) m[i] = kNegBig, s[i] = 0.f, picked[i] = 0.f, lse_old2[i] = kNegBig;
-    // one chunk into the running (max, sum) pairs: the chunk maximum rescales the sum once, CH + 1 exps per CH elements
-    auto reduce = [&](int n, const float (&v)[CH][VEC]) {
-      int c0, c1;
-      range(n, c0, c1);
-      if (n == n_old) {  // first chunk of the second group: what has been summed so far is lse over the old classes
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) lse_old2[i] = m[i] + lg2f(s[i]);
-      }
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        float cm = v[0][i];
-#pragma unroll
-        for (int k = 1; k < CH; ++k) cm = fmaxf(cm, v[k][i]);
-        const float nm = fmaxf(m[i], cm * kLog2e);
-        float acc = s[i] * ex2f(m[i] - nm);
-#pragma unroll
-        for (int k = 0; k < CH; ++k) {
-          acc += ex2f(fmaf(v[k][i], kLog2e, -nm));
-          picked[i] = (lab[i] == c0 + k) ? v[k][i] : picked[i];
-        }
-        m[i] = nm;
-        s[i] = acc;
-      }
-    };
-    float va[CH][VEC], vb[CH][VEC];
-    load(0, va);
-    for (int n = 0; n < n_chunks; n += 2) {
-      if (n + 1 < n_chunks) load(n + 1, vb);
-      reduce(n, va);
-      if (n + 1 < n_chunks) {
-        if (n + 2 < n_chunks) load(n + 2, va);
-        reduce(n + 1, vb);
-      }
-    }
-    if (n_old == n_chunks) {  // no channel beyond the old classes
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) lse_old2[i] = m[i] + lg2f(s[i]);
-    }
+    for (int i = 0; i < VEC; ++i) lse_old2[i] = m[i] + lg2f(s[i]);  // what has been summed so far: the old classes
+    lse_planes<VEC>(xc, HW, C - oc, m, s);
     float out[VEC], la[VEC], lo[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
@@ -299,8 +311,46 @@ unce_bwd_kernel(const float* __restrict__ x, const long long* __restrict__ y, co
 // UNKD forward:  q = softmax(alpha t);  S_b = {0} U {C_old..C-1}
 //   loss_px = [ q0 (lse_b - lse) + sum_{1<=c<C_old} q_c (x_c - lse) ] / C_old
 // ------------------------------------------------------------------------------------------
+// One chunk of 4 old-class planes of x (v) and t (u) into the running statistics of VEC pixels:
+//   x: log-sum-exp (m, s);  t: log-sum-exp of alpha*t (mt, st) and wx = sum_{c>=1} 2^(alpha t_c - mt) x_c.
+// nv < 4 (TAIL): only planes [0, nv) exist; skip0: plane 0 of this chunk is channel 0 (not part of wx).
+template <int VEC, bool TAIL>
+__device__ __forceinline__ void unkd_old_chunk(const float (&v)[4][VEC], const float (&u)[4][VEC], int nv, bool skip0,
+                                               float a2, float (&m)[VEC], float (&s)[VEC], float (&mt)[VEC],
+                                               float (&st)[VEC], float (&wx)[VEC]) {
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    float cm = v[0][i], ct = u[0][i] * a2;
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+      const bool live = !TAIL || k < nv;
+      cm = live ? fmaxf(cm, v[k][i]) : cm;
+      ct = live ? fmaxf(ct, u[k][i] * a2) : ct;
+    }
+    const float nm = fmaxf(m[i], cm * kLog2e), nt = fmaxf(mt[i], ct);
+    float acc = s[i] * ex2f(m[i] - nm);
+    const float rs = ex2f(mt[i] - nt);
+    float tacc = st[i] * rs, wacc = wx[i] * rs;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const bool live = !TAIL || k < nv;
+      const float ex = ex2f(fmaf(v[k][i], kLog2e, -nm));
+      const float et = ex2f(fmaf(u[k][i], a2, -nt));
+      acc += live ? ex : 0.f;
+      tacc += live ? et : 0.f;
+      const float w = (live && !(k == 0 && skip0)) ? et : 0.f;
+      wacc = fmaf(w, v[k][i], wacc);
+    }
+    m[i] = nm, s[i] = acc, mt[i] = nt, st[i] = tacc, wx[i] = wacc;
+  }
+}
+
+// Round 2 rewrite (same reasons as unce_fwd_kernel above: the first version ran 66 % issue-active with 128 registers
+// and two blocks per SM): one advancing pointer per tensor, chunks of 4 planes, the channels beyond the old classes
+// go into their OWN (max, sum) pair - one exp per element instead of two - and lse over all channels / over the
+// background set {0} U {C_old..} are combined from the pairs at the end.
 template <int VEC>
-__global__ void __launch_bounds__(kStreamThreads, 2)
+__global__ void __launch_bounds__(kStreamThreads, VEC == 4 ? 3 : 2)
 unkd_fwd_kernel(const float* __restrict__ x, const float* __restrict__ t, const float* __restrict__ mask,
                 float alpha, float* __restrict__ out_px, float* __restrict__ lse3, float* __restrict__ part,
                 int B, int C, int Cs, int C_old, int mask_zero, long long HW) {
@@ -308,96 +358,72 @@ unkd_fwd_kernel(const float* __restrict__ x, const float* __restrict__ t, const 
   // mask_zero: the weight of a pixel is [mask == 0] (MaskKnowledgeDistillationLoss) instead of mask itself
   const long long gpi = HW / VEC;
   const long long n_groups = gpi * B;
+  const bool small = n_groups < (1ll << 31) && gpi < (1ll << 31);
   const long long plane = (long long)B * HW;
   const float a2 = alpha * kLog2e;
   const float inv_cold = 1.f / (float)C_old;
   float acc = 0.f;
   for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n_groups;
        g += (long long)gridDim.x * blockDim.x) {
-    const long long b = g / gpi, p = (g - b * gpi) * VEC;
+    long long b, p;
+    group_to_bp(g, gpi, small, VEC, b, p);
     const float* xp = x + (b * Cs) * HW + p;
-    const float* tp = t + (b * C_old) * HW + p;
-    // x: lse over all channels (m,s) and over S_b (mb,sb); t: lse (mt,st) and weighted sum wx = sum_{c>=1} 2^(t_c-mt) x_c
-    // all in channel chunks (see lse_chunks): 2*CH*VEC loads in flight, no per-element dependency chain.
-    float m[VEC], s[VEC], mb[VEC], sb[VEC], mt[VEC], st[VEC], wx[VEC], t0[VEC];
+    const float* xc = xp;
+    const float* tc = t + (b * C_old) * HW + p;
+    float m[VEC], s[VEC], mt[VEC], st[VEC], wx[VEC], x0[VEC], t0[VEC];
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) m[i] = mb[i] = mt[i] = kNegBig, s[i] = sb[i] = st[i] = wx[i] = 0.f, t0[i] = 0.f;
-    for (int c = 0; c < C_old; c += kLseChunk) {
-      float v[kLseChunk][VEC], u[kLseChunk][VEC];
+    for (int i = 0; i < VEC; ++i) m[i] = mt[i] = kNegBig, s[i] = st[i] = wx[i] = 0.f;
+    int c = 0;
+    for (; c + 4 <= C_old; c += 4) {
+      float v[4][VEC], u[4][VEC];
 #pragma unroll
-      for (int k = 0; k < kLseChunk; ++k) {
-        if (c + k < C_old) {
-          Vec<VEC>::load(xp + (long long)(c + k) * HW, v[k]);
-          Vec<VEC>::load(tp + (long long)(c + k) * HW, u[k]);
+      for (int k = 0; k < 4; ++k) {
+        Vec<VEC>::load(xc + k * HW, v[k]);
+        Vec<VEC>::load(tc + k * HW, u[k]);
+      }
+      xc += 4 * HW, tc += 4 * HW;
+      if (c == 0) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) x0[i] = v[0][i], t0[i] = u[0][i] * a2;
+      }
+      unkd_old_chunk<VEC, false>(v, u, 4, c == 0, a2, m, s, mt, st, wx);
+    }
+    if (c < C_old) {  // 1-3 old planes left
+      const int nv = C_old - c;
+      float v[4][VEC], u[4][VEC];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (k < nv) {
+          Vec<VEC>::load(xc + k * HW, v[k]);
+          Vec<VEC>::load(tc + k * HW, u[k]);
         } else {
 #pragma unroll
-          for (int i = 0; i < VEC; ++i) v[k][i] = kNegBig, u[k][i] = kNegBig;
+          for (int i = 0; i < VEC; ++i) v[k][i] = 0.f, u[k][i] = 0.f;
         }
       }
+      if (c == 0) {
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        float cm = v[0][i], ct = u[0][i] * a2;
-#pragma unroll
-        for (int k = 1; k < kLseChunk; ++k) cm = fmaxf(cm, v[k][i]), ct = fmaxf(ct, u[k][i] * a2);
-        if (a2 < 0.f) {  // negative alpha flips the order of t
-          ct = u[0][i] * a2;
-#pragma unroll
-          for (int k = 1; k < kLseChunk; ++k) ct = fmaxf(ct, (c + k < C_old) ? u[k][i] * a2 : kNegBig);
-        }
-        const float nm = fmaxf(m[i], cm * kLog2e), nt = fmaxf(mt[i], ct);
-        float acc = s[i] * ex2f(m[i] - nm);
-        const float rs = ex2f(mt[i] - nt);
-        float tacc = st[i] * rs, wacc = wx[i] * rs;
-#pragma unroll
-        for (int k = 0; k < kLseChunk; ++k) {
-          acc += ex2f(fmaf(v[k][i], kLog2e, -nm));
-          const bool live = (c + k < C_old);
-          const float e = live ? ex2f(fmaf(u[k][i], a2, -nt)) : 0.f;
-          tacc += e;
-          if (c + k >= 1) wacc = fmaf(e, live ? v[k][i] : 0.f, wacc);
-        }
-        if (c == 0) {
-          mb[i] = v[0][i] * kLog2e;
-          sb[i] = 1.f;
-          t0[i] = u[0][i] * a2;
-        }
-        m[i] = nm, s[i] = acc, mt[i] = nt, st[i] = tacc, wx[i] = wacc;
+        for (int i = 0; i < VEC; ++i) x0[i] = v[0][i], t0[i] = u[0][i] * a2;
       }
+      unkd_old_chunk<VEC, true>(v, u, nv, c == 0, a2, m, s, mt, st, wx);
     }
-    for (int c = C_old; c < C; c += kLseChunk) {
-      float v[kLseChunk][VEC];
+    // channels beyond the old classes: their own (max, sum) pair
+    float mn[VEC], sn[VEC];
 #pragma unroll
-      for (int k = 0; k < kLseChunk; ++k) {
-        if (c + k < C) {
-          Vec<VEC>::load(xp + (long long)(c + k) * HW, v[k]);
-        } else {
-#pragma unroll
-          for (int i = 0; i < VEC; ++i) v[k][i] = kNegBig;
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        float cm = v[0][i];
-#pragma unroll
-        for (int k = 1; k < kLseChunk; ++k) cm = fmaxf(cm, v[k][i]);
-        const float nm = fmaxf(m[i], cm * kLog2e), nb = fmaxf(mb[i], cm * kLog2e);
-        float acc = s[i] * ex2f(m[i] - nm), bacc = sb[i] * ex2f(mb[i] - nb);
-#pragma unroll
-        for (int k = 0; k < kLseChunk; ++k) {
-          const float x2 = v[k][i] * kLog2e;
-          acc += ex2f(x2 - nm);
-          bacc += ex2f(x2 - nb);
-        }
-        m[i] = nm, s[i] = acc, mb[i] = nb, sb[i] = bacc;
-      }
-    }
+    for (int i = 0; i < VEC; ++i) mn[i] = kNegBig, sn[i] = 0.f;
+    xc = xp + (long long)C_old * HW;
+    lse_planes<VEC>(xc, HW, C - C_old, mn, sn);
     float o[VEC], l_all[VEC], l_bkg[VEC], l_t[VEC];
     float mk[VEC];
     if (mask != nullptr) Vec<VEC>::load_cached(mask + b * HW + p, mk);
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
-      const float lse2 = m[i] + lg2f(s[i]);
-      const float lseb2 = mb[i] + lg2f(sb[i]);
+      // all channels = old pair + new pair; background set = {channel 0} + new pair
+      const float ma = fmaxf(m[i], mn[i]);
+      const float lse2 = ma + lg2f(fmaf(s[i], ex2f(m[i] - ma), sn[i] * ex2f(mn[i] - ma)));
+      const float x02 = x0[i] * kLog2e;
+      const float mb = fmaxf(x02, mn[i]);
+      const float lseb2 = mb + lg2f(fmaf(sn[i], ex2f(mn[i] - mb), ex2f(x02 - mb)));
       const float lset2 = mt[i] + lg2f(st[i]);
       l_all[i] = lse2 * kLn2;
       l_bkg[i] = lseb2 * kLn2;

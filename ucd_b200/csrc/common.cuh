@@ -109,6 +109,17 @@ __device__ __forceinline__ void stg_stream1(float* p, float v) {
   asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 
+// 16-byte asynchronous global -> shared copy (LDGSTS, L1 bypass) and its group bookkeeping
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // ---- bilinear taps, ATen semantics (align_corners=False), exact fp32 op order -------------
 struct Tap {
   int i0, i1;

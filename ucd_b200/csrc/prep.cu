@@ -178,8 +178,16 @@ __device__ __forceinline__ size_t tile_chunk_off(long long tile, int chunks_per_
 
 // Pack kernel: block = 32 consecutive pixels, blockIdx.y = source (0: f_n -> anchors, 1: f_o -> pseudo columns).
 // fp32 rows / labels go to the REFERENCE slot (pixel order); bf16 tiles go to the CLASS-SORTED slot.
+// FT = element type of the NCHW head features: float, or __nv_bfloat16 when the head runs in bf16 (the
+// features are consumed as they leave the head, no fp32 round trip; everything downstream is identical).
+__device__ __forceinline__ float feat_ld(const float* p) { return *p; }
+__device__ __forceinline__ float feat_ld(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void feat_st(float* p, float v) { *p = v; }
+__device__ __forceinline__ void feat_st(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+template <typename FT>
 __global__ void __launch_bounds__(128)
-prep_pack_kernel(const float* __restrict__ f_n, const float* __restrict__ f_o, const int* __restrict__ px_meta,
+prep_pack_kernel(const FT* __restrict__ f_n, const FT* __restrict__ f_o, const int* __restrict__ px_meta,
                  int* __restrict__ blk_base, int nblk, int nb, const int* __restrict__ counts, int n_px, int hw,
                  float* __restrict__ anchor_f32, float* __restrict__ contrast_f32, void* __restrict__ la,
                  void* __restrict__ lc, int label_bytes, __nv_bfloat16* __restrict__ feat_tiles,
@@ -205,14 +213,14 @@ prep_pack_kernel(const float* __restrict__ f_n, const float* __restrict__ f_o, c
     }
   }
   if (!__syncthreads_or(slot >= 0)) return;
-  const float* f = src == 0 ? f_n : f_o;
+  const FT* f = src == 0 ? f_n : f_o;
   float part = 0.f;
   if (p < n_px) {
     const int b = p / hw, q = p - b * hw;
-    const float* fp = f + ((size_t)b * 256 + warp * 64) * hw + q;
+    const FT* fp = f + ((size_t)b * 256 + warp * 64) * hw + q;
 #pragma unroll 8
     for (int c = 0; c < 64; ++c) {
-      const float v = fp[(size_t)c * hw];
+      const float v = feat_ld(fp + (size_t)c * hw);
       tile[warp * 64 + c][lane] = v;
       part = fmaf(v, v, part);
     }
@@ -348,10 +356,11 @@ tile_range_kernel(const int* __restrict__ lab_tiles, long long n_tiles, const in
 }
 
 // adjoint of gather + normalize; block = 32 consecutive pixels, writes all 256 channels (zeros for non-anchors)
+template <typename FT>
 __global__ void __launch_bounds__(128)
 prep_bwd_kernel(const float* __restrict__ g_anchor, const float* __restrict__ anchor_f32,
                 const float* __restrict__ inv_norm, const int* __restrict__ px_meta, const int* __restrict__ blk_base,
-                float* __restrict__ df_n, int n_px, int hw) {
+                FT* __restrict__ df_n, int n_px, int hw) {
   __shared__ float tile[256][33];
   __shared__ int slot_s[32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -383,9 +392,9 @@ prep_bwd_kernel(const float* __restrict__ g_anchor, const float* __restrict__ an
   __syncthreads();
   if (p < n_px) {
     const int b = p / hw, q = p - b * hw;
-    float* dp = df_n + ((size_t)b * 256 + warp * 64) * hw + q;
+    FT* dp = df_n + ((size_t)b * 256 + warp * 64) * hw + q;
 #pragma unroll 8
-    for (int c = 0; c < 64; ++c) dp[(size_t)c * hw] = tile[warp * 64 + c][lane];
+    for (int c = 0; c < 64; ++c) feat_st(dp + (size_t)c * hw, tile[warp * 64 + c][lane]);
   }
 }
 
@@ -521,11 +530,12 @@ extern "C" int ucd_con_tile_ranges(const int32_t* lab_tiles, int64_t n_tiles, co
   return UCD_OK;
 }
 
-extern "C" int ucd_con_prep_pack(const float* f_n, const float* f_o, const float* l_po, const int32_t* px_meta,
-                                 int32_t* blk_meta, const int32_t* counts, int B, int C_old, int h, int w,
-                                 int max_label, float* anchor_f32, float* contrast_f32, void* la, void* lc,
-                                 int label_bytes, void* feat_tiles, void* prob_tiles, int32_t* lab_tiles, int32_t* tile_range,
-                                 int32_t* row_range, int32_t* row_ref, float* inv_norm, int64_t max_tiles, void* stream) {
+template <typename FT>
+static int prep_pack_impl(const FT* f_n, const FT* f_o, const float* l_po, const int32_t* px_meta,
+                          int32_t* blk_meta, const int32_t* counts, int B, int C_old, int h, int w,
+                          int max_label, float* anchor_f32, float* contrast_f32, void* la, void* lc,
+                          int label_bytes, void* feat_tiles, void* prob_tiles, int32_t* lab_tiles, int32_t* tile_range,
+                          int32_t* row_range, int32_t* row_ref, float* inv_norm, int64_t max_tiles, void* stream) {
   UCD_CHECK_ARG(f_n && f_o && l_po && px_meta && blk_meta && counts && anchor_f32 && contrast_f32 && la && lc &&
                     feat_tiles && prob_tiles && lab_tiles && tile_range && row_range && row_ref && inv_norm,
                 "ucd_con_prep_pack: null pointer");
@@ -545,9 +555,9 @@ extern "C" int ucd_con_prep_pack(const float* f_n, const float* f_o, const float
   if (e == cudaSuccess) e = cudaMemsetAsync(lab_tiles, 0xff, (size_t)max_tiles * 128 * sizeof(int32_t), st);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(tiles)");
   dim3 grid((n_px + 31) / 32, 2);
-  prep_pack_kernel<<<grid, 128, 0, st>>>(f_n, f_o, px_meta, blk_meta, nblk, nb, counts, n_px, h * w, anchor_f32,
-                                         contrast_f32, la, lc, label_bytes, (__nv_bfloat16*)feat_tiles, lab_tiles,
-                                         row_ref, inv_norm);
+  prep_pack_kernel<FT><<<grid, 128, 0, st>>>(f_n, f_o, px_meta, blk_meta, nblk, nb, counts, n_px, h * w, anchor_f32,
+                                             contrast_f32, la, lc, label_bytes, (__nv_bfloat16*)feat_tiles, lab_tiles,
+                                             row_ref, inv_norm);
   UCD_CHECK_LAUNCH("prep_pack_kernel");
   prep_prob_kernel<<<(n_px + 255) / 256, 256, 0, st>>>(l_po, px_meta, blk_meta, nblk, nb, counts, n_px, h * w, C_old,
                                                        kpad, (__nv_bfloat16*)prob_tiles);
@@ -559,13 +569,46 @@ extern "C" int ucd_con_prep_pack(const float* f_n, const float* f_o, const float
   return ucd_con_tile_ranges(lab_tiles, (n_px + 127) / 128, counts, row_range, stream);
 }
 
+extern "C" int ucd_con_prep_pack(const float* f_n, const float* f_o, const float* l_po, const int32_t* px_meta,
+                                 int32_t* blk_meta, const int32_t* counts, int B, int C_old, int h, int w,
+                                 int max_label, float* anchor_f32, float* contrast_f32, void* la, void* lc,
+                                 int label_bytes, void* feat_tiles, void* prob_tiles, int32_t* lab_tiles, int32_t* tile_range,
+                                 int32_t* row_range, int32_t* row_ref, float* inv_norm, int64_t max_tiles, void* stream) {
+  return prep_pack_impl<float>(f_n, f_o, l_po, px_meta, blk_meta, counts, B, C_old, h, w, max_label, anchor_f32,
+                               contrast_f32, la, lc, label_bytes, feat_tiles, prob_tiles, lab_tiles, tile_range,
+                               row_range, row_ref, inv_norm, max_tiles, stream);
+}
+
+extern "C" int ucd_con_prep_pack_bf16(const void* f_n, const void* f_o, const float* l_po, const int32_t* px_meta,
+                                      int32_t* blk_meta, const int32_t* counts, int B, int C_old, int h, int w,
+                                      int max_label, float* anchor_f32, float* contrast_f32, void* la, void* lc,
+                                      int label_bytes, void* feat_tiles, void* prob_tiles, int32_t* lab_tiles,
+                                      int32_t* tile_range, int32_t* row_range, int32_t* row_ref, float* inv_norm,
+                                      int64_t max_tiles, void* stream) {
+  return prep_pack_impl<__nv_bfloat16>((const __nv_bfloat16*)f_n, (const __nv_bfloat16*)f_o, l_po, px_meta, blk_meta,
+                                       counts, B, C_old, h, w, max_label, anchor_f32, contrast_f32, la, lc, label_bytes,
+                                       feat_tiles, prob_tiles, lab_tiles, tile_range, row_range, row_ref, inv_norm,
+                                       max_tiles, stream);
+}
+
 extern "C" int ucd_con_prep_bwd(const float* g_anchor, const float* anchor_f32, const float* inv_norm,
                                 const int32_t* px_meta, const int32_t* blk_meta, float* df_n, int B, int h, int w,
                                 void* stream) {
   UCD_CHECK_ARG(g_anchor && anchor_f32 && inv_norm && px_meta && blk_meta && df_n, "ucd_con_prep_bwd: null pointer");
   const int n_px = B * h * w;
-  prep_bwd_kernel<<<(n_px + 31) / 32, 128, 0, (cudaStream_t)stream>>>(g_anchor, anchor_f32, inv_norm, px_meta,
-                                                                       blk_meta, df_n, n_px, h * w);
+  prep_bwd_kernel<float><<<(n_px + 31) / 32, 128, 0, (cudaStream_t)stream>>>(g_anchor, anchor_f32, inv_norm, px_meta,
+                                                                              blk_meta, df_n, n_px, h * w);
+  UCD_CHECK_LAUNCH("prep_bwd_kernel");
+  return UCD_OK;
+}
+
+extern "C" int ucd_con_prep_bwd_bf16(const float* g_anchor, const float* anchor_f32, const float* inv_norm,
+                                     const int32_t* px_meta, const int32_t* blk_meta, void* df_n, int B, int h, int w,
+                                     void* stream) {
+  UCD_CHECK_ARG(g_anchor && anchor_f32 && inv_norm && px_meta && blk_meta && df_n, "ucd_con_prep_bwd_bf16: null pointer");
+  const int n_px = B * h * w;
+  prep_bwd_kernel<__nv_bfloat16><<<(n_px + 31) / 32, 128, 0, (cudaStream_t)stream>>>(
+      g_anchor, anchor_f32, inv_norm, px_meta, blk_meta, (__nv_bfloat16*)df_n, n_px, h * w);
   UCD_CHECK_LAUNCH("prep_bwd_kernel");
   return UCD_OK;
 }

@@ -493,3 +493,140 @@ extern "C" int ucd_selftest_mma_mix(int s_ts, int s_a, int s_acc0, int s_acc1, i
   *cycles_per_tile_host = (float)(h2[0] > h2[1] ? h2[0] : h2[1]) / (float)tiles;
   return UCD_OK;
 }
+
+
+// ---- HBM read probe: what a read-only streaming kernel can reach on this part (the denominator of the read-bound
+// kernels: UNCE / UNKD forward, upsample backward).  mode 0: UN 128-bit register loads in flight per thread, batch by
+// batch; mode 1: cp.async ring of UN 16-byte copies per thread (rolling); mode 2: planes walked with a stride like
+// the NCHW loss kernels (17 streams per thread block).  Returns microseconds per pass (best of `reps`).
+namespace ucd {
+template <int UN>
+__global__ void __launch_bounds__(256) read_probe_regs(const float4* __restrict__ p, long long n4, float* sink) {
+  float acc = 0.f;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + (UN - 1) * stride < n4; i += UN * stride) {
+    float4 v[UN];
+#pragma unroll
+    for (int j = 0; j < UN; ++j) v[j] = ldg_stream4(reinterpret_cast<const float*>(p + i + j * stride));
+#pragma unroll
+    for (int j = 0; j < UN; ++j) acc += v[j].x + v[j].y + v[j].z + v[j].w;
+  }
+  for (; i < n4; i += stride) {
+    const float4 v = ldg_stream4(reinterpret_cast<const float*>(p + i));
+    acc += v.x + v.y + v.z + v.w;
+  }
+  if (acc == 1.2345e-30f) *sink = acc;
+}
+template <int UN>
+__global__ void __launch_bounds__(256) read_probe_async(const float4* __restrict__ p, long long n4, float* sink) {
+  extern __shared__ __align__(16) float4 ring[];
+  float acc = 0.f;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long cnt = i0 < n4 ? (n4 - i0 + stride - 1) / stride : 0;
+  auto fetch = [&](long long k) {
+    if (k < cnt) cp_async16(ring + (size_t)(k % UN) * blockDim.x + threadIdx.x, p + i0 + k * stride);
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int j = 0; j < UN - 1; ++j) fetch(j);
+  for (long long k = 0; k < cnt; ++k) {
+    fetch(k + UN - 1);
+    cp_async_wait<UN - 1>();
+    const float4 v = ring[(size_t)(k % UN) * blockDim.x + threadIdx.x];
+    acc += v.x + v.y + v.z + v.w;
+  }
+  cp_async_wait<0>();
+  if (acc == 1.2345e-30f) *sink = acc;
+}
+// every block streams its OWN contiguous region front to back (the access pattern of a per-block row sweep)
+template <int UN>
+__global__ void __launch_bounds__(256) read_probe_regions(const float4* __restrict__ p, long long n4, float* sink) {
+  float acc = 0.f;
+  const long long lo = n4 * (long long)blockIdx.x / gridDim.x, hi = n4 * ((long long)blockIdx.x + 1) / gridDim.x;
+  long long i = lo + threadIdx.x;
+  for (; i + (UN - 1) * (long long)blockDim.x < hi; i += UN * (long long)blockDim.x) {
+    float4 v[UN];
+#pragma unroll
+    for (int j = 0; j < UN; ++j) v[j] = ldg_stream4(reinterpret_cast<const float*>(p + i + j * (long long)blockDim.x));
+#pragma unroll
+    for (int j = 0; j < UN; ++j) acc += v[j].x + v[j].y + v[j].z + v[j].w;
+  }
+  for (; i < hi; i += blockDim.x) {
+    const float4 v = ldg_stream4(reinterpret_cast<const float*>(p + i));
+    acc += v.x + v.y + v.z + v.w;
+  }
+  if (acc == 1.2345e-30f) *sink = acc;
+}
+// NCHW walk: thread = 4 adjacent pixels, C planes of HW floats each, CH channels in flight
+template <int CH>
+__global__ void __launch_bounds__(256) read_probe_planes(const float* __restrict__ p, int B, int C, long long HW,
+                                                         float* sink) {
+  float acc = 0.f;
+  const long long gpi = HW / 4, n_groups = gpi * B;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n_groups;
+       g += (long long)gridDim.x * blockDim.x) {
+    const long long b = g / gpi, px = (g - b * gpi) * 4;
+    const float* xp = p + (b * C) * HW + px;
+    for (int c = 0; c < C; c += CH) {
+      float4 v[CH];
+#pragma unroll
+      for (int k = 0; k < CH; ++k)
+        v[k] = (c + k < C) ? ldg_stream4(xp + (long long)(c + k) * HW) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < CH; ++k) acc += v[k].x + v[k].y + v[k].z + v[k].w;
+    }
+  }
+  if (acc == 1.2345e-30f) *sink = acc;
+}
+}  // namespace ucd
+
+extern "C" int ucd_selftest_read_probe(const void* buf, long long bytes, int mode, int un, int blocks_per_sm, int reps,
+                                       float* us_host) {
+  using namespace ucd;
+  UCD_CHECK_ARG(buf && us_host && bytes >= (1 << 20) && reps >= 1, "ucd_selftest_read_probe: bad argument");
+  float* sink = nullptr;
+  cudaMalloc(&sink, 4);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0), cudaEventCreate(&e1);
+  const long long n4 = bytes / 16;
+  const int grid = kNumSMs * blocks_per_sm;
+  float best = 1e30f;
+  for (int r = 0; r < reps + 1; ++r) {
+    cudaEventRecord(e0);
+    if (mode == 0) {
+      if (un == 4) read_probe_regs<4><<<grid, 256>>>((const float4*)buf, n4, sink);
+      else if (un == 8) read_probe_regs<8><<<grid, 256>>>((const float4*)buf, n4, sink);
+      else read_probe_regs<16><<<grid, 256>>>((const float4*)buf, n4, sink);
+    } else if (mode == 1) {
+      if (un == 4) read_probe_async<4><<<grid, 256, 4 * 256 * 16>>>((const float4*)buf, n4, sink);
+      else if (un == 8) read_probe_async<8><<<grid, 256, 8 * 256 * 16>>>((const float4*)buf, n4, sink);
+      else {
+        cudaFuncSetAttribute(read_probe_async<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 256 * 16);
+        read_probe_async<16><<<grid, 256, 16 * 256 * 16>>>((const float4*)buf, n4, sink);
+      }
+    } else if (mode == 3) {
+      if (un == 4) read_probe_regions<4><<<grid, 128>>>((const float4*)buf, n4, sink);
+      else if (un == 8) read_probe_regions<8><<<grid, 128>>>((const float4*)buf, n4, sink);
+      else read_probe_regions<16><<<grid, 128>>>((const float4*)buf, n4, sink);
+    } else {
+      const int C = 17, B = 24;
+      const long long HW = bytes / 4 / C / B / 4 * 4;
+      if (un == 4) read_probe_planes<4><<<grid, 256>>>((const float*)buf, B, C, HW, sink);
+      else if (un == 8) read_probe_planes<8><<<grid, 256>>>((const float*)buf, B, C, HW, sink);
+      else read_probe_planes<17><<<grid, 256>>>((const float*)buf, B, C, HW, sink);
+    }
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (r > 0 && ms < best) best = ms;
+  }
+  cudaError_t e = cudaGetLastError();
+  cudaEventDestroy(e0), cudaEventDestroy(e1);
+  cudaFree(sink);
+  if (e != cudaSuccess) return cuda_fail(e, "read_probe");
+  *us_host = best * 1e3f;
+  return UCD_OK;
+}

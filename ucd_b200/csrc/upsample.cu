@@ -280,41 +280,39 @@ upsample_bwd_kernel(const float* __restrict__ gout, float* __restrict__ gin, int
 }
 
 // Adjoint, sweep form (integer upscale factors that are a multiple of 8 along x, rows of <= 1024 elements: the
-// training shapes).  block = (plane, segment of seg_rows low-res rows); thread = 4 consecutive X, which then share
-// one pair of x taps.  The block walks the full-res rows of its segment top-down exactly once (plus the one interval
-// above it, whose lower-tap part belongs to the segment's first row): per 128-bit load 8 FMAs fold the x weights,
-// 4 more the y weights; a low-res row is emitted when the sweep leaves its interval (shared-memory gather over the
-// threads whose taps hit each cell, fixed order).  No atomics, no re-reads beyond 1/seg_rows.
-constexpr int kUpSweepCap = 640;  // tap-table rows: (seg_rows + 2) * scale + 8 must fit (footprint + margins)
+// training shapes).  thread = 4 consecutive X, which then share one pair of x taps; blockDim = W / 4.
+// Work = the planes * h low-res rows of the whole tensor, cut into gridDim.x EQUAL contiguous ranges (a range that
+// crosses a plane boundary is processed as two segments), so that every SM streams the same number of bytes whatever
+// the shape (24x17 planes of 32 rows and 3x151 planes alike; fixed 16-row segments left 8 % / 50 % of the SMs idle).
+// A segment walks the full-res rows of its intervals top-down exactly once through a rolling window of UN 16-byte
+// cp.async copies per thread that stays full across the row emits: per row 8 FMAs fold the x weights, 4 more the y
+// weights; a low-res row is emitted when the sweep leaves its interval (shared-memory gather over the threads whose
+// taps hit each cell, fixed order).  Nothing is read twice: the lower-tap sums of a segment's LAST interval belong to
+// the next segment's first row, which therefore receives exactly two contributions - its owner's and this carry -
+// added with atomicAdd onto a zeroed output.  Two operands commute, so the result does not depend on which block
+// comes first: deterministic without a second pass.  (Round 2: the first sweep kernel executed 78 instructions per
+// 16 bytes - ncu: 66 % issue-active, barrier + shared-memory stalls - and re-read one interval per range; a pure read
+// with this access pattern reaches 6.3 TB/s once ~1500 threads per SM are streaming, scripts/read_probe.py.)
 template <int UN>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 upsample_bwd_sweep_kernel(const float* __restrict__ gout, float* __restrict__ gin, int h, int w, int H, int W,
-                          float scale_h, float scale_w, int nseg, int seg_rows) {
-  __shared__ int s_k[kUpSweepCap];
-  __shared__ float s_h0[kUpSweepCap], s_h1[kUpSweepCap];
-  __shared__ float s_p0[256], s_p1[256];
-  __shared__ int s_x0[256], s_x1[256];
+                          float scale_h, float scale_w, long long total_rows, int cap_rows, int ny_cap) {
+  extern __shared__ __align__(16) uint8_t up_dyn[];
   const int wv = blockDim.x;  // == W / 4
-  const long long plane = blockIdx.x / nseg;
-  const int seg = (int)(blockIdx.x - plane * nseg);
-  const int y0 = seg * seg_rows, ylast = min(y0 + seg_rows, h) - 1;
-  const int kfirst = max(y0 - 1, 0);  // first interval read (for y0 > 0 only its lower-tap part is used)
-  const float inv = (float)H / (float)h;
-  int Ylo = (int)floorf(((float)kfirst - 0.5f) * inv) - 2, Yhi = (int)ceilf(((float)ylast + 1.5f) * inv) + 2;
-  Ylo = max(Ylo, 0), Yhi = min(Yhi, H - 1);
-  const int ny = min(Yhi - Ylo + 1, kUpSweepCap);
-  for (int i = threadIdx.x; i < ny; i += blockDim.x) {
-    const Tap ty = bilinear_tap(Ylo + i, scale_h, h, H);
-    s_k[i] = ty.i0;
-    const bool clamped = ty.i1 == ty.i0;  // bottom border: both taps hit the same low-res row
-    s_h0[i] = clamped ? ty.w0 + ty.w1 : ty.w0;
-    s_h1[i] = clamped ? 0.f : ty.w1;
-  }
-  const int X = (int)threadIdx.x * 4;
+  const int tid = threadIdx.x;
+  float4* ring = reinterpret_cast<float4*>(up_dyn);                       // [UN][wv]
+  float2* s_p = reinterpret_cast<float2*>(ring + (size_t)UN * wv);        // [2][wv] (p0, p1) of the row being emitted
+  float2* s_h = s_p + 2 * wv;                                             // [ny_cap] y weights (upper tap, lower tap)
+  int* s_k = reinterpret_cast<int*>(s_h + ny_cap);                        // [ny_cap] low-res row of the upper tap
+  int* s_x0 = s_k + ny_cap;                                               // [wv] upper / lower x tap of each thread
+  int* s_x1 = s_x0 + wv;
+  short4* s_j = reinterpret_cast<short4*>(s_x1 + wv);                     // [w] thread ranges hitting low-res x
+  __shared__ int s_lim[2];                                                // first / last+1 tap-table row actually read
+  const int X = tid * 4;
   float wx0[4], wx1[4];
   {
     const Tap t0 = bilinear_tap(X, scale_w, w, W);
-    s_x0[threadIdx.x] = t0.i0, s_x1[threadIdx.x] = t0.i1;
+    s_x0[tid] = t0.i0, s_x1[tid] = t0.i1;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const Tap tx = bilinear_tap(X + i, scale_w, w, W);  // same i0 / i1 as t0 (host-checked precondition)
@@ -322,60 +320,124 @@ upsample_bwd_sweep_kernel(const float* __restrict__ gout, float* __restrict__ gi
     }
   }
   __syncthreads();
-  const float* g = gout + (size_t)plane * H * W + (size_t)Ylo * W + X;
-  float* out = gin + (size_t)plane * h * w;
-  const int sc4 = (W / w) / 4;  // threads per low-res column
-  float a0p0 = 0.f, a0p1 = 0.f, a1p0 = 0.f, a1p1 = 0.f, c0 = 0.f, c1 = 0.f;  // current interval, carry from the one above
-  int cur = -1;
-  // leave interval `cur`: emit low-res row cur (if it belongs to this segment), its lower-tap sums become the carry
-  auto flush = [&]() {
-    if (cur >= y0 && cur <= ylast) {
-      s_p0[threadIdx.x] = a0p0 + c0;
-      s_p1[threadIdx.x] = a0p1 + c1;
-      __syncthreads();
-      if ((int)threadIdx.x < w) {
-        const int x = threadIdx.x;
-        const int j0 = max((x - 2) * sc4 - 2, 0), j1 = min((x + 2) * sc4 + 2, wv - 1);
+  if (tid < w) {  // thread ranges per low-res column (taps are monotone in X, so the hits are contiguous)
+    const int sc4 = (W / w) / 4;
+    const int j0 = max((tid - 2) * sc4 - 2, 0), j1 = min((tid + 2) * sc4 + 2, wv - 1);
+    int a0 = 0, a1 = 0, b0 = 0, b1 = 0;
+    bool fa = false, fb = false;
+    for (int j = j0; j <= j1; ++j) {
+      if (s_x0[j] == tid) {
+        if (!fa) a0 = j, fa = true;
+        a1 = j + 1;
+      }
+      if (s_x1[j] == tid) {
+        if (!fb) b0 = j, fb = true;
+        b1 = j + 1;
+      }
+    }
+    s_j[tid] = make_short4((short)a0, (short)a1, (short)b0, (short)b1);
+  }
+  const float inv = (float)H / (float)h;
+  const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring + tid);  // this thread's 16 B of slot 0
+  const uint32_t slot_b = (uint32_t)wv * 16u;
+  int flip = 0;
+  // this block's range of global low-res rows (plane * h + y)
+  const long long r_begin = total_rows * (long long)blockIdx.x / (long long)gridDim.x;
+  const long long r_end = total_rows * ((long long)blockIdx.x + 1) / (long long)gridDim.x;
+  for (long long r = r_begin; r < r_end;) {
+    const long long plane = r / h;
+    const int y0 = (int)(r - plane * h);
+    const int ylast = (int)min((long long)min(h, y0 + cap_rows), y0 + (r_end - r)) - 1;
+    r += ylast - y0 + 1;
+    int Ylo = (int)floorf(((float)y0 - 0.5f) * inv) - 2, Yhi = (int)ceilf(((float)ylast + 1.5f) * inv) + 2;
+    Ylo = max(Ylo, 0), Yhi = min(Yhi, H - 1);
+    const int ny = min(Yhi - Ylo + 1, ny_cap);
+    __syncthreads();  // the previous segment no longer reads the tap table
+    for (int i = tid; i < ny; i += wv) {
+      const Tap ty = bilinear_tap(Ylo + i, scale_h, h, H);
+      s_k[i] = ty.i0;
+      const bool clamped = ty.i1 == ty.i0;  // bottom border: both taps hit the same low-res row
+      s_h[i] = make_float2(clamped ? ty.w0 + ty.w1 : ty.w0, clamped ? 0.f : ty.w1);
+    }
+    __syncthreads();
+    // rows whose upper tap lies in [y0, ylast] are the ones to read (the rest are margins of the conservative range);
+    // s_k is monotone, so exactly one row starts and one row ends that run
+    for (int i = tid; i < ny; i += wv) {
+      const int k = s_k[i];
+      if (k >= y0 && k <= ylast) {
+        if (i == 0 || s_k[i - 1] < y0) s_lim[0] = i;
+        if (i == ny - 1 || s_k[i + 1] > ylast) s_lim[1] = i + 1;
+      }
+    }
+    __syncthreads();
+    const int i_lo = s_lim[0], i_hi = s_lim[1];
+    const float* gp = gout + (size_t)plane * H * W + (size_t)(Ylo + i_lo) * W + X;  // next row to fetch
+    float* out = gin + (size_t)plane * h * w;
+    float a0p0 = 0.f, a0p1 = 0.f, a1p0 = 0.f, a1p1 = 0.f, c0 = 0.f, c1 = 0.f;  // current interval, carry from the one above
+    int cur = -1;
+    // low-res row `row` += gather over x of the per-thread pairs (v0 -> upper x tap, v1 -> lower x tap); `shared`:
+    // another segment contributes to this row as well (see the header comment)
+    auto emit = [&](int row, float v0, float v1, bool shared) {
+      s_p[flip * wv + tid] = make_float2(v0, v1);
+      __syncthreads();  // one barrier per emit: the buffers alternate, so the next emit cannot overtake this gather
+      if (tid < w) {
+        const short4 jr = s_j[tid];
+        const float2* sp = s_p + flip * wv;
         float acc = 0.f;
-        for (int j = j0; j <= j1; ++j) {
-          if (s_x0[j] == x) acc += s_p0[j];
-          if (s_x1[j] == x) acc += s_p1[j];
-        }
-        out[(size_t)cur * w + x] = acc;
+        for (int j = jr.x; j < jr.y; ++j) acc += sp[j].x;
+        for (int j = jr.z; j < jr.w; ++j) acc += sp[j].y;
+        if (shared)
+          atomicAdd(out + (size_t)row * w + tid, acc);
+        else
+          out[(size_t)row * w + tid] = acc;
       }
-      __syncthreads();
-    }
-    c0 = a1p0, c1 = a1p1;
-    a0p0 = a0p1 = a1p0 = a1p1 = 0.f;
-  };
-  for (int base = 0; base < ny; base += UN) {
-    float4 v[UN];
-#pragma unroll
-    for (int j = 0; j < UN; ++j) {
-      const int i = base + j;
-      const bool use = i < ny && s_k[min(i, ny - 1)] >= kfirst && s_k[min(i, ny - 1)] <= ylast;
-      v[j] = use ? ldg_stream4(g + (size_t)i * W) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-#pragma unroll
-    for (int j = 0; j < UN; ++j) {
-      const int i = base + j;
-      if (i < ny) {
-        const int k = s_k[i];
-        if (k >= kfirst && k <= ylast) {  // uniform over the block
-          if (k != cur) {
-            if (cur >= 0) flush();
-            cur = k;
-          }
-          const float p0 = fmaf(v[j].w, wx0[3], fmaf(v[j].z, wx0[2], fmaf(v[j].y, wx0[1], v[j].x * wx0[0])));
-          const float p1 = fmaf(v[j].w, wx1[3], fmaf(v[j].z, wx1[2], fmaf(v[j].y, wx1[1], v[j].x * wx1[0])));
-          const float h0 = s_h0[i], h1 = s_h1[i];
-          a0p0 = fmaf(h0, p0, a0p0), a0p1 = fmaf(h0, p1, a0p1);
-          a1p0 = fmaf(h1, p0, a1p0), a1p1 = fmaf(h1, p1, a1p1);
-        }
+      flip ^= 1;
+    };
+    // leave interval `cur`: emit low-res row cur, its lower-tap sums become the carry
+    auto flush = [&]() {
+      emit(cur, a0p0 + c0, a0p1 + c1, cur == y0 && y0 > 0);
+      c0 = a1p0, c1 = a1p1;
+      a0p0 = a0p1 = a1p0 = a1p1 = 0.f;
+    };
+    // rolling window of UN rows in flight per thread: cp.async into the thread's own 16 B of ring slot (row % UN) (a
+    // thread only ever reads what it copied itself: no block barrier, just its own wait_group)
+    int nfetch = i_hi - i_lo;  // rows still to fetch
+    uint32_t fslot = 0, cslot = 0;
+    auto fetch = [&]() {
+      if (nfetch > 0) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring_s + fslot), "l"(gp) : "memory");
+        gp += W;
+        --nfetch;
       }
+      cp_async_commit();
+      fslot = (fslot + slot_b == slot_b * UN) ? 0u : fslot + slot_b;
+    };
+#pragma unroll
+    for (int j = 0; j < UN - 1; ++j) fetch();
+#pragma unroll 1
+    for (int i = i_lo; i < i_hi; ++i) {
+      fetch();
+      cp_async_wait<UN - 1>();
+      const int k = s_k[i];
+      if (k != cur) {  // uniform over the block
+        if (cur >= 0) flush();
+        cur = k;
+      }
+      float4 x;
+      asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(ring_s + cslot));
+      cslot = (cslot + slot_b == slot_b * UN) ? 0u : cslot + slot_b;
+      const float2 hw = s_h[i];
+      const float p0 = fmaf(x.w, wx0[3], fmaf(x.z, wx0[2], fmaf(x.y, wx0[1], x.x * wx0[0])));
+      const float p1 = fmaf(x.w, wx1[3], fmaf(x.z, wx1[2], fmaf(x.y, wx1[1], x.x * wx1[0])));
+      a0p0 = fmaf(hw.x, p0, a0p0), a0p1 = fmaf(hw.x, p1, a0p1);
+      a1p0 = fmaf(hw.y, p0, a1p0), a1p1 = fmaf(hw.y, p1, a1p1);
+    }
+    cp_async_wait<0>();
+    if (cur >= 0) {
+      flush();
+      if (ylast < h - 1) emit(ylast + 1, c0, c1, true);  // lower-tap sums of the last interval: the next segment's row
     }
   }
-  if (cur >= 0) flush();
 }
 
 }  // namespace ucd
@@ -438,17 +500,40 @@ extern "C" int ucd_upsample_bilinear_bwd(const float* gout, float* gin, int64_t 
   UCD_CHECK_ARG(smem <= 200 * 1024, "ucd_upsample_bilinear_bwd: W=%d / scale too large for one block", W);
   const float sh = (float)h / (float)H, sw = (float)w / (float)W;
   const bool v4 = (W % 4 == 0) && aligned16(gout);
-  // sweep form: integer scales, a multiple of 8 along x (4 consecutive X share their taps), one block row = W/4 threads
-  // low-res rows per block: 16 measured best (98 us vs 106 / 113 us for 8 / 4 at 24x17x512x512: re-reading the
-  // interval above the segment is not free), reduced until the tap table fits; 8 rows of loads in flight per thread
-  int seg_rows = 16;
-  while (seg_rows > 1 && (seg_rows + 2) * (H / (h > 0 ? h : 1)) + 8 > kUpSweepCap) seg_rows >>= 1;
+  // sweep form: integer scales, a multiple of 8 along x (4 consecutive X share their taps), one block row = W/4 threads.
+  // Grid = a whole number of blocks per SM (~1500 streaming threads per SM), each with an equal share of the
+  // planes * h low-res rows; small problems take fewer blocks so that a range keeps >= 4 rows.
+  const int up = H / (h > 0 ? h : 1);
+  constexpr int kUpSweepTaps = 640;  // tap-table rows a block may hold
+  const int cap_rows = up > 0 ? (kUpSweepTaps - 8) / up - 2 : 0;  // rows of one segment the tap table can hold
   if (v4 && H % h == 0 && W % w == 0 && (W / w) % 8 == 0 && W / 4 <= 256 && (W / 4) % 32 == 0 && w <= W / 4 &&
-      (seg_rows + 2) * (H / h) + 8 <= kUpSweepCap) {
-    const int nseg = (h + seg_rows - 1) / seg_rows;
-    UCD_CHECK_ARG(planes * nseg < (1ll << 31), "ucd_upsample_bilinear_bwd: too many blocks");
-    const unsigned nb = (unsigned)(planes * nseg);
-    upsample_bwd_sweep_kernel<8><<<nb, W / 4, 0, st>>>(gout, gin, h, w, H, W, sh, sw, nseg, seg_rows);
+      cap_rows >= 1) {
+    int un = 8, bps = (W / 4 <= 128 ? 4 : 2);  // rows in flight per thread, blocks per SM (measured best: scripts/up_bwd_probe.py)
+#ifdef UCD_DEBUG_KNOBS
+    if (const char* e = getenv("UCD_UPB_UN")) un = atoi(e);    // tuning knobs (debug library only)
+    if (const char* e = getenv("UCD_UPB_BPS")) bps = atoi(e);
+#endif
+    const long long total_rows = planes * h;
+    long long nb = (long long)kNumSMs * bps;
+    while (nb > kNumSMs && total_rows / nb < 4) nb -= kNumSMs;
+    if (nb > total_rows) nb = total_rows;
+    long long seg = (total_rows + nb - 1) / nb + 1;  // longest segment of a range
+    if (seg > cap_rows) seg = cap_rows;
+    const int ny_cap = (int)(seg + 2) * up + 8;
+    const int wv4 = W / 4;
+    const size_t dyn = (size_t)un * wv4 * 16 + (size_t)2 * wv4 * 8 + (size_t)ny_cap * 12 + (size_t)2 * wv4 * 4 + (size_t)w * 8;
+    // boundary rows of the ranges are accumulated by two blocks (see the kernel): the output starts from zero
+    cudaError_t e = cudaMemsetAsync(gin, 0, (size_t)planes * h * w * sizeof(float), st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(upsample_bwd)");
+    auto kern = upsample_bwd_sweep_kernel<8>;
+    if (un == 4) kern = upsample_bwd_sweep_kernel<4>;
+    if (un == 12) kern = upsample_bwd_sweep_kernel<12>;
+    if (un == 16) kern = upsample_bwd_sweep_kernel<16>;
+    if (dyn > 48 * 1024) {
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(upsample_bwd_sweep)");
+    }
+    kern<<<(unsigned)nb, wv4, dyn, st>>>(gout, gin, h, w, H, W, sh, sw, total_rows, cap_rows, ny_cap);
     UCD_CHECK_LAUNCH("upsample_bwd_sweep_kernel");
     return UCD_OK;
   }

@@ -143,6 +143,7 @@ class _GradChain:
             self.pending.append(term)
             return None, torch.zeros((), device=term["x"].device, dtype=torch.float32)
         terms, self.pending = self.pending + [term], []
+        self.token = None   # chain -> token -> grad_fn -> ctx -> chain would leave the pass's objects to the cycle collector
         return _launch_terms(terms), None
 
 
@@ -475,6 +476,7 @@ class ContrastPack:
         self.row_ref = self.inv_norm = None          # sorted anchor row -> reference row
         self.max_label = 20
         self.l_po = None
+        self.bf16_feats = False    # the head features arrived (and their gradient leaves) in bf16
 
     @property
     def n_c(self):
@@ -510,9 +512,17 @@ def _build_pack(f_n, f_o, l_po, labels, max_label, sync=True, require_new_class=
     L = _lib.lib()
     dev = f_n.device
     labels = labels.to(torch.int64).contiguous()
-    f_n, f_o, l_po = _f32c(f_n), _f32c(f_o), _f32c(l_po)
+    # N2 (feature hand-off): a head that runs in bf16 hands its features over as they are - the pack kernel reads bf16
+    # NCHW directly (no fp32 copy of the two feature maps) and the adjoint writes the bf16 gradient
+    bf16_feats = f_n.dtype == torch.bfloat16 and f_o.dtype == torch.bfloat16
+    if bf16_feats:
+        f_n, f_o = f_n.contiguous(), f_o.contiguous()
+    else:
+        f_n, f_o = _f32c(f_n), _f32c(f_o)
+    l_po = _f32c(l_po)
     H, W = labels.shape[-2:]
     pk = ContrastPack()
+    pk.bf16_feats = bf16_feats
     pk.shape, pk.n_px, pk.c_old = (B, h, w), B * h * w, l_po.shape[1]
     pk.kpad = L.ucd_con_prob_kpad(pk.c_old)
     pk.max_tiles = L.ucd_con_max_tiles(pk.n_px)
@@ -550,7 +560,8 @@ def _build_pack(f_n, f_o, l_po, labels, max_label, sync=True, require_new_class=
     pk.row_range = torch.empty((n_px + TILE - 1) // TILE, 2, **i32)
     pk.row_ref = torch.empty(n_px, **i32)
     pk.inv_norm = torch.empty(n_px, device=dev, dtype=torch.float32)
-    check(L.ucd_con_prep_pack(ptr(f_n), ptr(f_o), ptr(l_po), ptr(pk.px_meta), ptr(pk.blk_meta), ptr(pk.counts), B,
+    pack_fn = L.ucd_con_prep_pack_bf16 if bf16_feats else L.ucd_con_prep_pack
+    check(pack_fn(ptr(f_n), ptr(f_o), ptr(l_po), ptr(pk.px_meta), ptr(pk.blk_meta), ptr(pk.counts), B,
                               pk.c_old, h, w, pk.max_label, ptr(pk.anchor_f32), ptr(pk.contrast_f32), ptr(pk.la),
                               ptr(pk.lc), pk.la.element_size(), ptr(pk.feat_tiles), ptr(pk.prob_tiles), ptr(pk.lab_tiles),
                               ptr(pk.tile_range), ptr(pk.row_range), ptr(pk.row_ref), ptr(pk.inv_norm),
@@ -585,9 +596,11 @@ class _AnchorFn(torch.autograd.Function):
         g = _f32c(g)
         if pk.n_a == 0:   # no anchor in this batch: nothing flows back
             return torch.zeros(B, FEAT_DIM, h, w, device=g.device, dtype=ctx.in_dtype), None
-        df = torch.empty(B, FEAT_DIM, h, w, device=g.device, dtype=torch.float32)
-        check(_lib.lib().ucd_con_prep_bwd(ptr(g), ptr(pk.anchor_f32), ptr(pk.inv_norm), ptr(pk.px_meta),
-                                          ptr(pk.blk_meta), ptr(df), B, h, w, cur_stream()), "con_prep_bwd")
+        direct_bf16 = pk.bf16_feats and ctx.in_dtype == torch.bfloat16
+        df = torch.empty(B, FEAT_DIM, h, w, device=g.device, dtype=torch.bfloat16 if direct_bf16 else torch.float32)
+        bwd_fn = _lib.lib().ucd_con_prep_bwd_bf16 if direct_bf16 else _lib.lib().ucd_con_prep_bwd
+        check(bwd_fn(ptr(g), ptr(pk.anchor_f32), ptr(pk.inv_norm), ptr(pk.px_meta),
+                     ptr(pk.blk_meta), ptr(df), B, h, w, cur_stream()), "con_prep_bwd")
         return df.to(ctx.in_dtype), None
 
 
@@ -811,9 +824,12 @@ class _ConFn(torch.autograd.Function):
         pk = ctx.static_pack
         if pk is not None:  # continue through the anchor gather + normalise adjoint to f_n (rows >= N_a are never read)
             B, h, w = pk.shape
-            df = torch.empty(B, FEAT_DIM, h, w, device=g.device, dtype=torch.float32)
-            check(_lib.lib().ucd_con_prep_bwd(ptr(d_anchor), ptr(pk.anchor_f32), ptr(pk.inv_norm), ptr(pk.px_meta),
-                                              ptr(pk.blk_meta), ptr(df), B, h, w, cur_stream()), "con_prep_bwd")
+            direct_bf16 = pk.bf16_feats and ctx.in_dtype == torch.bfloat16
+            df = torch.empty(B, FEAT_DIM, h, w, device=g.device,
+                             dtype=torch.bfloat16 if direct_bf16 else torch.float32)
+            bwd_fn = _lib.lib().ucd_con_prep_bwd_bf16 if direct_bf16 else _lib.lib().ucd_con_prep_bwd
+            check(bwd_fn(ptr(d_anchor), ptr(pk.anchor_f32), ptr(pk.inv_norm), ptr(pk.px_meta),
+                         ptr(pk.blk_meta), ptr(df), B, h, w, cur_stream()), "con_prep_bwd")
             d_anchor = df.to(ctx.in_dtype)
         return d_anchor, None, None, None, None, None, None, None
 
