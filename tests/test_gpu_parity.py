@@ -192,7 +192,10 @@ def test_contrastive_prep_integer_artefacts_and_rows(U, golden_dir, name):
     rows = ft.permute(0, 2, 1, 3).reshape(-1, 256)[:pk.n_c]
     assert float((rows - Co[perm]).abs().max()) < 2 ** -8
     lt = pk.lab_tiles.cpu().reshape(-1)
-    assert torch.equal(lt[:pk.n_c].long(), lco[perm]) and bool((lt[pk.n_c:] == -1).all())
+    # padding of the last tile the sweeps read: label -1, zero features / probabilities (tiles beyond it are never read)
+    pad_end = ((pk.n_c + 127) // 128) * 128
+    assert torch.equal(lt[:pk.n_c].long(), lco[perm]) and bool((lt[pk.n_c:pad_end] == -1).all())
+    assert float(ft.permute(0, 2, 1, 3).reshape(-1, 256)[pk.n_c:pad_end].abs().sum()) == 0.0
     tr = pk.tile_range.cpu()
     for t in range((pk.n_c + 127) // 128):
         seg = lt[t * 128:min(pk.n_c, (t + 1) * 128)]
@@ -200,7 +203,9 @@ def test_contrastive_prep_integer_artefacts_and_rows(U, golden_dir, name):
     # bf16 softmax tiles follow the same order
     p_ref = torch.softmax(case["l_po"].permute(0, 2, 3, 1).reshape(-1, C_old), 1)
     pc = torch.cat([p_ref[torch.from_numpy(prep.anchor)], p_ref[torch.from_numpy(prep.pseudo_mask)]])[perm]
-    pt = pk.prob_tiles.float().cpu().permute(0, 2, 1, 3).reshape(-1, pk.kpad)[:pk.n_c]
+    pt_all = pk.prob_tiles.float().cpu().permute(0, 2, 1, 3).reshape(-1, pk.kpad)
+    assert float(pt_all[pk.n_c:pad_end].abs().sum()) == 0.0
+    pt = pt_all[:pk.n_c]
     assert float((pt[:, :C_old] - pc).abs().max()) < 2 ** -8
     assert pk.kpad == C_old or float(pt[:, C_old:].abs().max()) == 0.0
 
@@ -800,7 +805,8 @@ def test_bf16_feature_handoff(U, golden_dir, name):
     tup32 = U.pre_contrastive_pixel(x32, case["labels"].cuda(), l_po=case["l_po"].cuda(), f_o=fo16.float().cuda())
     assert not tup32[4].pack.bf16_feats
     assert torch.equal(tup32[0], tup[0]) and torch.equal(tup32[1], tup[1])
-    assert torch.equal(tup32[4].pack.feat_tiles, tup[4].pack.feat_tiles)
+    used = (tup[4].pack.n_c + 127) // 128
+    assert torch.equal(tup32[4].pack.feat_tiles[:used], tup[4].pack.feat_tiles[:used])
     loss32 = U.PixelConLossV2(temperature=0.07)(*tup32)
     loss32.backward()
     assert loss32.item() == loss.item()

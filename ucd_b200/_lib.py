@@ -144,8 +144,11 @@ def check(rc, what=""):
 
 
 def ptr(t):
-    """Device pointer of a tensor (None -> NULL)."""
-    return None if t is None else c_void_p(t.data_ptr())
+    """Device pointer of a tensor (None -> NULL); a plain int is taken as a device address (section of a buffer whose
+    typed view was never materialised as a tensor)."""
+    if t is None:
+        return None
+    return c_void_p(t) if isinstance(t, int) else c_void_p(t.data_ptr())
 
 
 _raw_stream = None

@@ -118,23 +118,33 @@ prep_labels_kernel(const long long* __restrict__ labels, const float* __restrict
 }
 
 // in-place exclusive scan of data[0..n) by one 1024-thread block; returns the total (valid in all threads)
-__device__ int block_excl_scan(int* __restrict__ data, int n, int* sh /*[1024]*/) {
-  const int t = threadIdx.x;
+__device__ int block_excl_scan(int* __restrict__ data, int n, int* sh /*[33]*/) {
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
   const int per = (n + 1023) / 1024;
   const int lo = min(t * per, n), hi = min(lo + per, n);
   int sum = 0;
   for (int i = lo; i < hi; ++i) sum += data[i];
-  __syncthreads();
-  sh[t] = sum;
-  __syncthreads();
-  for (int off = 1; off < 1024; off <<= 1) {
-    const int v = t >= off ? sh[t - off] : 0;
-    __syncthreads();
-    sh[t] += v;
-    __syncthreads();
+  int inc = sum;  // inclusive scan of the per-thread sums: shuffles within a warp, then over the 32 warp totals
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, inc, off);
+    if (lane >= off) inc += v;
   }
-  int run = sh[t] - sum;
-  const int total = sh[1023];
+  if (lane == 31) sh[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    int w = sh[lane];
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, w, off);
+      if (lane >= off) w += v;
+    }
+    sh[lane] = w;                // inclusive totals of warps 0..lane
+    if (lane == 31) sh[32] = w;  // grand total
+  }
+  __syncthreads();
+  int run = inc - sum + (wid > 0 ? sh[wid - 1] : 0);
+  const int total = sh[32];
   for (int i = lo; i < hi; ++i) {
     const int v = data[i];
     data[i] = run;
@@ -144,26 +154,49 @@ __device__ int block_excl_scan(int* __restrict__ data, int n, int* sh /*[1024]*/
   return total;
 }
 
-// counts -> exclusive offsets for the four tables; totals into counts[0..1]
+// counts -> exclusive offsets for the four tables, one block per table; totals into counts[0..1]
 __global__ void __launch_bounds__(1024)
 prep_scan_kernel(int* __restrict__ blk_base, int nblk, int nb, int* __restrict__ counts, int n_px,
                  int* __restrict__ counts_host) {
-  __shared__ int sh[1024];
+  __shared__ int sh[33];
   const BlkMeta bm(blk_base, nblk, nb);
-  const int ta = block_excl_scan(bm.ref, nblk, sh);
-  const int to = block_excl_scan(bm.ref + nblk, nblk, sh);
-  block_excl_scan(bm.cls, nb * nblk, sh);                        // class-major: sorted by label, then by pixel
-  block_excl_scan(bm.cls + (size_t)nb * nblk, nb * nblk, sh);
-  if (threadIdx.x == 0) {
-    counts[0] = ta;
-    counts[1] = to;
-    counts[3] = n_px;
-    if (counts_host != nullptr) {  // mapped pinned host memory: the host reads it after an event, no copy engine involved
-      volatile int* hp = counts_host;
-      hp[0] = ta, hp[1] = to, hp[2] = counts[2], hp[3] = n_px;
-      __threadfence_system();
+  volatile int* hp = counts_host;  // mapped pinned host memory: the host reads it after an event, no copy engine involved
+  if (blockIdx.x == 0) {
+    const int ta = block_excl_scan(bm.ref, nblk, sh);
+    if (threadIdx.x == 0) {
+      counts[0] = ta;
+      counts[3] = n_px;
+      if (hp != nullptr) hp[0] = ta, hp[2] = counts[2], hp[3] = n_px;
     }
+  } else if (blockIdx.x == 1) {
+    const int to = block_excl_scan(bm.ref + nblk, nblk, sh);
+    if (threadIdx.x == 0) {
+      counts[1] = to;
+      if (hp != nullptr) hp[1] = to;
+    }
+  } else {  // class-major: sorted by label, then by pixel
+    block_excl_scan(bm.cls + (size_t)(blockIdx.x - 2) * nb * nblk, nb * nblk, sh);
   }
+  if (threadIdx.x == 0 && hp != nullptr) __threadfence_system();
+}
+
+// The tiles are written row by row by the pack kernels; what they do not write of the tiles the sweeps read is the
+// padding of the LAST column tile (rows n_c % 128 .. 127): zero features / probabilities, label -1.  (Tiles beyond
+// ceil(n_c / 128) are never read: the sweeps bound their tile loops by the counts.  Clearing the worst-case buffers
+// with three memsets cost 17 us per step.)
+__global__ void __launch_bounds__(128)
+prep_pad_kernel(const int* __restrict__ counts, int kpad, long long max_tiles, __nv_bfloat16* __restrict__ feat_tiles,
+                __nv_bfloat16* __restrict__ prob_tiles, int* __restrict__ lab_tiles) {
+  const int n_c = counts[0] + counts[1];
+  const long long T = n_c >> 7;
+  const int r = threadIdx.x;
+  if (T >= max_tiles || r < (n_c & 127)) return;
+  if ((n_c & 127) == 0 && n_c > 0) return;  // the last tile is full (n_c == 0: tile 0 is all padding)
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  for (int ch = 0; ch < 32; ++ch) *reinterpret_cast<uint4*>(feat_tiles + (((size_t)T * 32 + ch) * 128 + r) * 8) = z;
+  for (int ch = 0; ch < kpad / 8; ++ch)
+    *reinterpret_cast<uint4*>(prob_tiles + (((size_t)T * (kpad / 8) + ch) * 128 + r) * 8) = z;
+  lab_tiles[T * 128 + r] = -1;
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -327,13 +360,20 @@ prep_prob_kernel(const float* __restrict__ l_po, const int* __restrict__ px_meta
   }
 }
 
-// label range of every tile (valid labels are >= 0): lets sweep 2 skip tiles that cannot hold a positive pair
+// label range of every tile (valid labels are >= 0): lets sweep 2 skip tiles that cannot hold a positive pair.
+// Tiles [0, n_tiles) -> range (entries below *n_limit only, if given); a second set of n_tiles2 tiles of the same
+// label array (the row tiles: entries below *n_limit2) -> range2, in the same launch.
 __global__ void __launch_bounds__(256)
 tile_range_kernel(const int* __restrict__ lab_tiles, long long n_tiles, const int* __restrict__ n_limit,
-                  int* __restrict__ range /*[n_tiles][2]*/) {
-  const long long t = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+                  int* __restrict__ range /*[n_tiles][2]*/, long long n_tiles2, const int* __restrict__ n_limit2,
+                  int* __restrict__ range2) {
+  long long t = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (t >= n_tiles) return;
+  if (t >= n_tiles) {  // second set
+    t -= n_tiles;
+    if (t >= n_tiles2) return;
+    n_limit = n_limit2, range = range2;
+  }
   const long long limit = n_limit ? (long long)*n_limit : (1ll << 62);  // only entries [0, limit) count
   const int4 v = reinterpret_cast<const int4*>(lab_tiles + t * 128)[lane];
   int lo = 0x7fffffff, hi = -1;
@@ -514,7 +554,7 @@ extern "C" int ucd_con_prep_labels(const int64_t* labels, const float* l_po, int
                                                      (float)H / (float)h, (float)W / (float)w, px_meta, blk_meta, nb,
                                                      counts);
   UCD_CHECK_LAUNCH("prep_labels_kernel");
-  prep_scan_kernel<<<1, 1024, 0, st>>>(blk_meta, nblk, nb, counts, n_px, counts_host);
+  prep_scan_kernel<<<4, 1024, 0, st>>>(blk_meta, nblk, nb, counts, n_px, counts_host);
   UCD_CHECK_LAUNCH("prep_scan_kernel");
   return UCD_OK;
 }
@@ -525,7 +565,7 @@ extern "C" int ucd_con_tile_ranges(const int32_t* lab_tiles, int64_t n_tiles, co
   UCD_CHECK_ARG(aligned16(lab_tiles), "ucd_con_tile_ranges: lab_tiles must be 16 B aligned");
   if (n_tiles == 0) return UCD_OK;
   tile_range_kernel<<<(unsigned)((n_tiles + 7) / 8), 256, 0, (cudaStream_t)stream>>>(lab_tiles, n_tiles, n_limit,
-                                                                                      tile_range);
+                                                                                      tile_range, 0, nullptr, nullptr);
   UCD_CHECK_LAUNCH("tile_range_kernel");
   return UCD_OK;
 }
@@ -550,10 +590,9 @@ static int prep_pack_impl(const FT* f_n, const FT* f_o, const float* l_po, const
   const int kpad = ucd_con_prob_kpad(C_old);
   const int nb = ucd_con_num_bins(max_label, C_old);
   const int nblk = (n_px + kPrepBlock - 1) / kPrepBlock;
-  cudaError_t e = cudaMemsetAsync(feat_tiles, 0, (size_t)max_tiles * 128 * 256 * 2, st);
-  if (e == cudaSuccess) e = cudaMemsetAsync(prob_tiles, 0, (size_t)max_tiles * 128 * kpad * 2, st);
-  if (e == cudaSuccess) e = cudaMemsetAsync(lab_tiles, 0xff, (size_t)max_tiles * 128 * sizeof(int32_t), st);
-  if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(tiles)");
+  prep_pad_kernel<<<1, 128, 0, st>>>(counts, kpad, max_tiles, (__nv_bfloat16*)feat_tiles, (__nv_bfloat16*)prob_tiles,
+                                     lab_tiles);
+  UCD_CHECK_LAUNCH("prep_pad_kernel");
   dim3 grid((n_px + 31) / 32, 2);
   prep_pack_kernel<FT><<<grid, 128, 0, st>>>(f_n, f_o, px_meta, blk_meta, nblk, nb, counts, n_px, h * w, anchor_f32,
                                              contrast_f32, la, lc, label_bytes, (__nv_bfloat16*)feat_tiles, lab_tiles,
@@ -562,11 +601,14 @@ static int prep_pack_impl(const FT* f_n, const FT* f_o, const float* l_po, const
   prep_prob_kernel<<<(n_px + 255) / 256, 256, 0, st>>>(l_po, px_meta, blk_meta, nblk, nb, counts, n_px, h * w, C_old,
                                                        kpad, (__nv_bfloat16*)prob_tiles);
   UCD_CHECK_LAUNCH("prep_prob_kernel");
-  int rc = ucd_con_tile_ranges(lab_tiles, max_tiles, nullptr, tile_range, stream);
-  if (rc != UCD_OK) return rc;
-  // rows are the first N_a (= counts[0]) columns: the last anchor tile also holds pseudo columns, which must not
-  // widen the ROW range (it would make every column tile "active" for that row block in sweep 2)
-  return ucd_con_tile_ranges(lab_tiles, (n_px + 127) / 128, counts, row_range, stream);
+  // column tiles, and in the same launch the row tiles.  Rows are the first N_a (= counts[0]) columns: the last anchor
+  // tile also holds pseudo columns, which must not widen the ROW range (it would make every column tile "active"
+  // for that row block in sweep 2)
+  const long long row_tiles = (n_px + 127) / 128;
+  tile_range_kernel<<<(unsigned)((max_tiles + row_tiles + 7) / 8), 256, 0, st>>>(lab_tiles, max_tiles, nullptr,
+                                                                                 tile_range, row_tiles, counts, row_range);
+  UCD_CHECK_LAUNCH("tile_range_kernel");
+  return UCD_OK;
 }
 
 extern "C" int ucd_con_prep_pack(const float* f_n, const float* f_o, const float* l_po, const int32_t* px_meta,

@@ -140,11 +140,12 @@ class _GradChain:
         if seq == self.calls:      # the last call runs first in a backward pass: drop what a pass that died left behind
             self.pending = []
         if not is_head:
-            self.pending.append(term)
-            return None, torch.zeros((), device=term["x"].device, dtype=torch.float32)
-        terms, self.pending = self.pending + [term], []
+            if term is not None:
+                self.pending.append(term)
+            return None, None   # the token's gradient stays undefined: the edge alone orders the backward passes
+        terms, self.pending = self.pending + ([term] if term is not None else []), []
         self.token = None   # chain -> token -> grad_fn -> ctx -> chain would leave the pass's objects to the cycle collector
-        return _launch_terms(terms), None
+        return (_launch_terms(terms) if terms else None), None
 
 
 def _launch_terms(terms):
@@ -187,8 +188,9 @@ class _UnceFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, inputs, targets, old_cl, ignore_index, reduction, chain=None, link=None):
         ctx.chain, ctx.is_head, ctx.seq = chain, link is None, (chain.calls if chain is not None else 0)
+        ctx.set_materialize_grads(False)   # the link token's gradient stays undefined: no zero tensors, no fill kernels
         B, C = inputs.shape[0], inputs.shape[1]
-        HW = inputs[0, 0].numel()
+        HW = inputs.numel() // max(B * C, 1)
         x = _f32c(inputs)
         dev = x.device
         loss_px = torch.empty(targets.shape, device=dev, dtype=torch.float32)
@@ -197,19 +199,26 @@ class _UnceFn(torch.autograd.Function):
         stats = torch.empty(2, device=dev, dtype=torch.float32) if want_stats else None
         scratch = (torch.empty(_lib.lib().ucd_reduce_scratch_floats(), device=dev, dtype=torch.float32)
                    if want_stats else None)
-        check(_lib.lib().ucd_unce_fwd(ptr(x), ptr(targets), ptr(loss_px), ptr(lse[0]), ptr(lse[1]), ptr(stats),
+        lse_p = lse.data_ptr()
+        check(_lib.lib().ucd_unce_fwd(ptr(x), ptr(targets), ptr(loss_px), lse_p, lse_p + 4 * B * HW, ptr(stats),
                                       ptr(scratch), B, C, old_cl, HW, ignore_index, cur_stream()), "unce_fwd")
         ctx.save_for_backward(x, targets, lse, stats)
         ctx.cfg = (B, C, HW, old_cl, ignore_index, reduction)
         out = loss_px if reduction == "none" else (stats[0].clone() if reduction == "sum" else stats[0] / stats[1])
         if chain is None:
             return out
-        return out, torch.zeros((), device=dev, dtype=torch.float32)   # token: orders the chain's backward passes
+        # token: orders the chain's backward passes; its value is never read (no fill kernel)
+        return out, torch.empty((), device=dev, dtype=torch.float32)
 
     @staticmethod
     def backward(ctx, g, g_token=None):
         x, targets, lse, stats = ctx.saved_tensors
         B, C, HW, old_cl, ignore_index, reduction = ctx.cfg
+        if g is None:   # this loss value was not used: only the chain bookkeeping remains
+            if ctx.chain is None:
+                return None, None, None, None, None, None, None
+            d_in, d_link = ctx.chain.submit(None, ctx.seq, ctx.is_head)
+            return d_in, None, None, None, None, None, d_link
         g_px, g_sc = None, None
         if reduction == "none":
             g_sc = _scalar_grad(g)
@@ -274,8 +283,9 @@ class _UnkdFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, inputs, targets, mask, alpha, reduction, variant=0, chain=None, link=None):
         ctx.chain, ctx.is_head, ctx.seq = chain, link is None, (chain.calls if chain is not None else 0)
+        ctx.set_materialize_grads(False)   # see _UnceFn
         B, C, C_old = inputs.shape[0], inputs.shape[1], targets.shape[1]
-        HW = inputs[0, 0].numel()
+        HW = inputs.numel() // max(B * C, 1)
         x, t = _f32c(inputs), _f32c(targets)
         m = None if mask is None else _f32c(mask)
         dev = x.device
@@ -293,12 +303,17 @@ class _UnkdFn(torch.autograd.Function):
         out = out_px if reduction == "none" else stats[0]
         if chain is None:
             return out
-        return out, torch.zeros((), device=dev, dtype=torch.float32)   # token: orders the chain's backward passes
+        return out, torch.empty((), device=dev, dtype=torch.float32)   # token: orders the chain's backward passes
 
     @staticmethod
     def backward(ctx, g, g_token=None):
         x, t, m, lse3 = ctx.saved_tensors
         B, C, C_old, HW, alpha, reduction, variant = ctx.cfg
+        if g is None:   # this loss value was not used: only the chain bookkeeping remains
+            if ctx.chain is None:
+                return None, None, None, None, None, None, None, None
+            d_in, d_link = ctx.chain.submit(None, ctx.seq, ctx.is_head)
+            return d_in, None, None, None, None, None, None, d_link
         g_px, g_sc, g_mul = None, None, 1.0
         if reduction == "none":
             g_sc = _scalar_grad(g)
@@ -464,14 +479,16 @@ class ContrastPack:
         self.kpad = 0
         self.max_tiles = 0
         self.payload = None        # uint8 [payload_layout(...)["nbytes"]]: counts + range + lab + prob + feat tiles
-        self.counts = None         # int32[4] device: N_a, N_o, min_new, n_px (view into payload, like the tile arrays)
+        self.addr = None           # device address of every payload section (what the C calls take)
+        self._views = None         # typed tensor views of the sections, built on first use (15 tensor ops: kept off
+                                   # the host's critical path between the prep kernels and the next loss module)
         self.n_a = self.n_o = self.min_new = None   # host copies (one sync)
         self.px_meta = self.blk_meta = None         # see include/ucd_b200.h (ucd_con_prep_labels)
         self.label_n = self.mix = self.flags = None  # views of px_meta planes 0..2
         self.anchor_f32 = self.contrast_f32 = None   # reference row order (b,y,x)
         self.la = self.lc = None
-        self.feat_tiles = self.prob_tiles = self.lab_tiles = None   # class-sorted bf16 / int32 tiles
-        self.tile_range = None                       # [T,2] min/max label per column tile
+        # feat_tiles / prob_tiles / lab_tiles (class-sorted bf16 / int32 tiles), tile_range ([T,2] min/max label per
+        # column tile) and counts (int32[4] device: N_a, N_o, min_new, n_px) are properties: views into the payload
         self.row_range = None                        # [ceil(n_px/128),2] same over the anchor rows only
         self.row_ref = self.inv_norm = None          # sorted anchor row -> reference row
         self.max_label = 20
@@ -481,6 +498,17 @@ class ContrastPack:
     @property
     def n_c(self):
         return self.n_a + self.n_o
+
+    def _view(self, name):
+        if self._views is None:
+            self._views = payload_views(self.payload, self.max_tiles, self.kpad)
+        return self._views[name]
+
+    counts = property(lambda self: self._view("counts"))
+    tile_range = property(lambda self: self._view("range"))
+    lab_tiles = property(lambda self: self._view("lab"))
+    prob_tiles = property(lambda self: self._view("prob"))
+    feat_tiles = property(lambda self: self._view("feat"))
 
 
 _PINNED = {}
@@ -535,16 +563,17 @@ def _build_pack(f_n, f_o, l_po, labels, max_label, sync=True, require_new_class=
     pk.blk_meta = torch.empty(L.ucd_con_blk_meta_ints(n_px, nb), **i32)
     # everything another rank needs of this rank's columns lives in ONE buffer (the exchange payload); the kernels
     # write their outputs straight into its sections
-    pk.payload = torch.empty(payload_layout(pk.max_tiles, pk.kpad)["nbytes"], device=dev, dtype=torch.uint8)
-    pv = payload_views(pk.payload, pk.max_tiles, pk.kpad)
-    pk.counts = pv["counts"]
+    lay = payload_layout(pk.max_tiles, pk.kpad)
+    pk.payload = torch.empty(lay["nbytes"], device=dev, dtype=torch.uint8)
+    base = pk.payload.data_ptr()
+    ad = pk.addr = {k: base + lay[k] for k in ("counts", "range", "lab", "prob", "feat")}
     st = cur_stream()
     # The tuple API needs N_a / N_o on the host (tensor shapes).  The scan kernel stores them straight into mapped
     # pinned host memory (no D2H copy that could queue behind other transfers on the copy engine); the host waits
     # for the event only after the pack kernels are queued, so the GPU has work while the host catches up.
     counts_host = _pinned_counts(dev)
     check(L.ucd_con_prep_labels(ptr(labels), ptr(l_po), B, pk.c_old, h, w, H, W, pk.max_label, ptr(pk.px_meta),
-                                ptr(pk.blk_meta), ptr(pk.counts), counts_host.data_ptr(), st), "con_prep_labels")
+                                ptr(pk.blk_meta), ad["counts"], counts_host.data_ptr(), st), "con_prep_labels")
     copied = None
     if sync:
         copied = torch.cuda.Event()
@@ -556,16 +585,15 @@ def _build_pack(f_n, f_o, l_po, labels, max_label, sync=True, require_new_class=
     ldt = _label_dtype(max(pk.max_label, pk.c_old - 1))
     pk.la = torch.empty(n_px, device=dev, dtype=ldt)
     pk.lc = torch.empty(2 * n_px, device=dev, dtype=ldt)
-    pk.feat_tiles, pk.prob_tiles, pk.lab_tiles, pk.tile_range = pv["feat"], pv["prob"], pv["lab"], pv["range"]
     pk.row_range = torch.empty((n_px + TILE - 1) // TILE, 2, **i32)
     pk.row_ref = torch.empty(n_px, **i32)
     pk.inv_norm = torch.empty(n_px, device=dev, dtype=torch.float32)
     pack_fn = L.ucd_con_prep_pack_bf16 if bf16_feats else L.ucd_con_prep_pack
-    check(pack_fn(ptr(f_n), ptr(f_o), ptr(l_po), ptr(pk.px_meta), ptr(pk.blk_meta), ptr(pk.counts), B,
-                              pk.c_old, h, w, pk.max_label, ptr(pk.anchor_f32), ptr(pk.contrast_f32), ptr(pk.la),
-                              ptr(pk.lc), pk.la.element_size(), ptr(pk.feat_tiles), ptr(pk.prob_tiles), ptr(pk.lab_tiles),
-                              ptr(pk.tile_range), ptr(pk.row_range), ptr(pk.row_ref), ptr(pk.inv_norm),
-                              pk.max_tiles, st),
+    check(pack_fn(ptr(f_n), ptr(f_o), ptr(l_po), ptr(pk.px_meta), ptr(pk.blk_meta), ad["counts"], B,
+                  pk.c_old, h, w, pk.max_label, ptr(pk.anchor_f32), ptr(pk.contrast_f32), ptr(pk.la),
+                  ptr(pk.lc), pk.la.element_size(), ad["feat"], ad["prob"], ad["lab"],
+                  ad["range"], ptr(pk.row_range), ptr(pk.row_ref), ptr(pk.inv_norm),
+                  pk.max_tiles, st),
           "con_prep_pack")
     pk.l_po = l_po
     if not sync:  # sync-free path: N_a / N_o stay on the device, buffers keep their worst-case sizes
@@ -730,8 +758,9 @@ pre_contractive_pixel = pre_contrastive_pixel  # spelling used by utils/utils.py
 # ----------------------------------------------------------------------------------------------
 def _local_cols(pack):
     """Column-side arguments of the sweeps for this rank's own pack (single chunk)."""
-    return dict(feat=pack.feat_tiles, prob=pack.prob_tiles, lab=pack.lab_tiles, range=pack.tile_range,
-                counts=pack.counts, n_chunks=1, chunk_tiles=pack.max_tiles, kpad=pack.kpad, min_new=pack.counts[2:3],
+    ad = pack.addr   # raw section addresses: no tensor views on the hot path (ptr() takes ints)
+    return dict(feat=ad["feat"], prob=ad["prob"], lab=ad["lab"], range=ad["range"],
+                counts=ad["counts"], n_chunks=1, chunk_tiles=pack.max_tiles, kpad=pack.kpad, min_new=ad["counts"] + 8,
                 payload=pack.payload)
 
 
@@ -802,7 +831,13 @@ class _ConFn(torch.autograd.Function):
             import torch.distributed as dist
             dist.all_reduce(out[:2], group=group)  # {sum of row losses, #valid rows} over all ranks
             world = dist.get_world_size(group)
-        ctx.save_for_backward(grad_unit, out, rows["n_rows"], rows.get("row_ref"))
+        n_rows = rows["n_rows"]
+        if isinstance(n_rows, int):   # a device address inside the pack's payload: keep that buffer alive instead
+            ctx.n_rows_addr, ctx.keep = n_rows, rows.get("keep")
+            ctx.save_for_backward(grad_unit, out, None, rows.get("row_ref"))
+        else:
+            ctx.n_rows_addr = None
+            ctx.save_for_backward(grad_unit, out, n_rows, rows.get("row_ref"))
         ctx.static_pack = rows.get("static_pack")   # sync-free path: `anchor` is f_n itself
         ctx.n_a = anchor.shape[0] if ctx.static_pack is None else ctx.static_pack.n_px
         ctx.in_dtype = anchor.dtype
@@ -814,6 +849,8 @@ class _ConFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         grad_unit, out, n_rows, row_ref = ctx.saved_tensors
+        if ctx.n_rows_addr is not None:
+            n_rows = ctx.n_rows_addr
         d_anchor = torch.empty(ctx.n_a, FEAT_DIM, device=g.device, dtype=torch.float32)
         if ctx.n_a == 0:   # a rank without anchors (it only took part in the collectives)
             return d_anchor.to(ctx.in_dtype), None, None, None, None, None, None, None
@@ -896,7 +933,8 @@ class PixelConLossV2(nn.Module):
         if pack is not None:
             # ---- fast path: operands packed by pre_contrastive_pixel ----
             group = self._group()
-            rows = dict(feat=pack.feat_tiles, prob=pack.prob_tiles, lab=pack.lab_tiles, n_rows=pack.counts[0:1],
+            ad = pack.addr
+            rows = dict(feat=ad["feat"], prob=ad["prob"], lab=ad["lab"], n_rows=ad["counts"], keep=pack.payload,
                         range=pack.row_range, row_ref=pack.row_ref, max_tiles=max(1, (pack.n_a + TILE - 1) // TILE),
                         self_tile0=0)
             cols = _local_cols(pack)
@@ -982,7 +1020,8 @@ class PixelContrastiveDistillation(nn.Module):
         pack = _build_pack(f_n.detach(), f_o.detach(), l_po.detach(), l_n, self.max_label, sync=False)
         cap_tiles = (pack.n_px + TILE - 1) // TILE
         plan_tiles = max(1, min(cap_tiles, int(cap_tiles * self.expected_anchor_fraction + 0.999)))
-        rows = dict(feat=pack.feat_tiles, prob=pack.prob_tiles, lab=pack.lab_tiles, n_rows=pack.counts[0:1],
+        ad = pack.addr
+        rows = dict(feat=ad["feat"], prob=ad["prob"], lab=ad["lab"], n_rows=ad["counts"], keep=pack.payload,
                     range=pack.row_range, row_ref=pack.row_ref, max_tiles=cap_tiles, self_tile0=0,
                     plan_tiles=plan_tiles, static_pack=pack)
         group = self._group()
