@@ -10,6 +10,10 @@ from bench import make_inputs, WORKLOAD
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 24
 inp = {k: v.cuda() for k, v in make_inputs(0, B, WORKLOAD).items()}
+if os.environ.get("UCD_SKEW"):   # one dominant new class (real label maps are far more skewed than the bench blobs)
+    H = inp["labels"].shape[-1]
+    inp["labels"][:, H // 25:, :] = WORKLOAD["C_old"]
+    inp["labels"][:, 9 * H // 10:, : H // 4] = WORKLOAD["C"] - 1
 con = U.PixelConLossV2(temperature=0.07)
 
 def run(grad):
@@ -43,12 +47,13 @@ for grad in (True, False):
     tup = U.pre_contrastive_pixel(f_n, inp["labels"], l_po=inp["l_po"], f_o=inp["f_o"])
     rt_act = (tup[0].shape[0] + 127) // 128
     splits = L.ucd_con_debug_splits(rt_act, ct)
-    trace = torch.zeros(2, rt_act * splits, 16, dtype=torch.int64, device="cuda")
+    trace = torch.zeros(2 * rt_act * splits, 16, dtype=torch.int64, device="cuda")
     L.ucd_con_debug_trace(_lib.ptr(trace))
     con(*tup)
     torch.cuda.synchronize()
     L.ucd_con_debug_trace(None)
     tr = trace.cpu().double()
+    tr = (tr[:rt_act * splits], tr[rt_act * splits:])
     for sw in (0, 1):
         x = tr[sw][tr[sw][:, 8] > 0]
         if x.numel() == 0:
@@ -60,3 +65,8 @@ for grad in (True, False):
                   (x[:, 4] / nt).mean(), (x[:, 5] / nt).mean(), (x[:, 0] / nt).mean(), (x[:, 1] / nt).mean(), (x[:, 2] / nt).mean()))
         print("      per CTA cycles: set-up %.0f | tile loop %.0f | tail (wait last MMAs, write partials) %.0f" % (
             x[:, 7].mean(), x[:, 8].mean(), x[:, 15].mean()))
+        tot = x[:, 7] + x[:, 8] + x[:, 15]
+        tiles = x[:, 11]
+        print("      balance: tiles total %.0f, per CTA max %.0f / mean %.1f | CTA cycles max %.0f mean %.0f | sum/148 SMs "
+              "%.0f cycles | loop cycles per tile (pooled) %.0f" % (tiles.sum(), tiles.max(), tiles.mean(), tot.max(),
+              tot.mean(), tot.sum() / 148, x[:, 8].sum() / tiles.sum().clamp_min(1)))
