@@ -236,6 +236,21 @@ int ucd_con_fwd(const void* feat_tiles, const void* prob_tiles, const int32_t* l
                 int64_t ldp, float inv_temperature, int need_grad, float* out, float* grad_unit,
                 void* workspace, size_t workspace_bytes, int64_t max_row_tiles, int64_t plan_row_tiles,
                 void* stream);
+/* Self-contrast losses of utils/loss_new.py on the same sweeps:
+ *   mode 0  PixelConLoss (v1), loss_new.py:354-400:  s = F F^T / tau, unshifted exponentials,
+ *           loss = mean_{num_i != 0} -(1/num_i) sum_j mp_ij [s_ij - log(exp(s_ij) + neg_j)]
+ *   mode 1  SupConLoss, loss_new.py:263-352 (labels or SimCLR; contrast_mode 'all': n_anchor = n, 'one': the first
+ *           n_anchor rows are the anchors), kappa = temperature / base_temperature
+ * on n rows packed by ucd_con_pack_rows (feat / lab tiles; tile_range from ucd_con_tile_ranges; counts = device
+ * {n, 0}; n_rows = device {n}).  Both losses back-propagate through BOTH operands of F F^T: the forward runs sweep 1
+ * (row max, negative sum, positive count), sweep 2 over the equal-label tiles (row terms), a per-pixel coefficient
+ * kernel and - with need_grad - a third sweep that forms H = G + G^T pair by pair and accumulates H F on the tensor cores.
+ *   out float[3] = {sum of the row losses, rows in the mean, their ratio (= the loss)}
+ *   grad_unit [n, 256] = d(sum of row losses)/dF (scaled by g / out[1] in ucd_con_bwd, row_ref = NULL) */
+size_t ucd_selfcon_workspace_bytes(int64_t tiles /* ceil(n / 128) */);
+int ucd_selfcon_fwd(const void* feat_tiles, const int32_t* lab_tiles, const int32_t* tile_range, const int32_t* counts,
+                    const int32_t* n_rows, int64_t n, int64_t n_anchor, int mode, float inv_temperature, float kappa,
+                    int need_grad, float* out, float* grad_unit, void* workspace, size_t workspace_bytes, void* stream);
 /* d_anchor[row_ref[i],:] = (*g_scalar) * g_mul / out[1] * grad_unit[i,:] for i < min(*n_rows, max_rows);
  * row_ref NULL = identity */
 int ucd_con_bwd(const float* grad_unit, const float* out, const float* g_scalar, float g_mul,

@@ -129,8 +129,42 @@ def gen_p2p():
     print("pixel_to_pixel", fx["single_out"].shape, fx["double_out"].shape, np.unique(fx["single_lab"]))
 
 
+def gen_selfcon():
+    """PixelConLoss (v1) and SupConLoss of utils/loss_new.py on the seeded cases of oracle.ucd_oracle.selfcon_case: loss
+    values, gradient norms and strided gradient samples of the UNMODIFIED reference classes, fp64."""
+    from utils.loss_new import PixelConLoss, SupConLoss
+    from oracle.ucd_oracle import SELFCON_CASES, selfcon_case
+    fx = {"stride": np.array([13])}
+
+    def put(key, loss, grad):
+        fx[key + "_loss"] = np.array([loss.item()])
+        fx[key + "_gnorm"] = np.array([grad.norm().item()])
+        fx[key + "_gsample"] = grad.reshape(-1)[::13].numpy()
+
+    for name, (n, n_cls, views) in SELFCON_CASES.items():
+        x, lab = selfcon_case(name)
+        fx[name + "_in_sums"] = np.array([x.sum().item(), float(lab.sum())])
+        if views == 1:
+            for tau in (1.0, 0.5):
+                xr = x.clone().requires_grad_(True)
+                loss = PixelConLoss(temperature=tau)(xr, lab)
+                loss.backward()
+                put("%s_v1_t%g" % (name, tau), loss, xr.grad)
+        for mode in ("all", "one"):
+            for use_lab in (True, False):
+                xr = x.clone().requires_grad_(True)
+                loss = SupConLoss(temperature=0.07, contrast_mode=mode)(xr, lab if use_lab else None)
+                loss.backward()
+                put("%s_sup_%s_%s" % (name, mode, "lab" if use_lab else "simclr"), loss, xr.grad)
+    np.savez_compressed(os.path.join(OUT, "selfcon_losses.npz"), **fx)
+    print("selfcon_losses:", {k: float(v[0]) for k, v in fx.items() if k.endswith("_loss")})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "selfcon":
+        return gen_selfcon()
+    gen_selfcon()
     if len(sys.argv) > 1 and sys.argv[1] == "p2p":
         return gen_p2p()
     gen_p2p()

@@ -208,6 +208,77 @@ def pixel_to_pixel(f_n: torch.Tensor, labels: torch.Tensor, f_o: Optional[torch.
     return out.unsqueeze(1), lab
 
 
+SELFCON_CASES = {"a": (300, 5, 1), "b": (777, 9, 1), "c": (260, 4, 2)}   # name: (rows, classes, views)
+
+
+def selfcon_case(name: str):
+    """Seeded inputs of the self-contrast fixtures (tests/golden/selfcon_losses.npz): unit-norm rows [n, views, 256]
+    around class prototypes, labels with a dominant class and (case a) a class with a single member."""
+    n, n_cls, views = SELFCON_CASES[name]
+    g = torch.Generator().manual_seed(4321 + ord(name))
+    proto = torch.randn(n_cls, 256, generator=g, dtype=torch.float64)
+    lab = torch.randint(0, n_cls, (n,), generator=g)
+    lab[:n // 3] = 0
+    if name == "a":
+        lab[lab == n_cls - 1] = 0
+        lab[n - 1] = n_cls - 1
+    x = 0.5 * torch.randn(n, views, 256, generator=g, dtype=torch.float64) + proto[lab][:, None, :]
+    return torch.nn.functional.normalize(x, dim=2), lab
+
+
+def pixel_con_loss_v1(features: torch.Tensor, labels: torch.Tensor, temperature: float = 1.0) -> torch.Tensor:
+    """``PixelConLoss`` (v1) of utils/loss_new.py:354-400 restated: self-contrast of ``features`` [n, 1, D] (what the
+    pixel-to-pixel branches of pre_contrastive_pixel return) with labels [n].
+
+        s = F F^T / tau ;  R_ij = [l_i == l_j] ;  mp = R - I ;  neg_j = sum_k (1 - R_jk) exp(s_jk)
+        loss = mean_{i: num_i != 0} ( -(1/num_i) sum_j mp_ij [ s_ij - log(exp(s_ij) + neg_j) ] )
+
+    (loss_new.py:395 adds the COLUMN's negative sum - ``neg_contrast.repeat(batch_size, 1)`` - to exp(s_ij); s, R and
+    mp are symmetric and num depends on the label only, so the value equals the row form, but the gradient reaches the
+    features through both operands, through exp(s_ij) and through neg_j.)  Unshifted exponentials, like the reference."""
+    f = features.reshape(features.shape[0], -1) if features.dim() == 2 else torch.cat(torch.unbind(features, dim=1), dim=0)
+    lab = labels.reshape(-1, 1)
+    n = f.shape[0]
+    R = (lab.T == lab).to(f.dtype)
+    mask_p = R - torch.eye(n, dtype=f.dtype)
+    mask_n = 1 - R
+    s = (f @ f.T) / temperature
+    neg = (torch.exp(s) * mask_n).sum(dim=1)
+    pos = s * mask_p - torch.log(torch.exp(s) + neg.repeat(n, 1)) * mask_p
+    num = mask_p.sum(dim=1)
+    keep = num != 0
+    return (-(pos.sum(dim=1)[keep] / num[keep])).mean()
+
+
+def sup_con_loss(features: torch.Tensor, labels: Optional[torch.Tensor] = None, temperature: float = 0.07,
+                 contrast_mode: str = "all", base_temperature: float = 0.07) -> torch.Tensor:
+    """``SupConLoss`` of utils/loss_new.py:263-352 restated (labels given, or None = SimCLR; the explicit ``mask``
+    argument is not part of the path).  features [bsz, n_views, D]."""
+    bsz, n_views = features.shape[0], features.shape[1]
+    feats = features.reshape(bsz, n_views, -1)
+    lab = (torch.arange(bsz) if labels is None else labels.reshape(-1)).reshape(-1, 1)
+    mask = (lab == lab.T).float()   # fp32 whatever the feature dtype, like loss_new.py:303 (so `+ 1e-8` acts in fp32)
+    contrast = torch.cat(torch.unbind(feats, dim=1), dim=0)
+    if contrast_mode == "one":
+        anchor, anchor_count = feats[:, 0], 1
+    elif contrast_mode == "all":
+        anchor, anchor_count = contrast, n_views
+    else:
+        raise ValueError("Unknown mode: {}".format(contrast_mode))
+    adc = (anchor @ contrast.T) / temperature
+    logits = adc - adc.max(dim=1, keepdim=True)[0].detach()
+    mask = mask.repeat(anchor_count, n_views)
+    logits_mask = torch.ones_like(mask)
+    idx = torch.arange(bsz * anchor_count)
+    logits_mask[idx, idx] = 0
+    mask = mask * logits_mask
+    exp_logits = torch.exp(logits) * logits_mask
+    log_prob = logits - torch.log(exp_logits.sum(1, keepdim=True) + 1e-6)
+    mean_log_prob_pos = (mask * log_prob).sum(1) / (mask.sum(1) + 1e-8)
+    loss = -(temperature / base_temperature) * mean_log_prob_pos
+    return loss.view(anchor_count, bsz).mean()
+
+
 def contrast_operands(f_n: torch.Tensor, labels: torch.Tensor, l_po: torch.Tensor, f_o: torch.Tensor,
                       max_label: int = 20):
     """``pre_contrastive_pixel`` without the dense joint-probability matrix: returns

@@ -146,6 +146,14 @@ def test_reference_signatures_preserved():
     assert U.pre_contractive_pixel is U.pre_contrastive_pixel
     m = U.PixelConLossV2(temperature=0.07)
     assert len(list(m.parameters())) == 0 and len(list(m.buffers())) == 0
+    # the self-contrast siblings of utils/loss_new.py:263-400
+    assert list(inspect.signature(U.PixelConLoss.__init__).parameters)[1:] == ["sample_method", "temperature"]
+    assert list(inspect.signature(U.PixelConLoss.forward).parameters)[1:] == ["features", "labels"]
+    assert list(inspect.signature(U.SupConLoss.__init__).parameters)[1:] == ["temperature", "contrast_mode", "base_temperature"]
+    assert list(inspect.signature(U.SupConLoss.forward).parameters)[1:] == ["features", "labels", "mask"]
+    assert U.PixelConLoss().temperature == 1 and U.SupConLoss().base_temperature == 0.07
+    with pytest.raises(ValueError):   # same message path as loss_new.py:292-294: fewer than 3 dimensions
+        U.SupConLoss()(torch.zeros(4, 8))
 
 
 def test_no_product_import_of_oracle():

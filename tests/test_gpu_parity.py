@@ -779,6 +779,66 @@ def test_raw_head_features_equal_att_map_features(U, golden_dir):
     assert loss2.item() == pytest.approx(loss.item(), rel=1e-4) and cos(x2.grad, x.grad) > 1 - 1e-5
 
 
+# ------------------------------------------------------------------------------------------------
+# SURVEY section 8(f) row N3, second half: the self-contrast losses of utils/loss_new.py on the sweep kernels
+@pytest.mark.parametrize("name", ["a", "b", "c"])
+def test_selfcon_losses_vs_reference_fixture(U, golden_dir, name):
+    """PixelConLoss (v1) and SupConLoss against the values and gradients of the UNMODIFIED reference classes
+    (tests/golden/selfcon_losses.npz, fp64): loss 1e-3, gradient cosine 0.999 on the stored samples, gradient norm 1 %."""
+    fx = np.load(os.path.join(golden_dir, "selfcon_losses.npz"))
+    st = int(fx["stride"][0])
+    n, n_cls, views = O.SELFCON_CASES[name]
+    x, lab = O.selfcon_case(name)
+    runs = []
+    if views == 1:
+        runs += [("%s_v1_t%g" % (name, tau), U.PixelConLoss(temperature=tau), True) for tau in (1.0, 0.5)]
+    for mode in ("all", "one"):
+        for use_lab in (True, False):
+            runs.append(("%s_sup_%s_%s" % (name, mode, "lab" if use_lab else "simclr"),
+                         U.SupConLoss(temperature=0.07, contrast_mode=mode), use_lab))
+    for key, module, use_lab in runs:
+        xr = x.float().cuda().requires_grad_(True)
+        loss = module(xr, lab.cuda()) if use_lab else module(xr)
+        loss.backward()
+        want = float(fx[key + "_loss"][0])
+        assert loss.item() == pytest.approx(want, rel=REL, abs=2e-6), key
+        gs = xr.grad.double().cpu().reshape(-1)[::st]
+        ref = torch.from_numpy(fx[key + "_gsample"])
+        if float(ref.norm()) > 1e-12:
+            assert cos(gs, ref) >= COS, key
+            assert xr.grad.double().norm().item() == pytest.approx(float(fx[key + "_gnorm"][0]), rel=1e-2), key
+        else:   # SimCLR with one view: no positives, zero loss and zero gradient
+            assert float(xr.grad.abs().max()) == 0.0, key
+
+
+def test_selfcon_losses_vs_oracle_on_pixel_to_pixel_rows(U):
+    """The use the reference made of v1: PixelConLoss on the rows of the pixel-to-pixel prep (every pixel a unit-norm row,
+    labels from the downsampled label map), ragged size (not a multiple of 128), narrow features, SupCon with 3 views."""
+    case = O.synthetic_case(2, 17, 19, 272, 304, 21, 16)
+    f_ref = case["f_n"].double().requires_grad_(True)
+    out_ref, lab_ref = O.pixel_to_pixel(f_ref, case["labels"])
+    ref = O.pixel_con_loss_v1(out_ref, lab_ref, 0.5)
+    ref.backward()
+    f = case["f_n"].cuda().requires_grad_(True)
+    out, lab = U.pre_contrastive_pixel(f, case["labels"].cuda())
+    loss = U.PixelConLoss(temperature=0.5)(out, lab)
+    loss.backward()
+    assert loss.item() == pytest.approx(ref.item(), rel=REL) and cos(f.grad, f_ref.grad) >= COS
+    g = torch.Generator().manual_seed(5)
+    x = torch.nn.functional.normalize(torch.randn(150, 3, 64, generator=g, dtype=torch.float64), dim=2)
+    lab = torch.randint(0, 7, (150,), generator=g)
+    for mode in ("all", "one"):
+        xr = x.clone().requires_grad_(True)
+        want = O.sup_con_loss(xr, lab, 0.1, mode, 0.07)
+        want.backward()
+        xc = x.float().cuda().requires_grad_(True)
+        got = U.SupConLoss(temperature=0.1, contrast_mode=mode, base_temperature=0.07)(xc, lab.cuda())
+        got.backward()
+        assert got.item() == pytest.approx(want.item(), rel=REL) and cos(xc.grad, xr.grad) >= COS
+    with pytest.raises(NotImplementedError):
+        U.SupConLoss()(x.float().cuda(), mask=torch.eye(150).cuda())
+
+
 @pytest.mark.parametrize("name", ["voc15-5s_b2_corr", "city13-6_b3"])
 def test_bf16_feature_handoff(U, golden_dir, name):
     """Row N2, second half: a head that runs in bf16 hands its features over as bf16 NCHW; the prep kernel reads them

@@ -53,6 +53,8 @@ _PROTOS = {
     "ucd_con_fwd": (c_int, [P, P, P, P, c_int, c_int64, c_int64, c_int, c_int, P, P, P, P, P, P, c_int64, P, c_int, c_int,
                             P, c_int64, c_float, c_int, P, P, P, c_size_t, c_int64, c_int64, P]),
     "ucd_con_bwd": (c_int, [P, P, P, c_float, P, P, P, c_int64, P]),
+    "ucd_selfcon_workspace_bytes": (c_size_t, [c_int64]),
+    "ucd_selfcon_fwd": (c_int, [P, P, P, P, P, c_int64, c_int64, c_int, c_float, c_float, c_int, P, P, P, c_size_t, P]),
 }
 EXPORTED = tuple(_PROTOS)
 # include/ucd_b200_debug.h: exported by libucd_b200_debug.so only (python -m ucd_b200.build --debug)

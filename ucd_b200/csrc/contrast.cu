@@ -124,6 +124,11 @@ struct ConArgs {
   const float* stats;  // [3][rows_pad]           sweep 2 in (combined)
   float* loss_part;    // [splits][2][rows_pad]   sweep 2 out: L_i, T_i
   long long* trace;    // debug: [grid][16] cycle counters per role (ucd_con_debug_trace), or NULL
+  // self-contrast losses (PixelConLoss v1 / SupConLoss, utils/loss_new.py:263-400; see sweep3_cols)
+  int shift;           // sweep 2: 1 = PixelConLossV2's exp(s - m) in the denominator, 0 = unshifted (v1)
+  const float* col_a;  // sweep 3: per-pixel coefficients in column (= row) order, see sweep3_cols
+  const float* col_b;
+  const float* col_c;
 };
 
 // mbar_wait that also accumulates the cycles spent waiting (debug tracing of the role pipelines)
@@ -289,6 +294,11 @@ __device__ __forceinline__ void sweep2_cols(const uint32_t (&r)[32], const uint3
         lacc = fmaf(w, fmaf(-x, kLog2e, s2), lacc);
         uo[u] = fmaf(-w, x, w);
         tacc += uo[u];  // times 1/neg_i at the end of the sweep
+      } else if (PMODE == 3) {  // SupCon statistics over the positive pairs: sum s_ij (log2 units), sum exp(s_ij)
+        const float s2 = acc * sc;
+        lacc = fmaf(w, s2, lacc);
+        tacc = fmaf(w, ex2f(s2), tacc);
+        uo[u] = 0.f;
       } else {
         const float sh2 = (acc - rc.mraw) * sc;  // (s - m) * log2(e)
         const float den = ex2f(sh2) + rc.negi;
@@ -336,6 +346,52 @@ __device__ __forceinline__ void sweep2_cols_uniform(const uint32_t (&r)[32], con
   }
 }
 
+// ---- sweep 3 (self-contrast losses) on 32 columns ---------------------------------------------
+// PixelConLoss v1 and SupConLoss contrast a set of rows with ITSELF and back-propagate through both operands:
+// dL/dF = (G + G^T) F / tau with G_ij = dL/ds_ij.  Row i's gradient is therefore sum_j H_ij f_j with H = G + G^T, which
+// needs the ROW statistics of pixel i and of pixel j.  They are known after sweeps 1 and 2 (ucd_selfcon_fwd), stored per
+// pixel in col_a / col_b / col_c, and this sweep forms H pair by pair and accumulates H F on the tensor cores exactly
+// like sweep 1 accumulates V.  e = exp(s_ij):
+//   MODE 0 (v1: loss_i = -(1/num_i) sum_j mp_ij [s_ij - log(e + neg_j)]):  a = [num != 0]/num, A = a T (T = sum_j mp_ij /
+//           (e + neg_i)), B = neg:   H_ij = (A_i + A_j) e for a negative pair, -a_i [B_i/(e + B_i) + B_j/(e + B_j)] for
+//           a positive one (a_j = a_i there: num depends on the label only)
+//   MODE 1 (SupCon: loss_i = -a_i [sum_j mp_ij s_ij - num_i (m_i + log D_i)], D_i = sum_{k != i} exp(s_ik - m_i) + 1e-6,
+//           a_i = (tau/tau_b)/(num_i + 1e-8) for anchor rows, else 0), A = a num exp(-m)/D:
+//           H_ij = (A_i + A_j) e - [positive pair] (a_i + a_j)
+// and H_ii = 0.  The common 1/(number of rows in the mean) is applied by ucd_con_bwd.
+template <int MODE>
+__device__ __forceinline__ void sweep3_cols(const uint32_t (&r)[32], const int* __restrict__ lab, int cbase, int nv, int la,
+                                            int rself, float sc, float row_a, float row_b, float row_c,
+                                            const float* __restrict__ ca, const float* __restrict__ cb,
+                                            uint32_t (&pk)[16]) {
+#pragma unroll
+  for (int j4 = 0; j4 < 32; j4 += 4) {
+    const int4 l4 = *reinterpret_cast<const int4*>(lab + cbase + j4);
+    const int ls[4] = {l4.x, l4.y, l4.z, l4.w};
+    const float4 a4 = __ldg(reinterpret_cast<const float4*>(ca + cbase + j4));
+    const float as[4] = {a4.x, a4.y, a4.z, a4.w};
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(cb + cbase + j4));  // MODE 0: B_j, MODE 1: a_j
+    const float bs[4] = {b4.x, b4.y, b4.z, b4.w};
+    float h[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int col = cbase + j4 + u;
+      const float e = ex2f(__uint_as_float(r[j4 + u]) * sc);
+      const bool same = ls[u] == la;
+      float v = (row_a + as[u]) * e;
+      if (MODE == 0) {
+        const float pos = -row_c * (row_b * rcpf(e + row_b) + bs[u] * rcpf(e + bs[u]));
+        v = same ? pos : v;
+      } else {
+        v = same ? v - (row_c + bs[u]) : v;  // a_j differs from a_i when only some rows are anchors ('one' mode)
+      }
+      h[u] = (col < nv && col != rself) ? v : 0.f;
+    }
+    pk[j4 / 2] = bf16x2_bits(h[0], h[1]);
+    pk[j4 / 2 + 1] = bf16x2_bits(h[2], h[3]);
+  }
+}
+
 template <int PHASE, int PMODE>
 __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];  // no-swizzle operands: 16 B alignment suffices
@@ -353,8 +409,8 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
   // Sweep 2 parks Ucoef in the consumed P columns, so P(t+1) waits for U(t).  (Tried in round 2: a Ucoef tile in shared
   // memory frees the P columns at once but costs one ring slot - with 1.5 tiles in flight every active tile waited for
   // its load: 158 us instead of 125 us per sweep.)
-  constexpr int NE = (PHASE == 1) ? 2 : 1;  // E buffers in TMEM (sweep 2 parks Ucoef in the consumed P columns)
-  constexpr int NSLOT = (PHASE == 1) ? 5 : 4;  // half-tile slots (sweep 2 keeps 32 KB for the probability operands)
+  constexpr int NE = (PHASE != 2) ? 2 : 1;  // E buffers in TMEM (sweep 2 parks Ucoef in the consumed P columns)
+  constexpr int NSLOT = (PHASE != 2) ? 5 : 4;  // half-tile slots (sweep 2 keeps 32 KB for the probability operands)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rb = blockIdx.x / a.splits, split = blockIdx.x - rb * a.splits;
   const int n_rows = *a.n_rows;
@@ -437,7 +493,7 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
   }
   // next tile index >= tt that this sweep has to process (sweep 1: every tile; sweep 2: next set mask bit)
   auto next_active = [&](int tt) -> int {
-    if (PHASE == 1) return tt;
+    if (PHASE != 2) return tt;
     while (tt < n) {
       const uint32_t bits = s_mask[tt >> 5] >> (tt & 31);
       if (bits) return tt + __ffs(bits) - 1;
@@ -547,7 +603,7 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
             for (int ks = 0; ks < 4; ++ks)
               umma_bf16(tS + sb * 128, umma_desc_adv(adesc, ks * 2 * kChunkB), umma_desc_adv(cdesc, ks * 2 * kChunkB),
                         idesc_s, (q > 0 || ks > 0) ? 1u : 0u);
-            if (q == 3 && PHASE == 1) {
+            if (q == 3 && PHASE != 2) {
               umma_commit(BAR(BAR_SF + sb));
               if (!a.need_grad) {  // no V pass: the slots are free once S is done
                 umma_commit(BAR(BAR_HE + slot_a));
@@ -625,7 +681,7 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
           mbar_wait_t(BAR(BAR_EF + (eb * 2 + h) * 2 + cc), (t / NE) & 1, c_idle);
           tc_fence_after();
           // 16 columns of packed bf16 pairs = 32 K values: E buffer eb (sweep 1), Ucoef over P (sweep 2)
-          const uint32_t te = tmem + 128 + (PHASE == 1 ? eb * 64 + h * 32 : h * 64) + cc * 16;
+          const uint32_t te = tmem + 128 + (PHASE != 2 ? eb * 64 + h * 32 : h * 64) + cc * 16;
           if (elect_one_sync()) {
             const uint32_t rowoff = (uint32_t)(h * 64 + cc * 32) * 16u;
             const uint64_t vda = umma_desc_adv(vdesc0, (uint32_t)slot_a * kSlotBytes + rowoff);
@@ -670,10 +726,12 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
     RowC rc = {0.f, 0.f, 0.f, 0.f, 0.f, false};
     int thr = 0x7fffffff;
     bool warp_series = false;
+    float row_a = 0.f, row_b = 0.f, row_c = 0.f;  // sweep 3: this pixel's coefficients
+    if (PHASE == 3 && grow < n_rows) row_a = a.col_a[grow], row_b = a.col_b[grow], row_c = a.col_c[grow];
     if (PHASE == 2) {
-      rc.mraw = a.stats[grow];
+      rc.mraw = a.shift ? a.stats[grow] : 0.f;
       rc.negi = a.stats[a.rows_pad + grow];
-      rc.series = rc.negi >= 4096.f;
+      rc.series = PMODE != 3 && rc.negi >= 4096.f;
       rc.inv_neg = rc.series ? 1.f / rc.negi : 0.f;
       rc.lneg2 = rc.series ? log2f(rc.negi) : 0.f;
       rc.c0 = -fmaf(rc.mraw, sc, rc.lneg2);
@@ -711,19 +769,22 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
       // own (already consumed) S range in tensor memory; the V/U MMA reads its A operand from there.
       auto emit = [&](int cc, const uint32_t (&pk)[16]) {  // cc = chunk 0/1 within this thread's column half
         if (!a.need_grad) return;
-        tmem_st16(tmem + lane_addr + 128 + (PHASE == 1 ? eb * 64 + half * 32 : half * 64) + cc * 16, pk);
+        tmem_st16(tmem + lane_addr + 128 + (PHASE != 2 ? eb * 64 + half * 32 : half * 64) + cc * 16, pk);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(BAR(BAR_EF + (eb * 2 + half) * 2 + cc));
       };
       const int c0 = half * 64;  // first column of this thread's half
-      if (PHASE == 1) {
+      if (PHASE != 2) {
         // software-pipelined TMEM reads: the second chunk is in flight while the first is processed
         uint32_t r0[32], r1[32];
         auto proc = [&](int cc, const uint32_t (&rv)[32]) {
           uint32_t pk[16];
-          if (all_neg)
+          if (PHASE == 3)
+            sweep3_cols<PMODE>(rv, lab, c0 + cc * 32, loc.nvalid, la, self ? r : -1, sc, row_a, row_b, row_c,
+                               a.col_a + loc.dcol0, (PMODE == 0 ? a.col_b : a.col_c) + loc.dcol0, pk);
+          else if (all_neg)
             sweep1_cols_neg(rv, sc, mx, neg, pk);
           else if (full && !self)
             sweep1_cols<true, false>(rv, lab, c0 + cc * 32, 128, la, r, sc, mx, neg, num, pk);
@@ -749,7 +810,7 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
       } else {
         // uniform tile: all 128 column labels equal this lane's row label, for every lane of the warp
         bool uniform = false;
-        if (PMODE != 2 && full && !self) {
+        if (PMODE != 2 && PMODE != 3 && full && !self) {
           const int4 l4 = *reinterpret_cast<const int4*>(lab + lane * 4);
           uniform = __all_sync(0xffffffffu, l4.x == la && l4.y == la && l4.z == la && l4.w == la);
         }
@@ -820,13 +881,13 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
     // by now.  (NOT the probability region: with no active tile the row-probability copy may still be in flight.)
     if (PHASE == 2 && rc.series) tacc *= rc.inv_neg;  // the series path accumulated sum_j Ucoef_ij = neg_i T_i
     float* comb = reinterpret_cast<float*>(smem + OFF_C);
-    if (half == 1) {
+    if (PHASE != 3 && half == 1) {
       comb[r * 3 + 0] = PHASE == 1 ? mx : lacc;
       comb[r * 3 + 1] = PHASE == 1 ? neg : tacc;
       comb[r * 3 + 2] = num;
     }
     asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
-    if (half == 0) {
+    if (PHASE != 3 && half == 0) {
       if (PHASE == 1) {
         const size_t slot = (size_t)(split + a.split_base);
         a.stats_part[slot * 3 * a.rows_pad + grow] = fmaxf(mx, comb[r * 3 + 0]);
@@ -842,7 +903,7 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
       // different 128-byte lines with 16 bytes each.  A per-warp [32][36] transposition buffer in the (now idle) C stage
       // turns that into 4 full lines per instruction.
       float* xp = reinterpret_cast<float*>(smem + OFF_C + 4096) + (size_t)(warp - 3) * (32 * 36);
-      const size_t prow0 = (size_t)(split + (PHASE == 1 ? a.split_base : 0)) * a.rows_pad + (size_t)rb * 128 +
+      const size_t prow0 = (size_t)(split + (PHASE != 2 ? a.split_base : 0)) * a.rows_pad + (size_t)rb * 128 +
                            quarter * 32;  // first row of this warp
       float* dstw = a.acc_part + prow0 * 256 + half * 128;
       const int orow = lane >> 3, ocol = (lane & 7) * 4;
@@ -973,6 +1034,64 @@ __global__ void con_bwd_kernel(const float* __restrict__ grad_unit, const float*
     const long long row = i >> 6;
     const long long dst = row_ref ? (long long)row_ref[row] : row;  // tile (class-sorted) row -> reference row
     reinterpret_cast<float4*>(d_anchor)[dst * 64 + (i & 63)] = g;
+  }
+}
+
+// Self-contrast losses, between sweep 2 and sweep 3: per-pixel coefficients of sweep3_cols, the per-row loss terms and
+// their per-block partial sums.  mode 0 = PixelConLoss v1, 1 = SupConLoss (n_anchor: rows that are anchors, the first
+// ones; kappa = temperature / base_temperature).  stats = {raw row max, neg, num} of sweep 1; loss_part = sweep 2's
+// {L_i, T_i} (v1: unshifted denominator) or {sum_pos s_ij, sum_pos exp(s_ij)} (SupCon).
+__global__ void __launch_bounds__(256)
+selfcon_rowcoef_kernel(const float* __restrict__ stats, const float* __restrict__ loss_part, int splits2,
+                       long long rows_pad, long long n, long long n_anchor, int mode, float inv_tau, float kappa,
+                       float* __restrict__ col_a, float* __restrict__ col_b, float* __restrict__ col_c,
+                       float* __restrict__ block_part) {
+  float lsum = 0.f, lcnt = 0.f;
+  for (long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x; row < rows_pad;
+       row += (long long)gridDim.x * blockDim.x) {
+    float ca = 0.f, cb = 0.f, cc = 0.f;
+    if (row < n) {
+      const float neg = stats[rows_pad + row], num = stats[2 * rows_pad + row];
+      float p0 = 0.f, p1 = 0.f;
+      for (int s = 0; s < splits2; ++s) {
+        p0 += loss_part[(size_t)s * 2 * rows_pad + row];
+        p1 += loss_part[(size_t)s * 2 * rows_pad + rows_pad + row];
+      }
+      if (mode == 0) {
+        const bool valid = num != 0.f;
+        cc = valid ? 1.f / num : 0.f;
+        ca = cc * p1;
+        cb = neg;
+        if (valid) lsum += -p0 / num, lcnt += 1.f;
+      } else {
+        const float m = stats[row] * inv_tau;                      // max_j s_ij, the row itself included
+        const float em = __expf(-m);
+        const float D = (neg + p1) * em + 1e-6f;                   // sum_{k != i} exp(s_ik - m) + 1e-6 (loss_new.py:340)
+        cc = row < n_anchor ? kappa / (num + 1e-8f) : 0.f;        // fp32 like the reference's float mask (loss_new.py:345)
+        ca = cc * num * em / D;
+        if (row < n_anchor) lsum += -cc * (p0 - num * (m + __logf(D))), lcnt += 1.f;
+      }
+    }
+    col_a[row] = ca, col_b[row] = cb, col_c[row] = cc;
+  }
+  __shared__ float red[32];
+  const float r0 = block_sum(lsum, red);
+  const float r1 = block_sum(lcnt, red);
+  if (threadIdx.x == 0) block_part[blockIdx.x] = r0, block_part[gridDim.x + blockIdx.x] = r1;
+}
+
+// unit gradient of the self-contrast losses: (1/tau) * sum over the column splits of sweep 3's partial products
+__global__ void __launch_bounds__(256)
+selfcon_grad_kernel(const float* __restrict__ v_part, int splits, long long rows_pad, long long n, float inv_tau,
+                    float* __restrict__ grad_unit) {
+  const long long n4 = n * 64;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < splits; ++s) {
+      const float4 t = __ldcs(reinterpret_cast<const float4*>(v_part + (size_t)s * rows_pad * 256) + i);
+      acc.x += t.x, acc.y += t.y, acc.z += t.z, acc.w += t.w;
+    }
+    reinterpret_cast<float4*>(grad_unit)[i] = make_float4(acc.x * inv_tau, acc.y * inv_tau, acc.z * inv_tau, acc.w * inv_tau);
   }
 }
 
@@ -1142,6 +1261,8 @@ extern "C" int ucd_con_fwd(const void* feat_tiles, const void* prob_tiles, const
 #else
   a.trace = nullptr;
 #endif
+  a.shift = 1;
+  a.col_a = a.col_b = a.col_c = nullptr;
   int rc;
   // sweep 1: one launch over every chunk, or (two-part run) the local chunk first - while the exchange of the other
   // ranks' columns is still in flight - and the remaining chunks in the second call
@@ -1181,6 +1302,74 @@ extern "C" int ucd_con_fwd(const void* feat_tiles, const void* prob_tiles, const
   UCD_CHECK_LAUNCH("con_finalize_kernel");
   con_reduce_out_kernel<<<1, 256, 0, st>>>(block_part, kFinalizeBlocks, out);
   UCD_CHECK_LAUNCH("con_reduce_out_kernel");
+  return UCD_OK;
+}
+
+// ---- self-contrast losses -----------------------------------------------------------------------------------------
+static size_t selfcon_extra_off(const ConPlan& p) { return (p.total + 255) & ~(size_t)255; }
+
+extern "C" size_t ucd_selfcon_workspace_bytes(int64_t tiles) {
+  if (tiles <= 0) return 0;
+  const ConPlan p = make_plan(tiles, tiles);
+  return selfcon_extra_off(p) + (size_t)3 * p.rows_pad * sizeof(float);
+}
+
+extern "C" int ucd_selfcon_fwd(const void* feat_tiles, const int32_t* lab_tiles, const int32_t* tile_range,
+                               const int32_t* counts, const int32_t* n_rows, int64_t n, int64_t n_anchor, int mode,
+                               float inv_temperature, float kappa, int need_grad, float* out, float* grad_unit,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+  UCD_CHECK_ARG(feat_tiles && lab_tiles && tile_range && counts && n_rows && out && workspace,
+                "ucd_selfcon_fwd: null pointer");
+  UCD_CHECK_ARG(n >= 1 && n_anchor >= 1 && n_anchor <= n, "ucd_selfcon_fwd: bad row counts");
+  UCD_CHECK_ARG(mode == 0 || mode == 1, "ucd_selfcon_fwd: mode must be 0 (PixelConLoss v1) or 1 (SupConLoss)");
+  UCD_CHECK_ARG(inv_temperature > 0.f, "ucd_selfcon_fwd: bad temperature");
+  UCD_CHECK_ARG(!need_grad || grad_unit, "ucd_selfcon_fwd: need_grad without grad_unit");
+  UCD_CHECK_ARG(aligned16(feat_tiles) && aligned16(lab_tiles), "ucd_selfcon_fwd: tile buffers must be 16 B aligned");
+  const int64_t tiles = (n + 127) / 128;
+  const ConPlan plan = make_plan(tiles, tiles);
+  const size_t off_x = selfcon_extra_off(plan);
+  UCD_CHECK_ARG(workspace_bytes >= off_x + (size_t)3 * plan.rows_pad * sizeof(float),
+                "ucd_selfcon_fwd: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* ws = (uint8_t*)workspace;
+  float* col = (float*)(ws + off_x);
+  ConArgs a;
+  a.feat_tiles = (const __nv_bfloat16*)feat_tiles, a.prob_tiles = nullptr, a.lab_tiles = lab_tiles;
+  a.chunk_counts = counts, a.n_chunks = 1, a.chunk_tiles = tiles, a.chunk_stride = 0, a.chunk_origin = 0;
+  a.chunk_lo = 0, a.chunk_hi = 1, a.chunk_skip = -1, a.split_base = 0;
+  a.row_feat = (const __nv_bfloat16*)feat_tiles, a.row_prob = nullptr, a.row_lab = lab_tiles;  // rows = columns
+  a.n_rows = n_rows, a.tile_range = tile_range, a.row_range = tile_range, a.self_tile0 = 0, a.min_new = nullptr;
+  a.dense_p = nullptr, a.ldp = 0, a.inv_tau = inv_temperature, a.kpad = 16, a.rows_pad = plan.rows_pad;
+  a.stats_part = (float*)(ws + plan.off_stats_part), a.stats = (const float*)(ws + plan.off_stats);
+  a.loss_part = (float*)(ws + plan.off_loss_part), a.trace = nullptr;
+  a.shift = 0;
+  a.col_a = col, a.col_b = col + plan.rows_pad, a.col_c = col + 2 * plan.rows_pad;
+  // sweep 1: raw row max, neg (different label), num (same label, the row itself excluded)
+  a.need_grad = 0, a.splits = plan.splits, a.acc_part = (float*)(ws + plan.off_v);
+  int rc = launch_sweep<1, 0>(a, tiles, st);
+  if (rc != UCD_OK) return rc;
+  con_combine_kernel<<<(unsigned)((plan.rows_pad + 255) / 256), 256, 0, st>>>(a.stats_part, plan.splits, plan.rows_pad,
+                                                                               (float*)(ws + plan.off_stats));
+  UCD_CHECK_LAUNCH("con_combine_kernel");
+  // sweep 2 over the positive pairs: v1 {L_i, T_i} with the unshifted denominator, SupCon {sum s, sum exp(s)}
+  a.splits = plan.splits2, a.acc_part = (float*)(ws + plan.off_u);
+  rc = mode == 0 ? launch_sweep<2, 0>(a, tiles, st) : launch_sweep<2, 3>(a, tiles, st);
+  if (rc != UCD_OK) return rc;
+  float* block_part = (float*)(ws + plan.off_block);
+  selfcon_rowcoef_kernel<<<kFinalizeBlocks, 256, 0, st>>>(a.stats, a.loss_part, plan.splits2, plan.rows_pad, n, n_anchor,
+                                                          mode, inv_temperature, kappa, col, col + plan.rows_pad,
+                                                          col + 2 * plan.rows_pad, block_part);
+  UCD_CHECK_LAUNCH("selfcon_rowcoef_kernel");
+  con_reduce_out_kernel<<<1, 256, 0, st>>>(block_part, kFinalizeBlocks, out);
+  UCD_CHECK_LAUNCH("con_reduce_out_kernel");
+  if (!need_grad) return UCD_OK;
+  // sweep 3: H F with H = G + G^T formed pair by pair (sweep3_cols)
+  a.need_grad = 1, a.splits = plan.splits, a.acc_part = (float*)(ws + plan.off_v);
+  rc = mode == 0 ? launch_sweep<3, 0>(a, tiles, st) : launch_sweep<3, 1>(a, tiles, st);
+  if (rc != UCD_OK) return rc;
+  selfcon_grad_kernel<<<kFinalizeBlocks, 256, 0, st>>>((const float*)(ws + plan.off_v), plan.splits, plan.rows_pad, n,
+                                                        inv_temperature, grad_unit);
+  UCD_CHECK_LAUNCH("selfcon_grad_kernel");
   return UCD_OK;
 }
 

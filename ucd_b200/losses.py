@@ -987,6 +987,122 @@ class PixelConLossV2(nn.Module):
         return _ConFn.apply(anchor_features, cols, rows, inv_tau, p_mode, dense_p, None, False)
 
 
+# ----------------------------------------------------------------------------------------------
+# N3: the self-contrast siblings of utils/loss_new.py (PixelConLoss v1, SupConLoss) on the same sweeps
+# ----------------------------------------------------------------------------------------------
+class _SelfConFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rows, labels, mode, n_anchor, inv_tau, kappa):
+        """rows [n, D <= 256] (any float dtype), labels [n] integer (>= 0); mode 0 = PixelConLoss v1, 1 = SupConLoss."""
+        L = _lib.lib()
+        dev = rows.device
+        n, D = rows.shape
+        x = _f32c(rows.detach())
+        if D < FEAT_DIM:   # zero columns change no dot product
+            x = torch.nn.functional.pad(x, (0, FEAT_DIM - D))
+        lab = labels.to(device=dev, dtype=torch.int32).contiguous()
+        tiles = (n + TILE - 1) // TILE
+        feat = torch.empty(tiles, FEAT_DIM // 8, TILE, 8, device=dev, dtype=torch.bfloat16)
+        ltile = torch.empty(tiles, TILE, device=dev, dtype=torch.int32)
+        rng = torch.empty(tiles, 2, device=dev, dtype=torch.int32)
+        st = cur_stream()
+        check(L.ucd_con_pack_rows(ptr(x), ptr(lab), n, ptr(feat), ptr(ltile), tiles, st), "con_pack_rows")
+        check(L.ucd_con_tile_ranges(ptr(ltile), tiles, None, ptr(rng), st), "con_tile_ranges")
+        meta = torch.tensor([n, 0, n], device=dev, dtype=torch.int32)   # {columns, 0} | rows
+        need_grad = bool(ctx.needs_input_grad[0])
+        out = torch.empty(3, device=dev, dtype=torch.float32)
+        grad_unit = torch.empty(n, FEAT_DIM, device=dev, dtype=torch.float32) if need_grad else None
+        ws_bytes = L.ucd_selfcon_workspace_bytes(tiles)
+        ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+        check(L.ucd_selfcon_fwd(ptr(feat), ptr(ltile), ptr(rng), ptr(meta), meta.data_ptr() + 8, n, n_anchor, mode,
+                                inv_tau, kappa, 1 if need_grad else 0, ptr(out), ptr(grad_unit), ptr(ws), ws_bytes, st),
+              "selfcon_fwd")
+        ctx.save_for_backward(grad_unit, out, meta)
+        ctx.shape, ctx.in_dtype = (n, D), rows.dtype
+        return out[2]
+
+    @staticmethod
+    def backward(ctx, g):
+        grad_unit, out, meta = ctx.saved_tensors
+        n, D = ctx.shape
+        d = torch.empty(n, FEAT_DIM, device=g.device, dtype=torch.float32)
+        check(_lib.lib().ucd_con_bwd(ptr(grad_unit), ptr(out), ptr(_f32c(g.reshape(1))), 1.0, meta.data_ptr() + 8, None,
+                                     ptr(d), n, cur_stream()), "con_bwd")
+        return d[:, :D].to(ctx.in_dtype), None, None, None, None, None
+
+
+def _selfcon_rows(features, what):
+    if features.dim() < 3:
+        raise ValueError('`features` needs to be [bsz, n_views, ...],'
+                         'at least 3 dimensions are required')
+    _need_cuda(features)
+    feats = features.reshape(features.shape[0], features.shape[1], -1)
+    if feats.shape[2] > FEAT_DIM:
+        raise NotImplementedError("%s: feature width %d > %d is not supported by the sweep kernels"
+                                  % (what, feats.shape[2], FEAT_DIM))
+    # torch.cat(torch.unbind(features, dim=1), dim=0): view-major rows (loss_new.py:309,383)
+    return feats, feats.transpose(0, 1).reshape(-1, feats.shape[2])
+
+
+class PixelConLoss(nn.Module):
+    """``PixelConLoss`` (v1) of utils/loss_new.py:354-400: supervised contrastive loss of a pixel set with itself (the
+    output of the pixel-to-pixel branches of ``pre_contrastive_pixel``), unshifted exponentials, gradients through both
+    operands.  Same constructor and ``forward(features [n, 1, D], labels [n])``; D <= 256."""
+
+    def __init__(self, sample_method='none', temperature=1):
+        super().__init__()
+        self.temperature = temperature
+        self.sample_method = sample_method
+
+    def forward(self, features, labels=None):
+        feats, rows = _selfcon_rows(features, "PixelConLoss")
+        if labels is None:
+            raise AttributeError("PixelConLoss: labels are required (the reference calls labels.view, loss_new.py:376)")
+        lab = labels.reshape(-1)
+        if lab.numel() != feats.shape[0] or feats.shape[1] != 1:
+            # the reference compares [bsz, bsz] masks with the [n_views*bsz]^2 logits: only n_views == 1 is well formed
+            raise ValueError("PixelConLoss: expected features [n, 1, D] and n labels")
+        lab = lab.to(rows.device)
+        lab = lab - lab.min()   # the kernels reserve negative labels for padding; equality is all that matters
+        return _SelfConFn.apply(rows, lab, 0, rows.shape[0], 1.0 / float(self.temperature), 1.0)
+
+
+class SupConLoss(nn.Module):
+    """``SupConLoss`` of utils/loss_new.py:263-352 (supervised contrastive learning / SimCLR when ``labels`` is None).
+    Same constructor and ``forward(features [bsz, n_views, ...], labels=None, mask=None)``.  An explicit ``mask`` (an
+    arbitrary, possibly asymmetric positive relation) is not a label structure the sweeps can skip tiles on: it raises
+    NotImplementedError.  Feature width <= 256."""
+
+    def __init__(self, temperature=0.07, contrast_mode='all', base_temperature=0.07):
+        super().__init__()
+        self.temperature = temperature
+        self.contrast_mode = contrast_mode
+        self.base_temperature = base_temperature
+
+    def forward(self, features, labels=None, mask=None):
+        feats, rows = _selfcon_rows(features, "SupConLoss")
+        bsz, n_views = feats.shape[0], feats.shape[1]
+        if labels is not None and mask is not None:
+            raise ValueError('Cannot define both `labels` and `mask`')
+        if mask is not None:
+            raise NotImplementedError("SupConLoss: an explicit `mask` is not supported; pass labels (or nothing: SimCLR)")
+        if labels is None:
+            lab = torch.arange(bsz, device=rows.device)
+        else:
+            lab = labels.contiguous().view(-1).to(rows.device)
+            if lab.shape[0] != bsz:
+                raise ValueError('Num of labels does not match num of features')
+            lab = lab - lab.min()
+        if self.contrast_mode == 'one':
+            n_anchor = bsz
+        elif self.contrast_mode == 'all':
+            n_anchor = bsz * n_views
+        else:
+            raise ValueError('Unknown mode: {}'.format(self.contrast_mode))
+        return _SelfConFn.apply(rows, lab.repeat(n_views), 1, n_anchor, 1.0 / float(self.temperature),
+                                float(self.temperature) / float(self.base_temperature))
+
+
 class PixelContrastiveDistillation(nn.Module):
     """Opt-in, sync-free form of ``PixelConLossV2()(*pre_contrastive_pixel(f_n, l_n, l_po=..., f_o=...))``
     (train.py:115-116): the same kernels, but the 5-tuple is never materialised, so N_a / N_o
