@@ -1,5 +1,5 @@
 """One small pass over every kernel of the library (for compute-sanitizer runs): drop-in step, fused N1, sync-free N4,
-compat path with dense P, sibling losses, pixel-to-pixel branches."""
+compat path with dense P, sibling losses, pixel-to-pixel branches, self-contrast losses, bf16 feature hand-off."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -30,5 +30,13 @@ U.MaskKnowledgeDistillationLoss()(out, old, mask=(case["labels"] > 0).float()).b
 U.MaskCrossEntropy(old_cl=C_old)(out, case["labels"].clone(), outputs_old=old).backward()
 o2, l2 = U.pre_contrastive_pixel(f_n, case["labels"], f_o=case["f_o"])
 o2.sum().backward()
+# self-contrast siblings (sweep 3) on the pixel-to-pixel rows, SupCon with two views
+o1, l1 = U.pre_contrastive_pixel(f_n, case["labels"])
+U.PixelConLoss(temperature=0.5)(o1, l1).backward()
+xs = torch.nn.functional.normalize(torch.randn(150, 2, 64, device="cuda"), dim=2).requires_grad_(True)
+U.SupConLoss(contrast_mode="one")(xs, torch.randint(0, 5, (150,), device="cuda")).backward()
+# bf16 feature hand-off
+fb = case["f_n"].to(torch.bfloat16).requires_grad_(True)
+con(*U.pre_contrastive_pixel(fb, case["labels"], l_po=case["l_po"], f_o=case["f_o"].to(torch.bfloat16))).backward()
 torch.cuda.synchronize()
 print("ok", float(loss), float(sf))

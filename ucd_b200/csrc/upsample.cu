@@ -526,9 +526,11 @@ extern "C" int ucd_upsample_bilinear_bwd(const float* gout, float* gin, int64_t 
     cudaError_t e = cudaMemsetAsync(gin, 0, (size_t)planes * h * w * sizeof(float), st);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(upsample_bwd)");
     auto kern = upsample_bwd_sweep_kernel<8>;
+#ifdef UCD_DEBUG_KNOBS
     if (un == 4) kern = upsample_bwd_sweep_kernel<4>;
     if (un == 12) kern = upsample_bwd_sweep_kernel<12>;
     if (un == 16) kern = upsample_bwd_sweep_kernel<16>;
+#endif
     if (dyn > 48 * 1024) {
       e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
       if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(upsample_bwd_sweep)");
