@@ -590,9 +590,11 @@ def main():
         traffic = None
         traffic_note = "not captured for this workload (ncu --set full is run on the default workload only)"
         if world == 1 and args.workload == "voc" and B == WORKLOADS["voc"]["B"]:
-            traffic = 8.75e7
+            traffic = 9.30e7
             traffic_note = ("RECORDED, not measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of the two "
-                            "sweep kernels per step from ncu --set full, profiles/r02_ncu_full.md")
+                            "sweep kernels per step from ncu --set full, profiles/r02c_ncu_full.md (21.5 + 45.1 MB sweep 1, "
+                            "22.9 + 3.5 MB sweep 2; algorithmic operands + gradient: 46 MB - the rest are the V / U partials "
+                            "of the column splits)")
         line = dict(
             metric=METRIC, value=pairs_total / (ms_dev_max * 1e-3) / 1e6, unit=UNIT, n_gpus=world, steps=args.steps,
             warmup=args.warmup, ms_per_step=ms_dev_max, higher_is_better=True, scaling="weak", vs_baseline=None,
