@@ -60,7 +60,10 @@ def test_umma_selftest(U):
                                         # largest scale of the interval kernel (40x) and beyond it (generic kernel)
                                         ((1, 2, 4, 8), (160, 320)), ((1, 1, 3, 8), (144, 384)), ((1, 1, 5, 7), (171, 93)),
                                         # sweep backward with a shortened segment (37x along y) over several segments
-                                        ((1, 2, 8, 8), (296, 256)), ((1, 1, 24, 8), (888, 256))])
+                                        ((1, 2, 8, 8), (296, 256)), ((1, 1, 24, 8), (888, 256)),
+                                        # sweep backward: row ranges that cross plane boundaries (100 planes of 5 rows on
+                                        # 148 blocks), a single low-res row per plane
+                                        ((4, 25, 5, 32), (80, 512)), ((2, 40, 1, 32), (16, 512))])
 def test_upsample_fwd_bwd(U, shape, size):
     g = torch.Generator().manual_seed(11)
     x = torch.randn(*shape, generator=g)
@@ -77,6 +80,12 @@ def test_upsample_fwd_bwd(U, shape, size):
     # adjoint: fixed but different summation order -> fp32 tolerance
     torch.testing.assert_close(xc.grad.cpu(), xr.grad, rtol=1e-4, atol=3e-6 * float(xr.grad.abs().max()))
     torch.testing.assert_close(out.cpu(), O.upsample_bilinear(x, *size), rtol=1e-5, atol=1e-5)
+    # the adjoint hands a range's trailing partial row to its neighbour with atomicAdd (two operands: commutative):
+    # repeated runs must be bit-identical
+    for _ in range(3):
+        xc2 = x.cuda().requires_grad_(True)
+        U.interpolate_bilinear(xc2, size).backward(go.cuda())
+        assert torch.equal(xc2.grad, xc.grad)
 
 
 @pytest.mark.parametrize("shape", [(2, 7, 9, 11), (2, 21, 64, 64), (1, 17, 33, 33), (3, 151, 16, 20)])
