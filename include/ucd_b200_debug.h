@@ -2,7 +2,7 @@
  * Debug / probe entry points of the ucd_b200 kernels.  NOT part of the product boundary: they are exported only by
  * ucd_b200/libucd_b200_debug.so (the same sources compiled with -DUCD_DEBUG_KNOBS, `python -m ucd_b200.build --debug`),
  * which is also the only build that keeps global debug state (the trace pointer) and reads environment variables
- * (UCD_SPLITS1, UCD_SPLITS2, UCD_UP_GY tuning knobs).  Used by scripts/ and by the tcgen05 building-block self-test.
+ * (UCD_SPLITS1, UCD_SPLITS2, UCD_UP_GY, UCD_UPB_UN, UCD_UPB_BPS tuning knobs).  Used by scripts/ and by the tcgen05 building-block self-test.
  */
 #ifndef UCD_B200_DEBUG_H
 #define UCD_B200_DEBUG_H

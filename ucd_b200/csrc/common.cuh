@@ -30,7 +30,7 @@ int cuda_fail(cudaError_t e, const char* what);
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-constexpr int kNumSMs = 148;           // B200: 2 dies x 74 SMs
+constexpr int kNumSMs = 148;           // B200: 2 dies x 74 SMs (grid sizing only: any SM count runs correctly)
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
