@@ -260,7 +260,10 @@ def test_pixelconloss_compat_dense_inputs(U, n_a, n_c, with_p):
     assert cos(Ac.grad, Ar.grad) >= COS
 
 
-@pytest.mark.parametrize("c_tot,c_old,max_label", [(151, 101, 150), (40, 30, 39), (70, 60, 69)])
+@pytest.mark.parametrize("c_tot,c_old,max_label", [(151, 101, 150), (40, 30, 39), (70, 60, 69),
+                                                    # beyond 112 old classes both probability operands are streamed
+                                                    # (ADE 100-10 from its second step on: 111, 121, ... 141 old classes)
+                                                    (151, 121, 150), (151, 141, 150), (230, 200, 229)])
 def test_contrastive_wide_joint_probability(U, c_tot, c_old, max_label):
     """ADE-like class counts (BASELINE config 3): joint-probability width > 16 (K-chunked P GEMM) and labels > 20.
     The reference itself cannot run this (hard-coded VOC clamp + int8 cast), so the bar is the oracle

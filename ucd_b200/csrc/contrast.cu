@@ -463,11 +463,14 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
   const int n = max(0, k1 - k0);
   const long long self_tile = a.self_tile0 >= 0 ? a.self_tile0 + rb : -1;  // the anchors' own column tile
   // sweep 2 probability operands: pA (kpad*256 B) stays resident; pC of a tile comes in K chunks of pc_k values
-  // (all of it when it fits: kpad <= 64; 16 at a time for kpad = 112, i.e. ADE's 101 old classes)
+  // (all of it when it fits: kpad <= 64; 16 at a time for kpad = 112, i.e. ADE's 101 old classes).  Beyond 112 old
+  // classes (ADE 100-10 / 100-5 from their second step on) pA no longer fits beside a pC chunk: then BOTH operands are
+  // streamed, 64 values of K at a time, and pA is re-read per tile (from L2: 256 B per K value, against 64 KB of features)
   const uint32_t pa_bytes = (uint32_t)a.kpad * 256u;
-  const int pc_k = min(a.kpad, (int)((kProbBytes - pa_bytes) / 256u) & ~15);
+  const bool pa_stream = a.kpad > 112;
+  const int pc_k = pa_stream ? 64 : min(a.kpad, (int)((kProbBytes - pa_bytes) / 256u) & ~15);
   const int n_pc = (PHASE == 2 && PMODE == 1) ? (a.kpad + pc_k - 1) / pc_k : 0;
-  const uint32_t off_pc = OFF_PA + pa_bytes;
+  const uint32_t off_pc = OFF_PA + (pa_stream ? 64u * 256u : pa_bytes);
   // Sweep 2 only touches pairs with equal labels (w_ij = 0 otherwise): a column tile whose label range misses the
   // row block's range contributes nothing and is skipped by all three roles (class-sorted tiles make this common).
   // Label-overlap mask of this CTA's column tiles, evaluated once by all threads (the range lookups are L2
@@ -515,11 +518,12 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
       const uint8_t* rpt = reinterpret_cast<const uint8_t*>(a.row_prob);
       const uint32_t pbytes = pa_bytes;
       if (elect_one_sync()) {
-        mbar_arrive_expect_tx(BAR(BAR_A), kTileBytes + ((PHASE == 2 && PMODE == 1) ? pbytes : 0u));
+        mbar_arrive_expect_tx(BAR(BAR_A), kTileBytes + ((PHASE == 2 && PMODE == 1 && !pa_stream) ? pbytes : 0u));
 #pragma unroll
         for (int q = 0; q < 4; ++q)
           bulk_g2s(sbase + OFF_A + q * 16384u, rft + (size_t)rb * kTileBytes + q * 16384u, 16384u, BAR(BAR_A));
-        if (PHASE == 2 && PMODE == 1) bulk_g2s(sbase + OFF_PA, rpt + (size_t)rb * pbytes, pbytes, BAR(BAR_A));
+        if (PHASE == 2 && PMODE == 1 && !pa_stream)
+          bulk_g2s(sbase + OFF_PA, rpt + (size_t)rb * pbytes, pbytes, BAR(BAR_A));
       }
       __syncwarp();
       long long w_ce = 0, w_pe = 0;
@@ -558,9 +562,11 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
           const uint32_t kb = (uint32_t)min(pc_k, a.kpad - c * pc_k) * 256u;
           mbar_wait_t(BAR(BAR_PE), (u & 1) ^ 1, w_pe);
           if (elect_one_sync()) {
-            mbar_arrive_expect_tx(BAR(BAR_PF), kb);
+            mbar_arrive_expect_tx(BAR(BAR_PF), pa_stream ? 2u * kb : kb);
             bulk_g2s(sbase + off_pc, pt + tile_off(loc, pbytes, a.chunk_tiles, a.chunk_stride, a.chunk_origin) +
                                          (size_t)c * pc_k * 256u, kb, BAR(BAR_PF));
+            if (pa_stream)  // the same K chunk of the row probabilities
+              bulk_g2s(sbase + OFF_PA, rpt + (size_t)rb * pbytes + (size_t)c * pc_k * 256u, kb, BAR(BAR_PF));
           }
           __syncwarp();
         }
@@ -637,7 +643,7 @@ __global__ void __launch_bounds__(kConThreads, 1) con_sweep_kernel(const ConArgs
             const int ksteps = min(pc_k, a.kpad - c * pc_k) >> 4;
             if (elect_one_sync()) {
               for (int ks = 0; ks < ksteps; ++ks)
-                umma_bf16(tP, umma_desc_adv(padesc0, (uint32_t)(c * (pc_k >> 3) + ks * 2) * kChunkB),
+                umma_bf16(tP, umma_desc_adv(padesc0, (uint32_t)((pa_stream ? 0 : c * (pc_k >> 3)) + ks * 2) * kChunkB),
                           umma_desc_adv(pcdesc0, ks * 2 * kChunkB), idesc_s, (c > 0 || ks > 0) ? 1u : 0u);
               umma_commit(BAR(BAR_PE));
               if (c == n_pc - 1) {
@@ -1220,8 +1226,8 @@ extern "C" int ucd_con_fwd(const void* feat_tiles, const void* prob_tiles, const
   UCD_CHECK_ARG(aligned16(feat_tiles) && aligned16(lab_tiles) && (!prob_tiles || aligned16(prob_tiles)),
                 "ucd_con_fwd: tile buffers must be 16 B aligned");
   UCD_CHECK_ARG(inv_temperature > 0.f, "ucd_con_fwd: bad temperature");
-  if (p_mode == 1 && (kpad < 16 || kpad > 112 || kpad % 16 != 0)) {
-    set_error("ucd_con_fwd: joint-probability width kpad=%d not supported (multiple of 16 up to 112, i.e. C_old <= 112)", kpad);
+  if (p_mode == 1 && (kpad < 16 || kpad > 256 || kpad % 16 != 0)) {
+    set_error("ucd_con_fwd: joint-probability width kpad=%d not supported (multiple of 16 up to 256, i.e. C_old <= 256)", kpad);
     return UCD_ENOSUP;
   }
   const ConPlan plan = make_plan(max_row_tiles, (int64_t)n_chunks * chunk_tiles, plan_row_tiles, part ? chunk_tiles : 0);
