@@ -5,7 +5,7 @@
                     [--workload voc|ade|city|sweep:<pixels>] [--batch B]
 
 One "step" = one pass of the hot path over one synthetic batch, forward + backward:
-  bilinear logit upsample (new: grad, old: no grad) -> pre_contrastive_pixel -> PixelConLossV2
+  bilinear logit upsample (old model under no_grad first, then the new one: train.py:100-108) -> pre_contrastive_pixel -> PixelConLossV2
   -> UnbiasedCrossEntropy(...).mean() + con/100 + 10 * UnbiasedKnowledgeDistillationLoss -> backward
 through the reference-shaped modules of ucd_b200 (train.py:115-116,133 wiring).
 
@@ -302,9 +302,9 @@ def main():
             state.update(n_a=tup[0].shape[0], n_c=tup[1].shape[0], con=con.detach(), g_fn=f_n.grad)
             return con
         lr = inp["logits_lr"].detach().requires_grad_(True)
-        outputs = U.interpolate_bilinear(lr, (H, W))
-        with torch.no_grad():
+        with torch.no_grad():   # the old model runs first (train.py:100-102), then the new one (:105-108)
             outputs_old = U.interpolate_bilinear(inp["l_po"], (H, W))
+        outputs = U.interpolate_bilinear(lr, (H, W))
         # evaluation order of train.py:115-116,133: prep, criterion, contrastive loss, distillation
         tup = U.pre_contrastive_pixel(f_n, inp["labels"], l_po=inp["l_po"], f_o=inp["f_o"], max_label=max_label)
         ce = unce(outputs, inp["labels"]).mean()

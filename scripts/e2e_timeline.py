@@ -19,9 +19,9 @@ state = {}
 def step(inp):
     f_n = inp["f_n"].detach().requires_grad_(True)
     lr = inp["logits_lr"].detach().requires_grad_(True)
-    outputs = U.interpolate_bilinear(lr, (H, W))
-    with torch.no_grad():
+    with torch.no_grad():   # the old model runs first (train.py:100-102), then the new one (:105-108)
         outputs_old = U.interpolate_bilinear(inp["l_po"], (H, W))
+    outputs = U.interpolate_bilinear(lr, (H, W))
     tup = U.pre_contrastive_pixel(f_n, inp["labels"], l_po=inp["l_po"], f_o=inp["f_o"])
     ce = unce(outputs, inp["labels"]).mean()
     con = conloss(*tup)

@@ -19,9 +19,9 @@ def step():
     f_n = inp["f_n"].detach().requires_grad_(True)
     lr = inp["logits_lr"].detach().requires_grad_(True)
     t = seg("inputs", t)
-    outputs = U.interpolate_bilinear(lr, (H, W))
-    with torch.no_grad():
+    with torch.no_grad():   # the old model runs first (train.py:100-102), then the new one (:105-108)
         outputs_old = U.interpolate_bilinear(inp["l_po"], (H, W))
+    outputs = U.interpolate_bilinear(lr, (H, W))
     t = seg("interpolate x2", t)
     tup = U.pre_contrastive_pixel(f_n, inp["labels"], l_po=inp["l_po"], f_o=inp["f_o"])
     t = seg("pre_contrastive_pixel (incl. sync)", t)
