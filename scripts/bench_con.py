@@ -65,6 +65,7 @@ for grad in (True, False):
                   (x[:, 4] / nt).mean(), (x[:, 5] / nt).mean(), (x[:, 0] / nt).mean(), (x[:, 1] / nt).mean(), (x[:, 2] / nt).mean()))
         print("      per CTA cycles: set-up %.0f | tile loop %.0f | tail (wait last MMAs, write partials) %.0f" % (
             x[:, 7].mean(), x[:, 8].mean(), x[:, 15].mean()))
+        print("      V/U(+P) issuer per tile: total %.0f (waiting %.0f)" % ((x[:, 12] / nt).mean(), (x[:, 13] / nt).mean()))
         tot = x[:, 7] + x[:, 8] + x[:, 15]
         tiles = x[:, 11]
         print("      balance: tiles total %.0f, per CTA max %.0f / mean %.1f | CTA cycles max %.0f mean %.0f | sum/148 SMs "
