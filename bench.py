@@ -567,7 +567,7 @@ def main():
             # SURVEY 8(d) algorithmic bytes per full-res pixel (fp32 logits, int64 labels); the per-pixel statistics a
             # kernel saves for its backward are extra traffic, listed as saved_stat_bytes, NOT counted as achieved
             for name, nbytes, extra in (
-                    ("ucd_unce_fwd", npx * (4 * C + 8 + 4), npx * 8), ("ucd_unce_bwd", npx * (8 * C + 8 + 4 + 4), npx * 4),
+                    ("ucd_unce_fwd", npx * (4 * C + 8 + 4), npx * 4), ("ucd_unce_bwd", npx * (8 * C + 8 + 4 + 4), npx * 4),
                     ("ucd_kd_fwd", npx * (4 * C + 4 * C_old), npx * 12), ("ucd_kd_bwd", npx * (8 * C + 4 * C_old), npx * 12),
                     # the two backward passes run as ONE kernel when both losses consume the same logits: judged
                     # against the fused lower bound of SURVEY 8(d) (read x, t and the labels once, write dx once)

@@ -44,7 +44,8 @@ int ucd_device_ok(void);
  * Unbiased cross-entropy   (utils/loss.py:96-109, alt utils/loss_new.py:89-115)
  *   x      [B,C,HW] fp32 logits (NCHW contiguous)       y [B,HW] int64 labels, REMAPPED IN PLACE
  *   loss_px[B,HW]   per-pixel loss (reduction 'none')   (y < old_cl -> 0, like loss.py:104-105)
- *   lse_all/lse_old [B,HW] saved log-sum-exp over all / over the first old_cl channels
+ *   lse_all [B,HW]  saved log-sum-exp over all channels;  lse_old [B,HW] or NULL: the same over the first old_cl
+ *                   channels (not needed by the backward: at label-0 pixels loss_px IS lse_all - lse_old)
  *   stats  float[2] : {sum of per-pixel losses, number of non-ignored pixels} (for mean/sum)
  * ---------------------------------------------------------------------------------------- */
 int ucd_unce_fwd(const float* x, int64_t* y, float* loss_px, float* lse_all, float* lse_old,
@@ -56,7 +57,9 @@ int ucd_unce_fwd(const float* x, int64_t* y, float* loss_px, float* lse_all, flo
  * accumulate != 0 (here and in ucd_unkd_bwd / ucd_kd_bwd): dx += ... instead of dx = ...: the second of two losses
  * on the same logits (train.py:116 and :133 both consume `outputs`) adds into the first one's gradient buffer, which
  * replaces autograd's own full-size add kernel (8 % of the drop-in step) by one extra read of dx. */
-int ucd_unce_bwd(const float* x, const int64_t* y, const float* lse_all, const float* lse_old,
+int ucd_unce_bwd(const float* x, const int64_t* y, const float* lse_all,
+                 const float* bkg_gap /* [B,HW]: lse_all - lse_old at the pixels whose (remapped) label is 0, anything
+                 elsewhere - the forward's loss_px as it stands */,
                  const float* g_px, const float* g_scalar, float g_mul, const float* stats,
                  int mean_over_valid, float* dx, int accumulate, int B, int C, int old_cl, int64_t HW,
                  int ignore_index, void* stream);
@@ -92,7 +95,7 @@ int ucd_kd_bwd(const float* x, const float* t, const float* mask, float alpha, c
 /* UNCE + UNKD backward in one pass (both losses consume the same `outputs`, train.py:116 and :133): the sum of what
  * ucd_unce_bwd and ucd_kd_bwd (variant 0 or 2) would write, with x read and dx written once.  lse_all is the statistic
  * both forwards saved (log-sum-exp over all C channels); lse3 as saved by ucd_kd_fwd. */
-int ucd_unce_unkd_bwd(const float* x, const int64_t* y, const float* lse_all, const float* lse_old,
+int ucd_unce_unkd_bwd(const float* x, const int64_t* y, const float* lse_all, const float* bkg_gap /* as above */,
                       const float* ce_g_px, const float* ce_g_scalar, float ce_g_mul, const float* ce_stats,
                       int mean_over_valid, int old_cl, int ignore_index, const float* t, const float* mask,
                       float alpha, const float* lse3, const float* kd_g_px, const float* kd_g_scalar, float kd_g_mul,

@@ -235,7 +235,7 @@ unce_fwd_kernel(const float* __restrict__ x, long long* __restrict__ y, float* _
     }
     Vec<VEC>::store(loss_px + b * HW + p, out);
     Vec<VEC>::store(lse_all_out + b * HW + p, la);
-    Vec<VEC>::store(lse_old_out + b * HW + p, lo);
+    if (lse_old_out != nullptr) Vec<VEC>::store(lse_old_out + b * HW + p, lo);
   }
   if (part != nullptr) {
     __shared__ float red[32];
@@ -252,7 +252,7 @@ unce_fwd_kernel(const float* __restrict__ x, long long* __restrict__ y, float* _
 template <int VEC, bool ACC>
 __global__ void __launch_bounds__(kStreamThreads)
 unce_bwd_kernel(const float* __restrict__ x, const long long* __restrict__ y, const float* __restrict__ lse_all,
-                const float* __restrict__ lse_old, const float* __restrict__ g_px,
+                const float* __restrict__ bkg_gap, const float* __restrict__ g_px,
                 const float* __restrict__ g_scalar, float g_mul, const float* __restrict__ stats,
                 int mean_over_valid, float* __restrict__ dx, int B, int C, int old_cl, long long HW,
                 int ignore_index) {
@@ -274,7 +274,7 @@ unce_bwd_kernel(const float* __restrict__ x, const long long* __restrict__ y, co
     {
       float la[VEC], lo[VEC], gp[VEC];
       Vec<VEC>::load_cached(lse_all + b * HW + p, la);
-      Vec<VEC>::load_cached(lse_old + b * HW + p, lo);
+      Vec<VEC>::load_cached(bkg_gap + b * HW + p, lo);  // lse_all - lse_old where the label is 0 (the forward's loss_px)
       if (g_px != nullptr) Vec<VEC>::load_cached(g_px + b * HW + p, gp);
 #pragma unroll
       for (int i = 0; i < VEC; ++i) {
@@ -284,8 +284,8 @@ unce_bwd_kernel(const float* __restrict__ x, const long long* __restrict__ y, co
         lab[i] = dead ? -1 : (int)t;
         up[i] = dead ? 0.f : (g_px != nullptr ? gp[i] : gs);
         la2[i] = la[i] * kLog2e;
-        // exp(x - lse_old) = exp(x - lse_all) * exp(lse_all - lse_old)
-        fold[i] = ex2f((la[i] - lo[i]) * kLog2e);
+        // exp(x - lse_old) = exp(x - lse_all) * exp(lse_all - lse_old); only read where the label is 0
+        fold[i] = ex2f(lo[i] * kLog2e);
       }
     }
 #pragma unroll 4
@@ -538,7 +538,7 @@ unkd_bwd_kernel(const float* __restrict__ x, const float* __restrict__ t, const 
 template <int VEC, bool ACC>
 __global__ void __launch_bounds__(kStreamThreads)
 unce_unkd_bwd_kernel(const float* __restrict__ x, const long long* __restrict__ y, const float* __restrict__ lse_all,
-                     const float* __restrict__ lse_old, const float* __restrict__ ce_g_px,
+                     const float* __restrict__ bkg_gap, const float* __restrict__ ce_g_px,
                      const float* __restrict__ ce_g_scalar, float ce_g_mul, const float* __restrict__ ce_stats,
                      int mean_over_valid, int old_cl, int ignore_index, const float* __restrict__ t,
                      const float* __restrict__ mask, float alpha, const float* __restrict__ lse3,
@@ -567,7 +567,7 @@ unce_unkd_bwd_kernel(const float* __restrict__ x, const long long* __restrict__ 
     {
       float la[VEC], lo[VEC], lb[VEC], lt[VEC], gp[VEC], gk[VEC], mk[VEC], u0[VEC];
       Vec<VEC>::load_cached(lse_all + b * HW + p, la);
-      Vec<VEC>::load_cached(lse_old + b * HW + p, lo);
+      Vec<VEC>::load_cached(bkg_gap + b * HW + p, lo);  // lse_all - lse_old where the label is 0 (the forward's loss_px)
       Vec<VEC>::load_cached(lse3 + plane + b * HW + p, lb);
       Vec<VEC>::load_cached(lse3 + 2 * plane + b * HW + p, lt);
       Vec<VEC>::load_cached(tp, u0);
@@ -583,7 +583,7 @@ unce_unkd_bwd_kernel(const float* __restrict__ x, const long long* __restrict__ 
         uce[i] = dead ? 0.f : (ce_g_px != nullptr ? gp[i] : gs_ce);
         la2[i] = la[i] * kLog2e;
         lt2[i] = lt[i] * kLog2e;
-        fold[i] = ex2f((la[i] - lo[i]) * kLog2e);
+        fold[i] = ex2f(lo[i] * kLog2e);
         float u = (kd_g_px != nullptr ? gk[i] : gs_kd) * inv_cold;
         if (mask != nullptr) u *= mask_zero ? (mk[i] == 0.f ? 1.f : 0.f) : mk[i];
         ukd[i] = u;
@@ -656,7 +656,7 @@ extern "C" size_t ucd_reduce_scratch_floats(void) { return (size_t)kScratchFloat
 extern "C" int ucd_unce_fwd(const float* x, int64_t* y, float* loss_px, float* lse_all, float* lse_old,
                             float* stats, float* scratch, int B, int C, int old_cl, int64_t HW,
                             int ignore_index, void* stream) {
-  UCD_CHECK_ARG(x && y && loss_px && lse_all && lse_old, "ucd_unce_fwd: null pointer");
+  UCD_CHECK_ARG(x && y && loss_px && lse_all, "ucd_unce_fwd: null pointer");
   UCD_CHECK_ARG(B > 0 && C > 0 && HW > 0, "ucd_unce_fwd: bad shape B=%d C=%d HW=%lld", B, C, (long long)HW);
   UCD_CHECK_ARG(old_cl >= 0 && old_cl <= C, "ucd_unce_fwd: old_cl=%d outside [0,%d]", old_cl, C);
   UCD_CHECK_ARG(stats == nullptr || scratch != nullptr, "ucd_unce_fwd: stats requested without scratch");
@@ -678,20 +678,20 @@ extern "C" int ucd_unce_fwd(const float* x, int64_t* y, float* loss_px, float* l
   return UCD_OK;
 }
 
-extern "C" int ucd_unce_bwd(const float* x, const int64_t* y, const float* lse_all, const float* lse_old,
+extern "C" int ucd_unce_bwd(const float* x, const int64_t* y, const float* lse_all, const float* bkg_gap,
                             const float* g_px, const float* g_scalar, float g_mul, const float* stats,
                             int mean_over_valid, float* dx, int accumulate, int B, int C, int old_cl, int64_t HW,
                             int ignore_index, void* stream) {
-  UCD_CHECK_ARG(x && y && lse_all && lse_old && dx, "ucd_unce_bwd: null pointer");
+  UCD_CHECK_ARG(x && y && lse_all && bkg_gap && dx, "ucd_unce_bwd: null pointer");
   UCD_CHECK_ARG(g_px || g_scalar, "ucd_unce_bwd: need g_px or g_scalar");
   UCD_CHECK_ARG(!mean_over_valid || stats, "ucd_unce_bwd: mean_over_valid needs stats");
   UCD_CHECK_ARG(B > 0 && C > 0 && HW > 0, "ucd_unce_bwd: bad shape");
   cudaStream_t st = (cudaStream_t)stream;
-  const bool v4 = can_vec4(HW, {x, lse_all, lse_old, g_px, dx}) && aligned16(y);
+  const bool v4 = can_vec4(HW, {x, lse_all, bkg_gap, g_px, dx}) && aligned16(y);
   const int grid = stream_grid((long long)B * HW / (v4 ? 4 : 1));
   auto kern = v4 ? (accumulate ? unce_bwd_kernel<4, true> : unce_bwd_kernel<4, false>)
                  : (accumulate ? unce_bwd_kernel<1, true> : unce_bwd_kernel<1, false>);
-  kern<<<grid, kStreamThreads, 0, st>>>(x, (const long long*)y, lse_all, lse_old, g_px, g_scalar, g_mul, stats,
+  kern<<<grid, kStreamThreads, 0, st>>>(x, (const long long*)y, lse_all, bkg_gap, g_px, g_scalar, g_mul, stats,
                                         mean_over_valid, dx, B, C, old_cl, HW, ignore_index);
   UCD_CHECK_LAUNCH("unce_bwd_kernel");
   return UCD_OK;
@@ -771,24 +771,24 @@ extern "C" int ucd_bkg_mask(const float* t_old, const int64_t* labels, float* ma
   return UCD_OK;
 }
 
-extern "C" int ucd_unce_unkd_bwd(const float* x, const int64_t* y, const float* lse_all, const float* lse_old,
+extern "C" int ucd_unce_unkd_bwd(const float* x, const int64_t* y, const float* lse_all, const float* bkg_gap,
                                  const float* ce_g_px, const float* ce_g_scalar, float ce_g_mul, const float* ce_stats,
                                  int mean_over_valid, int old_cl, int ignore_index, const float* t, const float* mask,
                                  float alpha, const float* lse3, const float* kd_g_px, const float* kd_g_scalar,
                                  float kd_g_mul, int kd_variant, float* dx, int accumulate, int B, int C, int C_old,
                                  int64_t HW, void* stream) {
-  UCD_CHECK_ARG(x && y && lse_all && lse_old && t && lse3 && dx, "ucd_unce_unkd_bwd: null pointer");
+  UCD_CHECK_ARG(x && y && lse_all && bkg_gap && t && lse3 && dx, "ucd_unce_unkd_bwd: null pointer");
   UCD_CHECK_ARG((ce_g_px || ce_g_scalar) && (kd_g_px || kd_g_scalar), "ucd_unce_unkd_bwd: need g_px or g_scalar for both terms");
   UCD_CHECK_ARG(!mean_over_valid || ce_stats, "ucd_unce_unkd_bwd: mean_over_valid needs stats");
   UCD_CHECK_ARG(B > 0 && HW > 0 && C_old >= 1 && C >= C_old, "ucd_unce_unkd_bwd: bad shape");
   UCD_CHECK_ARG(kd_variant == 0 || kd_variant == 2, "ucd_unce_unkd_bwd: KD variant must be 0 (unbiased) or 2 (masked)");
   cudaStream_t st = (cudaStream_t)stream;
-  const bool v4 = can_vec4(HW, {x, lse_all, lse_old, ce_g_px, t, mask, lse3, kd_g_px, dx}) && aligned16(y) &&
+  const bool v4 = can_vec4(HW, {x, lse_all, bkg_gap, ce_g_px, t, mask, lse3, kd_g_px, dx}) && aligned16(y) &&
                   ((long long)B * HW) % 4 == 0;
   const int grid = stream_grid((long long)B * HW / (v4 ? 4 : 1));
   auto kern = v4 ? (accumulate ? unce_unkd_bwd_kernel<4, true> : unce_unkd_bwd_kernel<4, false>)
                  : (accumulate ? unce_unkd_bwd_kernel<1, true> : unce_unkd_bwd_kernel<1, false>);
-  kern<<<grid, kStreamThreads, 0, st>>>(x, (const long long*)y, lse_all, lse_old, ce_g_px, ce_g_scalar, ce_g_mul,
+  kern<<<grid, kStreamThreads, 0, st>>>(x, (const long long*)y, lse_all, bkg_gap, ce_g_px, ce_g_scalar, ce_g_mul,
                                         ce_stats, mean_over_valid, old_cl, ignore_index, t, mask, alpha, lse3, kd_g_px,
                                         kd_g_scalar, kd_g_mul, kd_variant == 2 ? 1 : 0, dx, B, C, C_old, HW);
   UCD_CHECK_LAUNCH("unce_unkd_bwd_kernel");

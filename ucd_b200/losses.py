@@ -194,15 +194,16 @@ class _UnceFn(torch.autograd.Function):
         x = _f32c(inputs)
         dev = x.device
         loss_px = torch.empty(targets.shape, device=dev, dtype=torch.float32)
-        lse = torch.empty((2,) + tuple(targets.shape), device=dev, dtype=torch.float32)
+        # ONE saved statistic plane: lse over all channels.  The backward's other need, lse_all - lse_old at label-0
+        # pixels, is loss_px itself there (saved below: autograd guards it against in-place changes by the caller)
+        lse = torch.empty(targets.shape, device=dev, dtype=torch.float32)
         want_stats = reduction != "none"
         stats = torch.empty(2, device=dev, dtype=torch.float32) if want_stats else None
         scratch = (torch.empty(_lib.lib().ucd_reduce_scratch_floats(), device=dev, dtype=torch.float32)
                    if want_stats else None)
-        lse_p = lse.data_ptr()
-        check(_lib.lib().ucd_unce_fwd(ptr(x), ptr(targets), ptr(loss_px), lse_p, lse_p + 4 * B * HW, ptr(stats),
+        check(_lib.lib().ucd_unce_fwd(ptr(x), ptr(targets), ptr(loss_px), ptr(lse), None, ptr(stats),
                                       ptr(scratch), B, C, old_cl, HW, ignore_index, cur_stream()), "unce_fwd")
-        ctx.save_for_backward(x, targets, lse, stats)
+        ctx.save_for_backward(x, targets, lse, stats, loss_px)
         ctx.cfg = (B, C, HW, old_cl, ignore_index, reduction)
         out = loss_px if reduction == "none" else (stats[0].clone() if reduction == "sum" else stats[0] / stats[1])
         if chain is None:
@@ -212,7 +213,7 @@ class _UnceFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g, g_token=None):
-        x, targets, lse, stats = ctx.saved_tensors
+        x, targets, lse, stats, loss_px = ctx.saved_tensors
         B, C, HW, old_cl, ignore_index, reduction = ctx.cfg
         if g is None:   # this loss value was not used: only the chain bookkeeping remains
             if ctx.chain is None:
@@ -228,7 +229,7 @@ class _UnceFn(torch.autograd.Function):
             g_sc = g.reshape(1)
         if g_sc is not None:
             g_sc = _f32c(g_sc)
-        term = dict(kind="ce", x=x, targets=targets, lse=lse, stats=stats, g_px=g_px, g_sc=g_sc,
+        term = dict(kind="ce", x=x, targets=targets, lse=(lse, loss_px), stats=stats, g_px=g_px, g_sc=g_sc,
                     mean_over_valid=1 if reduction == "mean" else 0, B=B, C=C, HW=HW, old_cl=old_cl,
                     ignore_index=ignore_index)
         if ctx.chain is None:
