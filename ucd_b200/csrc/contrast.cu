@@ -973,6 +973,7 @@ con_finalize_kernel(const float* __restrict__ stats, const float* __restrict__ l
   const int n_rows = *n_rows_p;
   const int sub = threadIdx.x >> 6, q = threadIdx.x & 63;
   float lsum = 0.f, lcnt = 0.f;
+#pragma unroll 2  // two rows' loads in flight: 30 -> 27 us at the bench size (6.3 TB/s, the read ceiling)
   for (long long row = (long long)blockIdx.x * 4 + sub; row < n_rows; row += (long long)gridDim.x * 4) {
     const float num = stats[2 * rows_pad + row];
     float L = 0.f, T = 0.f;
