@@ -410,24 +410,32 @@ prep_bwd_kernel(const float* __restrict__ g_anchor, const float* __restrict__ an
     slot = blk_base[p / kPrepBlock] + px_meta[(size_t)PX_RANK_A * n_px + p];  // ref_off[0][blk]
   if (warp == 0) slot_s[lane] = slot;
   __syncthreads();
-  for (int pi = warp; pi < 32; pi += 4) {
-    const int s = slot_s[pi];
-    if (s < 0) {
+  // two pixels per pass: the rows of both are requested before either dot product is reduced (a warp working on one
+  // pixel at a time had 2 KB in flight and a shuffle reduction between loads: latency-bound at 3.7 TB/s)
+  for (int pi = warp; pi < 32; pi += 8) {
+    const int s0 = slot_s[pi], s1 = slot_s[pi + 4];
+    float g[2][8], a[2][8], dot[2] = {0.f, 0.f};
 #pragma unroll
-      for (int k = 0; k < 8; ++k) tile[lane + 32 * k][pi] = 0.f;
-      continue;
+    for (int j = 0; j < 2; ++j) {
+      const int s = j ? s1 : s0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        g[j][k] = s >= 0 ? g_anchor[(size_t)s * 256 + lane + 32 * k] : 0.f;
+        a[j][k] = s >= 0 ? anchor_f32[(size_t)s * 256 + lane + 32 * k] : 0.f;
+      }
     }
-    float g[8], a[8], dot = 0.f;
+    const float inv0 = s0 >= 0 ? inv_norm[s0] : 0.f, inv1 = s1 >= 0 ? inv_norm[s1] : 0.f;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) dot[j] = fmaf(g[j][k], a[j][k], dot[j]);
+      dot[j] = warp_sum(dot[j]);
+    }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      g[k] = g_anchor[(size_t)s * 256 + lane + 32 * k];
-      a[k] = anchor_f32[(size_t)s * 256 + lane + 32 * k];
-      dot = fmaf(g[k], a[k], dot);
+      tile[lane + 32 * k][pi] = (g[0][k] - dot[0] * a[0][k]) * inv0;       // non-anchor pixel: zeros
+      tile[lane + 32 * k][pi + 4] = (g[1][k] - dot[1] * a[1][k]) * inv1;
     }
-    dot = warp_sum(dot);
-    const float inv = inv_norm[s];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) tile[lane + 32 * k][pi] = (g[k] - dot * a[k]) * inv;
   }
   __syncthreads();
   if (p < n_px) {
